@@ -1,0 +1,158 @@
+/* neucor_b200.h — C ABI of the B200-native simulation core for NeuroCorrelation's per-step
+ * spiking-network update (libneucor_b200.so).
+ *
+ * The reference has no FFI/plugin layer: its boundary is the C++ class `NeuCor`
+ * (/root/reference/src/NeuCor.h:36-138) exported by the static library `neurocorrelation_core`
+ * (CMakeLists.txt:13-25).  The drop-in keeps that class on the host
+ * (neurocorrelation_b200/host/NeuCor.h, same public members) and drives the GPU through the
+ * entry points below — plain pointers and sizes, `int` status returns (0 = ok, negative = error,
+ * text via nc_last_error), no exceptions and no torch types across the boundary, one calling
+ * thread per handle, device memory owned by the handle, host arrays borrowed for the duration of
+ * a call.  There is NO CPU fallback: every entry point fails with NC_ERR_NO_DEVICE when no CUDA
+ * device is usable.
+ *
+ * Each entry point names the reference code it replaces (file:line under /root/reference/src).
+ */
+#ifndef NEUCOR_B200_H
+#define NEUCOR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NC_OK 0
+#define NC_ERR_INVALID (-1)    /* bad argument / precondition (message says which) */
+#define NC_ERR_NO_DEVICE (-2)  /* no usable CUDA device — there is no CPU path */
+#define NC_ERR_CUDA (-3)       /* a CUDA call failed */
+#define NC_ERR_CAPACITY (-4)   /* a fixed-capacity device buffer overflowed (fires per step) */
+#define NC_ERR_STATE (-5)      /* call order (e.g. step before upload) */
+
+/* nc_step `sweep` flags */
+#define NC_SWEEP_END 1    /* after the window, run every neuron at t1 in ascending ID (detector read / renderer) */
+#define NC_SWEEP_START 2  /* before the window, run every neuron at t0 — NeuCor::runAll (NeuCor.cpp:595-597),
+                             in ascending ID instead of the reference's heap order */
+
+typedef struct nc_engine nc_engine;
+
+typedef struct nc_config {
+    int32_t device;            /* CUDA device ordinal */
+    int32_t rank, world;       /* neuron-range shard of this engine (world = 1: whole network) */
+    uint32_t fire_capacity;    /* max fire records per step (0 = default: 4*N_global + 1024) */
+    uint32_t cand_smem;        /* per-row candidate slots staged in shared memory (0 = default 256) */
+    void* stream;              /* cudaStream_t to launch on (NULL = the engine creates its own) */
+    uint32_t reserved[2];
+} nc_config;
+
+/* Host-generated event of one step (NeuCor::run's scheduling phase, NeuCor.cpp:599-607).
+ * kind 0: input firer `index` fires `neuron` at `time` (InputFirer::run, NeuCor.cpp:326-331)
+ * kind 2: neuron is run at `time` (Neuron::scheduleFire's queue entry, NeuCor.cpp:658-661);
+ *         flags bit 0: `time` is the neuron's scheduledFireTime (the last one drawn this step). */
+typedef struct nc_event {
+    uint32_t neuron;
+    float time;
+    uint32_t kind;
+    uint32_t index_or_flags;
+} nc_event;
+
+typedef struct nc_step_stats {
+    uint64_t fires;             /* Neuron::fire calls (NeuCor.cpp:643) */
+    uint64_t deliveries;        /* Synapse::run past its guard (NeuCor.cpp:719-721) */
+    uint64_t loads_accepted;    /* Synapse::fire that took the slot (NeuCor.cpp:728-737) */
+    uint64_t loads_dropped;     /* Synapse::fire returning early on a busy slot (NeuCor.cpp:728) */
+    uint64_t plasticity_calls;  /* Synapse::synapticPlasticity (NeuCor.cpp:740) */
+    uint64_t hidden_rand_calls; /* rand() evaluated by the short-circuit at NeuCor.cpp:752 */
+    uint64_t neuron_runs;       /* Neuron::run with deltaT != 0 (NeuCor.cpp:626) */
+    uint64_t active_visits;     /* in-synapse contributions added (NeuCor.cpp:695) */
+} nc_step_stats;
+
+/* Library-level: text of the last error of a failed nc_create (no handle exists then). */
+const char* nc_global_error(void);
+/* Number of usable CUDA devices (0 when there is none; never throws). */
+int nc_device_count(void);
+
+/* Replaces NeuCor::NeuCor's device-independent setup (NeuCor.cpp:17-30). */
+int nc_create(const nc_config* cfg, nc_engine** out);
+void nc_destroy(nc_engine* e);
+const char* nc_last_error(const nc_engine* e);
+
+/* Network upload — replaces the deque<Neuron>/vector<Synapse>/map containers (NeuCor.h:116,
+ * 211-212) by a post-synaptic-sorted CSR: rows = target neurons [row0, row0+n_rows) owned by this
+ * engine, in-row ascending presynaptic ID (the iteration order of Neuron::inSynapses that
+ * charge_insynapses uses, NeuCor.cpp:690).  rowptr has n_rows+1 entries starting at 0.
+ * `length` is Synapse::length (delay = length * 2.0f, NeuCor.cpp:485,733); `inhibitory` the flag
+ * byte that selects the weight clamp (NeuCor.cpp:760-761).  Initial state is the reference's:
+ * potential -70, lastFire NaN, idle slots, lastSpikeArrival -inf (NeuCor.cpp:376-394,469,484). */
+int nc_upload_network(nc_engine* e, uint64_t n_global, uint64_t row0, uint64_t n_rows, const uint64_t* rowptr,
+                      const uint32_t* pre, const float* weight, const float* length, const uint8_t* inhibitory);
+/* Smallest synaptic delay (2*length) of the uploaded shard; a step window must be shorter. */
+int nc_min_delay(const nc_engine* e, float* out);
+
+/* NeuCor::learningRate / presynapticFactor / postsynapticFactor are read live on every plasticity
+ * call (NeuCor.cpp:757-758); the trace decays are the per-object copies (NeuCor.cpp:369,464). */
+int nc_set_plasticity(nc_engine* e, float learning_rate, float pre_factor, float post_factor, float pre_decay,
+                      float post_decay);
+
+/* One window (t0, t1] of NeuCor::run()'s hot loop (NeuCor.cpp:609-616) on the device: neuron pass
+ * (Neuron::run/fire/transfer, NeuCor.cpp:619-714), fire-event exchange, synapse pass
+ * (Synapse::fire/run/synapticPlasticity, NeuCor.cpp:718-764).  `events` are the host-scheduled
+ * input-firer and background events with t0 <= time <= t1, sorted by (neuron, time).
+ * sweep != 0: afterwards every neuron is run at t1 in ascending ID — what the reference's
+ * VoltageDetector::getVoltage does to its `near` neurons (NeuCor.cpp:359-366) and what
+ * runAll / the renderer rely on.  Requires t1 - t0 < nc_min_delay().
+ * hidden_rand_calls: number of rand() evaluations the reference would have made inside
+ * synapticPlasticity during this window (NeuCor.cpp:752); the host must advance rand() by it. */
+int nc_step(nc_engine* e, float t0, float t1, int sweep, const nc_event* events, uint32_t n_events,
+            uint64_t* hidden_rand_calls, nc_step_stats* stats_or_null);
+
+/* The side effect of VoltageDetector::getVoltage (NeuCor.cpp:361-362): run the listed neurons
+ * (ascending IDs of this shard; NULL = all) at time `now`, including any fires this causes. */
+int nc_run_neurons(nc_engine* e, float now, const uint32_t* ids, uint32_t n_ids, uint64_t* hidden_rand_calls,
+                   nc_step_stats* stats_or_null);
+
+/* Renderer-/snapshot-visible state (NeuCor.h:104-105, NeuCor.cpp:99-134, Renderer.cpp:655-699).
+ * Any pointer may be NULL. potAct is the interleaved (potential, activity) array of this shard. */
+int nc_read_neurons(nc_engine* e, float* potAct, float* lastFire, float* lastRan);
+int nc_read_synapses(nc_engine* e, float* weight, float* arrive, float* depol, float* lastArrival, float* lastStart);
+/* Fire events of the last step, all shards: (neuron, time); returns the total count in *count. */
+int nc_read_fires(nc_engine* e, uint32_t capacity, uint32_t* neuron, float* time, uint32_t* count);
+/* Synapse::getPrePot / getPostPot at time `now` for every synapse of the shard (NeuCor.cpp:547-567). */
+int nc_read_synapse_pots(nc_engine* e, float now, float* prePot, float* postPot);
+/* NeuCor::resetActivities (NeuCor.cpp:233-235,460). */
+int nc_reset_activities(nc_engine* e, float now);
+/* VoltageDetector::getVoltage's averaging (NeuCor.cpp:360-365) over `near` (ascending IDs of this
+ * shard), summed sequentially in float on the device; the neurons must already be at `now`. */
+int nc_detector_mean(nc_engine* e, const uint32_t* near, uint32_t n_near, float* out);
+
+/* Device-resident stepping for measurement: record the event lists of live steps on the device
+ * ("tape"), snapshot/restore the full state, and replay the taped steps back to back with no
+ * host<->device traffic inside the timed region.  Replay is bit-identical to the live run. */
+int nc_tape_begin(nc_engine* e, uint32_t max_steps, uint64_t max_events);
+int nc_tape_end(nc_engine* e);
+int nc_snapshot(nc_engine* e);
+int nc_restore(nc_engine* e);
+/* Replays taped steps [first, first+count); ms_total = CUDA-event time of the whole region,
+ * ms_pass1 / ms_pass2 = summed per-kernel times (may be NULL). */
+int nc_tape_replay(nc_engine* e, uint32_t first, uint32_t count, float* ms_total, float* ms_pass1, float* ms_pass2,
+                   uint64_t* hidden_rand_calls, nc_step_stats* stats_or_null);
+/* Number of kernel launches issued by this engine since creation. */
+uint64_t nc_launch_count(const nc_engine* e);
+
+/* Multi-GPU: engines of one process group exchange fire records through caller-provided
+ * callbacks is NOT done here — the exchange buffer is exposed so that the host (NCCL via
+ * torch.distributed, or ncclAllGather directly) can all-gather it between the two passes. */
+int nc_step_begin(nc_engine* e, float t0, float t1, int sweep, const nc_event* events, uint32_t n_events);
+/* Device pointer and byte size of this shard's fire-record block: [count u32, pad u32 x3, records...]. */
+int nc_exchange_buffer(nc_engine* e, void** dev_ptr, uint64_t* bytes);
+/* Device pointer where the gathered blocks of all `world` shards must be placed (world * bytes). */
+int nc_gather_buffer(nc_engine* e, void** dev_ptr, uint64_t* bytes);
+int nc_step_end(nc_engine* e, uint64_t* hidden_rand_calls, nc_step_stats* stats_or_null);
+/* world > 1: per-shard record counts and the record stride used when placing the gathered blocks. */
+int nc_step_end_counts(nc_engine* e, const uint32_t* counts, uint32_t stride, uint64_t* hidden_rand_calls,
+                       nc_step_stats* stats_or_null);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEUCOR_B200_H */

@@ -1,0 +1,856 @@
+// libneucor_b200.so — the device engine behind include/neucor_b200.h.
+//
+// One window (t0, t1] of the reference's event loop (NeuCor::run, /root/reference/src/NeuCor.cpp:583-617)
+// is executed as two data-parallel passes over a post-synaptic-sorted CSR:
+//
+//   neuron pass  (k_neuron_pass)  — one warp per target neuron q.  Stages the row's occupied slots
+//       (arrive != 0 && arrive <= t1) from HBM into shared memory with ballot compaction, derives q's
+//       in-window events (deliveries, +2 ms requeues, host-scheduled input/background events), and
+//       replays them in the canonical order with Neuron::run / fire semantics (NeuCor.cpp:619-714):
+//       ordered accumulation over active slots in ascending presynaptic ID, passive decay, threshold /
+//       refractory check, AP waveform, activity.  Emits fire records (warp-aggregated append) and
+//       marks cleared slots in place.  Never touches weights.
+//   exchange     — fire records of all shards are made visible to every shard (NCCL all-gather by the
+//       host between nc_step_begin and nc_step_end; a no-op for world = 1), then k_index_build turns
+//       them into a per-neuron lookup (bitmask + linked records).
+//   synapse pass (k_synapse_pass) — one warp per row, one lane per slot: tests "did my presynaptic
+//       neuron fire" against the bitmask (the pull gather), and resolves each eventful slot's
+//       operations — load (Synapse::fire, NeuCor.cpp:727-738), clear (NeuCor.cpp:697), post-fire
+//       plasticity and delivery plasticity (Synapse::run / synapticPlasticity, NeuCor.cpp:718-764) — in
+//       the canonical event order.
+//
+// Arithmetic mirrors the reference's float/double typing operator by operator with explicit-rounding
+// intrinsics (no FMA contraction; built with -fmad=false) and glibc-exact powf/exp (glibc_math.cuh).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/neucor_b200.h"
+#include "step_logic.cuh"
+
+using namespace ncm;
+using namespace ncs;
+
+#define NC_WARPS_PER_BLOCK 8
+
+// ------------------------------------------------------------------------------------------------
+// Neuron pass
+// ------------------------------------------------------------------------------------------------
+struct EvPick {  // (time, rank<<32|k2) ordering; src: candidate index, or 0x80000000|host event index
+    float t;
+    unsigned long long code;
+    uint32_t src;
+};
+__global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32) k_neuron_pass(View v, StepArgs s) {
+    extern __shared__ unsigned char smem[];
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    const uint32_t cap = s.candCap;
+    float* sA = reinterpret_cast<float*>(smem) + (size_t)wib * 3 * cap;
+    CandView cv;
+    cv.a = sA; cv.d = sA + cap; cv.j = reinterpret_cast<uint32_t*>(sA + 2 * cap); cv.cap = cap;
+    const uint64_t gw = (uint64_t)blockIdx.x * NC_WARPS_PER_BLOCK + wib, nW = (uint64_t)gridDim.x * NC_WARPS_PER_BLOCK;
+    cv.sa = v.spillA + gw * v.spillPerWarp; cv.sd = v.spillD + gw * v.spillPerWarp; cv.sj = v.spillJ + gw * v.spillPerWarp;
+    unsigned long long nFires = 0, nRuns = 0, nVisits = 0, nDeliv = 0;
+
+    for (uint64_t row = gw; row < v.nRows; row += nW) {
+        const uint32_t q = (uint32_t)(v.row0 + row);
+        if (s.subset) {  // nc_run_neurons: zero-length window, only the listed neurons are run
+            uint32_t lo = 0, hi = s.nSubset;
+            while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (s.subset[mid] < q) lo = mid + 1; else hi = mid; }
+            if (lo >= s.nSubset || s.subset[lo] != q) continue;
+        }
+        const uint64_t rs = v.rowptr[row], re = v.rowptr[row + 1];
+        // ---- stage occupied slots (arrive != 0 && arrive <= t1), preserving row order ----
+        uint32_t cnt = 0;
+        for (uint64_t base = rs; base < re; base += 32) {
+            uint64_t j = base + lane;
+            float a = (j < re) ? v.arrive[j] : 0.0f;
+            bool is = (a != 0.0f) && (a <= s.t1);
+            uint32_t m = __ballot_sync(0xffffffffu, is);
+            if (is) {
+                uint32_t pos = cnt + __popc(m & ((1u << lane) - 1u));
+                cv.A(pos) = a;
+                cv.D(pos) = v.depol[j];
+                cv.J(pos) = (uint32_t)(j - rs);
+            }
+            cnt += __popc(m);
+        }
+        __syncwarp();
+        // ---- host events of this neuron: [evLo, evHi) in the (neuron, time)-sorted list ----
+        uint32_t evLo = 0, evHi = 0;
+        if (s.nEv) {
+            uint32_t lo = 0, hi = s.nEv;
+            while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (s.ev[mid].neuron < q) lo = mid + 1; else hi = mid; }
+            evLo = lo; hi = s.nEv;
+            while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (s.ev[mid].neuron <= q) lo = mid + 1; else hi = mid; }
+            evHi = lo;
+        }
+        NeuronState n;
+        {
+            float2 pa = v.potAct[row];
+            n.pot = pa.x; n.act = pa.y;
+            n.lastRan = v.lastRan[row]; n.lastFire = v.lastFire[row]; n.actStart = v.actStart[row];
+            n.firings = v.firings[row];
+            n.sched = __uint_as_float(0x7fc00000u);
+            for (uint32_t e = evLo; e < evHi; e++)
+                if (s.ev[e].kind == 2u && (s.ev[e].index_or_flags & 1u)) n.sched = s.ev[e].time;
+            if (lane == 0) v.lfStart[row] = n.lastFire;
+        }
+        // ---- replay in-window events in canonical order ----
+        if (cnt || evHi > evLo || (s.sweep & NC_SWEEP_START)) {
+            float curT = s.t0;
+            unsigned long long curC = 0;
+            bool first = true;  // events at exactly t0 are allowed for host events only
+            for (;;) {
+                EvPick best;
+                best.t = INFINITY; best.code = ~0ull; best.src = 0xffffffffu;
+                for (uint32_t c = lane; c < cnt; c += 32) {
+                    float a = fabsf(cv.A(c));
+                    if (a > s.t0) {  // delivery in this window (a <= t1 by staging)
+                        uint32_t p = v.pre[rs + cv.J(c)] & 0x7fffffffu;
+                        unsigned long long code = (1ull << 32) | p;
+                        if ((first || pick_less(curT, curC, a, code)) && pick_less(a, code, best.t, best.code)) {
+                            best.t = a; best.code = code; best.src = c;
+                        }
+                    }
+                    float tR = add32(a, 2.0f);  // Neuron::transfer's requeue (NeuCor.cpp:665)
+                    if (tR > s.t0 && tR <= s.t1) {
+                        unsigned long long code = (2ull << 32);
+                        if ((first || pick_less(curT, curC, tR, code)) && pick_less(tR, code, best.t, best.code)) {
+                            best.t = tR; best.code = code; best.src = c;
+                        }
+                    }
+                }
+                if ((s.sweep & NC_SWEEP_START) && lane == 0 && (first || pick_less(curT, curC, s.t0, 2ull << 32)) &&
+                    pick_less(s.t0, 2ull << 32, best.t, best.code)) {
+                    best.t = s.t0; best.code = 2ull << 32; best.src = 0xfffffffeu;  // runAll: queued at t0 (NeuCor.cpp:596)
+                }
+                for (uint32_t e = evLo + lane; e < evHi; e += 32) {
+                    nc_event ev = s.ev[e];
+                    unsigned long long code = ev.kind == 0u ? (unsigned long long)ev.index_or_flags : (2ull << 32);
+                    bool after = first ? (ev.time >= s.t0) : pick_less(curT, curC, ev.time, code);
+                    if (after && ev.time <= s.t1 && pick_less(ev.time, code, best.t, best.code)) {
+                        best.t = ev.time; best.code = code; best.src = 0x80000000u | e;
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    float ot = __shfl_xor_sync(0xffffffffu, best.t, o);
+                    unsigned long long oc = __shfl_xor_sync(0xffffffffu, best.code, o);
+                    uint32_t os = __shfl_xor_sync(0xffffffffu, best.src, o);
+                    if (pick_less(ot, oc, best.t, best.code)) { best.t = ot; best.code = oc; best.src = os; }
+                }
+                if (best.code == ~0ull) break;
+                if (lane == 0) {
+                    uint32_t rank = (uint32_t)(best.code >> 32), k = (uint32_t)best.code;
+                    if (rank == 0) {  // InputFirer::run → Neuron::fire, no update, ignores refractory (NeuCor.cpp:326-331)
+                        neuron_fire(v, n, q, best.t, k, q, nFires);
+                    } else if (rank == 1) {  // Synapse::run → Neuron::transfer (NeuCor.cpp:718-726,663-666)
+                        nDeliv++;
+                        neuron_run(v, n, cv, cnt, rs, q, best.t, (1u << 30) | q, k, NC_SENT | (1u << 29) | cv.J(best.src), nFires, nRuns, nVisits);
+                    } else {
+                        neuron_run(v, n, cv, cnt, rs, q, best.t, (2u << 30) | q, 0u, NC_SENT | (2u << 29), nFires, nRuns, nVisits);
+                    }
+                }
+                __syncwarp();
+                curT = best.t; curC = best.code; first = false;
+            }
+        }
+        if (lane == 0) {
+            if (s.sweep & NC_SWEEP_END) neuron_run(v, n, cv, cnt, rs, q, s.t1, (3u << 30) | q, 0u, NC_SENT | (3u << 29), nFires, nRuns, nVisits);
+            v.potAct[row] = make_float2(n.pot, n.act);
+            v.lastRan[row] = n.lastRan; v.lastFire[row] = n.lastFire; v.firings[row] = n.firings;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        if (nFires) atomicAdd(&v.stats[0], nFires);
+        if (nDeliv) atomicAdd(&v.stats[1], nDeliv);
+        if (nRuns) atomicAdd(&v.stats[6], nRuns);
+        if (nVisits) atomicAdd(&v.stats[7], nVisits);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fire index (bitmask + per-neuron record lists) over the gathered records of all shards
+// ------------------------------------------------------------------------------------------------
+__global__ void k_index_build(View v, StepArgs s) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t b = blockIdx.y;
+    if (b >= s.world || i >= s.counts[b]) return;
+    uint32_t idx = b * s.gStride + i;
+    uint32_t nrn = v.gRecs[idx].neuron;
+    v.next[idx] = atomicExch(&v.head[nrn], (int32_t)idx);
+    atomicOr(&v.mask[nrn >> 5], 1u << (nrn & 31u));
+}
+__global__ void k_index_reset(View v, StepArgs s) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t b = blockIdx.y;
+    if (b >= s.world || i >= s.counts[b]) return;
+    uint32_t nrn = v.gRecs[b * s.gStride + i].neuron;
+    v.head[nrn] = -1;
+    v.mask[nrn >> 5] = 0u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Synapse pass
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32) k_synapse_pass(View v, StepArgs s) {
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    const uint64_t gw = (uint64_t)blockIdx.x * NC_WARPS_PER_BLOCK + wib, nW = (uint64_t)gridDim.x * NC_WARPS_PER_BLOCK;
+    uint32_t cnt[5] = {0, 0, 0, 0, 0};  // loads accepted, dropped, plasticity calls, hidden rand, deliveries
+    for (uint64_t row = gw; row < v.nRows; row += nW) {
+        const uint32_t q = (uint32_t)(v.row0 + row);
+        const uint64_t rs = v.rowptr[row], re = v.rowptr[row + 1];
+        const bool qFired = (v.mask[q >> 5] >> (q & 31u)) & 1u;
+        const float lfS = v.lfStart[row];
+        for (uint64_t j = rs + lane; j < re; j += 32) {
+            uint32_t pw = v.pre[j];
+            uint32_t p = pw & 0x7fffffffu;
+            uint32_t ab = __float_as_uint(v.arrive[j]);
+            bool pFired = (v.mask[p >> 5] >> (p & 31u)) & 1u;
+            float a = __uint_as_float(ab);
+            bool eventful = qFired || pFired || (ab & NC_SENT) || (ab != 0u && a > s.t0 && a <= s.t1);
+            if (eventful) resolve_slot(v, s, j, rs, q, p, (pw >> 31) != 0u, ab, pFired, qFired, lfS, cnt);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        uint32_t x = cnt[i];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        cnt[i] = x;
+    }
+    if (lane == 0) {
+        if (cnt[0]) atomicAdd(&v.stats[2], (unsigned long long)cnt[0]);
+        if (cnt[1]) atomicAdd(&v.stats[3], (unsigned long long)cnt[1]);
+        if (cnt[2]) atomicAdd(&v.stats[4], (unsigned long long)cnt[2]);
+        if (cnt[3]) atomicAdd(&v.stats[5], (unsigned long long)cnt[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small utility kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void k_init_neurons(View v) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.nRows) return;
+    v.potAct[i] = make_float2(-70.0f, 0.0f);  // NeuCor.cpp:389,394
+    v.lastRan[i] = 0.0f;
+    v.lastFire[i] = __uint_as_float(0x7fc00000u);  // NAN, NeuCor.cpp:392
+    v.lfStart[i] = __uint_as_float(0x7fc00000u);
+    v.actStart[i] = 0.0f;
+    v.firings[i] = 0u;
+}
+__global__ void k_init_synapses(View v, const float* length, const unsigned char* inh, float* delay) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.S) return;
+    v.arrive[i] = 0.0f; v.depol[i] = 0.0f; v.lastStart[i] = 0.0f;
+    v.lastArr[i] = __uint_as_float(0xff800000u);  // -INFINITY, NeuCor.cpp:469
+    delay[i] = mul32(length[i], 2.0f);             // length * AP_speed, NeuCor.cpp:485,733
+    if (inh[i]) v.pre[i] |= 0x80000000u;
+}
+__global__ void k_fill_i32(int32_t* p, uint64_t n, int32_t val) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = val;
+}
+__global__ void k_reset_activities(View v, float now) {  // Neuron::resetActivity, NeuCor.cpp:460
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.nRows) return;
+    v.firings[i] = 0u; v.actStart[i] = now;
+    float2 pa = v.potAct[i]; pa.y = 0.0f; v.potAct[i] = pa;
+}
+// VoltageDetector::getVoltage's sequential float sum (NeuCor.cpp:360-365) — one thread, exact order.
+__global__ void k_detector_mean(View v, const uint32_t* near, uint32_t n, float* out) {
+    if (blockIdx.x || threadIdx.x) return;
+    float avg = 0.0f;
+    for (uint32_t i = 0; i < n; i++) avg = add32(avg, v.potAct[near[i] - v.row0].x);
+    *out = div32(avg, (float)n);
+}
+// Synapse::getPrePot / getPostPot (NeuCor.cpp:547-567)
+__device__ __forceinline__ float render_behaviour(float valf) {  // AP_RENDER_BEHAVIOUR, NeuCor.cpp:547-550
+    float val = (float)fmin(fmax((double)valf, 0.0), 0.7);
+    if ((double)val < 0.5) {
+        float x = (float)div64((double)val, 5.0);
+        float p = (x >= 1.17549435e-38f) ? powf_pos(x, 3.0f) : 0.0f;
+        return (float)mul64(mul64(8.0, 1000.0), (double)p);
+    }
+    float x = (float)sub64(3.5, (double)mul32(5.0f, val));
+    return (float)mul64(8.0, (double)mul32(x, x));
+}
+__global__ void k_synapse_pots(View v, float now, float* prePot, float* postPot) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.S) return;
+    float a = v.arrive[i], w = v.weight[i], dl = v.delay[i];
+    float pre = 0.0f, post = 0.0f;
+    if (a != 0.0f) {
+        pre = mul32(render_behaviour(div32(sub32(now, v.lastStart[i]), dl)), w);
+        if (now < a) post = mul32(render_behaviour(div32(sub32(a, now), dl)), w);
+    }
+    if (prePot) prePot[i] = pre;
+    if (postPot) postPot[i] = post;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side of the C ABI
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+struct TapeStep { float t0, t1; int sweep; uint64_t evOff; uint32_t nEv; };
+
+struct nc_engine {
+    nc_config cfg;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    bool uploaded = false;
+    View v;
+    float* dDelay = nullptr;
+    nc_event* dEv = nullptr; uint32_t evCap = 0;
+    nc_event* hEvPinned = nullptr; uint32_t hEvCap = 0;
+    unsigned long long* hStats = nullptr;  // pinned, 8 + 2
+    uint32_t* hHdr = nullptr;              // pinned, 4
+    FireRec* dGather = nullptr;            // world * fireCap (own) or bound by the host
+    bool gatherBound = false;
+    float lr = 1.0f, preF = 0.13f, postF = 0.30f, preD = 0.75f, postD = 0.65f;
+    float minDelay = INFINITY;
+    uint32_t candCap = 256, grid1 = 0, grid2 = 0;
+    size_t smem1 = 0;
+    uint64_t launches = 0;
+    // in-flight step (nc_step_begin .. nc_step_end)
+    StepArgs cur; bool inStep = false;
+    // tape
+    bool taping = false; std::vector<TapeStep> tape; nc_event* dTape = nullptr; uint64_t tapeCap = 0, tapeUsed = 0; uint32_t tapeMaxSteps = 0;
+    // snapshot
+    struct Snap { float *arrive, *depol, *weight, *lastArr, *lastStart, *lastRan, *lastFire, *lfStart, *actStart; float2* potAct; uint32_t* firings; bool valid; } snap = {};
+    int smCount = 148;
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            e->err = std::string(#call) + ": " + cudaGetErrorString(_e);                           \
+            return NC_ERR_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+static int fail(nc_engine* e, int code, const std::string& msg) { e->err = msg; return code; }
+
+extern "C" const char* nc_global_error(void) { return g_err.c_str(); }
+extern "C" const char* nc_last_error(const nc_engine* e) { return e ? e->err.c_str() : g_err.c_str(); }
+extern "C" uint64_t nc_launch_count(const nc_engine* e) { return e->launches; }
+
+extern "C" int nc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int nc_create(const nc_config* cfg, nc_engine** out) {
+    if (!cfg || !out) { g_err = "nc_create: null argument"; return NC_ERR_INVALID; }
+    int n = nc_device_count();
+    if (n <= 0) { g_err = "nc_create: no usable CUDA device (this library has no CPU path)"; return NC_ERR_NO_DEVICE; }
+    if (cfg->device < 0 || cfg->device >= n) { g_err = "nc_create: device ordinal out of range"; return NC_ERR_INVALID; }
+    if (cfg->world < 1 || cfg->world > NC_MAX_WORLD || cfg->rank < 0 || cfg->rank >= cfg->world) { g_err = "nc_create: bad rank/world"; return NC_ERR_INVALID; }
+    nc_engine* e = new nc_engine();
+    e->cfg = *cfg;
+    memset(&e->v, 0, sizeof(View));
+    cudaError_t ce = cudaSetDevice(cfg->device);
+    if (ce == cudaSuccess) {
+        if (cfg->stream) { e->stream = (cudaStream_t)cfg->stream; }
+        else { ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking); e->ownStream = true; }
+    }
+    if (ce == cudaSuccess) ce = cudaMemcpyToSymbol(d_POWF_LOG2_TAB, NC_POWF_LOG2_TAB, sizeof(NC_POWF_LOG2_TAB));
+    if (ce == cudaSuccess) ce = cudaMemcpyToSymbol(d_EXP2F_TAB, NC_EXP2F_TAB, sizeof(NC_EXP2F_TAB));
+    if (ce == cudaSuccess) ce = cudaMemcpyToSymbol(d_EXP_TAB, NC_EXP_TAB, sizeof(NC_EXP_TAB));
+    if (ce == cudaSuccess) ce = cudaMallocHost(&e->hStats, 16 * sizeof(unsigned long long));
+    if (ce == cudaSuccess) ce = cudaMallocHost(&e->hHdr, 4 * sizeof(uint32_t));
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->v.stats, 8 * sizeof(unsigned long long));
+    if (ce == cudaSuccess) ce = cudaMemset(e->v.stats, 0, 8 * sizeof(unsigned long long));
+    cudaDeviceProp prop;
+    if (ce == cudaSuccess) ce = cudaGetDeviceProperties(&prop, cfg->device);
+    if (ce != cudaSuccess) { g_err = std::string("nc_create: ") + cudaGetErrorString(ce); delete e; return NC_ERR_CUDA; }
+    e->smCount = prop.multiProcessorCount;
+    if (cfg->cand_smem) e->candCap = cfg->cand_smem;
+    *out = e;
+    return NC_OK;
+}
+
+static void free_all(nc_engine* e) {
+    View& v = e->v;
+    cudaFree((void*)v.rowptr); cudaFree(v.pre); cudaFree(v.arrive); cudaFree(v.depol); cudaFree(v.weight); cudaFree(v.lastArr);
+    cudaFree(v.lastStart); cudaFree(e->dDelay); cudaFree(v.potAct); cudaFree(v.lastRan); cudaFree(v.lastFire); cudaFree(v.lfStart);
+    cudaFree(v.actStart); cudaFree(v.firings); cudaFree(v.localHdr); cudaFree(v.head); cudaFree(v.next); cudaFree(v.mask);
+    cudaFree(v.spillA); cudaFree(v.spillD); cudaFree(v.spillJ);
+    if (!e->gatherBound) cudaFree(e->dGather);
+    cudaFree(e->dEv); cudaFree(e->dTape);
+    auto& s = e->snap;
+    cudaFree(s.arrive); cudaFree(s.depol); cudaFree(s.weight); cudaFree(s.lastArr); cudaFree(s.lastStart); cudaFree(s.lastRan);
+    cudaFree(s.lastFire); cudaFree(s.lfStart); cudaFree(s.actStart); cudaFree(s.potAct); cudaFree(s.firings);
+}
+
+extern "C" void nc_destroy(nc_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    cudaStreamSynchronize(e->stream);
+    free_all(e);
+    cudaFree(e->v.stats);
+    cudaFreeHost(e->hStats); cudaFreeHost(e->hHdr); cudaFreeHost(e->hEvPinned);
+    if (e->ownStream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+extern "C" int nc_set_plasticity(nc_engine* e, float lr, float preF, float postF, float preD, float postD) {
+    auto okbase = [](float x) { return x > 0.0f && x < INFINITY && x >= 1.17549435e-38f; };
+    if (!okbase(preD) || !okbase(postD)) return fail(e, NC_ERR_INVALID, "nc_set_plasticity: trace decays must be positive normal floats");
+    e->lr = lr; e->preF = preF; e->postF = postF; e->preD = preD; e->postD = postD;
+    return NC_OK;
+}
+
+extern "C" int nc_upload_network(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t nRows, const uint64_t* rowptr,
+                                 const uint32_t* pre, const float* weight, const float* length, const uint8_t* inh) {
+    if (e->uploaded) return fail(e, NC_ERR_STATE, "nc_upload_network: network already uploaded");
+    if (!rowptr) return fail(e, NC_ERR_INVALID, "nc_upload_network: rowptr is null");
+    if (nGlobal >= (1ull << 30)) return fail(e, NC_ERR_INVALID, "nc_upload_network: at most 2^30-1 neurons");
+    if (row0 + nRows > nGlobal) return fail(e, NC_ERR_INVALID, "nc_upload_network: row range exceeds neuron count");
+    if (rowptr[0] != 0) return fail(e, NC_ERR_INVALID, "nc_upload_network: rowptr[0] must be 0");
+    uint64_t S = rowptr[nRows], maxRow = 0;
+    if (S && (!pre || !weight || !length || !inh)) return fail(e, NC_ERR_INVALID, "nc_upload_network: null synapse array");
+    float minDelay = INFINITY;
+    for (uint64_t r = 0; r < nRows; r++) {
+        if (rowptr[r + 1] < rowptr[r]) return fail(e, NC_ERR_INVALID, "nc_upload_network: rowptr not monotone");
+        uint64_t len = rowptr[r + 1] - rowptr[r];
+        maxRow = std::max(maxRow, len);
+        if (len >= (1ull << 29)) return fail(e, NC_ERR_INVALID, "nc_upload_network: row longer than 2^29-1");
+        for (uint64_t j = rowptr[r]; j < rowptr[r + 1]; j++) {
+            if (pre[j] >= nGlobal) return fail(e, NC_ERR_INVALID, "nc_upload_network: presynaptic ID out of range");
+            if (j > rowptr[r] && pre[j] <= pre[j - 1]) return fail(e, NC_ERR_INVALID, "nc_upload_network: row not strictly ascending in presynaptic ID");
+            float d = length[j] * 2.0f;
+            if (!(d > 0.0f)) return fail(e, NC_ERR_INVALID, "nc_upload_network: synapse length must be positive");
+            minDelay = std::min(minDelay, d);
+        }
+    }
+    cudaSetDevice(e->cfg.device);
+    View& v = e->v;
+    v.nGlobal = nGlobal; v.row0 = row0; v.nRows = nRows; v.S = S;
+    const uint64_t S1 = std::max<uint64_t>(S, 1), N1 = std::max<uint64_t>(nRows, 1), G1 = std::max<uint64_t>(nGlobal, 1);
+    CK(cudaMalloc((void**)&v.rowptr, (nRows + 1) * 8));
+    CK(cudaMalloc(&v.pre, S1 * 4)); CK(cudaMalloc(&v.arrive, S1 * 4)); CK(cudaMalloc(&v.depol, S1 * 4));
+    CK(cudaMalloc(&v.weight, S1 * 4)); CK(cudaMalloc(&v.lastArr, S1 * 4)); CK(cudaMalloc(&v.lastStart, S1 * 4));
+    CK(cudaMalloc(&e->dDelay, S1 * 4)); v.delay = e->dDelay;
+    CK(cudaMalloc(&v.potAct, N1 * 8)); CK(cudaMalloc(&v.lastRan, N1 * 4)); CK(cudaMalloc(&v.lastFire, N1 * 4));
+    CK(cudaMalloc(&v.lfStart, N1 * 4)); CK(cudaMalloc(&v.actStart, N1 * 4)); CK(cudaMalloc(&v.firings, N1 * 4));
+    v.fireCap = e->cfg.fire_capacity ? e->cfg.fire_capacity : (uint32_t)std::min<uint64_t>(4 * nRows + 1024, 1u << 28);
+    CK(cudaMalloc(&v.localHdr, 16 + (uint64_t)v.fireCap * sizeof(FireRec)));
+    v.localRecs = reinterpret_cast<FireRec*>(reinterpret_cast<unsigned char*>(v.localHdr) + 16);
+    CK(cudaMemsetAsync(v.localHdr, 0, 16, e->stream));
+    if (e->cfg.world > 1) { CK(cudaMalloc(&e->dGather, (uint64_t)e->cfg.world * v.fireCap * sizeof(FireRec))); v.gRecs = e->dGather; }
+    else v.gRecs = v.localRecs;
+    CK(cudaMalloc(&v.head, G1 * 4)); CK(cudaMalloc(&v.next, (uint64_t)e->cfg.world * v.fireCap * 4));
+    CK(cudaMalloc(&v.mask, ((G1 + 31) / 32) * 4));
+    CK(cudaMemsetAsync(v.mask, 0, ((G1 + 31) / 32) * 4, e->stream));
+    // temporaries for init
+    float* dLen; unsigned char* dInh;
+    CK(cudaMalloc(&dLen, S1 * 4)); CK(cudaMalloc(&dInh, S1));
+    CK(cudaMemcpyAsync((void*)v.rowptr, rowptr, (nRows + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+    if (S) {
+        CK(cudaMemcpyAsync(v.pre, pre, S * 4, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(v.weight, weight, S * 4, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(dLen, length, S * 4, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(dInh, inh, S, cudaMemcpyHostToDevice, e->stream));
+        k_init_synapses<<<(unsigned)((S + 255) / 256), 256, 0, e->stream>>>(v, dLen, dInh, e->dDelay);
+        e->launches++;
+    }
+    if (nRows) { k_init_neurons<<<(unsigned)((nRows + 255) / 256), 256, 0, e->stream>>>(v); e->launches++; }
+    k_fill_i32<<<(unsigned)((G1 + 255) / 256), 256, 0, e->stream>>>(v.head, G1, -1); e->launches++;
+    CK(cudaGetLastError());
+    // launch geometry: persistent grids sized to the SM count
+    e->candCap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(std::min<uint64_t>(e->candCap, maxRow), 32), 1024);
+    e->smem1 = (size_t)NC_WARPS_PER_BLOCK * 3 * e->candCap * 4;
+    CK(cudaFuncSetAttribute(k_neuron_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem1));
+    int occ1 = 1, occ2 = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_neuron_pass, NC_WARPS_PER_BLOCK * 32, e->smem1));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_synapse_pass, NC_WARPS_PER_BLOCK * 32, 0));
+    uint64_t needBlocks = (nRows + NC_WARPS_PER_BLOCK - 1) / NC_WARPS_PER_BLOCK;
+    e->grid1 = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(needBlocks, (uint64_t)e->smCount * std::max(occ1, 1)));
+    e->grid2 = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(needBlocks, (uint64_t)e->smCount * std::max(occ2, 1)));
+    v.spillPerWarp = (uint32_t)(maxRow > e->candCap ? maxRow - e->candCap : 0);
+    uint64_t spillN = std::max<uint64_t>(1, (uint64_t)e->grid1 * NC_WARPS_PER_BLOCK * v.spillPerWarp);
+    CK(cudaMalloc(&v.spillA, spillN * 4)); CK(cudaMalloc(&v.spillD, spillN * 4)); CK(cudaMalloc(&v.spillJ, spillN * 4));
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(dLen); cudaFree(dInh);
+    e->minDelay = minDelay;
+    e->uploaded = true;
+    return NC_OK;
+}
+
+extern "C" int nc_min_delay(const nc_engine* e, float* out) {
+    if (!e->uploaded) return NC_ERR_STATE;
+    *out = e->minDelay;
+    return NC_OK;
+}
+
+static int check_window(nc_engine* e, float t0, float t1) {
+    if (!e->uploaded) return fail(e, NC_ERR_STATE, "step: no network uploaded");
+    if (!(t1 > t0)) return fail(e, NC_ERR_INVALID, "step: window must have t1 > t0");
+    if (!(t1 - t0 < e->minDelay)) return fail(e, NC_ERR_INVALID, "step: window t1-t0 must be shorter than the smallest synaptic delay (split it)");
+    if (!(t1 - t0 < 2.0f)) return fail(e, NC_ERR_INVALID, "step: window must be shorter than the 2 ms spike duration");
+    return NC_OK;
+}
+
+static void fill_args(nc_engine* e, StepArgs& a, float t0, float t1, int sweep, const nc_event* dEv, uint32_t nEv) {
+    memset(&a, 0, sizeof(a));
+    a.t0 = t0; a.t1 = t1; a.sweep = sweep;
+    a.lr = e->lr; a.preFactor = e->preF; a.postFactor = e->postF; a.preDecay = e->preD; a.postDecay = e->postD;
+    a.ev = dEv; a.nEv = nEv; a.candCap = e->candCap; a.gStride = e->v.fireCap; a.world = (uint32_t)e->cfg.world;
+}
+
+static int launch_pass1(nc_engine* e, const StepArgs& a) {
+    k_neuron_pass<<<e->grid1, NC_WARPS_PER_BLOCK * 32, e->smem1, e->stream>>>(e->v, a);
+    e->launches++;
+    CK(cudaGetLastError());
+    return NC_OK;
+}
+// `a.counts` / `a.gStride` must be final. Launches index build, synapse pass, index reset, header reset.
+static int launch_pass2(nc_engine* e, const StepArgs& a) {
+    uint32_t maxc = 0;
+    for (uint32_t b = 0; b < a.world; b++) maxc = std::max(maxc, a.counts[b]);
+    dim3 g((maxc + 255) / 256, a.world);
+    if (maxc) { k_index_build<<<g, 256, 0, e->stream>>>(e->v, a); e->launches++; }
+    k_synapse_pass<<<e->grid2, NC_WARPS_PER_BLOCK * 32, 0, e->stream>>>(e->v, a);
+    e->launches++;
+    if (maxc) { k_index_reset<<<g, 256, 0, e->stream>>>(e->v, a); e->launches++; }
+    CK(cudaMemsetAsync(e->v.localHdr, 0, 16, e->stream));
+    CK(cudaGetLastError());
+    return NC_OK;
+}
+
+static int upload_events(nc_engine* e, const nc_event* events, uint32_t nEv, const nc_event** dOut) {
+    *dOut = nullptr;
+    if (!nEv) return NC_OK;
+    for (uint32_t i = 1; i < nEv; i++)
+        if (events[i].neuron < events[i - 1].neuron) return fail(e, NC_ERR_INVALID, "step: events must be sorted by neuron");
+    if (e->taping) {
+        if (e->tapeUsed + nEv > e->tapeCap) return fail(e, NC_ERR_CAPACITY, "tape: event capacity exceeded");
+        nc_event* dst = e->dTape + e->tapeUsed;
+        if (nEv > e->hEvCap) { cudaFreeHost(e->hEvPinned); e->hEvCap = nEv * 2 + 1024; CK(cudaMallocHost(&e->hEvPinned, (size_t)e->hEvCap * sizeof(nc_event))); }
+        memcpy(e->hEvPinned, events, (size_t)nEv * sizeof(nc_event));
+        CK(cudaMemcpyAsync(dst, e->hEvPinned, (size_t)nEv * sizeof(nc_event), cudaMemcpyHostToDevice, e->stream));
+        *dOut = dst;
+        return NC_OK;
+    }
+    if (nEv > e->evCap) { cudaFree(e->dEv); e->evCap = nEv * 2 + 1024; CK(cudaMalloc(&e->dEv, (size_t)e->evCap * sizeof(nc_event))); }
+    if (nEv > e->hEvCap) { cudaFreeHost(e->hEvPinned); e->hEvCap = nEv * 2 + 1024; CK(cudaMallocHost(&e->hEvPinned, (size_t)e->hEvCap * sizeof(nc_event))); }
+    memcpy(e->hEvPinned, events, (size_t)nEv * sizeof(nc_event));
+    CK(cudaMemcpyAsync(e->dEv, e->hEvPinned, (size_t)nEv * sizeof(nc_event), cudaMemcpyHostToDevice, e->stream));
+    *dOut = e->dEv;
+    return NC_OK;
+}
+
+static int finish_counters(nc_engine* e, uint64_t* hidden, nc_step_stats* st) {
+    CK(cudaMemcpyAsync(e->hStats, e->v.stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemsetAsync(e->v.stats, 0, 8 * sizeof(unsigned long long), e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (hidden) *hidden = e->hStats[5];
+    if (st) {
+        st->fires = e->hStats[0]; st->deliveries = e->hStats[1]; st->loads_accepted = e->hStats[2]; st->loads_dropped = e->hStats[3];
+        st->plasticity_calls = e->hStats[4]; st->hidden_rand_calls = e->hStats[5]; st->neuron_runs = e->hStats[6]; st->active_visits = e->hStats[7];
+    }
+    return NC_OK;
+}
+
+extern "C" int nc_step_begin(nc_engine* e, float t0, float t1, int sweep, const nc_event* events, uint32_t nEv) {
+    if (e->inStep) return fail(e, NC_ERR_STATE, "nc_step_begin: previous step not ended");
+    int rc = check_window(e, t0, t1);
+    if (rc) return rc;
+    cudaSetDevice(e->cfg.device);
+    const nc_event* dEv = nullptr;
+    rc = upload_events(e, events, nEv, &dEv);
+    if (rc) return rc;
+    if (e->taping) {
+        if (e->tape.size() >= e->tapeMaxSteps) return fail(e, NC_ERR_CAPACITY, "tape: step capacity exceeded");
+        e->tape.push_back({t0, t1, sweep, e->tapeUsed, nEv});
+        e->tapeUsed += nEv;
+    }
+    fill_args(e, e->cur, t0, t1, sweep, dEv, nEv);
+    rc = launch_pass1(e, e->cur);
+    if (rc) return rc;
+    // fire count of this shard (needed by the host to size the exchange and by the index kernels)
+    CK(cudaMemcpyAsync(e->hHdr, e->v.localHdr, 16, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (e->hHdr[1]) return fail(e, NC_ERR_CAPACITY, "step: fire-record capacity exceeded (raise nc_config.fire_capacity)");
+    e->inStep = true;
+    return NC_OK;
+}
+
+extern "C" int nc_exchange_buffer(nc_engine* e, void** p, uint64_t* bytes) {
+    if (!e->uploaded) return NC_ERR_STATE;
+    *p = e->v.localRecs;
+    *bytes = (uint64_t)e->hHdr[0] * sizeof(FireRec);
+    return NC_OK;
+}
+extern "C" int nc_gather_buffer(nc_engine* e, void** p, uint64_t* bytes) {
+    if (!e->uploaded) return NC_ERR_STATE;
+    *p = (void*)e->v.gRecs;
+    *bytes = (uint64_t)e->cfg.world * e->v.fireCap * sizeof(FireRec);
+    return NC_OK;
+}
+// For world > 1 the host passes the per-shard record counts and the record stride it used when placing the
+// gathered blocks into nc_gather_buffer (counts == NULL: world 1).
+extern "C" int nc_step_end_counts(nc_engine* e, const uint32_t* counts, uint32_t stride, uint64_t* hidden, nc_step_stats* st) {
+    if (!e->inStep) return fail(e, NC_ERR_STATE, "nc_step_end: no step in flight");
+    cudaSetDevice(e->cfg.device);
+    e->inStep = false;
+    if (e->cfg.world == 1) { e->cur.counts[0] = e->hHdr[0]; e->cur.gStride = e->v.fireCap; }
+    else {
+        if (!counts) return fail(e, NC_ERR_INVALID, "nc_step_end: counts required for world > 1");
+        for (int b = 0; b < e->cfg.world; b++) {
+            if (counts[b] > stride) return fail(e, NC_ERR_INVALID, "nc_step_end: count exceeds stride");
+            e->cur.counts[b] = counts[b];
+        }
+        if ((uint64_t)stride * e->cfg.world > (uint64_t)e->v.fireCap * e->cfg.world) return fail(e, NC_ERR_INVALID, "nc_step_end: stride too large");
+        e->cur.gStride = stride;
+    }
+    int rc = launch_pass2(e, e->cur);
+    if (rc) return rc;
+    return finish_counters(e, hidden, st);
+}
+extern "C" int nc_step_end(nc_engine* e, uint64_t* hidden, nc_step_stats* st) { return nc_step_end_counts(e, nullptr, 0, hidden, st); }
+
+extern "C" int nc_step(nc_engine* e, float t0, float t1, int sweep, const nc_event* events, uint32_t nEv, uint64_t* hidden,
+                       nc_step_stats* st) {
+    if (e->cfg.world != 1) return fail(e, NC_ERR_STATE, "nc_step: sharded engines use nc_step_begin / exchange / nc_step_end");
+    int rc = nc_step_begin(e, t0, t1, sweep, events, nEv);
+    if (rc) return rc;
+    return nc_step_end(e, hidden, st);
+}
+
+extern "C" int nc_run_neurons(nc_engine* e, float now, const uint32_t* ids, uint32_t nIds, uint64_t* hidden, nc_step_stats* st) {
+    if (e->cfg.world != 1) return fail(e, NC_ERR_STATE, "nc_run_neurons: single-shard engines only");
+    if (!e->uploaded) return fail(e, NC_ERR_STATE, "nc_run_neurons: no network uploaded");
+    if (e->inStep) return fail(e, NC_ERR_STATE, "nc_run_neurons: a step is in flight");
+    cudaSetDevice(e->cfg.device);
+    uint32_t* dIds = nullptr;
+    if (ids) {
+        if (!nIds) return NC_OK;
+        for (uint32_t i = 0; i < nIds; i++) {
+            if (ids[i] < e->v.row0 || ids[i] >= e->v.row0 + e->v.nRows) return fail(e, NC_ERR_INVALID, "nc_run_neurons: neuron outside this shard");
+            if (i && ids[i] <= ids[i - 1]) return fail(e, NC_ERR_INVALID, "nc_run_neurons: ids must be strictly ascending");
+        }
+        CK(cudaMalloc(&dIds, (size_t)nIds * 4));
+        CK(cudaMemcpyAsync(dIds, ids, (size_t)nIds * 4, cudaMemcpyHostToDevice, e->stream));
+    }
+    StepArgs a;
+    fill_args(e, a, now, now, NC_SWEEP_END, nullptr, 0);
+    a.subset = dIds; a.nSubset = nIds;
+    int rc = launch_pass1(e, a);
+    if (!rc) {
+        cudaError_t ce = cudaMemcpyAsync(e->hHdr, e->v.localHdr, 16, cudaMemcpyDeviceToHost, e->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+        if (ce != cudaSuccess) { e->err = cudaGetErrorString(ce); rc = NC_ERR_CUDA; }
+    }
+    if (!rc && e->hHdr[1]) rc = fail(e, NC_ERR_CAPACITY, "nc_run_neurons: fire-record capacity exceeded");
+    if (!rc) { a.counts[0] = e->hHdr[0]; e->cur = a; rc = launch_pass2(e, a); }
+    if (!rc) rc = finish_counters(e, hidden, st);
+    cudaFree(dIds);
+    return rc;
+}
+
+extern "C" int nc_read_neurons(nc_engine* e, float* potAct, float* lastFire, float* lastRan) {
+    if (!e->uploaded) return fail(e, NC_ERR_STATE, "read: no network");
+    cudaSetDevice(e->cfg.device);
+    CK(cudaStreamSynchronize(e->stream));
+    if (potAct) CK(cudaMemcpy(potAct, e->v.potAct, e->v.nRows * 8, cudaMemcpyDeviceToHost));
+    if (lastFire) CK(cudaMemcpy(lastFire, e->v.lastFire, e->v.nRows * 4, cudaMemcpyDeviceToHost));
+    if (lastRan) CK(cudaMemcpy(lastRan, e->v.lastRan, e->v.nRows * 4, cudaMemcpyDeviceToHost));
+    return NC_OK;
+}
+extern "C" int nc_read_synapses(nc_engine* e, float* weight, float* arrive, float* depol, float* lastArr, float* lastStart) {
+    if (!e->uploaded) return fail(e, NC_ERR_STATE, "read: no network");
+    cudaSetDevice(e->cfg.device);
+    CK(cudaStreamSynchronize(e->stream));
+    uint64_t b = e->v.S * 4;
+    if (weight) CK(cudaMemcpy(weight, e->v.weight, b, cudaMemcpyDeviceToHost));
+    if (arrive) CK(cudaMemcpy(arrive, e->v.arrive, b, cudaMemcpyDeviceToHost));
+    if (depol) CK(cudaMemcpy(depol, e->v.depol, b, cudaMemcpyDeviceToHost));
+    if (lastArr) CK(cudaMemcpy(lastArr, e->v.lastArr, b, cudaMemcpyDeviceToHost));
+    if (lastStart) CK(cudaMemcpy(lastStart, e->v.lastStart, b, cudaMemcpyDeviceToHost));
+    return NC_OK;
+}
+extern "C" int nc_read_fires(nc_engine* e, uint32_t capacity, uint32_t* neuron, float* time, uint32_t* count) {
+    if (!e->uploaded) return fail(e, NC_ERR_STATE, "read: no network");
+    cudaSetDevice(e->cfg.device);
+    CK(cudaStreamSynchronize(e->stream));
+    uint32_t total = 0;
+    std::vector<FireRec> tmp;
+    for (uint32_t b = 0; b < (uint32_t)e->cfg.world; b++) {
+        uint32_t c = e->cur.counts[b];
+        if (!c) continue;
+        tmp.resize(c);
+        CK(cudaMemcpy(tmp.data(), e->v.gRecs + (uint64_t)b * e->cur.gStride, (uint64_t)c * sizeof(FireRec), cudaMemcpyDeviceToHost));
+        for (uint32_t i = 0; i < c; i++, total++)
+            if (total < capacity) { if (neuron) neuron[total] = tmp[i].neuron; if (time) time[total] = tmp[i].time; }
+    }
+    *count = total;
+    return NC_OK;
+}
+extern "C" int nc_read_synapse_pots(nc_engine* e, float now, float* prePot, float* postPot) {
+    if (!e->uploaded) return fail(e, NC_ERR_STATE, "read: no network");
+    cudaSetDevice(e->cfg.device);
+    uint64_t S = e->v.S;
+    if (!S) return NC_OK;
+    float *dPre, *dPost;
+    CK(cudaMalloc(&dPre, S * 4)); CK(cudaMalloc(&dPost, S * 4));
+    k_synapse_pots<<<(unsigned)((S + 255) / 256), 256, 0, e->stream>>>(e->v, now, dPre, dPost); e->launches++;
+    CK(cudaStreamSynchronize(e->stream));
+    if (prePot) CK(cudaMemcpy(prePot, dPre, S * 4, cudaMemcpyDeviceToHost));
+    if (postPot) CK(cudaMemcpy(postPot, dPost, S * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dPre); cudaFree(dPost);
+    return NC_OK;
+}
+extern "C" int nc_reset_activities(nc_engine* e, float now) {
+    if (!e->uploaded) return fail(e, NC_ERR_STATE, "reset: no network");
+    cudaSetDevice(e->cfg.device);
+    if (e->v.nRows) { k_reset_activities<<<(unsigned)((e->v.nRows + 255) / 256), 256, 0, e->stream>>>(e->v, now); e->launches++; }
+    CK(cudaStreamSynchronize(e->stream));
+    return NC_OK;
+}
+extern "C" int nc_detector_mean(nc_engine* e, const uint32_t* near, uint32_t n, float* out) {
+    if (!e->uploaded) return fail(e, NC_ERR_STATE, "detector: no network");
+    cudaSetDevice(e->cfg.device);
+    if (!n) { *out = NAN; return NC_OK; }  // 0/0 as in the reference
+    for (uint32_t i = 0; i < n; i++)
+        if (near[i] < e->v.row0 || near[i] >= e->v.row0 + e->v.nRows) return fail(e, NC_ERR_INVALID, "detector: neuron outside this shard");
+    uint32_t* dNear; float* dOut;
+    CK(cudaMalloc(&dNear, (size_t)n * 4)); CK(cudaMalloc(&dOut, 4));
+    CK(cudaMemcpyAsync(dNear, near, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+    k_detector_mean<<<1, 32, 0, e->stream>>>(e->v, dNear, n, dOut); e->launches++;
+    CK(cudaMemcpyAsync(out, dOut, 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(dNear); cudaFree(dOut);
+    return NC_OK;
+}
+
+// ---- tape / snapshot / replay ----
+extern "C" int nc_tape_begin(nc_engine* e, uint32_t maxSteps, uint64_t maxEvents) {
+    if (!e->uploaded) return fail(e, NC_ERR_STATE, "tape: no network");
+    cudaSetDevice(e->cfg.device);
+    cudaFree(e->dTape); e->dTape = nullptr;
+    e->tapeCap = std::max<uint64_t>(maxEvents, 1);
+    CK(cudaMalloc(&e->dTape, e->tapeCap * sizeof(nc_event)));
+    e->tape.clear(); e->tapeUsed = 0; e->tapeMaxSteps = maxSteps; e->taping = true;
+    return NC_OK;
+}
+extern "C" int nc_tape_end(nc_engine* e) { e->taping = false; return NC_OK; }
+
+template <typename T>
+static cudaError_t snap_copy(T*& dst, const T* src, uint64_t n, cudaStream_t st, bool toSnap) {
+    cudaError_t ce = cudaSuccess;
+    if (toSnap && !dst) ce = cudaMalloc(&dst, std::max<uint64_t>(n, 1) * sizeof(T));
+    if (ce != cudaSuccess) return ce;
+    if (toSnap) return cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToDevice, st);
+    return cudaMemcpyAsync((void*)src, dst, n * sizeof(T), cudaMemcpyDeviceToDevice, st);
+}
+static int snap_all(nc_engine* e, bool toSnap) {
+    View& v = e->v; auto& s = e->snap;
+    CK(snap_copy(s.arrive, v.arrive, v.S, e->stream, toSnap)); CK(snap_copy(s.depol, v.depol, v.S, e->stream, toSnap));
+    CK(snap_copy(s.weight, v.weight, v.S, e->stream, toSnap)); CK(snap_copy(s.lastArr, v.lastArr, v.S, e->stream, toSnap));
+    CK(snap_copy(s.lastStart, v.lastStart, v.S, e->stream, toSnap)); CK(snap_copy(s.lastRan, v.lastRan, v.nRows, e->stream, toSnap));
+    CK(snap_copy(s.lastFire, v.lastFire, v.nRows, e->stream, toSnap)); CK(snap_copy(s.lfStart, v.lfStart, v.nRows, e->stream, toSnap));
+    CK(snap_copy(s.actStart, v.actStart, v.nRows, e->stream, toSnap)); CK(snap_copy(s.potAct, v.potAct, v.nRows, e->stream, toSnap));
+    CK(snap_copy(s.firings, v.firings, v.nRows, e->stream, toSnap));
+    CK(cudaStreamSynchronize(e->stream));
+    return NC_OK;
+}
+extern "C" int nc_snapshot(nc_engine* e) {
+    if (!e->uploaded) return fail(e, NC_ERR_STATE, "snapshot: no network");
+    cudaSetDevice(e->cfg.device);
+    int rc = snap_all(e, true);
+    if (!rc) e->snap.valid = true;
+    return rc;
+}
+extern "C" int nc_restore(nc_engine* e) {
+    if (!e->snap.valid) return fail(e, NC_ERR_STATE, "restore: no snapshot");
+    cudaSetDevice(e->cfg.device);
+    return snap_all(e, false);
+}
+
+// Device-side copy of the shard's fire count into a StepArgs-free path is avoided by reading the header
+// in the index kernels through a second, count-agnostic pair of kernels used only by replay.
+__global__ void k_index_build_dev(View v, StepArgs s) {
+    uint32_t n = min(v.localHdr[0], v.fireCap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t nrn = v.gRecs[i].neuron;
+        v.next[i] = atomicExch(&v.head[nrn], (int32_t)i);
+        atomicOr(&v.mask[nrn >> 5], 1u << (nrn & 31u));
+    }
+}
+__global__ void k_index_reset_dev(View v, StepArgs s) {
+    uint32_t n = min(v.localHdr[0], v.fireCap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t nrn = v.gRecs[i].neuron;
+        v.head[nrn] = -1;
+        v.mask[nrn >> 5] = 0u;
+    }
+}
+__global__ void k_hdr_reset(View v, uint32_t* overflowAccum) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        if (v.localHdr[1]) *overflowAccum = 1u;
+        v.localHdr[0] = 0u; v.localHdr[1] = 0u;
+    }
+}
+
+extern "C" int nc_tape_replay(nc_engine* e, uint32_t first, uint32_t count, float* msTotal, float* msP1, float* msP2,
+                              uint64_t* hidden, nc_step_stats* st) {
+    if (e->cfg.world != 1) return fail(e, NC_ERR_STATE, "replay: single-shard engines only");
+    if ((uint64_t)first + count > e->tape.size()) return fail(e, NC_ERR_INVALID, "replay: step range outside the tape");
+    cudaSetDevice(e->cfg.device);
+    uint32_t* dOvf; CK(cudaMalloc(&dOvf, 4)); CK(cudaMemsetAsync(dOvf, 0, 4, e->stream));
+    CK(cudaMemsetAsync(e->v.stats, 0, 8 * sizeof(unsigned long long), e->stream));
+    const bool perKernel = msP1 || msP2;
+    std::vector<cudaEvent_t> evs;
+    if (perKernel) { evs.resize((size_t)count * 3); for (auto& x : evs) CK(cudaEventCreate(&x)); }
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const uint32_t idxGrid = (uint32_t)std::min<uint64_t>(std::max<uint64_t>((e->v.nRows / 64 + 255) / 256, 1), 1024);
+    CK(cudaEventRecord(e0, e->stream));
+    for (uint32_t k = 0; k < count; k++) {
+        const TapeStep& ts = e->tape[first + k];
+        StepArgs a;
+        fill_args(e, a, ts.t0, ts.t1, ts.sweep, e->dTape + ts.evOff, ts.nEv);
+        if (perKernel) CK(cudaEventRecord(evs[3 * k], e->stream));
+        k_neuron_pass<<<e->grid1, NC_WARPS_PER_BLOCK * 32, e->smem1, e->stream>>>(e->v, a);
+        if (perKernel) CK(cudaEventRecord(evs[3 * k + 1], e->stream));
+        k_index_build_dev<<<idxGrid, 256, 0, e->stream>>>(e->v, a);
+        k_synapse_pass<<<e->grid2, NC_WARPS_PER_BLOCK * 32, 0, e->stream>>>(e->v, a);
+        if (perKernel) CK(cudaEventRecord(evs[3 * k + 2], e->stream));
+        k_index_reset_dev<<<idxGrid, 256, 0, e->stream>>>(e->v, a);
+        k_hdr_reset<<<1, 32, 0, e->stream>>>(e->v, dOvf);
+        e->launches += 5;
+    }
+    CK(cudaEventRecord(e1, e->stream));
+    CK(cudaGetLastError());
+    uint32_t ovf = 0;
+    CK(cudaMemcpyAsync(&ovf, dOvf, 4, cudaMemcpyDeviceToHost, e->stream));
+    int rc = finish_counters(e, hidden, st);
+    if (rc) return rc;
+    if (msTotal) CK(cudaEventElapsedTime(msTotal, e0, e1));
+    if (perKernel) {
+        float s1 = 0, s2 = 0, x;
+        for (uint32_t k = 0; k < count; k++) {
+            CK(cudaEventElapsedTime(&x, evs[3 * k], evs[3 * k + 1])); s1 += x;
+            CK(cudaEventElapsedTime(&x, evs[3 * k + 1], evs[3 * k + 2])); s2 += x;
+        }
+        if (msP1) *msP1 = s1;
+        if (msP2) *msP2 = s2;
+        for (auto& x2 : evs) cudaEventDestroy(x2);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(dOvf);
+    if (ovf) return fail(e, NC_ERR_CAPACITY, "replay: fire-record capacity exceeded");
+    return NC_OK;
+}

@@ -1,0 +1,304 @@
+// Per-neuron and per-synapse step logic shared by the CUDA kernels (engine.cu) and — compiled for the
+// host by tests/native/model_twopass.cpp — by the CPU test model that lets the algorithm be checked
+// against the oracle without a GPU.  Nothing here is a fallback: the product library only ever runs
+// these functions inside kernels.
+//
+// Reference semantics restated (file:line under /root/reference/src):
+//   neuron_run     Neuron::run            NeuCor.cpp:619-641  (charge_insynapses :688-700, charge_passive
+//                                          :677-680, charge_thresholdCheck :682-686, AP :706-714, activity :640)
+//   neuron_fire    Neuron::fire           NeuCor.cpp:643-645  (neuron-local part)
+//   plasticity     Synapse::synapticPlasticity NeuCor.cpp:740-764, Neuron::getTrace :671-675
+//   resolve_slot   Synapse::fire :727-738, the slot clear at :697, Synapse::run :718-726
+// Every operator keeps the reference's float/double typing; no contraction (explicit-rounding helpers).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/neucor_b200.h"
+#include "glibc_math.cuh"
+
+#if !defined(__CUDACC__)
+struct float2 { float x, y; };
+static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+#endif
+
+namespace ncs {
+using namespace ncm;
+
+struct FireRec {       // 16 B; canonical key of the event that caused the fire
+    uint32_t neuron;   // global ID
+    float time;
+    uint32_t rk1;      // rank << 30 | k1
+    uint32_t k2;
+};
+// Canonical event order: (time, rank, k1, k2)
+//   rank 0 input firer  (k1 = firer index, k2 = neuron)      InputFirer::run
+//   rank 1 delivery     (k1 = target,      k2 = parent)      Synapse::run
+//   rank 2 neuron event (k1 = neuron,      k2 = 0)           Neuron::run queued by transfer/scheduleFire
+//   rank 3 sweep        (k1 = neuron,      k2 = 0)           end-of-window run of every neuron, ascending ID
+// Within one event the operations on a synapse are ordered load/clear (0) < post-fire plasticity (1) < delivery (2).
+
+#define NC_SENT 0x80000000u  // arrive[] bit-pattern marker: slot cleared during this window's neuron pass
+                             // bits 30..29 = rank of the clearing event, bits 28..0 = delivering slot (rank 1);
+                             // the clear time is parked in depol[] (dead once the slot is idle)
+#define NC_MAX_WORLD 8
+
+struct Key {
+    float t;
+    uint32_t rk1, k2, local;
+};
+NC_HD bool key_less(const Key& a, const Key& b) {
+    if (a.t != b.t) return a.t < b.t;
+    if (a.rk1 != b.rk1) return a.rk1 < b.rk1;
+    if (a.k2 != b.k2) return a.k2 < b.k2;
+    return a.local < b.local;
+}
+NC_HD bool key_le3(float t, uint32_t rk1, uint32_t k2, const Key& b) {  // (t, rk1, k2) <= b's, ignoring `local`
+    if (t != b.t) return t < b.t;
+    if (rk1 != b.rk1) return rk1 < b.rk1;
+    return k2 <= b.k2;
+}
+NC_HD bool pick_less(float t1, unsigned long long c1, float t2, unsigned long long c2) {
+    return t1 < t2 || (t1 == t2 && c1 < c2);
+}
+
+struct View {
+    uint64_t nGlobal, row0, nRows, S;
+    const uint64_t* rowptr;
+    uint32_t* pre;  // bit 31 = inhibitory flag
+    float *arrive, *depol, *weight, *lastArr, *lastStart;
+    const float* delay;
+    float2* potAct;
+    float *lastRan, *lastFire, *lfStart, *actStart;
+    uint32_t* firings;
+    // exchange
+    uint32_t* localHdr;  // [0] = fire count of this shard, [1] = overflow flag
+    FireRec* localRecs;
+    uint32_t fireCap;
+    // gathered fire index
+    const FireRec* gRecs;  // `world` blocks of `gStride` records
+    int32_t* head;         // per global neuron: first record index or -1
+    int32_t* next;         // per record
+    uint32_t* mask;        // one bit per global neuron: fired in this window
+    // spill area for rows with more occupied slots than fit in shared memory
+    float* spillA;
+    float* spillD;
+    uint32_t* spillJ;
+    uint32_t spillPerWarp;
+    unsigned long long* stats;  // 8 counters (nc_step_stats order)
+};
+
+struct StepArgs {
+    float t0, t1;
+    int sweep;  // NC_SWEEP_END | NC_SWEEP_START
+    float lr, preFactor, postFactor, preDecay, postDecay;
+    const nc_event* ev;
+    uint32_t nEv;
+    const uint32_t* subset;  // nc_run_neurons: ascending IDs that take part in the sweep (NULL = all)
+    uint32_t nSubset;
+    uint32_t candCap;
+    uint32_t gStride;
+    uint32_t world;
+    uint32_t counts[NC_MAX_WORLD];
+};
+
+struct NeuronState {
+    float pot, act, lastRan, lastFire, actStart, sched;
+    uint32_t firings;
+};
+
+struct CandView {  // occupied slots of the current row: shared memory first, spill area after
+    float* a;      // arrive time; negated once cleared in this window
+    float* d;      // depolarisation factor
+    uint32_t* j;   // slot index within the row
+    float* sa;
+    float* sd;
+    uint32_t* sj;
+    uint32_t cap;
+    NC_HDM float& A(uint32_t c) { return c < cap ? a[c] : sa[c - cap]; }
+    NC_HDM float& D(uint32_t c) { return c < cap ? d[c] : sd[c - cap]; }
+    NC_HDM uint32_t& J(uint32_t c) { return c < cap ? j[c] : sj[c - cap]; }
+};
+
+NC_HD void emit_fire(const View& v, uint32_t q, float T, uint32_t rk1, uint32_t k2) {
+#if defined(__CUDA_ARCH__)
+    uint32_t idx = atomicAdd(&v.localHdr[0], 1u);
+#else
+    uint32_t idx = v.localHdr[0]++;
+#endif
+    if (idx < v.fireCap) {
+        FireRec r;
+        r.neuron = q; r.time = T; r.rk1 = rk1; r.k2 = k2;
+        v.localRecs[idx] = r;
+    } else {
+        v.localHdr[1] = 1u;
+    }
+}
+
+NC_HD void neuron_fire(const View& v, NeuronState& n, uint32_t q, float T, uint32_t rk1, uint32_t k2,
+                       unsigned long long& nFires) {
+    n.lastFire = T;
+    n.firings++;
+    nFires++;
+    emit_fire(v, q, T, rk1, k2);
+}
+
+// Neuron::run at time T, executed by one thread. (rk1, k2) = canonical key of the causing event: it is the
+// key recorded for slots cleared here (through `sentinel`) and for a fire triggered here.
+NC_HD void neuron_run(const View& v, NeuronState& n, CandView& cv, uint32_t cnt, uint64_t rs, uint32_t q, float T,
+                      uint32_t rk1, uint32_t k2, uint32_t sentinel, unsigned long long& nFires,
+                      unsigned long long& nRuns, unsigned long long& nVisits) {
+    const float baselevel = -70.0f, threshold = -55.0f, recharge = 0.5f, AP_cutoff = 2.0f;
+    float dT = sub32(T, n.lastRan);
+    n.lastRan = T;
+    if (dT == 0.0f) return;
+    nRuns++;
+    // charge_insynapses: newPot += deltaT*depolFac*0.9943*exp(0.3702*deltaT), ascending presynaptic ID,
+    // each addition rounded to float through a double sum
+    float np = n.pot;
+    if (cnt) {
+        double E = exp_glibc(mul64(0.3702, (double)dT));
+        for (uint32_t c = 0; c < cnt; c++) {
+            float a = cv.A(c);
+            if (!(a > 0.0f)) continue;  // cleared earlier in this window
+            float off = sub32(T, a);
+            if (off <= 0.0f) continue;  // still in flight
+            double term = mul64(mul64((double)mul32(dT, cv.D(c)), 0.9943), E);
+            np = (float)add64((double)np, term);
+            nVisits++;
+            if (AP_cutoff < off) {  // the slot becomes idle; leave the when-and-why for the synapse pass
+                cv.A(c) = -a;
+                uint64_t s = rs + cv.J(c);
+                v.arrive[s] = as_f32(sentinel);
+                v.depol[s] = T;
+            }
+        }
+    }
+    // charge_passive
+    np = add32(mul32(sub32(np, baselevel), powf_pos(recharge, dT)), baselevel);
+    n.pot = np;
+    // charge_thresholdCheck (the vesicle term is always true)
+    float lf = n.lastFire;
+    if ((threshold < n.pot || n.sched == T) && (lf != lf || AP_cutoff < sub32(T, lf))) neuron_fire(v, n, q, T, rk1, k2, nFires);
+    // AP: analytic double-Gaussian waveform while within the cutoff; powf(x, 2.0) is x*x in the -O3 reference
+    lf = n.lastFire;
+    if (!(lf != lf || AP_cutoff < sub32(T, lf))) {
+        const double D1 = (2.0 * (double)0.3f) * (double)0.3f, D2 = (2.0 * (double)0.6f) * (double)0.6f;
+        float t = sub32(T, lf);
+        float x1 = sub32(t, 1.0f);
+        float x2 = sub32(sub32(t, 1.0f), 1.16f);
+        double e1 = exp_glibc(div64((double)(-mul32(x1, x1)), D1));
+        double e2 = exp_glibc(div64((double)(-mul32(x2, x2)), D2));
+        double wave = mul64(100.0, sub64(e1, mul64(e2, (double)0.2f)));
+        double tail = mul64((double)sub32(threshold, baselevel), fmax(sub64(add64(1.0, (double)lf), (double)T), 0.0));
+        n.pot = (float)add64(add64(wave, (double)baselevel), tail);
+    }
+    // activity
+    n.act = (float)div64((double)n.firings, div64((double)sub32(T, n.actStart), 10.0));
+}
+
+// Synapse::synapticPlasticity at time T with the target's lastFire `lfq`.
+NC_HD float plasticity(const StepArgs& s, float w, bool inh, float T, float lastArr, float lfq, uint32_t& hidden) {
+    float traceS = powf_pos(s.preDecay, sub32(T, lastArr));
+    float traceT = powf_pos(s.postDecay, sub32(T, lfq));
+    if (traceT != traceT) traceT = 0.0f;
+    if (traceT == 1.0f) traceT = 0.0f;
+    if (traceS == 1.0f) traceS = 0.0f;
+    if (w == 0.0f && !inh) hidden++;  // the rand() hidden in NeuCor.cpp:752's short-circuit
+    float change = sub32(mul32(s.preFactor, traceS), mul32(s.postFactor, traceT));
+    w = add32(w, mul32(change, s.lr));
+    if (!inh) w = (float)fmax(fmin((double)w, 1.0), 0.0);
+    else w = (float)fmax(fmin((double)w, 0.0), -1.0);
+    return w;
+}
+
+// All operations of one window on synapse j = (p -> q), applied in canonical order:
+//   L  one per fire of p   Synapse::fire (slot busy -> dropped)
+//   C  slot cleared by one of q's runs (recorded by the neuron pass)
+//   P  one per fire of q   synapticPlasticity from Neuron::fire
+//   D  delivery when t0 < arrive <= t1: lastSpikeArrival = now; synapticPlasticity
+// cnt: [0] loads accepted, [1] loads dropped, [2] plasticity calls, [3] hidden rand, [4] deliveries
+NC_HD void resolve_slot(const View& v, const StepArgs& s, uint64_t j, uint64_t rs, uint32_t q, uint32_t p, bool inh,
+                        uint32_t abits, bool pFired, bool qFired, float lfStart, uint32_t* cnt) {
+    float a = as_f32(abits);
+    const bool cleared = (abits & NC_SENT) != 0u;
+    Key kc;
+    kc.local = 0; kc.t = 0.0f; kc.rk1 = 0; kc.k2 = 0;
+    if (cleared) {
+        uint32_t rank = (abits >> 29) & 3u;
+        kc.rk1 = (rank << 30) | q;
+        if (rank == 3u) { kc.t = s.t1; kc.k2 = 0u; }
+        else if (rank == 2u) { kc.t = v.depol[j]; kc.k2 = 0u; }
+        else { kc.t = v.depol[j]; kc.k2 = v.pre[rs + (abits & 0x1fffffffu)] & 0x7fffffffu; }
+    }
+    const bool hasD = !cleared && a != 0.0f && a > s.t0 && a <= s.t1;
+    Key kd;
+    kd.t = a; kd.rk1 = (1u << 30) | q; kd.k2 = p; kd.local = 2;
+    bool busy = cleared || a != 0.0f;
+    float w = v.weight[j], lastArr = v.lastArr[j];
+    float newArrive = cleared ? 0.0f : a, newDepol = 0.0f, newStart = 0.0f;
+    bool loaded = false, wChanged = false, laChanged = false;
+    Key cur;
+    cur.t = 0.0f; cur.rk1 = 0; cur.k2 = 0; cur.local = 0;
+    bool have = false;
+    for (;;) {
+        Key best;
+        best.t = 0.0f; best.rk1 = 0; best.k2 = 0; best.local = 0;
+        int kind = -1;  // 0 L, 1 C, 2 P, 3 D
+        float bestT = 0.0f;
+        if (pFired)
+            for (int32_t f = v.head[p]; f >= 0; f = v.next[f]) {
+                FireRec r = v.gRecs[f];
+                Key k; k.t = r.time; k.rk1 = r.rk1; k.k2 = r.k2; k.local = 0;
+                if ((!have || key_less(cur, k)) && (kind < 0 || key_less(k, best))) { best = k; kind = 0; bestT = r.time; }
+            }
+        if (cleared && (!have || key_less(cur, kc)) && (kind < 0 || key_less(kc, best))) { best = kc; kind = 1; }
+        if (qFired)
+            for (int32_t f = v.head[q]; f >= 0; f = v.next[f]) {
+                FireRec r = v.gRecs[f];
+                Key k; k.t = r.time; k.rk1 = r.rk1; k.k2 = r.k2; k.local = 1;
+                if ((!have || key_less(cur, k)) && (kind < 0 || key_less(k, best))) { best = k; kind = 2; bestT = r.time; }
+            }
+        if (hasD && (!have || key_less(cur, kd)) && (kind < 0 || key_less(kd, best))) { best = kd; kind = 3; }
+        if (kind < 0) break;
+        if (kind == 0) {
+            if (busy) cnt[1]++;
+            else {
+                float d = (float)mul64((double)0.2f, 52.0);  // AP_depolFac *= 52.0 (float *= double)
+                newDepol = mul32(d, w);                      // AP_depolFac *= weight
+                newArrive = add32(v.delay[j], bestT);        // length*AP_speed + now
+                newStart = bestT;
+                busy = true; loaded = true;
+                cnt[0]++;
+            }
+        } else if (kind == 1) {
+            busy = false;
+            newArrive = 0.0f;
+        } else {
+            float T = (kind == 2) ? bestT : a;
+            if (kind == 3) { lastArr = T; laChanged = true; cnt[4]++; }
+            // the target's lastFire as of this operation: latest fire of q whose event key is <= this one's
+            float lfq = lfStart;
+            if (qFired) {
+                Key lk; lk.t = 0.0f; lk.rk1 = 0; lk.k2 = 0; lk.local = 0;
+                bool lhave = false;
+                for (int32_t f = v.head[q]; f >= 0; f = v.next[f]) {
+                    FireRec r = v.gRecs[f];
+                    if (!key_le3(r.time, r.rk1, r.k2, best)) continue;
+                    Key k; k.t = r.time; k.rk1 = r.rk1; k.k2 = r.k2; k.local = 0;
+                    if (!lhave || key_less(lk, k)) { lk = k; lhave = true; lfq = r.time; }
+                }
+            }
+            w = plasticity(s, w, inh, T, lastArr, lfq, cnt[3]);
+            wChanged = true;
+            cnt[2]++;
+        }
+        cur = best; have = true;
+    }
+    if (cleared || loaded) v.arrive[j] = newArrive;
+    if (loaded) { v.depol[j] = newDepol; v.lastStart[j] = newStart; }
+    if (wChanged) v.weight[j] = w;
+    if (laChanged) v.lastArr[j] = lastArr;
+}
+
+}  // namespace ncs

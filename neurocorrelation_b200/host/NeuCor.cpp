@@ -1,0 +1,439 @@
+// Host side of the drop-in NeuCor class: network construction and per-run scheduling exactly as the
+// reference does them on the CPU (/root/reference/src/NeuCor.cpp:17-366, 583-617), with the hot loop
+// (NeuCor.cpp:609-616 and everything it dispatches to) handed to the CUDA engine through the C ABI.
+// Compile with -ffp-contract=off: every float expression below is typed as in the reference.
+#include "NeuCor.h"
+
+#include <stdlib.h>
+
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <stdexcept>
+#include <unordered_map>
+
+#include "../../include/neucor_b200.h"
+
+namespace {
+inline float randomUnit() {  // NeuCor.cpp:12-14
+    return static_cast<float>(rand()) / static_cast<float>(RAND_MAX);
+}
+}  // namespace
+
+NeuCor::NeuCor(int n_neurons) {  // NeuCor.cpp:17-42
+    runSpeed = 1.0;
+    runAll = false;
+    learningRate = 1.0;
+    presynapticTraceDecay = 0.75;
+    postsynapticTraceDecay = 0.65;
+    presynapticFactor = 0.13;
+    postsynapticFactor = 0.30;
+
+    totalGenNeurons = n_neurons;
+    for (int n = 0; n < n_neurons; n++) {
+        coord3 d;
+        d.setNAN();
+        createNeuron(d);
+    }
+    totalGenNeurons = 0;
+    if (n_neurons > 0) makeConnections();
+}
+
+NeuCor::~NeuCor() {
+    if (engine_) nc_destroy(engine_);
+}
+
+void NeuCor::check(int rc, const char* what) {
+    if (rc == NC_OK) return;
+    std::string msg = std::string(what) + ": " + (engine_ ? nc_last_error(engine_) : nc_global_error());
+    throw std::runtime_error(msg);
+}
+
+float NeuCor::getTime() const { return currentTime; }
+std::size_t NeuCor::getNeuronCount() const { return positions.size(); }
+std::size_t NeuCor::synapseCount() const {
+    if (engine_ || imported_) return pre_.size();
+    std::size_t s = 0;
+    for (auto& o : out_) s += o.size();
+    return s;
+}
+
+void NeuCor::createNeuron(coord3 position) {  // NeuCor.cpp:154-186 (SPAWN_SPHERE branch)
+    if (engine_ || imported_) throw std::logic_error("NeuCor::createNeuron: the network is frozen once it is on the device");
+    float spawnSize = 2.0;
+    if (position.x != position.x) {
+        if (totalGenNeurons != 0) spawnSize = powf(totalGenNeurons / (1.3333 * 3.1459 * 8), 0.33333) * 2.0;
+        do {
+            position.x = (randomUnit() - 0.5f) * spawnSize;
+            position.y = (randomUnit() - 0.5f) * spawnSize;
+            position.z = (randomUnit() - 0.5f) * spawnSize;
+        } while ((double)position.x * (double)position.x + (double)position.y * (double)position.y +
+                     (double)position.z * (double)position.z >
+                 (spawnSize / 2.0) * (spawnSize / 2.0));
+    }
+    positions.push_back(position);
+    potAct.push_back(-70.0f);  // Neuron ctor: setPotential(baselevel), setActivity(0)  NeuCor.cpp:389,394
+    potAct.push_back(0.0f);
+    out_.emplace_back();
+}
+
+void NeuCor::createSynapse(std::size_t toID, std::size_t fromID, float weight) {  // NeuCor.cpp:187-195
+    if (engine_ || imported_) throw std::logic_error("NeuCor::createSynapse: the network is frozen once it is on the device");
+    auto& outs = out_.at(fromID);
+    for (auto& t : outs)
+        if (t.to == toID) return;  // silently ignores duplicates
+    coord3 n1 = positions.at(toID);
+    coord3 n2 = positions.at(fromID);
+    // the Synapse ctor still draws its random weight and sign before setWeight overrides them (NeuCor.cpp:471-473)
+    (void)randomUnit();
+    (void)randomUnit();
+    OutSyn s;
+    s.to = (uint32_t)toID;
+    s.weight = weight;
+    s.flag = weight < 0.0;
+    s.length = n2.getDist(n1);
+    outs.push_back(s);
+}
+
+void NeuCor::makeConnections() {  // NeuCor.cpp:89-93 → Neuron::makeConnections NeuCor.cpp:418-444
+    if (engine_ || imported_) throw std::logic_error("NeuCor::makeConnections: the network is frozen once it is on the device");
+    const std::size_t N = positions.size();
+    // Uniform grid with unit cells: candidates come from the 27 surrounding cells and are visited in ascending ID,
+    // which is the order the reference's O(N^2) loop meets them in (and so the order rand() is consumed in).
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (auto& p : positions) {
+        lo[0] = std::min(lo[0], p.x); lo[1] = std::min(lo[1], p.y); lo[2] = std::min(lo[2], p.z);
+        hi[0] = std::max(hi[0], p.x); hi[1] = std::max(hi[1], p.y); hi[2] = std::max(hi[2], p.z);
+    }
+    auto cellOf = [&](float v, int a) { return (long)std::floor((double)v - (double)lo[a]); };
+    long dim[3];
+    for (int a = 0; a < 3; a++) dim[a] = N ? cellOf(hi[a], a) + 1 : 1;
+    std::unordered_map<long, std::vector<uint32_t>> grid;
+    auto keyOf = [&](long cx, long cy, long cz) { return (cx * dim[1] + cy) * dim[2] + cz; };
+    for (std::size_t i = 0; i < N; i++) grid[keyOf(cellOf(positions[i].x, 0), cellOf(positions[i].y, 1), cellOf(positions[i].z, 2))].push_back((uint32_t)i);
+    std::vector<uint32_t> cand;
+    for (std::size_t n = 0; n < N; n++) {
+        coord3 nPos = positions[n];
+        long cx = cellOf(nPos.x, 0), cy = cellOf(nPos.y, 1), cz = cellOf(nPos.z, 2);
+        cand.clear();
+        for (long dx = -1; dx <= 1; dx++)
+            for (long dy = -1; dy <= 1; dy++)
+                for (long dz = -1; dz <= 1; dz++) {
+                    long x = cx + dx, y = cy + dy, z = cz + dz;
+                    if (x < 0 || y < 0 || z < 0 || x >= dim[0] || y >= dim[1] || z >= dim[2]) continue;
+                    auto it = grid.find(keyOf(x, y, z));
+                    if (it != grid.end()) cand.insert(cand.end(), it->second.begin(), it->second.end());
+                }
+        std::sort(cand.begin(), cand.end());
+        auto& outs = out_[n];
+        for (uint32_t i : cand) {
+            float distance = nPos.getDist(positions[i]);
+            if (distance < 1.0 && i != n) {
+                bool allowed = true;
+                for (auto& o : outs)
+                    if (o.to == i) { allowed = false; break; }
+                if (!allowed) continue;
+                // Synapse ctor, NeuCor.cpp:463-486
+                OutSyn s;
+                s.to = i;
+                s.weight = randomUnit() * 0.8f + 0.2f;
+                if (randomUnit() < 0.2f) s.weight = -s.weight;
+                s.flag = s.weight < 0.0;
+                s.length = nPos.getDist(positions[i]);
+                outs.push_back(s);
+            }
+        }
+    }
+}
+
+void NeuCor::importNetwork(std::size_t n, const uint64_t* rowptr, const uint32_t* pre, const float* weight, const float* length,
+                           const uint8_t* inhibitory, const float* xyz) {
+    if (engine_) throw std::logic_error("NeuCor::importNetwork: the network is already on the device");
+    positions.resize(n);
+    potAct.assign(2 * n, 0.0f);
+    for (std::size_t i = 0; i < n; i++) {
+        if (xyz) positions[i] = coord3{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+        else positions[i].setNAN();
+        potAct[2 * i] = -70.0f;
+    }
+    out_.clear();
+    rowptr_.assign(rowptr, rowptr + n + 1);
+    uint64_t S = rowptr[n];
+    pre_.assign(pre, pre + S);
+    weight_.assign(weight, weight + S);
+    length_.assign(length, length + S);
+    flag_.assign(inhibitory, inhibitory + S);
+    imported_ = true;
+}
+
+void NeuCor::finalize() {
+    if (engine_) return;
+    const std::size_t N = positions.size();
+    if (!imported_) {  // rows = target, in-row ascending presynaptic ID: Neuron::inSynapses' std::map order (NeuCor.h:212)
+        rowptr_.assign(N + 1, 0);
+        for (auto& outs : out_)
+            for (auto& s : outs) rowptr_[s.to + 1]++;
+        for (std::size_t i = 0; i < N; i++) rowptr_[i + 1] += rowptr_[i];
+        uint64_t S = rowptr_[N];
+        pre_.resize(S); weight_.resize(S); length_.resize(S); flag_.resize(S);
+        std::vector<uint64_t> fill(rowptr_.begin(), rowptr_.end() - 1);
+        for (std::size_t p = 0; p < N; p++)  // ascending p => each row ends up ascending in presynaptic ID
+            for (auto& s : out_[p]) {
+                uint64_t k = fill[s.to]++;
+                pre_[k] = (uint32_t)p; weight_[k] = s.weight; length_[k] = s.length; flag_[k] = s.flag;
+            }
+    }
+    nc_config cfg = {};
+    cfg.device = deviceOrdinal;
+    cfg.rank = 0;
+    cfg.world = 1;
+    cfg.cand_smem = candidateSmem;
+    nc_engine* e = nullptr;
+    int rc = nc_create(&cfg, &e);
+    if (rc != NC_OK) throw std::runtime_error(std::string("NeuCor: cannot create the CUDA engine: ") + nc_global_error());
+    engine_ = e;
+    check(nc_upload_network(engine_, N, 0, N, rowptr_.data(), pre_.data(), weight_.data(), length_.data(), flag_.data()), "nc_upload_network");
+    h2dBytes_ += (N + 1) * 8 + pre_.size() * 13;
+    minDelay_ = INFINITY;
+    if (!pre_.empty()) check(nc_min_delay(engine_, &minDelay_), "nc_min_delay");
+    lastFireMirror_.assign(N, NAN);
+}
+
+// ---- inputs and detectors ---------------------------------------------------------------------------------
+void NeuCor::setInputRateArray(float inputs[], unsigned inputCount, coord3 inputPositions[], float inputRadius[]) {  // NeuCor.cpp:46-64
+    inputArray = inputs;
+    inputArraySize = inputCount;
+    int change = (int)inputArraySize - (int)inputHandler.size();
+    if (0 < change) {
+        for (int i = 0; i < change; i++) {
+            InputFirer f;  // InputFirer ctor, NeuCor.cpp:305-324
+            f.lastFire = 0.0f;
+            f.enabled = true;
+            if (inputPositions != NULL) { f.a = inputPositions[i]; f.radius = inputRadius[i]; }
+            else { f.radius = 1.0f; f.a.setNAN(); }
+            if (!(f.a.x == f.a.x)) {
+                f.a.x = (randomUnit() - 0.5f) * 5.f; f.a.y = (randomUnit() - 0.5f) * 5.f; f.a.z = (randomUnit() - 0.5f) * 5.f;
+            }
+            for (std::size_t n = 0; n < positions.size(); n++)
+                if (positions[n].getDist(f.a) < f.radius) f.near.push_back((uint32_t)n);
+            inputHandler.push_back(std::move(f));
+        }
+    } else if (change < 0) {
+        for (int i = 0; i < -change; i++) inputHandler.pop_back();
+    }
+}
+void NeuCor::addInputOffset(unsigned inputID, float t) { inputHandler.at(inputID).lastFire += t; }
+void NeuCor::setInputEnabled(unsigned inputID, bool en) { inputHandler.at(inputID).enabled = en; }
+void NeuCor::setInputNear(unsigned inputID, const uint32_t* ids, std::size_t n) { inputHandler.at(inputID).near.assign(ids, ids + n); }
+void NeuCor::setInputLastFire(unsigned inputID, float t) { inputHandler.at(inputID).lastFire = t; }
+std::vector<float> NeuCor::inputLastFire() const {
+    std::vector<float> r;
+    for (auto& f : inputHandler) r.push_back(f.lastFire);
+    return r;
+}
+std::vector<std::vector<uint32_t>> NeuCor::inputNear() const {
+    std::vector<std::vector<uint32_t>> r;
+    for (auto& f : inputHandler) r.push_back(f.near);
+    return r;
+}
+
+void NeuCor::setDetectors(unsigned detectorNumber, coord3 detectorPositions[], float detectorRadius[]) {  // NeuCor.cpp:70-77,347-357
+    for (unsigned i = 0; i < detectorNumber; i++) {
+        VoltageDetector d;
+        if (detectorPositions != NULL) { d.a = detectorPositions[i]; d.radius = detectorRadius[i]; }
+        else { d.radius = 1.0f; d.a.setNAN(); }
+        if (!(d.a.x == d.a.x)) {
+            d.a.x = (randomUnit() - 0.5f) * 3.f; d.a.y = (randomUnit() - 0.5f) * 3.f; d.a.z = (randomUnit() - 0.5f) * 3.f;
+        }
+        for (std::size_t n = 0; n < positions.size(); n++)
+            if (positions[n].getDist(d.a) < d.radius) d.near.push_back((uint32_t)n);
+        voltageDetectors.push_back(std::move(d));
+    }
+}
+
+float NeuCor::getDetectorVoltage(unsigned ID) {  // VoltageDetector::getVoltage, NeuCor.cpp:359-366
+    VoltageDetector& d = voltageDetectors.at(ID);
+    finalize();
+    uint64_t hidden = 0;
+    nc_step_stats st;
+    check(nc_run_neurons(engine_, currentTime, d.near.data(), (uint32_t)d.near.size(), &hidden, &st), "nc_run_neurons");
+    for (uint64_t k = 0; k < hidden; k++) (void)rand();
+    float out = 0.0f;
+    check(nc_detector_mean(engine_, d.near.data(), (uint32_t)d.near.size(), &out), "nc_detector_mean");
+    return out;
+}
+std::vector<float> NeuCor::getDetectorVoltages() {
+    std::vector<float> voltages;
+    for (unsigned i = 0; i < voltageDetectors.size(); i++) voltages.push_back(getDetectorVoltage(i));
+    return voltages;
+}
+
+// ---- the step ---------------------------------------------------------------------------------------------
+// InputFirer::schedule, NeuCor.cpp:333-345 — emits one event per (fire time, near neuron)
+void NeuCor::scheduleInput(unsigned i, float deltaT, float frequency, std::vector<nc_event>& ev) {
+    InputFirer& f = inputHandler[i];
+    if (frequency == 0 || !f.enabled) return;
+    if (f.lastFire != f.lastFire) f.lastFire = 0;
+    float currentT = currentTime;
+    for (float fireTime = f.lastFire + 1000.0 / frequency; fireTime < currentT + deltaT; fireTime += 1000.0 / frequency) {
+        if (currentT < fireTime) {
+            float stime = currentTime + (fireTime - currentT);  // queueSimulation, NeuCor.cpp:227-229
+            for (uint32_t n : f.near) ev.push_back(nc_event{n, stime, 0u, i});
+            f.lastFire = fireTime;
+        }
+    }
+}
+
+void NeuCor::window(float t0, float t1, int flags, std::vector<nc_event>& ev) {
+    uint64_t hidden = 0;
+    nc_step_stats st;
+    check(nc_step(engine_, t0, t1, flags, ev.data(), (uint32_t)ev.size(), &hidden, &st), "nc_step");
+    h2dBytes_ += ev.size() * sizeof(nc_event);
+    d2hBytes_ += 16 + 8 * sizeof(uint64_t);
+    // the rand() calls hidden in synapticPlasticity's short-circuit (NeuCor.cpp:752): only their number matters
+    for (uint64_t k = 0; k < hidden; k++) (void)rand();
+    lastStats_.fires += st.fires; lastStats_.deliveries += st.deliveries; lastStats_.loadsAccepted += st.loads_accepted;
+    lastStats_.loadsDropped += st.loads_dropped; lastStats_.plasticityCalls += st.plasticity_calls; lastStats_.hiddenRand += st.hidden_rand_calls;
+    lastStats_.neuronRuns += st.neuron_runs; lastStats_.activeVisits += st.active_visits;
+}
+
+float NeuCor::stepInternal(bool sweep) {  // NeuCor::run, NeuCor.cpp:583-617
+    assert(0 <= runSpeed);
+    if (runSpeed <= 0.0f) return 0.0f;
+    finalize();
+    check(nc_set_plasticity(engine_, learningRate, presynapticFactor, postsynapticFactor, presynapticTraceDecay, postsynapticTraceDecay), "nc_set_plasticity");
+    lastStats_ = StepStats{};
+    const std::size_t N = positions.size();
+    events_.clear();
+    for (unsigned i = 0; i < inputHandler.size(); i++) {
+        const float inputFrequency = inputArray != nullptr && i < inputArraySize ? inputArray[i] : 0.0f;
+        scheduleInput(i, runSpeed, inputFrequency, events_);
+    }
+    // background firing, NeuCor.cpp:604-607
+    const std::size_t bgBegin = events_.size();
+    {
+        const int backgroundFirePeriod = std::max(1, static_cast<int>(600.0f / runSpeed));
+        for (std::size_t i = 0; i < N; ++i) {
+            if (rand() % backgroundFirePeriod == 0) {
+                uint32_t n = (uint32_t)(rand() % N);
+                float t = randomUnit() * runSpeed;
+                events_.push_back(nc_event{n, currentTime + t, 2u, 0u});  // Neuron::scheduleFire, NeuCor.cpp:658-661
+            }
+        }
+        // scheduledFireTime keeps the LAST value drawn for a neuron
+        for (std::size_t k = events_.size(); k-- > bgBegin;) {
+            bool later = false;
+            for (std::size_t m = k + 1; m < events_.size() && !later; m++) later = events_[m].neuron == events_[k].neuron;
+            if (!later) events_[k].index_or_flags = 1u;
+        }
+    }
+    std::stable_sort(events_.begin(), events_.end(), [](const nc_event& a, const nc_event& b) { return a.neuron < b.neuron; });
+
+    const float t0 = currentTime;
+    const float targetTime = currentTime + runSpeed;
+    const float limit = std::min(minDelay_, 2.0f);
+    int startFlag = runAll ? NC_SWEEP_START : 0;
+    if (targetTime - t0 < limit) {
+        window(t0, targetTime, startFlag | (sweep ? NC_SWEEP_END : 0), events_);
+    } else {
+        // The window must be shorter than the smallest synaptic delay: split it. Boundaries are invisible to the
+        // semantics (no neuron is run at them); only the last sub-window carries the end sweep.
+        int pieces = (int)std::ceil((double)(targetTime - t0) / ((double)limit * 0.5)) + 1;
+        float a = t0;
+        for (int k = 1; k <= pieces; k++) {
+            float b = (k == pieces) ? targetTime : (float)((double)t0 + ((double)targetTime - (double)t0) * k / pieces);
+            if (!(b > a)) continue;
+            winEvents_.clear();
+            for (auto& e : events_)
+                if ((k == 1 ? e.time >= a : e.time > a) && e.time <= b) winEvents_.push_back(e);
+            window(a, b, (k == 1 ? startFlag : 0) | ((sweep && k == pieces) ? NC_SWEEP_END : 0), winEvents_);
+            a = b;
+        }
+    }
+    currentTime = targetTime;
+    totalStats_.fires += lastStats_.fires; totalStats_.deliveries += lastStats_.deliveries; totalStats_.loadsAccepted += lastStats_.loadsAccepted;
+    totalStats_.loadsDropped += lastStats_.loadsDropped; totalStats_.plasticityCalls += lastStats_.plasticityCalls; totalStats_.hiddenRand += lastStats_.hiddenRand;
+    totalStats_.neuronRuns += lastStats_.neuronRuns; totalStats_.activeVisits += lastStats_.activeVisits;
+    return 0.0f;
+}
+
+void NeuCor::run() { stepInternal(false); }
+
+float NeuCor::runSwept() {
+    stepInternal(true);
+    // mean potential of all neurons, summed in ID order in float — VoltageDetector::getVoltage, NeuCor.cpp:360-365
+    syncState();
+    d2hBytes_ += potAct.size() * 4;
+    float avgV = 0;
+    const std::size_t N = positions.size();
+    for (std::size_t i = 0; i < N; i++) avgV += potAct[2 * i];
+    return avgV / N;
+}
+
+// ---- state read-back --------------------------------------------------------------------------------------
+void NeuCor::syncState() {
+    if (!engine_) return;
+    check(nc_read_neurons(engine_, potAct.data(), lastFireMirror_.data(), nullptr), "nc_read_neurons");
+}
+void NeuCor::readNeurons(float* pot, float* act, float* lastFire, float* lastRan) {
+    finalize();
+    const std::size_t N = positions.size();
+    check(nc_read_neurons(engine_, potAct.data(), lastFire, lastRan), "nc_read_neurons");
+    for (std::size_t i = 0; i < N; i++) {
+        if (pot) pot[i] = potAct[2 * i];
+        if (act) act[i] = potAct[2 * i + 1];
+    }
+}
+void NeuCor::readSynapses(float* weight, float* arrive, float* depol, float* lastArrival, float* lastStart) {
+    finalize();
+    check(nc_read_synapses(engine_, weight, arrive, depol, lastArrival, lastStart), "nc_read_synapses");
+}
+void NeuCor::resetActivities() {  // NeuCor.cpp:233-235
+    finalize();
+    check(nc_reset_activities(engine_, currentTime), "nc_reset_activities");
+}
+
+std::vector<NeuCor::NeuronSnapshot> NeuCor::getNeuronSnapshots() const {  // NeuCor.cpp:99-113
+    const_cast<NeuCor*>(this)->syncState();
+    std::vector<NeuronSnapshot> snapshots;
+    snapshots.reserve(positions.size());
+    for (std::size_t i = 0; i < positions.size(); i++) snapshots.push_back({i, positions[i], potAct[2 * i], potAct[2 * i + 1]});
+    return snapshots;
+}
+std::vector<NeuCor::SynapseSnapshot> NeuCor::getSynapseSnapshots() const {  // NeuCor.cpp:115-134
+    NeuCor* self = const_cast<NeuCor*>(this);
+    self->finalize();
+    const std::size_t S = pre_.size(), N = positions.size();
+    std::vector<float> w(S), prePot(S), postPot(S);
+    self->check(nc_read_synapses(engine_, w.data(), nullptr, nullptr, nullptr, nullptr), "nc_read_synapses");
+    self->check(nc_read_synapse_pots(engine_, currentTime, prePot.data(), postPot.data()), "nc_read_synapse_pots");
+    // the reference iterates neurons in ID order and each neuron's outSynapses in creation order; an imported network
+    // has no creation order, so it is listed by (from, to)
+    std::vector<SynapseSnapshot> snapshots;
+    snapshots.reserve(S);
+    std::vector<std::vector<std::pair<uint32_t, uint64_t>>> byFrom(N);
+    for (std::size_t q = 0; q < N; q++)
+        for (uint64_t k = rowptr_[q]; k < rowptr_[q + 1]; k++) byFrom[pre_[k]].push_back({(uint32_t)q, k});
+    for (std::size_t p = 0; p < N; p++) {
+        auto emit = [&](uint32_t to, uint64_t k) {
+            snapshots.push_back({p, to, positions[p], positions[to], w[k], prePot[k], postPot[k], w[k] < 0.0f});
+        };
+        if (!imported_ && p < out_.size()) {
+            for (auto& o : out_[p])
+                for (auto& e : byFrom[p])
+                    if (e.first == o.to) { emit(e.first, e.second); break; }
+        } else {
+            for (auto& e : byFrom[p]) emit(e.first, e.second);
+        }
+    }
+    return snapshots;
+}
+std::vector<NeuCor::InputSnapshot> NeuCor::getInputSnapshots() const {  // NeuCor.cpp:136-152
+    std::vector<InputSnapshot> snapshots;
+    snapshots.reserve(inputHandler.size());
+    for (std::size_t i = 0; i < inputHandler.size(); ++i) {
+        const InputFirer& input = inputHandler.at(i);
+        snapshots.push_back({i, input.a, input.radius, inputArray != nullptr && i < inputArraySize ? inputArray[i] : 0.0f, input.enabled});
+    }
+    return snapshots;
+}

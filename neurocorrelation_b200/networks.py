@@ -1,0 +1,140 @@
+"""Synthetic spatial networks for configs C2-C5 in the engine's exchange format:
+post-sorted CSR (rows = target neuron, in-row ascending presynaptic ID), the iteration order of the
+reference's Neuron::inSynapses map (NeuCor.h:212, NeuCor.cpp:690).
+
+Recipe (the reference has no large-network builder; NeuCor(int) is O(N^2) and fixed-degree):
+  * positions uniform in a cube of side (N/8)^(1/3) — the reference's spawn density of 8 neurons
+    per unit volume (NeuCor.cpp:155);
+  * every neuron draws K distinct presynaptic partners uniformly from the neurons within radius R
+    of it (R chosen so the ball holds ~2K neurons), rejecting lengths < MIN_LENGTH so that every
+    synaptic delay 2*length exceeds the step dt = 0.0625 ms; neurons close to the cube's faces
+    that see fewer than K candidates take all of them;
+  * weights U(0.2, 1), 20 % negated, inhibitory flag = sign (Synapse ctor, NeuCor.cpp:471-475);
+  * G = N/250 input firers on a jittered grid, radius 0.8 (as the STANDARD preset, main.cpp:87),
+    `near` lists in ascending neuron ID (NeuCor.cpp:319-323).
+"""
+import numpy as np
+
+MIN_LENGTH = 0.04
+DENSITY = 8.0
+
+
+def _dist32(a, b):
+    """coord3::getDist (NeuCor.h:16-18) in float32: sqrtf(dx*dx + dy*dy + dz*dz), left to right."""
+    d = a[:, None, :] - b[None, :, :]
+    d2 = d[..., 0] * d[..., 0]
+    d2 = d2 + d[..., 1] * d[..., 1]
+    d2 = d2 + d[..., 2] * d[..., 2]
+    return np.sqrt(d2)
+
+
+def radius_for(K):
+    """Ball radius that holds ~2K neurons at the reference density."""
+    return float((2.0 * K / (DENSITY * 4.0 / 3.0 * np.pi)) ** (1.0 / 3.0))
+
+
+def synthetic_network(N, K, seed=1, R=None, inputs_per_neuron=1.0 / 250.0, input_radius=0.8):
+    rng = np.random.default_rng(seed)
+    N, K = int(N), int(K)
+    L = (N / DENSITY) ** (1.0 / 3.0)
+    R = radius_for(K) if R is None else float(R)
+    pos = (rng.random((N, 3)) * L).astype(np.float32)
+    nc = max(1, int(np.floor(L / R)))
+    cs = L / nc
+    cell = np.minimum((pos / cs).astype(np.int64), nc - 1)
+    cid = (cell[:, 0] * nc + cell[:, 1]) * nc + cell[:, 2]
+    order = np.argsort(cid, kind="stable")
+    starts = np.searchsorted(cid[order], np.arange(nc ** 3 + 1))
+
+    def members(cx, cy, cz):
+        out = []
+        for dx in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for dz in (-1, 0, 1):
+                    x, y, z = cx + dx, cy + dy, cz + dz
+                    if 0 <= x < nc and 0 <= y < nc and 0 <= z < nc:
+                        c = (x * nc + y) * nc + z
+                        out.append(order[starts[c]:starts[c + 1]])
+        return np.concatenate(out) if out else np.zeros(0, np.int64)
+
+    rowlen = np.zeros(N, np.int64)
+    rows_pre = [None] * N
+    rows_len = [None] * N
+    for cx in range(nc):
+        for cy in range(nc):
+            for cz in range(nc):
+                c = (cx * nc + cy) * nc + cz
+                mine = order[starts[c]:starts[c + 1]]
+                if len(mine) == 0:
+                    continue
+                cand = members(cx, cy, cz)
+                d = _dist32(pos[mine], pos[cand])
+                ok = (d < R) & (d >= MIN_LENGTH) & (mine[:, None] != cand[None, :])
+                keys = rng.random(d.shape)
+                keys[~ok] = 2.0
+                take = min(K, d.shape[1])
+                sel = np.argpartition(keys, take - 1, axis=1)[:, :take] if take < d.shape[1] else np.tile(np.arange(d.shape[1]), (len(mine), 1))
+                for i, q in enumerate(mine):
+                    s = sel[i]
+                    s = s[keys[i, s] < 1.5]
+                    p = cand[s]
+                    o = np.argsort(p)
+                    rows_pre[q] = p[o].astype(np.uint32)
+                    rows_len[q] = d[i, s][o].astype(np.float32)
+                    rowlen[q] = len(p)
+    rowptr = np.zeros(N + 1, np.uint64)
+    rowptr[1:] = np.cumsum(rowlen)
+    S = int(rowptr[N])
+    pre = np.concatenate([r for r in rows_pre if r is not None and len(r)]) if S else np.zeros(0, np.uint32)
+    length = np.concatenate([r for r in rows_len if r is not None and len(r)]) if S else np.zeros(0, np.float32)
+    w = (rng.random(S).astype(np.float32) * np.float32(0.8) + np.float32(0.2)).astype(np.float32)
+    neg = rng.random(S) < 0.2
+    w[neg] = -w[neg]
+    net = dict(N=N, S=S, rowptr=rowptr, pre=pre.astype(np.uint32), weight=w, length=length,
+               flag=(w < 0).astype(np.uint8), positions=pos)
+    # input firers on a jittered grid
+    G = max(1, int(round(N * inputs_per_neuron)))
+    gpos = (rng.random((G, 3)) * L).astype(np.float32)
+    near = []
+    for g in range(G):
+        d = _dist32(gpos[g:g + 1], pos)[0]
+        near.append(np.nonzero(d < np.float32(input_radius))[0].astype(np.uint32))
+    net["inputs"] = dict(G=G, positions=gpos, radius=np.full(G, input_radius, np.float32), near=near)
+    return net
+
+
+def uniform_random_network(N, K, seed=1, max_length=None):
+    """Cheap stand-in used for throughput runs at sizes the spatial builder cannot reach from numpy:
+    K distinct uniformly random presynaptic partners per neuron, lengths drawn from the distance
+    distribution of uniform points in a ball of radius R (pdf ~ r^2) truncated to >= MIN_LENGTH."""
+    rng = np.random.default_rng(seed)
+    N, K = int(N), int(K)
+    R = radius_for(K) if max_length is None else float(max_length)
+    pre = np.empty((N, K), np.uint32)
+    for q0 in range(0, N, 4096):
+        q1 = min(N, q0 + 4096)
+        # K distinct draws per row: sample with replacement, redraw duplicates/self until clean
+        p = rng.integers(0, N, size=(q1 - q0, K), dtype=np.int64)
+        for _ in range(64):
+            p.sort(axis=1)
+            bad = np.zeros_like(p, bool)
+            bad[:, 1:] = p[:, 1:] == p[:, :-1]
+            bad |= p == np.arange(q0, q1)[:, None]
+            nb = int(bad.sum())
+            if nb == 0:
+                break
+            p[bad] = rng.integers(0, N, size=nb, dtype=np.int64)
+        p.sort(axis=1)
+        pre[q0:q1] = p
+    S = N * K
+    length = (R * rng.random(S) ** (1.0 / 3.0)).astype(np.float32)
+    length = np.maximum(length, np.float32(MIN_LENGTH))
+    w = (rng.random(S).astype(np.float32) * np.float32(0.8) + np.float32(0.2)).astype(np.float32)
+    neg = rng.random(S) < 0.2
+    w[neg] = -w[neg]
+    rowptr = (np.arange(N + 1, dtype=np.uint64) * np.uint64(K))
+    G = max(1, N // 250)
+    near = [np.sort(rng.choice(N, size=min(N, 17), replace=False)).astype(np.uint32) for _ in range(G)]
+    return dict(N=N, S=S, rowptr=rowptr, pre=pre.reshape(-1), weight=w, length=length,
+                flag=(w < 0).astype(np.uint8), positions=None,
+                inputs=dict(G=G, positions=None, radius=np.full(G, 0.8, np.float32), near=near))

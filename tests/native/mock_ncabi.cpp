@@ -1,0 +1,235 @@
+// TEST DOUBLE — a single-threaded CPU model of the device engine behind include/neucor_b200.h.
+//
+// It exists so that the two-pass algorithm and the host class can be checked against the oracle in
+// CI without a GPU.  It is built only by tests/ into tests/native/_build/ and is
+// never part of, linked into, or loaded by the product (libneucor_b200.so has no CPU path).  The
+// per-neuron / per-synapse logic is the SAME source the kernels compile (csrc/step_logic.cuh); only
+// the warp-cooperative scaffolding of engine.cu (ballot staging, shuffle min-reduction, grid loops) is
+// restated serially here.
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../neurocorrelation_b200/csrc/step_logic.cuh"
+
+using namespace ncm;
+using namespace ncs;
+
+struct nc_engine {
+    std::string err;
+    View v;
+    std::vector<uint64_t> rowptr;
+    std::vector<uint32_t> pre, firings, hdr, mask, spillJ;
+    std::vector<float> arrive, depol, weight, lastArr, lastStart, delay, lastRan, lastFire, lfStart, actStart, spillA, spillD;
+    std::vector<float2> potAct;
+    std::vector<FireRec> recs;
+    std::vector<int32_t> head, next;
+    unsigned long long stats[8];
+    float lr = 1.0f, preF = 0.13f, postF = 0.30f, preD = 0.75f, postD = 0.65f, minDelay = INFINITY;
+    uint32_t candCap = 8;  // deliberately tiny so that the spill path is exercised
+    bool uploaded = false;
+    uint32_t lastCount = 0;
+};
+static std::string g_err;
+static int fail(nc_engine* e, int code, const char* m) { e->err = m; return code; }
+
+extern "C" {
+const char* nc_global_error(void) { return g_err.c_str(); }
+const char* nc_last_error(const nc_engine* e) { return e ? e->err.c_str() : g_err.c_str(); }
+int nc_device_count(void) { return 1; }
+uint64_t nc_launch_count(const nc_engine*) { return 0; }
+int nc_create(const nc_config* cfg, nc_engine** out) {
+    nc_engine* e = new nc_engine();
+    memset(&e->v, 0, sizeof(View));
+    memset(e->stats, 0, sizeof(e->stats));
+    if (cfg->cand_smem) e->candCap = cfg->cand_smem;
+    *out = e;
+    return NC_OK;
+}
+void nc_destroy(nc_engine* e) { delete e; }
+int nc_set_plasticity(nc_engine* e, float lr, float a, float b, float c, float d) { e->lr = lr; e->preF = a; e->postF = b; e->preD = c; e->postD = d; return NC_OK; }
+int nc_min_delay(const nc_engine* e, float* out) { *out = e->minDelay; return NC_OK; }
+
+int nc_upload_network(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t nRows, const uint64_t* rowptr, const uint32_t* pre,
+                      const float* weight, const float* length, const uint8_t* inh) {
+    uint64_t S = rowptr[nRows], maxRow = 0;
+    e->rowptr.assign(rowptr, rowptr + nRows + 1);
+    e->pre.assign(pre, pre + S); e->weight.assign(weight, weight + S);
+    e->arrive.assign(S, 0.0f); e->depol.assign(S, 0.0f); e->lastStart.assign(S, 0.0f); e->lastArr.assign(S, -INFINITY); e->delay.resize(S);
+    for (uint64_t i = 0; i < S; i++) { e->delay[i] = length[i] * 2.0f; e->minDelay = std::min(e->minDelay, e->delay[i]); if (inh[i]) e->pre[i] |= 0x80000000u; }
+    for (uint64_t r = 0; r < nRows; r++) maxRow = std::max(maxRow, rowptr[r + 1] - rowptr[r]);
+    e->potAct.assign(nRows, make_float2(-70.0f, 0.0f)); e->lastRan.assign(nRows, 0.0f); e->lastFire.assign(nRows, NAN);
+    e->lfStart.assign(nRows, NAN); e->actStart.assign(nRows, 0.0f); e->firings.assign(nRows, 0u);
+    uint32_t cap = (uint32_t)(4 * nRows + 1024);
+    e->hdr.assign(4, 0u); e->recs.resize(cap); e->head.assign(nGlobal, -1); e->next.assign(cap, -1); e->mask.assign((nGlobal + 31) / 32 + 1, 0u);
+    e->spillA.resize(maxRow + 1); e->spillD.resize(maxRow + 1); e->spillJ.resize(maxRow + 1);
+    View& v = e->v;
+    v.nGlobal = nGlobal; v.row0 = row0; v.nRows = nRows; v.S = S; v.rowptr = e->rowptr.data(); v.pre = e->pre.data();
+    v.arrive = e->arrive.data(); v.depol = e->depol.data(); v.weight = e->weight.data(); v.lastArr = e->lastArr.data(); v.lastStart = e->lastStart.data();
+    v.delay = e->delay.data(); v.potAct = e->potAct.data(); v.lastRan = e->lastRan.data(); v.lastFire = e->lastFire.data(); v.lfStart = e->lfStart.data();
+    v.actStart = e->actStart.data(); v.firings = e->firings.data(); v.localHdr = e->hdr.data(); v.localRecs = e->recs.data(); v.fireCap = cap;
+    v.gRecs = e->recs.data(); v.head = e->head.data(); v.next = e->next.data(); v.mask = e->mask.data();
+    v.spillA = e->spillA.data(); v.spillD = e->spillD.data(); v.spillJ = e->spillJ.data(); v.spillPerWarp = (uint32_t)maxRow; v.stats = e->stats;
+    e->uploaded = true;
+    return NC_OK;
+}
+
+// serial restatement of k_neuron_pass
+static void model_pass1(nc_engine* e, const StepArgs& s) {
+    View& v = e->v;
+    std::vector<float> sa(s.candCap), sd(s.candCap);
+    std::vector<uint32_t> sj(s.candCap);
+    CandView cv;
+    cv.a = sa.data(); cv.d = sd.data(); cv.j = sj.data(); cv.cap = s.candCap; cv.sa = v.spillA; cv.sd = v.spillD; cv.sj = v.spillJ;
+    unsigned long long nFires = 0, nRuns = 0, nVisits = 0, nDeliv = 0;
+    for (uint64_t row = 0; row < v.nRows; row++) {
+        const uint32_t q = (uint32_t)(v.row0 + row);
+        if (s.subset && !std::binary_search(s.subset, s.subset + s.nSubset, q)) continue;
+        const uint64_t rs = v.rowptr[row], re = v.rowptr[row + 1];
+        uint32_t cnt = 0;
+        for (uint64_t j = rs; j < re; j++) {
+            float a = v.arrive[j];
+            if (a != 0.0f && a <= s.t1) { cv.A(cnt) = a; cv.D(cnt) = v.depol[j]; cv.J(cnt) = (uint32_t)(j - rs); cnt++; }
+        }
+        uint32_t evLo = (uint32_t)(std::lower_bound(s.ev, s.ev + s.nEv, q, [](const nc_event& x, uint32_t k) { return x.neuron < k; }) - s.ev);
+        uint32_t evHi = (uint32_t)(std::upper_bound(s.ev, s.ev + s.nEv, q, [](uint32_t k, const nc_event& x) { return k < x.neuron; }) - s.ev);
+        NeuronState n;
+        n.pot = v.potAct[row].x; n.act = v.potAct[row].y; n.lastRan = v.lastRan[row]; n.lastFire = v.lastFire[row];
+        n.actStart = v.actStart[row]; n.firings = v.firings[row]; n.sched = NAN;
+        for (uint32_t k = evLo; k < evHi; k++) if (s.ev[k].kind == 2u && (s.ev[k].index_or_flags & 1u)) n.sched = s.ev[k].time;
+        v.lfStart[row] = n.lastFire;
+        if (cnt || evHi > evLo || (s.sweep & NC_SWEEP_START)) {
+            float curT = s.t0; unsigned long long curC = 0; bool first = true;
+            for (;;) {
+                float bt = INFINITY; unsigned long long bc = ~0ull; uint32_t bsrc = 0xffffffffu;
+                for (uint32_t c = 0; c < cnt; c++) {
+                    float a = fabsf(cv.A(c));
+                    if (a > s.t0) {
+                        uint32_t p = v.pre[rs + cv.J(c)] & 0x7fffffffu;
+                        unsigned long long code = (1ull << 32) | p;
+                        if ((first || pick_less(curT, curC, a, code)) && pick_less(a, code, bt, bc)) { bt = a; bc = code; bsrc = c; }
+                    }
+                    float tR = add32(a, 2.0f);
+                    if (tR > s.t0 && tR <= s.t1) {
+                        unsigned long long code = (2ull << 32);
+                        if ((first || pick_less(curT, curC, tR, code)) && pick_less(tR, code, bt, bc)) { bt = tR; bc = code; bsrc = c; }
+                    }
+                }
+                if ((s.sweep & NC_SWEEP_START) && (first || pick_less(curT, curC, s.t0, 2ull << 32)) && pick_less(s.t0, 2ull << 32, bt, bc)) { bt = s.t0; bc = 2ull << 32; bsrc = 0xfffffffeu; }
+                for (uint32_t k = evLo; k < evHi; k++) {
+                    nc_event ev = s.ev[k];
+                    unsigned long long code = ev.kind == 0u ? (unsigned long long)ev.index_or_flags : (2ull << 32);
+                    bool after = first ? (ev.time >= s.t0) : pick_less(curT, curC, ev.time, code);
+                    if (after && ev.time <= s.t1 && pick_less(ev.time, code, bt, bc)) { bt = ev.time; bc = code; bsrc = 0x80000000u | k; }
+                }
+                if (bc == ~0ull) break;
+                uint32_t rank = (uint32_t)(bc >> 32), k = (uint32_t)bc;
+                if (rank == 0) neuron_fire(v, n, q, bt, k, q, nFires);
+                else if (rank == 1) { nDeliv++; neuron_run(v, n, cv, cnt, rs, q, bt, (1u << 30) | q, k, NC_SENT | (1u << 29) | cv.J(bsrc), nFires, nRuns, nVisits); }
+                else neuron_run(v, n, cv, cnt, rs, q, bt, (2u << 30) | q, 0u, NC_SENT | (2u << 29), nFires, nRuns, nVisits);
+                curT = bt; curC = bc; first = false;
+            }
+        }
+        if (s.sweep & NC_SWEEP_END) neuron_run(v, n, cv, cnt, rs, q, s.t1, (3u << 30) | q, 0u, NC_SENT | (3u << 29), nFires, nRuns, nVisits);
+        v.potAct[row] = make_float2(n.pot, n.act); v.lastRan[row] = n.lastRan; v.lastFire[row] = n.lastFire; v.firings[row] = n.firings;
+    }
+    v.stats[0] += nFires; v.stats[1] += nDeliv; v.stats[6] += nRuns; v.stats[7] += nVisits;
+}
+// serial restatement of k_index_build / k_synapse_pass / k_index_reset
+static void model_pass2(nc_engine* e, const StepArgs& s) {
+    View& v = e->v;
+    uint32_t count = v.localHdr[0];
+    // records were appended in row order here; on the device the order is arbitrary — shuffle to make sure nothing depends on it
+    for (uint32_t i = 0; i + 1 < count; i += 2) std::swap(e->recs[i], e->recs[i + 1]);
+    for (uint32_t i = 0; i < count; i++) { uint32_t nrn = v.gRecs[i].neuron; v.next[i] = v.head[nrn]; v.head[nrn] = (int32_t)i; v.mask[nrn >> 5] |= 1u << (nrn & 31u); }
+    uint32_t cnt[5] = {0, 0, 0, 0, 0};
+    for (uint64_t row = 0; row < v.nRows; row++) {
+        const uint32_t q = (uint32_t)(v.row0 + row);
+        const uint64_t rs = v.rowptr[row], re = v.rowptr[row + 1];
+        const bool qFired = (v.mask[q >> 5] >> (q & 31u)) & 1u;
+        const float lfS = v.lfStart[row];
+        for (uint64_t j = rs; j < re; j++) {
+            uint32_t pw = v.pre[j], p = pw & 0x7fffffffu, ab = as_u32(v.arrive[j]);
+            bool pFired = (v.mask[p >> 5] >> (p & 31u)) & 1u;
+            float a = as_f32(ab);
+            bool eventful = qFired || pFired || (ab & NC_SENT) || (ab != 0u && a > s.t0 && a <= s.t1);
+            if (eventful) resolve_slot(v, s, j, rs, q, p, (pw >> 31) != 0u, ab, pFired, qFired, lfS, cnt);
+        }
+    }
+    v.stats[2] += cnt[0]; v.stats[3] += cnt[1]; v.stats[4] += cnt[2]; v.stats[5] += cnt[3];
+    for (uint32_t i = 0; i < count; i++) { uint32_t nrn = v.gRecs[i].neuron; v.head[nrn] = -1; v.mask[nrn >> 5] = 0u; }
+    e->lastCount = count;
+    v.localHdr[0] = 0; v.localHdr[1] = 0;
+}
+static void fill(nc_engine* e, StepArgs& a, float t0, float t1, int sweep, const nc_event* ev, uint32_t nEv) {
+    memset(&a, 0, sizeof(a));
+    a.t0 = t0; a.t1 = t1; a.sweep = sweep; a.lr = e->lr; a.preFactor = e->preF; a.postFactor = e->postF; a.preDecay = e->preD; a.postDecay = e->postD;
+    a.ev = ev; a.nEv = nEv; a.candCap = e->candCap; a.gStride = e->v.fireCap; a.world = 1;
+}
+static void finish(nc_engine* e, uint64_t* hidden, nc_step_stats* st) {
+    if (hidden) *hidden = e->stats[5];
+    if (st) { st->fires = e->stats[0]; st->deliveries = e->stats[1]; st->loads_accepted = e->stats[2]; st->loads_dropped = e->stats[3];
+              st->plasticity_calls = e->stats[4]; st->hidden_rand_calls = e->stats[5]; st->neuron_runs = e->stats[6]; st->active_visits = e->stats[7]; }
+    memset(e->stats, 0, sizeof(e->stats));
+}
+int nc_step(nc_engine* e, float t0, float t1, int sweep, const nc_event* ev, uint32_t nEv, uint64_t* hidden, nc_step_stats* st) {
+    if (!e->uploaded) return fail(e, NC_ERR_STATE, "step: no network uploaded");
+    if (!(t1 > t0)) return fail(e, NC_ERR_INVALID, "step: window must have t1 > t0");
+    if (!(t1 - t0 < e->minDelay) || !(t1 - t0 < 2.0f)) return fail(e, NC_ERR_INVALID, "step: window too long");
+    StepArgs a; fill(e, a, t0, t1, sweep, ev, nEv);
+    model_pass1(e, a);
+    if (e->v.localHdr[1]) return fail(e, NC_ERR_CAPACITY, "fire capacity");
+    model_pass2(e, a);
+    finish(e, hidden, st);
+    return NC_OK;
+}
+int nc_run_neurons(nc_engine* e, float now, const uint32_t* ids, uint32_t n, uint64_t* hidden, nc_step_stats* st) {
+    if (ids && !n) return NC_OK;
+    StepArgs a; fill(e, a, now, now, NC_SWEEP_END, nullptr, 0);
+    a.subset = ids; a.nSubset = n;
+    model_pass1(e, a);
+    model_pass2(e, a);
+    finish(e, hidden, st);
+    return NC_OK;
+}
+int nc_read_neurons(nc_engine* e, float* potAct, float* lastFire, float* lastRan) {
+    uint64_t N = e->v.nRows;
+    if (potAct) memcpy(potAct, e->potAct.data(), N * 8);
+    if (lastFire) memcpy(lastFire, e->lastFire.data(), N * 4);
+    if (lastRan) memcpy(lastRan, e->lastRan.data(), N * 4);
+    return NC_OK;
+}
+int nc_read_synapses(nc_engine* e, float* w, float* a, float* d, float* la, float* ls) {
+    uint64_t b = e->v.S * 4;
+    if (w) memcpy(w, e->weight.data(), b);
+    if (a) memcpy(a, e->arrive.data(), b);
+    if (d) memcpy(d, e->depol.data(), b);
+    if (la) memcpy(la, e->lastArr.data(), b);
+    if (ls) memcpy(ls, e->lastStart.data(), b);
+    return NC_OK;
+}
+int nc_read_fires(nc_engine* e, uint32_t cap, uint32_t* neuron, float* time, uint32_t* count) {
+    for (uint32_t i = 0; i < e->lastCount && i < cap; i++) { if (neuron) neuron[i] = e->recs[i].neuron; if (time) time[i] = e->recs[i].time; }
+    *count = e->lastCount;
+    return NC_OK;
+}
+int nc_read_synapse_pots(nc_engine* e, float, float* pre, float* post) {
+    if (pre) memset(pre, 0, e->v.S * 4);
+    if (post) memset(post, 0, e->v.S * 4);
+    return NC_OK;
+}
+int nc_reset_activities(nc_engine* e, float now) {
+    for (uint64_t i = 0; i < e->v.nRows; i++) { e->firings[i] = 0; e->actStart[i] = now; e->potAct[i].y = 0.0f; }
+    return NC_OK;
+}
+int nc_detector_mean(nc_engine* e, const uint32_t* near, uint32_t n, float* out) {
+    float avg = 0.0f;
+    for (uint32_t i = 0; i < n; i++) avg = avg + e->potAct[near[i] - e->v.row0].x;
+    *out = avg / (float)n;
+    return NC_OK;
+}
+}  // extern "C"

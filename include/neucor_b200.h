@@ -152,6 +152,11 @@ int nc_step_end(nc_engine* e, uint64_t* hidden_rand_calls, nc_step_stats* stats_
 int nc_step_end_counts(nc_engine* e, const uint32_t* counts, uint32_t stride, uint64_t* hidden_rand_calls,
                        nc_step_stats* stats_or_null);
 
+/* Self-test: the device replicas of glibc's powf / exp (the libm calls at NeuCor.cpp:672,678,695,710-711,741)
+ * evaluated on host arrays, for bit-for-bit comparison against the host libm. x > 0 normal for powf. */
+int nc_selftest_powf(nc_engine* e, const float* x, const float* y, float* out, uint64_t n);
+int nc_selftest_exp(nc_engine* e, const double* x, double* out, uint64_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -854,3 +854,39 @@ extern "C" int nc_tape_replay(nc_engine* e, uint32_t first, uint32_t count, floa
     if (ovf) return fail(e, NC_ERR_CAPACITY, "replay: fire-record capacity exceeded");
     return NC_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Self-test entry points: evaluate the device math replicas on caller-provided arrays so that tests can
+// compare them bit-for-bit with the host libm the reference uses (SURVEY.md hard part #1).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_selftest_powf(const float* x, const float* y, float* out, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = powf_pos(x[i], y[i]);
+}
+__global__ void k_selftest_exp(const double* x, double* out, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = exp_glibc(x[i]);
+}
+extern "C" int nc_selftest_powf(nc_engine* e, const float* x, const float* y, float* out, uint64_t n) {
+    cudaSetDevice(e->cfg.device);
+    float *dx, *dy, *dout;
+    CK(cudaMalloc(&dx, n * 4)); CK(cudaMalloc(&dy, n * 4)); CK(cudaMalloc(&dout, n * 4));
+    CK(cudaMemcpyAsync(dx, x, n * 4, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(dy, y, n * 4, cudaMemcpyHostToDevice, e->stream));
+    k_selftest_powf<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(dx, dy, dout, n); e->launches++;
+    CK(cudaMemcpyAsync(out, dout, n * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(dx); cudaFree(dy); cudaFree(dout);
+    return NC_OK;
+}
+extern "C" int nc_selftest_exp(nc_engine* e, const double* x, double* out, uint64_t n) {
+    cudaSetDevice(e->cfg.device);
+    double *dx, *dout;
+    CK(cudaMalloc(&dx, n * 8)); CK(cudaMalloc(&dout, n * 8));
+    CK(cudaMemcpyAsync(dx, x, n * 8, cudaMemcpyHostToDevice, e->stream));
+    k_selftest_exp<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(dx, dout, n); e->launches++;
+    CK(cudaMemcpyAsync(out, dout, n * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(dx); cudaFree(dout);
+    return NC_OK;
+}

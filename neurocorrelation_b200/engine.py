@@ -1,0 +1,269 @@
+"""ctypes binding of the engine's C ABI (include/neucor_b200.h, csrc/libneucor_b200.so).
+
+This is the drop-in boundary itself: the parity tests call the CUDA path through these entry points.
+Loading never touches a GPU; creating an Engine does, and raises EngineError without one.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+
+NC_SWEEP_END = 1
+NC_SWEEP_START = 2
+
+# every symbol include/neucor_b200.h declares
+ABI_SYMBOLS = (
+    "nc_global_error", "nc_device_count", "nc_create", "nc_destroy", "nc_last_error", "nc_upload_network", "nc_min_delay",
+    "nc_set_plasticity", "nc_step", "nc_run_neurons", "nc_read_neurons", "nc_read_synapses", "nc_read_fires",
+    "nc_read_synapse_pots", "nc_reset_activities", "nc_detector_mean", "nc_tape_begin", "nc_tape_end", "nc_snapshot",
+    "nc_restore", "nc_tape_replay", "nc_launch_count", "nc_step_begin", "nc_exchange_buffer", "nc_gather_buffer",
+    "nc_step_end", "nc_step_end_counts", "nc_selftest_powf", "nc_selftest_exp",
+)
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32), ("fire_capacity", C.c_uint32),
+                ("cand_smem", C.c_uint32), ("stream", C.c_void_p), ("reserved", C.c_uint32 * 2)]
+
+
+class StepStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("fires", "deliveries", "loads_accepted", "loads_dropped", "plasticity_calls",
+                                          "hidden_rand_calls", "neuron_runs", "active_visits")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+EVENT_DTYPE = np.dtype([("neuron", np.uint32), ("time", np.float32), ("kind", np.uint32), ("index_or_flags", np.uint32)])
+
+_L = None
+
+
+def load(path=None):
+    global _L
+    if _L is not None and path is None:
+        return _L
+    if path is None:
+        if not os.path.exists(_build.ENGINE_SO):
+            _build.build_engine()
+        path = _build.ENGINE_SO
+    L = C.CDLL(path)
+    vp = C.c_void_p
+    L.nc_global_error.restype = C.c_char_p
+    L.nc_last_error.restype = C.c_char_p
+    L.nc_last_error.argtypes = [vp]
+    L.nc_device_count.restype = C.c_int
+    L.nc_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.nc_destroy.argtypes = [vp]
+    L.nc_upload_network.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, u64p, vp, vp, vp, vp]
+    L.nc_min_delay.argtypes = [vp, C.POINTER(C.c_float)]
+    L.nc_set_plasticity.argtypes = [vp] + [C.c_float] * 5
+    L.nc_step.argtypes = [vp, C.c_float, C.c_float, C.c_int, vp, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(StepStats)]
+    L.nc_run_neurons.argtypes = [vp, C.c_float, vp, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(StepStats)]
+    L.nc_read_neurons.argtypes = [vp, vp, vp, vp]
+    L.nc_read_synapses.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.nc_read_fires.argtypes = [vp, C.c_uint32, vp, vp, C.POINTER(C.c_uint32)]
+    L.nc_read_synapse_pots.argtypes = [vp, C.c_float, vp, vp]
+    L.nc_reset_activities.argtypes = [vp, C.c_float]
+    L.nc_detector_mean.argtypes = [vp, vp, C.c_uint32, C.POINTER(C.c_float)]
+    L.nc_tape_begin.argtypes = [vp, C.c_uint32, C.c_uint64]
+    L.nc_tape_end.argtypes = [vp]
+    L.nc_snapshot.argtypes = [vp]
+    L.nc_restore.argtypes = [vp]
+    L.nc_tape_replay.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                 C.POINTER(C.c_uint64), C.POINTER(StepStats)]
+    L.nc_launch_count.argtypes = [vp]
+    L.nc_launch_count.restype = C.c_uint64
+    L.nc_step_begin.argtypes = [vp, C.c_float, C.c_float, C.c_int, vp, C.c_uint32]
+    L.nc_exchange_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
+    L.nc_gather_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
+    L.nc_step_end.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(StepStats)]
+    L.nc_step_end_counts.argtypes = [vp, u32p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(StepStats)]
+    L.nc_selftest_powf.argtypes = [vp, f32p, f32p, f32p, C.c_uint64]
+    L.nc_selftest_exp.argtypes = [vp, f64p, f64p, C.c_uint64]
+    if path == _build.ENGINE_SO:
+        _L = L
+    return L
+
+
+class Engine:
+    """One nc_engine handle. All methods raise EngineError with nc_last_error's text on failure."""
+
+    def __init__(self, device=0, rank=0, world=1, fire_capacity=0, cand_smem=0, stream=None, borrowed=None, library=None):
+        self.L = load(library)
+        self.owned = borrowed is None
+        if borrowed is not None:
+            self.h = C.c_void_p(borrowed)
+            return
+        cfg = Config(device=device, rank=rank, world=world, fire_capacity=fire_capacity, cand_smem=cand_smem,
+                     stream=stream)
+        h = C.c_void_p()
+        rc = self.L.nc_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise EngineError("nc_create failed (%d): %s" % (rc, self.L.nc_global_error().decode()))
+        self.h = h
+        self.N = self.S = 0
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise EngineError("%d: %s" % (rc, self.L.nc_last_error(self.h).decode()))
+
+    def close(self):
+        if self.owned and self.h:
+            self.L.nc_destroy(self.h)
+        self.h = None
+
+    def upload(self, net, row0=0, n_rows=None):
+        N = int(net["N"])
+        n_rows = N - row0 if n_rows is None else int(n_rows)
+        rp = np.ascontiguousarray(net["rowptr"], np.uint64)
+        lo, hi = int(rp[row0]), int(rp[row0 + n_rows])
+        local_rp = np.ascontiguousarray(rp[row0:row0 + n_rows + 1] - rp[row0])
+        self._keep = [np.ascontiguousarray(net[k][lo:hi], t) for k, t in
+                      (("pre", np.uint32), ("weight", np.float32), ("length", np.float32), ("flag", np.uint8))]
+        self._ck(self.L.nc_upload_network(self.h, N, row0, n_rows, local_rp, *[a.ctypes.data for a in self._keep]))
+        self.N, self.S, self.row0, self.n_rows = N, hi - lo, row0, n_rows
+        self._keep = None
+
+    def min_delay(self):
+        out = C.c_float()
+        self._ck(self.L.nc_min_delay(self.h, C.byref(out)))
+        return out.value
+
+    def set_plasticity(self, lr=1.0, pre_factor=0.13, post_factor=0.30, pre_decay=0.75, post_decay=0.65):
+        self._ck(self.L.nc_set_plasticity(self.h, lr, pre_factor, post_factor, pre_decay, post_decay))
+
+    @staticmethod
+    def _events(events):
+        if events is None or len(events) == 0:
+            return None, 0, None
+        ev = np.ascontiguousarray(events, EVENT_DTYPE)
+        return ev.ctypes.data, len(ev), ev
+
+    def step(self, t0, t1, sweep=NC_SWEEP_END, events=None):
+        p, n, keep = self._events(events)
+        hidden = C.c_uint64()
+        st = StepStats()
+        self._ck(self.L.nc_step(self.h, t0, t1, sweep, p, n, C.byref(hidden), C.byref(st)))
+        return hidden.value, st.as_dict()
+
+    def run_neurons(self, now, ids=None):
+        hidden = C.c_uint64()
+        st = StepStats()
+        if ids is None:
+            self._ck(self.L.nc_run_neurons(self.h, now, None, 0, C.byref(hidden), C.byref(st)))
+        else:
+            ids = np.ascontiguousarray(ids, np.uint32)
+            self._ck(self.L.nc_run_neurons(self.h, now, ids.ctypes.data, len(ids), C.byref(hidden), C.byref(st)))
+        return hidden.value, st.as_dict()
+
+    def read_neurons(self):
+        n = max(self.n_rows, 1)
+        pa = np.zeros(2 * n, np.float32)
+        lf = np.zeros(n, np.float32)
+        lr = np.zeros(n, np.float32)
+        self._ck(self.L.nc_read_neurons(self.h, pa.ctypes.data, lf.ctypes.data, lr.ctypes.data))
+        k = self.n_rows
+        return dict(pot=pa[0:2 * k:2].copy(), act=pa[1:2 * k:2].copy(), lastFire=lf[:k], lastRan=lr[:k])
+
+    def read_synapses(self):
+        a = [np.zeros(max(self.S, 1), np.float32) for _ in range(5)]
+        self._ck(self.L.nc_read_synapses(self.h, *[x.ctypes.data for x in a]))
+        return dict(weight=a[0][:self.S], arrive=a[1][:self.S], depol=a[2][:self.S], lastArr=a[3][:self.S],
+                    lastStart=a[4][:self.S])
+
+    def read_fires(self, capacity=1 << 20):
+        n = np.zeros(capacity, np.uint32)
+        t = np.zeros(capacity, np.float32)
+        c = C.c_uint32()
+        self._ck(self.L.nc_read_fires(self.h, capacity, n.ctypes.data, t.ctypes.data, C.byref(c)))
+        k = min(c.value, capacity)
+        return n[:k].copy(), t[:k].copy()
+
+    def read_synapse_pots(self, now):
+        a = [np.zeros(max(self.S, 1), np.float32) for _ in range(2)]
+        self._ck(self.L.nc_read_synapse_pots(self.h, now, a[0].ctypes.data, a[1].ctypes.data))
+        return a[0][:self.S], a[1][:self.S]
+
+    def reset_activities(self, now):
+        self._ck(self.L.nc_reset_activities(self.h, now))
+
+    def detector_mean(self, near):
+        near = np.ascontiguousarray(near, np.uint32)
+        out = C.c_float()
+        self._ck(self.L.nc_detector_mean(self.h, near.ctypes.data, len(near), C.byref(out)))
+        return out.value
+
+    # ---- measurement helpers ----
+    def tape_begin(self, max_steps, max_events):
+        self._ck(self.L.nc_tape_begin(self.h, max_steps, max_events))
+
+    def tape_end(self):
+        self._ck(self.L.nc_tape_end(self.h))
+
+    def snapshot(self):
+        self._ck(self.L.nc_snapshot(self.h))
+
+    def restore(self):
+        self._ck(self.L.nc_restore(self.h))
+
+    def tape_replay(self, first, count, per_kernel=False):
+        ms, m1, m2 = C.c_float(), C.c_float(), C.c_float()
+        hidden = C.c_uint64()
+        st = StepStats()
+        self._ck(self.L.nc_tape_replay(self.h, first, count, C.byref(ms), C.byref(m1) if per_kernel else None,
+                                       C.byref(m2) if per_kernel else None, C.byref(hidden), C.byref(st)))
+        return dict(ms_total=ms.value, ms_pass1=m1.value, ms_pass2=m2.value, hidden=hidden.value, stats=st.as_dict())
+
+    def launch_count(self):
+        return int(self.L.nc_launch_count(self.h))
+
+    # ---- sharded stepping (world > 1): begin -> host all-gathers fire records -> end ----
+    def step_begin(self, t0, t1, sweep, events=None):
+        p, n, keep = self._events(events)
+        self._ck(self.L.nc_step_begin(self.h, t0, t1, sweep, p, n))
+
+    def exchange_buffer(self):
+        p, b = C.c_void_p(), C.c_uint64()
+        self._ck(self.L.nc_exchange_buffer(self.h, C.byref(p), C.byref(b)))
+        return p.value, b.value
+
+    def gather_buffer(self):
+        p, b = C.c_void_p(), C.c_uint64()
+        self._ck(self.L.nc_gather_buffer(self.h, C.byref(p), C.byref(b)))
+        return p.value, b.value
+
+    def step_end(self, counts=None, stride=0):
+        hidden = C.c_uint64()
+        st = StepStats()
+        if counts is None:
+            self._ck(self.L.nc_step_end(self.h, C.byref(hidden), C.byref(st)))
+        else:
+            self._ck(self.L.nc_step_end_counts(self.h, np.ascontiguousarray(counts, np.uint32), int(stride), C.byref(hidden), C.byref(st)))
+        return hidden.value, st.as_dict()
+
+    # ---- self-tests ----
+    def selftest_powf(self, x, y):
+        x = np.ascontiguousarray(x, np.float32)
+        y = np.ascontiguousarray(y, np.float32)
+        out = np.zeros_like(x)
+        self._ck(self.L.nc_selftest_powf(self.h, x, y, out, len(x)))
+        return out
+
+    def selftest_exp(self, x):
+        x = np.ascontiguousarray(x, np.float64)
+        out = np.zeros_like(x)
+        self._ck(self.L.nc_selftest_exp(self.h, x, out, len(x)))
+        return out

@@ -19,7 +19,7 @@ if [ ! -f "$REF/NeuCor.cpp" ]; then
     exit 0
 fi
 mkdir -p "$OUT"
-CXXFLAGS="-O3 -std=c++17 -fPIC -shared"
+CXXFLAGS="-O3 -std=c++17 -fPIC -shared -Wl,-Bsymbolic"
 
 g++ $CXXFLAGS -I"$REF" "$REF/NeuCor.cpp" "$HERE/ref_harness.cpp" -o "$OUT/libneucor_ref.so"
 

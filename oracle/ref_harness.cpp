@@ -21,7 +21,26 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <new>
 #include <vector>
+
+// Deterministic heap for the reference: every C++ allocation made inside this library is zero-filled.
+// The reference reads two members it never initialises — Neuron::scheduledFireTime (NeuCor.h:241, compared at
+// NeuCor.cpp:683) and Synapse::inhibitory after a copy (NeuCor.cpp:487-524, read at :760) — so on a recycled
+// heap its results depend on whatever bytes the allocator hands back (e.g. a stale 1.0f makes a neuron fire
+// spuriously at t = 1 ms).  Zero-filled memory is what the reference sees on a pristine heap; it makes
+// oracle/_ref reproducible across processes without touching the reference's source.  (-Wl,-Bsymbolic keeps
+// these definitions private to this library.)
+void* operator new(std::size_t n) {
+    void* p = calloc(1, n ? n : 1);
+    if (!p) throw std::bad_alloc();
+    return p;
+}
+void* operator new[](std::size_t n) { return operator new(n); }
+void operator delete(void* p) noexcept { free(p); }
+void operator delete[](void* p) noexcept { free(p); }
+void operator delete(void* p, std::size_t) noexcept { free(p); }
+void operator delete[](void* p, std::size_t) noexcept { free(p); }
 
 class NeuCor_Renderer {
 public:

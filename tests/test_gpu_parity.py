@@ -1,0 +1,114 @@
+"""Parity tests proper: the CUDA engine, through the host NeuCor class and the C ABI, against the committed golden
+vectors generated from the reference itself and against the CPU oracle on the same seeded inputs. Bit-exact."""
+import numpy as np
+import pytest
+
+import scenarios
+from helpers import libc, same_bits, state_signature, synthetic_drive
+
+pytestmark = pytest.mark.gpu
+
+
+def test_c1_golden_seed1_full(native_libs):
+    scenarios.c1_golden(None, "c1_seed1_normalised.npz", 3000, check_every=1)
+
+
+def test_c1_golden_seed4(native_libs):
+    scenarios.c1_golden(None, "c1_seed4_normalised.npz", 3000, check_every=7)
+
+
+def test_c1_golden_seed2_raw_flags(native_libs):
+    scenarios.c1_golden(None, "c1_seed2_raw.npz", 2000, check_every=5)
+
+
+def test_c1_golden_tiny_shared_memory_spill(native_libs):
+    """Rows with more occupied slots than staged in shared memory take the spill path: same results."""
+    scenarios.c1_golden(None, "c1_seed1_normalised.npz", 800, check_every=1, cand_smem=32)
+
+
+def test_synthetic_dense_activity(native_libs):
+    st = scenarios.synthetic_vs_oracle(None, 1500, 60, 600)
+    assert st["deliveries"] > 100_000 and st["loads_dropped"] > 0 and st["hidden_rand"] > 0
+
+
+def test_synthetic_c2_recipe_10k(native_libs):
+    """The C2 recipe shrunk to N = 10^4: every field of every step for 150 steps."""
+    scenarios.synthetic_vs_oracle(None, 10_000, 100, 150)
+
+
+def test_synthetic_small_dt_and_run_all(native_libs):
+    scenarios.synthetic_vs_oracle(None, 300, 30, 400, dt=0.03125, run_all=True)
+
+
+def test_lazy_mode_with_window_splitting(native_libs):
+    scenarios.lazy_vs_oracle(None, 300, 30, 60, dt=0.5)
+
+
+def test_edge_cases(native_libs):
+    scenarios.edge_cases(None)
+
+
+def test_detector_offsets_reset(native_libs):
+    scenarios.detector_and_reset(None)
+
+
+def test_host_constructor_network_runs(native_libs):
+    """NeuCor(750) built by the host class itself (the reference constructor's rand() stream) steps on the device and
+    agrees with the oracle run on the exported network."""
+    import neurocorrelation_b200 as nb
+    from oracle.orcbind import OracleBrain
+    from neurocorrelation_b200.presets import StandardDriver
+    libc.srand(1)
+    g = nb.NeuCor(750)
+    drv = StandardDriver(g, libc.rand)
+    net, ins = g.export_network(), g.export_inputs()
+    rates0 = drv.rates.copy()
+    libc.srand(777)
+    hist = []
+    for k in range(400):
+        drv.step()
+        hist.append(state_signature(g.read_neurons(), g.read_synapses()))
+    from helpers import NearInputs
+    o = OracleBrain(net)
+    no = NearInputs(o, [i["near"] for i in ins], False)
+    no.set_inputs(rates0)
+    o.enable_sweep()
+    o.set_params(0.0625, 1.0, False)
+    from neurocorrelation_b200.presets import standard_on_frame
+    libc.srand(777)
+    rates = rates0.copy()
+    for k in range(400):
+        standard_on_frame(rates, libc.rand)
+        for i, v in enumerate(rates):
+            o.set_rate(i, v)
+        o.step()
+        assert np.array_equal(state_signature(o.read_neurons(), o.read_synapses()), hist[k]), "step %d" % k
+
+
+def test_replay_is_bit_identical_and_deterministic(native_libs):
+    """Size-independent properties at a size the oracle cannot reach quickly (N = 50 000, K = 100): the device-resident
+    replay of taped steps reproduces the live run bit-for-bit, twice (determinism: no float atomics, no order dependence
+    on the warp-aggregated fire append)."""
+    import neurocorrelation_b200 as nb
+    from neurocorrelation_b200 import engine
+    from neurocorrelation_b200.networks import uniform_random_network
+    net = uniform_random_network(50_000, 100, seed=2)
+    g = nb.NeuCor.from_network(net)
+    synthetic_drive(g, net, True)
+    g.finalize()
+    E = engine.Engine(borrowed=g.engine_handle())
+    E.N, E.S, E.row0, E.n_rows = net["N"], net["S"], 0, net["N"]
+    for _ in range(20):
+        g.step()
+    E.snapshot()
+    E.tape_begin(64, 1 << 20)
+    for _ in range(40):
+        g.step()
+    E.tape_end()
+    live = state_signature(E.read_neurons(), E.read_synapses())
+    live_stats = g.stats(total=False)
+    for _ in range(2):
+        E.restore()
+        r = E.tape_replay(0, 40)
+        assert np.array_equal(state_signature(E.read_neurons(), E.read_synapses()), live)
+    assert r["stats"]["fires"] > 0

@@ -37,6 +37,7 @@ WORKLOADS = {
     "c1": (750, None, "default main.cpp network (750 neurons, ~20.7k synapses), C1"),
     "c2": (100_000, 100, "100k neurons x 100 synapses (10M synapses), C2"),
     "c3": (1_000_000, 1000, "1M neurons x 1000 synapses (1B synapses), C3"),
+    "m100": (100_000, 1000, "100k neurons x 1000 synapses (100M synapses), profiling-sized slice of C3"),
 }
 
 
@@ -92,19 +93,29 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_network(workload, seed=1):
-    from neurocorrelation_b200.networks import synthetic_network, uniform_random_network
+def build_brain(workload, dev, seed=1):
+    """Returns (host-class brain, network description). C2: spatial recipe built on the host (numpy) and uploaded;
+    C3: stratified stand-in built directly in device memory (torch) and handed over as device pointers."""
+    import neurocorrelation_b200 as nb
+    from neurocorrelation_b200.networks import stratified_network_torch, synthetic_network
     N, K, _ = WORKLOADS[workload]
-    if workload == "c2":
-        return synthetic_network(N, K, seed=seed)
-    return uniform_random_network(N, K, seed=seed)
+    if workload in ("c3", "m100"):
+        import torch
+        net = stratified_network_torch(N, K, "cuda:%d" % dev, seed=seed)
+        torch.cuda.synchronize()
+        g = nb.NeuCor.from_device_network(net["N"], net["S"], net["rowptr"].data_ptr(), net["pre"].data_ptr(), net["weight"].data_ptr(),
+                                          net["length"].data_ptr(), net["flag"].data_ptr(), device=dev)
+        g._keepalive = net
+        return g, net
+    net = synthetic_network(N if K else 750, K if K else 28, seed=seed)
+    return nb.NeuCor.from_network(net, device=dev), net
 
 
 def sample_network(workload, seed=1):
     """Bounded sample of the workload's recipe for the single-core CPU reference (cost ~ S * K_out per step)."""
     from neurocorrelation_b200.networks import synthetic_network
     _, K, _ = WORKLOADS[workload]
-    n = 2500 if K <= 100 else 1200
+    n = 2500 if (K or 28) <= 100 else 800
     return synthetic_network(n, K if K else 28, seed=seed)
 
 
@@ -203,7 +214,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     N, K, wl_desc = WORKLOADS[args.workload]
     config = {"workload": wl_desc, "dt_ms": DT, "mode": "sweep (run() + full detector read), STDP on, background firing on",
-              "l2": "inputs larger than L2" if args.workload == "c3" else "state (%.0f MB) fits the 126 MB L2: HBM fraction is an upper-bound exercise, see DESIGN.md" % (N * (K or 28) * 24 / 1e6)}
+              "l2": "inputs larger than L2" if args.workload in ("c3", "m100") else "state (%.0f MB) fits the 126 MB L2: HBM fraction is an upper-bound exercise, see DESIGN.md" % (N * (K or 28) * 24 / 1e6)}
 
     if args.impl == "reference":
         if rank != 0:
@@ -233,11 +244,18 @@ def main():
     if world > 1:
         raise SystemExit("multi-GPU bench path: see bench_multi in a later round")
 
-    net = build_network(args.workload)
+    t_build = time.perf_counter()
+    g, net = build_brain(args.workload, dev)
     S = net["S"]
-    g = nb.NeuCor.from_network(net, device=dev)
     drive_setup(g, net, True, libc)
+    g.set_sweep_mean(False)  # the per-step device->host result is the counter block (hidden rand() count, fires, ...)
     g.finalize()
+    if args.workload in ("c3", "m100"):
+        g._keepalive = None
+        for k in ("pre", "weight", "length", "flag", "rowptr"):
+            net[k] = None
+        torch.cuda.empty_cache()
+    t_build = time.perf_counter() - t_build
     E = engine.Engine(borrowed=g.engine_handle())
     E.N, E.S, E.row0, E.n_rows = net["N"], S, 0, net["N"]
 
@@ -294,7 +312,7 @@ def main():
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 state, f64 intermediates", "data": "synthetic", "config": config,
         "sim_ms_per_wall_s": DT / (ms_step * 1e-3), "synapse_updates_per_s": S / (ms_step * 1e-3),
-        "neurons": net["N"], "synapses": S, "mean_rate_hz": d["fires"] / args.steps / net["N"] / DT * 1e3,
+        "neurons": net["N"], "synapses": S, "build_s": t_build, "mean_rate_hz": d["fires"] / args.steps / net["N"] / DT * 1e3,
         "per_step": {k: v / args.steps for k, v in d.items()},
         "kernel_ms": {"k_neuron_pass": p1, "k_synapse_pass": p2, "step_total": ms_step},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,

@@ -86,6 +86,9 @@ const char* nc_last_error(const nc_engine* e);
  * potential -70, lastFire NaN, idle slots, lastSpikeArrival -inf (NeuCor.cpp:376-394,469,484). */
 int nc_upload_network(nc_engine* e, uint64_t n_global, uint64_t row0, uint64_t n_rows, const uint64_t* rowptr,
                       const uint32_t* pre, const float* weight, const float* length, const uint8_t* inhibitory);
+/* Same, with the five arrays already resident on this engine's device (they are copied; the caller keeps ownership). */
+int nc_upload_network_device(nc_engine* e, uint64_t n_global, uint64_t row0, uint64_t n_rows, const uint64_t* d_rowptr,
+                             const uint32_t* d_pre, const float* d_weight, const float* d_length, const uint8_t* d_inhibitory);
 /* Smallest synaptic delay (2*length) of the uploaded shard; a step window must be shorter. */
 int nc_min_delay(const nc_engine* e, float* out);
 

@@ -57,6 +57,8 @@ def load_host_library(path=None):
     L.nch_create_synapse.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_float]
     L.nch_make_connections.argtypes = [vp]
     L.nch_import_network.argtypes = [vp, C.c_uint64, u64p, u32p, f32p, f32p, u8p, vp]
+    L.nch_import_network_device.argtypes = [vp, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp]
+    L.nch_set_sweep_mean.argtypes = [vp, C.c_int]
     L.nch_set_inputs.argtypes = [vp, vp, C.c_uint, vp, vp]
     L.nch_set_rate.argtypes = [vp, C.c_uint, C.c_float]
     L.nch_set_input_near.argtypes = [vp, C.c_uint, u32p, C.c_uint64]
@@ -125,6 +127,17 @@ class NeuCor:
                                      np.ascontiguousarray(net["pre"], np.uint32), np.ascontiguousarray(net["weight"], np.float32),
                                      np.ascontiguousarray(net["length"], np.float32), np.ascontiguousarray(net["flag"], np.uint8), pp))
         return b
+
+    @classmethod
+    def from_device_network(cls, N, S, d_rowptr, d_pre, d_weight, d_length, d_flag, device=0, library=None):
+        """CSR arrays already on `device`, given as raw device pointers (e.g. torch tensors' data_ptr())."""
+        b = cls(0, device, library)
+        b._ck(b.L.nch_import_network_device(b.h, int(N), int(S), d_rowptr, d_pre, d_weight, d_length, d_flag))
+        return b
+
+    def set_sweep_mean(self, on):
+        """step() in sweep mode returns the mean potential (a device->host read of every potential) only when on."""
+        self._ck(self.L.nch_set_sweep_mean(self.h, int(on)))
 
     def _ck(self, rc):
         if rc != 0:

@@ -38,6 +38,8 @@ using namespace ncm;
 using namespace ncs;
 
 #define NC_WARPS_PER_BLOCK 8
+#define NC_UNROLL 8          // independent coalesced row loads kept in flight per warp
+#define NC_P2_THREADS 1024   // synapse pass: one persistent block per SM, fire bitmask staged in its shared memory
 
 // ------------------------------------------------------------------------------------------------
 // Neuron pass
@@ -68,23 +70,34 @@ __global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32) k_neuron_pass(View v,
         const uint64_t rs = v.rowptr[row], re = v.rowptr[row + 1];
         // ---- stage occupied slots (arrive != 0 && arrive <= t1), preserving row order ----
         uint32_t cnt = 0;
-        for (uint64_t base = rs; base < re; base += 32) {
-            uint64_t j = base + lane;
-            float a = (j < re) ? v.arrive[j] : 0.0f;
-            bool is = (a != 0.0f) && (a <= s.t1);
-            uint32_t m = __ballot_sync(0xffffffffu, is);
-            if (is) {
-                uint32_t pos = cnt + __popc(m & ((1u << lane) - 1u));
-                cv.A(pos) = a;
-                cv.D(pos) = v.depol[j];
-                cv.J(pos) = (uint32_t)(j - rs);
+        for (uint64_t base = rs; base < re; base += 32 * NC_UNROLL) {
+            float av[NC_UNROLL];
+#pragma unroll
+            for (int u = 0; u < NC_UNROLL; u++) {  // NC_UNROLL independent 128-byte requests in flight per warp
+                uint64_t j = base + (uint64_t)u * 32 + lane;
+                av[u] = (j < re) ? __ldcs(&v.arrive[j]) : 0.0f;
             }
-            cnt += __popc(m);
+#pragma unroll
+            for (int u = 0; u < NC_UNROLL; u++) {
+                float a = av[u];
+                bool is = (a != 0.0f) && (a <= s.t1);
+                uint32_t m = __ballot_sync(0xffffffffu, is);
+                if (m) {
+                    if (is) {
+                        uint64_t j = base + (uint64_t)u * 32 + lane;
+                        uint32_t pos = cnt + __popc(m & ((1u << lane) - 1u));
+                        cv.A(pos) = a;
+                        cv.D(pos) = v.depol[j];
+                        cv.J(pos) = (uint32_t)(j - rs);
+                    }
+                    cnt += __popc(m);
+                }
+            }
         }
         __syncwarp();
         // ---- host events of this neuron: [evLo, evHi) in the (neuron, time)-sorted list ----
         uint32_t evLo = 0, evHi = 0;
-        if (s.nEv) {
+        if (s.nEv && ((v.evMask[row >> 5] >> (row & 31u)) & 1u)) {  // bit set by k_mark_events for rows that have host events
             uint32_t lo = 0, hi = s.nEv;
             while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (s.ev[mid].neuron < q) lo = mid + 1; else hi = mid; }
             evLo = lo; hi = s.nEv;
@@ -201,23 +214,42 @@ __global__ void k_index_reset(View v, StepArgs s) {
 // ------------------------------------------------------------------------------------------------
 // Synapse pass
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32) k_synapse_pass(View v, StepArgs s) {
-    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
-    const uint64_t gw = (uint64_t)blockIdx.x * NC_WARPS_PER_BLOCK + wib, nW = (uint64_t)gridDim.x * NC_WARPS_PER_BLOCK;
+__global__ void __launch_bounds__(NC_P2_THREADS) k_synapse_pass(View v, StepArgs s, uint32_t maskWordsInSmem) {
+    extern __shared__ uint32_t smask[];
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    // the fire bitmask (1 bit per neuron of the whole network) is probed once per synapse: keep it in shared memory
+    const uint32_t* mask = v.mask;
+    if (maskWordsInSmem) {
+        for (uint32_t i = threadIdx.x; i < maskWordsInSmem; i += blockDim.x) smask[i] = v.mask[i];
+        __syncthreads();
+        mask = smask;
+    }
+    const uint64_t gw = (uint64_t)blockIdx.x * wpb + wib, nW = (uint64_t)gridDim.x * wpb;
     uint32_t cnt[5] = {0, 0, 0, 0, 0};  // loads accepted, dropped, plasticity calls, hidden rand, deliveries
     for (uint64_t row = gw; row < v.nRows; row += nW) {
         const uint32_t q = (uint32_t)(v.row0 + row);
         const uint64_t rs = v.rowptr[row], re = v.rowptr[row + 1];
-        const bool qFired = (v.mask[q >> 5] >> (q & 31u)) & 1u;
+        const bool qFired = (mask[q >> 5] >> (q & 31u)) & 1u;
         const float lfS = v.lfStart[row];
-        for (uint64_t j = rs + lane; j < re; j += 32) {
-            uint32_t pw = v.pre[j];
-            uint32_t p = pw & 0x7fffffffu;
-            uint32_t ab = __float_as_uint(v.arrive[j]);
-            bool pFired = (v.mask[p >> 5] >> (p & 31u)) & 1u;
-            float a = __uint_as_float(ab);
-            bool eventful = qFired || pFired || (ab & NC_SENT) || (ab != 0u && a > s.t0 && a <= s.t1);
-            if (eventful) resolve_slot(v, s, j, rs, q, p, (pw >> 31) != 0u, ab, pFired, qFired, lfS, cnt);
+        for (uint64_t base = rs; base < re; base += 32 * NC_UNROLL) {
+            uint32_t pv[NC_UNROLL], abv[NC_UNROLL];
+#pragma unroll
+            for (int u = 0; u < NC_UNROLL; u++) {
+                uint64_t j = base + (uint64_t)u * 32 + lane;
+                bool in = j < re;
+                pv[u] = in ? __ldcs(&v.pre[j]) : 0xffffffffu;
+                abv[u] = in ? __float_as_uint(__ldcs(&v.arrive[j])) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < NC_UNROLL; u++) {
+                uint64_t j = base + (uint64_t)u * 32 + lane;
+                if (j >= re) continue;
+                uint32_t pw = pv[u], p = pw & 0x7fffffffu, ab = abv[u];
+                bool pFired = (mask[p >> 5] >> (p & 31u)) & 1u;
+                float a = __uint_as_float(ab);
+                bool eventful = qFired || pFired || (ab & NC_SENT) || (ab != 0u && a > s.t0 && a <= s.t1);
+                if (eventful) resolve_slot(v, s, j, rs, q, p, (pw >> 31) != 0u, ab, pFired, qFired, lfS, cnt);
+            }
         }
     }
 #pragma unroll
@@ -232,6 +264,17 @@ __global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32) k_synapse_pass(View v
         if (cnt[2]) atomicAdd(&v.stats[4], (unsigned long long)cnt[2]);
         if (cnt[3]) atomicAdd(&v.stats[5], (unsigned long long)cnt[3]);
     }
+}
+
+// Marks (set = 1) or unmarks the rows of this shard that have host events in this window.
+__global__ void k_mark_events(View v, const nc_event* ev, uint32_t nEv, int set) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nEv) return;
+    uint64_t n = ev[i].neuron;
+    if (n < v.row0 || n >= v.row0 + v.nRows) return;
+    uint64_t row = n - v.row0;
+    if (set) atomicOr(&v.evMask[row >> 5], 1u << (row & 31u));
+    else v.evMask[row >> 5] = 0u;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -319,8 +362,8 @@ struct nc_engine {
     bool gatherBound = false;
     float lr = 1.0f, preF = 0.13f, postF = 0.30f, preD = 0.75f, postD = 0.65f;
     float minDelay = INFINITY;
-    uint32_t candCap = 256, grid1 = 0, grid2 = 0;
-    size_t smem1 = 0;
+    uint32_t candCap = 256, grid1 = 0, grid2 = 0, maskWordsSmem = 0;
+    size_t smem1 = 0, smem2 = 0;
     uint64_t launches = 0;
     // in-flight step (nc_step_begin .. nc_step_end)
     StepArgs cur; bool inStep = false;
@@ -386,7 +429,7 @@ static void free_all(nc_engine* e) {
     View& v = e->v;
     cudaFree((void*)v.rowptr); cudaFree(v.pre); cudaFree(v.arrive); cudaFree(v.depol); cudaFree(v.weight); cudaFree(v.lastArr);
     cudaFree(v.lastStart); cudaFree(e->dDelay); cudaFree(v.potAct); cudaFree(v.lastRan); cudaFree(v.lastFire); cudaFree(v.lfStart);
-    cudaFree(v.actStart); cudaFree(v.firings); cudaFree(v.localHdr); cudaFree(v.head); cudaFree(v.next); cudaFree(v.mask);
+    cudaFree(v.actStart); cudaFree(v.firings); cudaFree(v.localHdr); cudaFree(v.head); cudaFree(v.next); cudaFree(v.mask); cudaFree(v.evMask);
     cudaFree(v.spillA); cudaFree(v.spillD); cudaFree(v.spillJ);
     if (!e->gatherBound) cudaFree(e->dGather);
     cudaFree(e->dEv); cudaFree(e->dTape);
@@ -413,30 +456,35 @@ extern "C" int nc_set_plasticity(nc_engine* e, float lr, float preF, float postF
     return NC_OK;
 }
 
-extern "C" int nc_upload_network(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t nRows, const uint64_t* rowptr,
-                                 const uint32_t* pre, const float* weight, const float* length, const uint8_t* inh) {
-    if (e->uploaded) return fail(e, NC_ERR_STATE, "nc_upload_network: network already uploaded");
-    if (!rowptr) return fail(e, NC_ERR_INVALID, "nc_upload_network: rowptr is null");
-    if (nGlobal >= (1ull << 30)) return fail(e, NC_ERR_INVALID, "nc_upload_network: at most 2^30-1 neurons");
-    if (row0 + nRows > nGlobal) return fail(e, NC_ERR_INVALID, "nc_upload_network: row range exceeds neuron count");
-    if (rowptr[0] != 0) return fail(e, NC_ERR_INVALID, "nc_upload_network: rowptr[0] must be 0");
-    uint64_t S = rowptr[nRows], maxRow = 0;
-    if (S && (!pre || !weight || !length || !inh)) return fail(e, NC_ERR_INVALID, "nc_upload_network: null synapse array");
-    float minDelay = INFINITY;
-    for (uint64_t r = 0; r < nRows; r++) {
-        if (rowptr[r + 1] < rowptr[r]) return fail(e, NC_ERR_INVALID, "nc_upload_network: rowptr not monotone");
-        uint64_t len = rowptr[r + 1] - rowptr[r];
-        maxRow = std::max(maxRow, len);
-        if (len >= (1ull << 29)) return fail(e, NC_ERR_INVALID, "nc_upload_network: row longer than 2^29-1");
-        for (uint64_t j = rowptr[r]; j < rowptr[r + 1]; j++) {
-            if (pre[j] >= nGlobal) return fail(e, NC_ERR_INVALID, "nc_upload_network: presynaptic ID out of range");
-            if (j > rowptr[r] && pre[j] <= pre[j - 1]) return fail(e, NC_ERR_INVALID, "nc_upload_network: row not strictly ascending in presynaptic ID");
-            float d = length[j] * 2.0f;
-            if (!(d > 0.0f)) return fail(e, NC_ERR_INVALID, "nc_upload_network: synapse length must be positive");
-            minDelay = std::min(minDelay, d);
+// Validation of a device-resident CSR (nc_upload_network_device): row lengths, ascending presynaptic IDs, ranges,
+// smallest delay. out[0] = error bits, out[1] = max row length, out[2] = min delay (float bits; positive floats order as uints)
+__global__ void k_validate_csr(uint64_t nGlobal, uint64_t nRows, const uint64_t* rowptr, const uint32_t* pre, const float* length,
+                               unsigned int* out) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nW = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    unsigned int err = 0, maxRow = 0, minD = 0x7f800000u;
+    for (uint64_t row = gw; row < nRows; row += nW) {
+        uint64_t rs = rowptr[row], re = rowptr[row + 1];
+        if (re < rs) { err |= 1u; continue; }
+        if (re - rs >= (1ull << 29)) { err |= 2u; continue; }
+        maxRow = max(maxRow, (unsigned int)(re - rs));
+        for (uint64_t j = rs + lane; j < re; j += 32) {
+            uint32_t p = pre[j];
+            if (p >= nGlobal) err |= 4u;
+            if (j > rs && p <= pre[j - 1]) err |= 8u;
+            float d = __fmul_rn(length[j], 2.0f);
+            if (!(d > 0.0f)) err |= 16u; else minD = min(minD, __float_as_uint(d));
         }
     }
-    cudaSetDevice(e->cfg.device);
+    if (err) atomicOr(&out[0], err);
+    atomicMax(&out[1], maxRow);
+    atomicMin(&out[2], minD);
+}
+
+// common tail of the two upload entry points: allocate state, copy the CSR (host->device or device->device), initialise
+static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t nRows, uint64_t S, uint64_t maxRow, float minDelay,
+                         const uint64_t* rowptr, const uint32_t* pre, const float* weight, const float* length, const uint8_t* inh,
+                         cudaMemcpyKind kind) {
     View& v = e->v;
     v.nGlobal = nGlobal; v.row0 = row0; v.nRows = nRows; v.S = S;
     const uint64_t S1 = std::max<uint64_t>(S, 1), N1 = std::max<uint64_t>(nRows, 1), G1 = std::max<uint64_t>(nGlobal, 1);
@@ -455,39 +503,112 @@ extern "C" int nc_upload_network(nc_engine* e, uint64_t nGlobal, uint64_t row0, 
     CK(cudaMalloc(&v.head, G1 * 4)); CK(cudaMalloc(&v.next, (uint64_t)e->cfg.world * v.fireCap * 4));
     CK(cudaMalloc(&v.mask, ((G1 + 31) / 32) * 4));
     CK(cudaMemsetAsync(v.mask, 0, ((G1 + 31) / 32) * 4, e->stream));
-    // temporaries for init
-    float* dLen; unsigned char* dInh;
-    CK(cudaMalloc(&dLen, S1 * 4)); CK(cudaMalloc(&dInh, S1));
-    CK(cudaMemcpyAsync((void*)v.rowptr, rowptr, (nRows + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMalloc(&v.evMask, ((N1 + 31) / 32) * 4));
+    CK(cudaMemsetAsync(v.evMask, 0, ((N1 + 31) / 32) * 4, e->stream));
+    const float* dLen = length; const unsigned char* dInh = inh;
+    float* tmpLen = nullptr; unsigned char* tmpInh = nullptr;
+    CK(cudaMemcpyAsync((void*)v.rowptr, rowptr, (nRows + 1) * 8, kind, e->stream));
     if (S) {
-        CK(cudaMemcpyAsync(v.pre, pre, S * 4, cudaMemcpyHostToDevice, e->stream));
-        CK(cudaMemcpyAsync(v.weight, weight, S * 4, cudaMemcpyHostToDevice, e->stream));
-        CK(cudaMemcpyAsync(dLen, length, S * 4, cudaMemcpyHostToDevice, e->stream));
-        CK(cudaMemcpyAsync(dInh, inh, S, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(v.pre, pre, S * 4, kind, e->stream));
+        CK(cudaMemcpyAsync(v.weight, weight, S * 4, kind, e->stream));
+        if (kind == cudaMemcpyHostToDevice) {
+            CK(cudaMalloc(&tmpLen, S1 * 4)); CK(cudaMalloc(&tmpInh, S1));
+            CK(cudaMemcpyAsync(tmpLen, length, S * 4, kind, e->stream));
+            CK(cudaMemcpyAsync(tmpInh, inh, S, kind, e->stream));
+            dLen = tmpLen; dInh = tmpInh;
+        }
         k_init_synapses<<<(unsigned)((S + 255) / 256), 256, 0, e->stream>>>(v, dLen, dInh, e->dDelay);
         e->launches++;
     }
     if (nRows) { k_init_neurons<<<(unsigned)((nRows + 255) / 256), 256, 0, e->stream>>>(v); e->launches++; }
     k_fill_i32<<<(unsigned)((G1 + 255) / 256), 256, 0, e->stream>>>(v.head, G1, -1); e->launches++;
     CK(cudaGetLastError());
-    // launch geometry: persistent grids sized to the SM count
+    // launch geometry: persistent grids sized to the SM count x resident blocks per SM
     e->candCap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(std::min<uint64_t>(e->candCap, maxRow), 32), 1024);
     e->smem1 = (size_t)NC_WARPS_PER_BLOCK * 3 * e->candCap * 4;
     CK(cudaFuncSetAttribute(k_neuron_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem1));
     int occ1 = 1, occ2 = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_neuron_pass, NC_WARPS_PER_BLOCK * 32, e->smem1));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_synapse_pass, NC_WARPS_PER_BLOCK * 32, 0));
+    // synapse pass: the whole-network fire bitmask goes to shared memory when it fits (<= 200 KB, i.e. 1.6 M neurons)
+    uint64_t maskWords = (G1 + 31) / 32;
+    e->maskWordsSmem = maskWords * 4 <= 200 * 1024 ? (uint32_t)maskWords : 0u;
+    e->smem2 = (size_t)e->maskWordsSmem * 4;
+    CK(cudaFuncSetAttribute(k_synapse_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem2));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_synapse_pass, NC_P2_THREADS, e->smem2));
     uint64_t needBlocks = (nRows + NC_WARPS_PER_BLOCK - 1) / NC_WARPS_PER_BLOCK;
+    uint64_t needBlocks2 = (nRows + NC_P2_THREADS / 32 - 1) / (NC_P2_THREADS / 32);
     e->grid1 = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(needBlocks, (uint64_t)e->smCount * std::max(occ1, 1)));
-    e->grid2 = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(needBlocks, (uint64_t)e->smCount * std::max(occ2, 1)));
+    e->grid2 = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(needBlocks2, (uint64_t)e->smCount * std::max(occ2, 1)));
     v.spillPerWarp = (uint32_t)(maxRow > e->candCap ? maxRow - e->candCap : 0);
     uint64_t spillN = std::max<uint64_t>(1, (uint64_t)e->grid1 * NC_WARPS_PER_BLOCK * v.spillPerWarp);
     CK(cudaMalloc(&v.spillA, spillN * 4)); CK(cudaMalloc(&v.spillD, spillN * 4)); CK(cudaMalloc(&v.spillJ, spillN * 4));
     CK(cudaStreamSynchronize(e->stream));
-    cudaFree(dLen); cudaFree(dInh);
+    cudaFree(tmpLen); cudaFree(tmpInh);
     e->minDelay = minDelay;
     e->uploaded = true;
     return NC_OK;
+}
+
+static int upload_precheck(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t nRows, const void* rowptr) {
+    if (e->uploaded) return fail(e, NC_ERR_STATE, "nc_upload_network: network already uploaded");
+    if (!rowptr) return fail(e, NC_ERR_INVALID, "nc_upload_network: rowptr is null");
+    if (nGlobal >= (1ull << 30)) return fail(e, NC_ERR_INVALID, "nc_upload_network: at most 2^30-1 neurons");
+    if (row0 + nRows > nGlobal) return fail(e, NC_ERR_INVALID, "nc_upload_network: row range exceeds neuron count");
+    return NC_OK;
+}
+
+extern "C" int nc_upload_network(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t nRows, const uint64_t* rowptr,
+                                 const uint32_t* pre, const float* weight, const float* length, const uint8_t* inh) {
+    int rc = upload_precheck(e, nGlobal, row0, nRows, rowptr);
+    if (rc) return rc;
+    if (rowptr[0] != 0) return fail(e, NC_ERR_INVALID, "nc_upload_network: rowptr[0] must be 0");
+    uint64_t S = rowptr[nRows], maxRow = 0;
+    if (S && (!pre || !weight || !length || !inh)) return fail(e, NC_ERR_INVALID, "nc_upload_network: null synapse array");
+    float minDelay = INFINITY;
+    for (uint64_t r = 0; r < nRows; r++) {
+        if (rowptr[r + 1] < rowptr[r]) return fail(e, NC_ERR_INVALID, "nc_upload_network: rowptr not monotone");
+        uint64_t len = rowptr[r + 1] - rowptr[r];
+        maxRow = std::max(maxRow, len);
+        if (len >= (1ull << 29)) return fail(e, NC_ERR_INVALID, "nc_upload_network: row longer than 2^29-1");
+        for (uint64_t j = rowptr[r]; j < rowptr[r + 1]; j++) {
+            if (pre[j] >= nGlobal) return fail(e, NC_ERR_INVALID, "nc_upload_network: presynaptic ID out of range");
+            if (j > rowptr[r] && pre[j] <= pre[j - 1]) return fail(e, NC_ERR_INVALID, "nc_upload_network: row not strictly ascending in presynaptic ID");
+            float d = length[j] * 2.0f;
+            if (!(d > 0.0f)) return fail(e, NC_ERR_INVALID, "nc_upload_network: synapse length must be positive");
+            minDelay = std::min(minDelay, d);
+        }
+    }
+    cudaSetDevice(e->cfg.device);
+    return upload_common(e, nGlobal, row0, nRows, S, maxRow, minDelay, rowptr, pre, weight, length, inh, cudaMemcpyHostToDevice);
+}
+
+// Same as nc_upload_network with all five arrays already resident on this engine's device (e.g. built there by the
+// caller); they are copied, so the caller may free them afterwards.
+extern "C" int nc_upload_network_device(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t nRows, const uint64_t* dRowptr,
+                                        const uint32_t* dPre, const float* dWeight, const float* dLength, const uint8_t* dInh) {
+    int rc = upload_precheck(e, nGlobal, row0, nRows, dRowptr);
+    if (rc) return rc;
+    cudaSetDevice(e->cfg.device);
+    uint64_t ends[1], first[1];
+    CK(cudaMemcpy(first, dRowptr, 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ends, dRowptr + nRows, 8, cudaMemcpyDeviceToHost));
+    if (first[0] != 0) return fail(e, NC_ERR_INVALID, "nc_upload_network: rowptr[0] must be 0");
+    uint64_t S = ends[0];
+    if (S && (!dPre || !dWeight || !dLength || !dInh)) return fail(e, NC_ERR_INVALID, "nc_upload_network: null synapse array");
+    unsigned int* dOut; unsigned int hOut[3] = {0u, 0u, 0x7f800000u};
+    CK(cudaMalloc(&dOut, 12));
+    CK(cudaMemcpy(dOut, hOut, 12, cudaMemcpyHostToDevice));
+    k_validate_csr<<<e->smCount * 8, 256>>>(nGlobal, nRows, dRowptr, dPre, dLength, dOut); e->launches++;
+    CK(cudaMemcpy(hOut, dOut, 12, cudaMemcpyDeviceToHost));
+    cudaFree(dOut);
+    if (hOut[0] & 1u) return fail(e, NC_ERR_INVALID, "nc_upload_network: rowptr not monotone");
+    if (hOut[0] & 2u) return fail(e, NC_ERR_INVALID, "nc_upload_network: row longer than 2^29-1");
+    if (hOut[0] & 4u) return fail(e, NC_ERR_INVALID, "nc_upload_network: presynaptic ID out of range");
+    if (hOut[0] & 8u) return fail(e, NC_ERR_INVALID, "nc_upload_network: row not strictly ascending in presynaptic ID");
+    if (hOut[0] & 16u) return fail(e, NC_ERR_INVALID, "nc_upload_network: synapse length must be positive");
+    float minDelay;
+    memcpy(&minDelay, &hOut[2], 4);
+    return upload_common(e, nGlobal, row0, nRows, S, hOut[1], minDelay, dRowptr, dPre, dWeight, dLength, dInh, cudaMemcpyDeviceToDevice);
 }
 
 extern "C" int nc_min_delay(const nc_engine* e, float* out) {
@@ -512,8 +633,10 @@ static void fill_args(nc_engine* e, StepArgs& a, float t0, float t1, int sweep, 
 }
 
 static int launch_pass1(nc_engine* e, const StepArgs& a) {
+    if (a.nEv) { k_mark_events<<<(a.nEv + 255) / 256, 256, 0, e->stream>>>(e->v, a.ev, a.nEv, 1); e->launches++; }
     k_neuron_pass<<<e->grid1, NC_WARPS_PER_BLOCK * 32, e->smem1, e->stream>>>(e->v, a);
     e->launches++;
+    if (a.nEv) { k_mark_events<<<(a.nEv + 255) / 256, 256, 0, e->stream>>>(e->v, a.ev, a.nEv, 0); e->launches++; }
     CK(cudaGetLastError());
     return NC_OK;
 }
@@ -523,7 +646,7 @@ static int launch_pass2(nc_engine* e, const StepArgs& a) {
     for (uint32_t b = 0; b < a.world; b++) maxc = std::max(maxc, a.counts[b]);
     dim3 g((maxc + 255) / 256, a.world);
     if (maxc) { k_index_build<<<g, 256, 0, e->stream>>>(e->v, a); e->launches++; }
-    k_synapse_pass<<<e->grid2, NC_WARPS_PER_BLOCK * 32, 0, e->stream>>>(e->v, a);
+    k_synapse_pass<<<e->grid2, NC_P2_THREADS, e->smem2, e->stream>>>(e->v, a, e->maskWordsSmem);
     e->launches++;
     if (maxc) { k_index_reset<<<g, 256, 0, e->stream>>>(e->v, a); e->launches++; }
     CK(cudaMemsetAsync(e->v.localHdr, 0, 16, e->stream));
@@ -815,7 +938,7 @@ extern "C" int nc_tape_replay(nc_engine* e, uint32_t first, uint32_t count, floa
     CK(cudaMemsetAsync(e->v.stats, 0, 8 * sizeof(unsigned long long), e->stream));
     const bool perKernel = msP1 || msP2;
     std::vector<cudaEvent_t> evs;
-    if (perKernel) { evs.resize((size_t)count * 3); for (auto& x : evs) CK(cudaEventCreate(&x)); }
+    if (perKernel) { evs.resize((size_t)count * 4); for (auto& x : evs) CK(cudaEventCreate(&x)); }
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     const uint32_t idxGrid = (uint32_t)std::min<uint64_t>(std::max<uint64_t>((e->v.nRows / 64 + 255) / 256, 1), 1024);
     CK(cudaEventRecord(e0, e->stream));
@@ -823,12 +946,15 @@ extern "C" int nc_tape_replay(nc_engine* e, uint32_t first, uint32_t count, floa
         const TapeStep& ts = e->tape[first + k];
         StepArgs a;
         fill_args(e, a, ts.t0, ts.t1, ts.sweep, e->dTape + ts.evOff, ts.nEv);
-        if (perKernel) CK(cudaEventRecord(evs[3 * k], e->stream));
+        if (a.nEv) { k_mark_events<<<(a.nEv + 255) / 256, 256, 0, e->stream>>>(e->v, a.ev, a.nEv, 1); e->launches++; }
+        if (perKernel) CK(cudaEventRecord(evs[4 * k], e->stream));
         k_neuron_pass<<<e->grid1, NC_WARPS_PER_BLOCK * 32, e->smem1, e->stream>>>(e->v, a);
-        if (perKernel) CK(cudaEventRecord(evs[3 * k + 1], e->stream));
+        if (perKernel) CK(cudaEventRecord(evs[4 * k + 1], e->stream));
+        if (a.nEv) { k_mark_events<<<(a.nEv + 255) / 256, 256, 0, e->stream>>>(e->v, a.ev, a.nEv, 0); e->launches++; }
         k_index_build_dev<<<idxGrid, 256, 0, e->stream>>>(e->v, a);
-        k_synapse_pass<<<e->grid2, NC_WARPS_PER_BLOCK * 32, 0, e->stream>>>(e->v, a);
-        if (perKernel) CK(cudaEventRecord(evs[3 * k + 2], e->stream));
+        if (perKernel) CK(cudaEventRecord(evs[4 * k + 2], e->stream));
+        k_synapse_pass<<<e->grid2, NC_P2_THREADS, e->smem2, e->stream>>>(e->v, a, e->maskWordsSmem);
+        if (perKernel) CK(cudaEventRecord(evs[4 * k + 3], e->stream));
         k_index_reset_dev<<<idxGrid, 256, 0, e->stream>>>(e->v, a);
         k_hdr_reset<<<1, 32, 0, e->stream>>>(e->v, dOvf);
         e->launches += 5;
@@ -843,8 +969,8 @@ extern "C" int nc_tape_replay(nc_engine* e, uint32_t first, uint32_t count, floa
     if (perKernel) {
         float s1 = 0, s2 = 0, x;
         for (uint32_t k = 0; k < count; k++) {
-            CK(cudaEventElapsedTime(&x, evs[3 * k], evs[3 * k + 1])); s1 += x;
-            CK(cudaEventElapsedTime(&x, evs[3 * k + 1], evs[3 * k + 2])); s2 += x;
+            CK(cudaEventElapsedTime(&x, evs[4 * k], evs[4 * k + 1])); s1 += x;
+            CK(cudaEventElapsedTime(&x, evs[4 * k + 2], evs[4 * k + 3])); s2 += x;
         }
         if (msP1) *msP1 = s1;
         if (msP2) *msP2 = s2;

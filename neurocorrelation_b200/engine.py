@@ -21,7 +21,8 @@ NC_SWEEP_START = 2
 
 # every symbol include/neucor_b200.h declares
 ABI_SYMBOLS = (
-    "nc_global_error", "nc_device_count", "nc_create", "nc_destroy", "nc_last_error", "nc_upload_network", "nc_min_delay",
+    "nc_global_error", "nc_device_count", "nc_create", "nc_destroy", "nc_last_error", "nc_upload_network",
+    "nc_upload_network_device", "nc_min_delay",
     "nc_set_plasticity", "nc_step", "nc_run_neurons", "nc_read_neurons", "nc_read_synapses", "nc_read_fires",
     "nc_read_synapse_pots", "nc_reset_activities", "nc_detector_mean", "nc_tape_begin", "nc_tape_end", "nc_snapshot",
     "nc_restore", "nc_tape_replay", "nc_launch_count", "nc_step_begin", "nc_exchange_buffer", "nc_gather_buffer",
@@ -68,6 +69,7 @@ def load(path=None):
     L.nc_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
     L.nc_destroy.argtypes = [vp]
     L.nc_upload_network.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, u64p, vp, vp, vp, vp]
+    L.nc_upload_network_device.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp]
     L.nc_min_delay.argtypes = [vp, C.POINTER(C.c_float)]
     L.nc_set_plasticity.argtypes = [vp] + [C.c_float] * 5
     L.nc_step.argtypes = [vp, C.c_float, C.c_float, C.c_int, vp, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(StepStats)]
@@ -136,6 +138,11 @@ class Engine:
         self._ck(self.L.nc_upload_network(self.h, N, row0, n_rows, local_rp, *[a.ctypes.data for a in self._keep]))
         self.N, self.S, self.row0, self.n_rows = N, hi - lo, row0, n_rows
         self._keep = None
+
+    def upload_device(self, N, row0, n_rows, S, d_rowptr, d_pre, d_weight, d_length, d_flag):
+        """CSR arrays given as raw device pointers (ints), e.g. torch tensors' data_ptr()."""
+        self._ck(self.L.nc_upload_network_device(self.h, int(N), int(row0), int(n_rows), d_rowptr, d_pre, d_weight, d_length, d_flag))
+        self.N, self.S, self.row0, self.n_rows = int(N), int(S), int(row0), int(n_rows)
 
     def min_delay(self):
         out = C.c_float()

@@ -52,6 +52,7 @@ void NeuCor::check(int rc, const char* what) {
 float NeuCor::getTime() const { return currentTime; }
 std::size_t NeuCor::getNeuronCount() const { return positions.size(); }
 std::size_t NeuCor::synapseCount() const {
+    if (dev_.set) return dev_.S;
     if (engine_ || imported_) return pre_.size();
     std::size_t s = 0;
     for (auto& o : out_) s += o.size();
@@ -166,6 +167,17 @@ void NeuCor::importNetwork(std::size_t n, const uint64_t* rowptr, const uint32_t
     imported_ = true;
 }
 
+void NeuCor::importNetworkDevice(std::size_t n, uint64_t synapses, const uint64_t* d_rowptr, const uint32_t* d_pre, const float* d_weight,
+                                 const float* d_length, const uint8_t* d_inhibitory) {
+    if (engine_) throw std::logic_error("NeuCor::importNetworkDevice: the network is already on the device");
+    positions.resize(n);
+    potAct.assign(2 * n, 0.0f);
+    for (std::size_t i = 0; i < n; i++) { positions[i].setNAN(); potAct[2 * i] = -70.0f; }
+    out_.clear();
+    dev_.rowptr = d_rowptr; dev_.pre = d_pre; dev_.weight = d_weight; dev_.length = d_length; dev_.inh = d_inhibitory; dev_.S = synapses; dev_.set = true;
+    imported_ = true;
+}
+
 void NeuCor::finalize() {
     if (engine_) return;
     const std::size_t N = positions.size();
@@ -192,10 +204,14 @@ void NeuCor::finalize() {
     int rc = nc_create(&cfg, &e);
     if (rc != NC_OK) throw std::runtime_error(std::string("NeuCor: cannot create the CUDA engine: ") + nc_global_error());
     engine_ = e;
-    check(nc_upload_network(engine_, N, 0, N, rowptr_.data(), pre_.data(), weight_.data(), length_.data(), flag_.data()), "nc_upload_network");
-    h2dBytes_ += (N + 1) * 8 + pre_.size() * 13;
+    if (dev_.set) {
+        check(nc_upload_network_device(engine_, N, 0, N, dev_.rowptr, dev_.pre, dev_.weight, dev_.length, dev_.inh), "nc_upload_network_device");
+    } else {
+        check(nc_upload_network(engine_, N, 0, N, rowptr_.data(), pre_.data(), weight_.data(), length_.data(), flag_.data()), "nc_upload_network");
+        h2dBytes_ += (N + 1) * 8 + pre_.size() * 13;
+    }
     minDelay_ = INFINITY;
-    if (!pre_.empty()) check(nc_min_delay(engine_, &minDelay_), "nc_min_delay");
+    if (synapseCount()) check(nc_min_delay(engine_, &minDelay_), "nc_min_delay");
     lastFireMirror_.assign(N, NAN);
 }
 
@@ -361,6 +377,7 @@ void NeuCor::run() { stepInternal(false); }
 
 float NeuCor::runSwept() {
     stepInternal(true);
+    if (!sweepReturnsMean) return 0.0f;
     // mean potential of all neurons, summed in ID order in float — VoltageDetector::getVoltage, NeuCor.cpp:360-365
     syncState();
     d2hBytes_ += potAct.size() * 4;
@@ -403,6 +420,7 @@ std::vector<NeuCor::NeuronSnapshot> NeuCor::getNeuronSnapshots() const {  // Neu
 std::vector<NeuCor::SynapseSnapshot> NeuCor::getSynapseSnapshots() const {  // NeuCor.cpp:115-134
     NeuCor* self = const_cast<NeuCor*>(this);
     self->finalize();
+    if (dev_.set) throw std::logic_error("NeuCor::getSynapseSnapshots: not available for a network imported from device memory");
     const std::size_t S = pre_.size(), N = positions.size();
     std::vector<float> w(S), prePot(S), postPot(S);
     self->check(nc_read_synapses(engine_, w.data(), nullptr, nullptr, nullptr, nullptr), "nc_read_synapses");

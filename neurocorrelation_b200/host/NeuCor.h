@@ -93,9 +93,13 @@ public:
     // Replaces the network by an exported one (post-sorted CSR incl. the reference's flag byte). Only before the first run().
     void importNetwork(std::size_t n, const uint64_t* rowptr, const uint32_t* pre, const float* weight, const float* length,
                        const uint8_t* inhibitory, const float* positions_xyz /* may be null */);
+    // Same with the CSR already resident on the device `deviceOrdinal` (device pointers; copied at finalize()).
+    void importNetworkDevice(std::size_t n, uint64_t synapses, const uint64_t* d_rowptr, const uint32_t* d_pre, const float* d_weight,
+                             const float* d_length, const uint8_t* d_inhibitory);
     void setInputNear(unsigned inputID, const uint32_t* ids, std::size_t n);  // overrides an input's `near` list
     void setInputLastFire(unsigned inputID, float t);
     float runSwept();               // run() + "run every neuron at the new time, ascending ID"; returns the mean potential
+    bool sweepReturnsMean = true;   // false: runSwept() skips the device->host read of all potentials and returns 0
     void syncState();               // device -> potAct / lastFire mirrors
     // network in CSR order (valid after finalize) and raw state readers
     void finalize();                // builds the CSR and uploads it (implicit on first run)
@@ -143,6 +147,7 @@ private:
     std::vector<float> weight_, length_;
     std::vector<uint8_t> flag_;
     bool imported_ = false;
+    struct { const uint64_t* rowptr; const uint32_t* pre; const float *weight, *length; const uint8_t* inh; uint64_t S; bool set; } dev_ = {};
     nc_engine* engine_ = nullptr;
     float minDelay_ = 0.0f;
     std::vector<float> lastFireMirror_;

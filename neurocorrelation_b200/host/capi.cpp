@@ -50,6 +50,10 @@ int nch_import_network(void* hv, uint64_t n, const uint64_t* rowptr, const uint3
                        const uint8_t* flag, const float* xyz) {
     return guard([&] { B->importNetwork(n, rowptr, pre, weight, length, flag, xyz); });
 }
+int nch_import_network_device(void* hv, uint64_t n, uint64_t S, const void* rowptr, const void* pre, const void* weight, const void* length, const void* flag) {
+    return guard([&] { B->importNetworkDevice(n, S, (const uint64_t*)rowptr, (const uint32_t*)pre, (const float*)weight, (const float*)length, (const uint8_t*)flag); });
+}
+int nch_set_sweep_mean(void* hv, int on) { return guard([&] { B->sweepReturnsMean = on != 0; }); }
 int nch_set_inputs(void* hv, const float* rates, unsigned n, const float* pos_xyz, const float* radius) {
     return guard([&] {
         Handle* h = (Handle*)hv;

@@ -78,6 +78,10 @@ int nc_upload_network(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t nR
     return NC_OK;
 }
 
+int nc_upload_network_device(nc_engine* e, uint64_t, uint64_t, uint64_t, const uint64_t*, const uint32_t*, const float*, const float*, const uint8_t*) {
+    return fail(e, NC_ERR_INVALID, "the CPU test double has no device memory");
+}
+
 // serial restatement of k_neuron_pass
 static void model_pass1(nc_engine* e, const StepArgs& s) {
     View& v = e->v;

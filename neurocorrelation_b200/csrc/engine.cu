@@ -49,6 +49,83 @@ struct EvPick {  // (time, rank<<32|k2) ordering; src: candidate index, or 0x800
     unsigned long long code;
     uint32_t src;
 };
+struct P1Counters { unsigned long long fires, runs, visits, deliveries; };
+
+// Neuron::run (NeuCor.cpp:619-641) executed by a whole warp: the neuron's state is replicated in every lane, the ordered
+// accumulation over the row's active slots (charge_insynapses) is evaluated 32 slots at a time with the exact
+// prefix-sum scheme of step_logic.cuh, slots that expire are marked by their own lane.
+__device__ __forceinline__ void warp_neuron_run(const View& v, NeuronState& n, CandView& cv, uint32_t cnt, uint64_t rs, uint32_t q, float T,
+                                                uint32_t rk1, uint32_t k2, uint32_t sentinel, uint32_t lane, P1Counters& ctr) {
+    const uint32_t FULL = 0xffffffffu;
+    float dT;
+    if (!neuron_run_begin(n, T, dT)) return;
+    ctr.runs++;
+    float np = n.pot;
+    if (cnt) {
+        const double E = exp_glibc(mul64(0.3702, (double)dT));
+        for (uint32_t base = 0; base < cnt; base += 32) {
+            const uint32_t c = base + lane;
+            bool act = false;
+            double t = 0.0;
+            if (c < cnt) {
+                float a = cv.A(c);
+                if (a > 0.0f) {                 // not cleared earlier in this window
+                    float off = sub32(T, a);
+                    if (off > 0.0f) {           // arrived
+                        act = true;
+                        t = chain_term(dT, cv.D(c), E);
+                        if (2.0f < off) {       // NeuCor.cpp:697 — the slot becomes idle; leave the when-and-why for the synapse pass
+                            cv.A(c) = -a;
+                            uint64_t sidx = rs + cv.J(c);
+                            v.arrive[sidx] = __uint_as_float(sentinel);
+                            v.depol[sidx] = T;
+                        }
+                    }
+                }
+            }
+            uint32_t todo = __ballot_sync(FULL, act);
+            ctr.visits += __popc(todo);
+            while (todo) {
+                const Binade b = binade_of(np);
+                const bool neg = np < 0.0f;
+                const bool mine = (todo >> lane) & 1u;
+                double r = 0.0;
+                bool flag = false;
+                if (mine) flag = !chain_lane(b, neg, t, r);
+                double pre = r;  // inclusive prefix sum over lanes; all values are multiples of u, the sums are exact
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    double y = __shfl_up_sync(FULL, pre, o);
+                    if (lane >= (uint32_t)o) pre = add64(pre, y);
+                }
+                const double m = fabs((double)np);
+                const double mi = add64(m, pre);
+                if (mine && !(mi > b.lo && mi < b.hi)) flag = true;  // the running value would leave the open binade
+                const uint32_t bad = __ballot_sync(FULL, flag) & todo;
+                if (!bad) {
+                    double tot = __shfl_sync(FULL, pre, 31);
+                    double mm = add64(m, tot);
+                    np = (float)(neg ? -mm : mm);
+                    todo = 0u;
+                } else {
+                    const int f = __ffs(bad) - 1;
+                    double acc = __shfl_sync(FULL, pre, f > 0 ? f - 1 : 0);
+                    if (f == 0) acc = 0.0;
+                    double mm = add64(m, acc);
+                    np = (float)(neg ? -mm : mm);
+                    double tf = __shfl_sync(FULL, t, f);
+                    np = (float)add64((double)np, tf);  // this one slot exactly as the reference adds it
+                    todo &= ~((2u << f) - 1u);
+                }
+            }
+        }
+    }
+    if (neuron_run_finish(n, np, T, dT)) {
+        ctr.fires++;
+        if (lane == 0) emit_fire(v, q, T, rk1, k2);
+    }
+}
+
 __global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32) k_neuron_pass(View v, StepArgs s) {
     extern __shared__ unsigned char smem[];
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
@@ -58,7 +135,7 @@ __global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32) k_neuron_pass(View v,
     cv.a = sA; cv.d = sA + cap; cv.j = reinterpret_cast<uint32_t*>(sA + 2 * cap); cv.cap = cap;
     const uint64_t gw = (uint64_t)blockIdx.x * NC_WARPS_PER_BLOCK + wib, nW = (uint64_t)gridDim.x * NC_WARPS_PER_BLOCK;
     cv.sa = v.spillA + gw * v.spillPerWarp; cv.sd = v.spillD + gw * v.spillPerWarp; cv.sj = v.spillJ + gw * v.spillPerWarp;
-    unsigned long long nFires = 0, nRuns = 0, nVisits = 0, nDeliv = 0;
+    P1Counters ctr = {0, 0, 0, 0};
 
     for (uint64_t row = gw; row < v.nRows; row += nW) {
         const uint32_t q = (uint32_t)(v.row0 + row);
@@ -160,33 +237,36 @@ __global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32) k_neuron_pass(View v,
                     if (pick_less(ot, oc, best.t, best.code)) { best.t = ot; best.code = oc; best.src = os; }
                 }
                 if (best.code == ~0ull) break;
-                if (lane == 0) {
+                {
                     uint32_t rank = (uint32_t)(best.code >> 32), k = (uint32_t)best.code;
-                    if (rank == 0) {  // InputFirer::run → Neuron::fire, no update, ignores refractory (NeuCor.cpp:326-331)
-                        neuron_fire(v, n, q, best.t, k, q, nFires);
+                    if (rank == 0) {  // InputFirer::run → Neuron::fire, no update, ignores refractory (NeuCor.cpp:326-331,643-645)
+                        n.lastFire = best.t;
+                        n.firings++;
+                        ctr.fires++;
+                        if (lane == 0) emit_fire(v, q, best.t, k, q);
                     } else if (rank == 1) {  // Synapse::run → Neuron::transfer (NeuCor.cpp:718-726,663-666)
-                        nDeliv++;
-                        neuron_run(v, n, cv, cnt, rs, q, best.t, (1u << 30) | q, k, NC_SENT | (1u << 29) | cv.J(best.src), nFires, nRuns, nVisits);
+                        ctr.deliveries++;
+                        warp_neuron_run(v, n, cv, cnt, rs, q, best.t, (1u << 30) | q, k, NC_SENT | (1u << 29) | cv.J(best.src), lane, ctr);
                     } else {
-                        neuron_run(v, n, cv, cnt, rs, q, best.t, (2u << 30) | q, 0u, NC_SENT | (2u << 29), nFires, nRuns, nVisits);
+                        warp_neuron_run(v, n, cv, cnt, rs, q, best.t, (2u << 30) | q, 0u, NC_SENT | (2u << 29), lane, ctr);
                     }
                 }
                 __syncwarp();
                 curT = best.t; curC = best.code; first = false;
             }
         }
+        if (s.sweep & NC_SWEEP_END) warp_neuron_run(v, n, cv, cnt, rs, q, s.t1, (3u << 30) | q, 0u, NC_SENT | (3u << 29), lane, ctr);
         if (lane == 0) {
-            if (s.sweep & NC_SWEEP_END) neuron_run(v, n, cv, cnt, rs, q, s.t1, (3u << 30) | q, 0u, NC_SENT | (3u << 29), nFires, nRuns, nVisits);
             v.potAct[row] = make_float2(n.pot, n.act);
             v.lastRan[row] = n.lastRan; v.lastFire[row] = n.lastFire; v.firings[row] = n.firings;
         }
         __syncwarp();
     }
-    if (lane == 0) {
-        if (nFires) atomicAdd(&v.stats[0], nFires);
-        if (nDeliv) atomicAdd(&v.stats[1], nDeliv);
-        if (nRuns) atomicAdd(&v.stats[6], nRuns);
-        if (nVisits) atomicAdd(&v.stats[7], nVisits);
+    if (lane == 0) {  // every lane counted the same (warp-uniform) events
+        if (ctr.fires) atomicAdd(&v.stats[0], ctr.fires);
+        if (ctr.deliveries) atomicAdd(&v.stats[1], ctr.deliveries);
+        if (ctr.runs) atomicAdd(&v.stats[6], ctr.runs);
+        if (ctr.visits) atomicAdd(&v.stats[7], ctr.visits);
     }
 }
 
@@ -214,16 +294,23 @@ __global__ void k_index_reset(View v, StepArgs s) {
 // ------------------------------------------------------------------------------------------------
 // Synapse pass
 // ------------------------------------------------------------------------------------------------
+#define NC_P2_QUEUE 64  // per-warp queue of eventful slots (drained 32 at a time so that every lane resolves one)
+
 __global__ void __launch_bounds__(NC_P2_THREADS) k_synapse_pass(View v, StepArgs s, uint32_t maskWordsInSmem) {
-    extern __shared__ uint32_t smask[];
+    extern __shared__ uint32_t smem2[];
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     // the fire bitmask (1 bit per neuron of the whole network) is probed once per synapse: keep it in shared memory
+    uint32_t* smask = smem2 + (size_t)wpb * 3 * NC_P2_QUEUE;
     const uint32_t* mask = v.mask;
     if (maskWordsInSmem) {
         for (uint32_t i = threadIdx.x; i < maskWordsInSmem; i += blockDim.x) smask[i] = v.mask[i];
         __syncthreads();
         mask = smask;
     }
+    // eventful slots are rare and scattered: queue them per warp and resolve 32 at a time instead of diverging in place
+    uint32_t* qJ = smem2 + (size_t)wib * 3 * NC_P2_QUEUE;
+    uint32_t* qP = qJ + NC_P2_QUEUE;
+    uint32_t* qA = qP + NC_P2_QUEUE;
     const uint64_t gw = (uint64_t)blockIdx.x * wpb + wib, nW = (uint64_t)gridDim.x * wpb;
     uint32_t cnt[5] = {0, 0, 0, 0, 0};  // loads accepted, dropped, plasticity calls, hidden rand, deliveries
     for (uint64_t row = gw; row < v.nRows; row += nW) {
@@ -231,6 +318,7 @@ __global__ void __launch_bounds__(NC_P2_THREADS) k_synapse_pass(View v, StepArgs
         const uint64_t rs = v.rowptr[row], re = v.rowptr[row + 1];
         const bool qFired = (mask[q >> 5] >> (q & 31u)) & 1u;
         const float lfS = v.lfStart[row];
+        uint32_t qn = 0;
         for (uint64_t base = rs; base < re; base += 32 * NC_UNROLL) {
             uint32_t pv[NC_UNROLL], abv[NC_UNROLL];
 #pragma unroll
@@ -240,17 +328,52 @@ __global__ void __launch_bounds__(NC_P2_THREADS) k_synapse_pass(View v, StepArgs
                 pv[u] = in ? __ldcs(&v.pre[j]) : 0xffffffffu;
                 abv[u] = in ? __float_as_uint(__ldcs(&v.arrive[j])) : 0u;
             }
+            uint32_t evb = 0;  // bit u: my slot of sub-group u is eventful
 #pragma unroll
             for (int u = 0; u < NC_UNROLL; u++) {
-                uint64_t j = base + (uint64_t)u * 32 + lane;
-                if (j >= re) continue;
-                uint32_t pw = pv[u], p = pw & 0x7fffffffu, ab = abv[u];
+                uint32_t pw = pv[u], ab = abv[u];
+                if (pw == 0xffffffffu) continue;  // past the end of the row
+                uint32_t p = pw & 0x7fffffffu;
                 bool pFired = (mask[p >> 5] >> (p & 31u)) & 1u;
                 float a = __uint_as_float(ab);
-                bool eventful = qFired || pFired || (ab & NC_SENT) || (ab != 0u && a > s.t0 && a <= s.t1);
-                if (eventful) resolve_slot(v, s, j, rs, q, p, (pw >> 31) != 0u, ab, pFired, qFired, lfS, cnt);
+                if (qFired || pFired || (ab & NC_SENT) || (ab != 0u && a > s.t0 && a <= s.t1)) evb |= 1u << u;
+            }
+            if (!__any_sync(0xffffffffu, evb != 0u)) continue;
+#pragma unroll
+            for (int u = 0; u < NC_UNROLL; u++) {
+                bool ev = (evb >> u) & 1u;
+                uint32_t m = __ballot_sync(0xffffffffu, ev);
+                if (!m) continue;
+                if (ev) {
+                    uint32_t pos = qn + __popc(m & ((1u << lane) - 1u));
+                    qJ[pos] = (uint32_t)(base + (uint64_t)u * 32 + lane - rs);
+                    qP[pos] = pv[u];
+                    qA[pos] = abv[u];
+                }
+                qn += __popc(m);
+                if (qn >= 32) {
+                    __syncwarp();
+                    uint32_t jj = qJ[lane], pw = qP[lane], ab = qA[lane];
+                    uint32_t mv = (lane < qn - 32) ? 1u : 0u;
+                    uint32_t j2 = mv ? qJ[32 + lane] : 0u, p2 = mv ? qP[32 + lane] : 0u, a2 = mv ? qA[32 + lane] : 0u;
+                    __syncwarp();
+                    if (mv) { qJ[lane] = j2; qP[lane] = p2; qA[lane] = a2; }
+                    qn -= 32;
+                    uint32_t p = pw & 0x7fffffffu;
+                    bool pFired = (mask[p >> 5] >> (p & 31u)) & 1u;
+                    resolve_slot(v, s, rs + jj, rs, q, p, (pw >> 31) != 0u, ab, pFired, qFired, lfS, cnt);
+                    __syncwarp();
+                }
             }
         }
+        __syncwarp();
+        if (lane < qn) {
+            uint32_t jj = qJ[lane], pw = qP[lane], ab = qA[lane];
+            uint32_t p = pw & 0x7fffffffu;
+            bool pFired = (mask[p >> 5] >> (p & 31u)) & 1u;
+            resolve_slot(v, s, rs + jj, rs, q, p, (pw >> 31) != 0u, ab, pFired, qFired, lfS, cnt);
+        }
+        __syncwarp();
     }
 #pragma unroll
     for (int i = 0; i < 5; i++) {
@@ -362,7 +485,7 @@ struct nc_engine {
     bool gatherBound = false;
     float lr = 1.0f, preF = 0.13f, postF = 0.30f, preD = 0.75f, postD = 0.65f;
     float minDelay = INFINITY;
-    uint32_t candCap = 256, grid1 = 0, grid2 = 0, maskWordsSmem = 0;
+    uint32_t candCap = 512, grid1 = 0, grid2 = 0, maskWordsSmem = 0;
     size_t smem1 = 0, smem2 = 0;
     uint64_t launches = 0;
     // in-flight step (nc_step_begin .. nc_step_end)
@@ -532,7 +655,7 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
     // synapse pass: the whole-network fire bitmask goes to shared memory when it fits (<= 200 KB, i.e. 1.6 M neurons)
     uint64_t maskWords = (G1 + 31) / 32;
     e->maskWordsSmem = maskWords * 4 <= 200 * 1024 ? (uint32_t)maskWords : 0u;
-    e->smem2 = (size_t)e->maskWordsSmem * 4;
+    e->smem2 = (size_t)e->maskWordsSmem * 4 + (size_t)(NC_P2_THREADS / 32) * 3 * NC_P2_QUEUE * 4;
     CK(cudaFuncSetAttribute(k_synapse_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem2));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_synapse_pass, NC_P2_THREADS, e->smem2));
     uint64_t needBlocks = (nRows + NC_WARPS_PER_BLOCK - 1) / NC_WARPS_PER_BLOCK;

@@ -4,9 +4,8 @@
 // these functions inside kernels.
 //
 // Reference semantics restated (file:line under /root/reference/src):
-//   neuron_run     Neuron::run            NeuCor.cpp:619-641  (charge_insynapses :688-700, charge_passive
-//                                          :677-680, charge_thresholdCheck :682-686, AP :706-714, activity :640)
-//   neuron_fire    Neuron::fire           NeuCor.cpp:643-645  (neuron-local part)
+//   chain_* / neuron_run_begin / neuron_run_finish   Neuron::run NeuCor.cpp:619-641 (charge_insynapses :688-700,
+//                  charge_passive :677-680, charge_thresholdCheck :682-686, Neuron::fire :643-645, AP :706-714, activity :640)
 //   plasticity     Synapse::synapticPlasticity NeuCor.cpp:740-764, Neuron::getTrace :671-675
 //   resolve_slot   Synapse::fire :727-738, the slot clear at :697, Synapse::run :718-726
 // Every operator keeps the reference's float/double typing; no contraction (explicit-rounding helpers).
@@ -136,52 +135,74 @@ NC_HD void emit_fire(const View& v, uint32_t q, float T, uint32_t rk1, uint32_t 
     }
 }
 
-NC_HD void neuron_fire(const View& v, NeuronState& n, uint32_t q, float T, uint32_t rk1, uint32_t k2,
-                       unsigned long long& nFires) {
-    n.lastFire = T;
-    n.firings++;
-    nFires++;
-    emit_fire(v, q, T, rk1, k2);
+// ---- ordered accumulation over the active slots (charge_insynapses, NeuCor.cpp:688-700) -------------------------
+// Reference semantics, one slot after the other in ascending presynaptic ID:
+//     newPot = (float)((double)newPot + (double)(deltaT*depolFac) * 0.9943 * exp(0.3702*deltaT))
+// i.e. every addition is rounded to double and then to float, so the result depends on the order.  The kernels
+// evaluate a whole group of 32 slots at once without changing a single bit:
+//   while the running value stays strictly inside one binade [2^e, 2^(e+1)) its float grid is u = 2^(e-23) and its
+//   double grid g = 2^(e-52); the running value is a multiple of u, so   fl64(np + t) = np + RN_g(t)   and
+//   fl32(np + t') = np + RN_u(t')  — both roundings act on the TERM alone (ties-to-even included for the first one
+//   because np is an even multiple of g).  RN_u(RN_g(t)) is therefore an order-independent per-slot quantity r_i, the
+//   partial sums  np + r_1 + ... + r_i  are exact in double, and a warp prefix sum reproduces the serial chain.
+//   The three cases where this does not hold are detected and that one slot is added serially in plain double
+//   arithmetic before the group continues: (1) an exact tie of the float rounding (then the parity of the running value
+//   decides), (2) a partial sum that leaves the open binade (the grids change), (3) |t| >= 2^(e-1) or np not a
+//   normal number.
+NC_HD double chain_term(float dT, float depol, double E) { return mul64(mul64((double)mul32(dT, depol), 0.9943), E); }
+
+struct Binade {
+    double lo, hi;   // 2^e, 2^(e+1)
+    double C1, C2;   // 1.5*2^e (ulp = g), 1.5*2^(e+29) (ulp = u)
+    double halfu;    // u/2
+    double tmax;     // 2^(e-1)
+    int ok;
+};
+NC_HD Binade binade_of(float np) {
+    Binade b;
+    uint32_t ex = (as_u32(np) >> 23) & 0xffu;
+    b.ok = (ex != 0u && ex != 255u);
+    unsigned long long e = (unsigned long long)ex + (1023ull - 127ull);  // biased double exponent of 2^e
+    b.lo = as_f64(e << 52);
+    b.hi = as_f64((e + 1ull) << 52);
+    b.C1 = as_f64((e << 52) | 0x0008000000000000ULL);
+    b.C2 = as_f64(((e + 29ull) << 52) | 0x0008000000000000ULL);
+    b.halfu = as_f64((e - 24ull) << 52);
+    b.tmax = as_f64((e - 1ull) << 52);
+    return b;
+}
+// r = this slot's contribution to the MAGNITUDE of the running value, rounded as the reference's two roundings would;
+// returns false when the slot must be added serially (cases 1 and 3 above; case 2 is checked on the prefix sums).
+NC_HD bool chain_lane(const Binade& b, bool neg, double t, double& r) {
+    if (!b.ok || !(fabs(t) < b.tmax)) { r = 0.0; return false; }
+    double te = neg ? -t : t;
+    double tp = sub64(add64(te, b.C1), b.C1);
+    r = sub64(add64(tp, b.C2), b.C2);
+    return fabs(sub64(tp, r)) != b.halfu;
 }
 
-// Neuron::run at time T, executed by one thread. (rk1, k2) = canonical key of the causing event: it is the
-// key recorded for slots cleared here (through `sentinel`) and for a fire triggered here.
-NC_HD void neuron_run(const View& v, NeuronState& n, CandView& cv, uint32_t cnt, uint64_t rs, uint32_t q, float T,
-                      uint32_t rk1, uint32_t k2, uint32_t sentinel, unsigned long long& nFires,
-                      unsigned long long& nRuns, unsigned long long& nVisits) {
-    const float baselevel = -70.0f, threshold = -55.0f, recharge = 0.5f, AP_cutoff = 2.0f;
-    float dT = sub32(T, n.lastRan);
+// Neuron::run, part 1: deltaT bookkeeping. Returns false when no time has passed (NeuCor.cpp:626).
+NC_HD bool neuron_run_begin(NeuronState& n, float T, float& dT) {
+    dT = sub32(T, n.lastRan);
     n.lastRan = T;
-    if (dT == 0.0f) return;
-    nRuns++;
-    // charge_insynapses: newPot += deltaT*depolFac*0.9943*exp(0.3702*deltaT), ascending presynaptic ID,
-    // each addition rounded to float through a double sum
-    float np = n.pot;
-    if (cnt) {
-        double E = exp_glibc(mul64(0.3702, (double)dT));
-        for (uint32_t c = 0; c < cnt; c++) {
-            float a = cv.A(c);
-            if (!(a > 0.0f)) continue;  // cleared earlier in this window
-            float off = sub32(T, a);
-            if (off <= 0.0f) continue;  // still in flight
-            double term = mul64(mul64((double)mul32(dT, cv.D(c)), 0.9943), E);
-            np = (float)add64((double)np, term);
-            nVisits++;
-            if (AP_cutoff < off) {  // the slot becomes idle; leave the when-and-why for the synapse pass
-                cv.A(c) = -a;
-                uint64_t s = rs + cv.J(c);
-                v.arrive[s] = as_f32(sentinel);
-                v.depol[s] = T;
-            }
-        }
-    }
-    // charge_passive
+    return dT != 0.0f;
+}
+// Neuron::run, part 3 (after charge_insynapses produced `np`): passive decay, threshold check, AP waveform, activity.
+// Returns true when the neuron fired; the caller emits the fire record.
+NC_HD bool neuron_run_finish(NeuronState& n, float np, float T, float dT) {
+    const float baselevel = -70.0f, threshold = -55.0f, recharge = 0.5f, AP_cutoff = 2.0f;
+    // charge_passive (NeuCor.cpp:677-680)
     np = add32(mul32(sub32(np, baselevel), powf_pos(recharge, dT)), baselevel);
     n.pot = np;
-    // charge_thresholdCheck (the vesicle term is always true)
+    // charge_thresholdCheck (NeuCor.cpp:682-686; the vesicle term is always true)
+    bool fired = false;
     float lf = n.lastFire;
-    if ((threshold < n.pot || n.sched == T) && (lf != lf || AP_cutoff < sub32(T, lf))) neuron_fire(v, n, q, T, rk1, k2, nFires);
-    // AP: analytic double-Gaussian waveform while within the cutoff; powf(x, 2.0) is x*x in the -O3 reference
+    if ((threshold < n.pot || n.sched == T) && (lf != lf || AP_cutoff < sub32(T, lf))) {
+        n.lastFire = T;  // Neuron::fire, NeuCor.cpp:644-645
+        n.firings++;
+        fired = true;
+    }
+    // AP (NeuCor.cpp:706-714): analytic double-Gaussian waveform while within the cutoff; powf(x, 2.0) is x*x at -O3
     lf = n.lastFire;
     if (!(lf != lf || AP_cutoff < sub32(T, lf))) {
         const double D1 = (2.0 * (double)0.3f) * (double)0.3f, D2 = (2.0 * (double)0.6f) * (double)0.6f;
@@ -194,8 +215,9 @@ NC_HD void neuron_run(const View& v, NeuronState& n, CandView& cv, uint32_t cnt,
         double tail = mul64((double)sub32(threshold, baselevel), fmax(sub64(add64(1.0, (double)lf), (double)T), 0.0));
         n.pot = (float)add64(add64(wave, (double)baselevel), tail);
     }
-    // activity
+    // activity (NeuCor.cpp:640)
     n.act = (float)div64((double)n.firings, div64((double)sub32(T, n.actStart), 10.0));
+    return fired;
 }
 
 // Synapse::synapticPlasticity at time T with the target's lastFire `lfq`.

@@ -82,6 +82,59 @@ int nc_upload_network_device(nc_engine* e, uint64_t, uint64_t, uint64_t, const u
     return fail(e, NC_ERR_INVALID, "the CPU test double has no device memory");
 }
 
+// serial emulation of engine.cu's warp_neuron_run: the same 32-slot groups, the same per-lane math (chain_lane),
+// the same first-flagged-lane handling — lanes become loop iterations
+static void model_neuron_run(const View& v, NeuronState& n, CandView& cv, uint32_t cnt, uint64_t rs, uint32_t q, float T, uint32_t rk1,
+                             uint32_t k2, uint32_t sentinel, unsigned long long& nFires, unsigned long long& nRuns, unsigned long long& nVisits) {
+    float dT;
+    if (!neuron_run_begin(n, T, dT)) return;
+    nRuns++;
+    float np = n.pot;
+    if (cnt) {
+        const double E = exp_glibc(mul64(0.3702, (double)dT));
+        for (uint32_t base = 0; base < cnt; base += 32) {
+            double t[32]; uint32_t todo = 0;
+            for (uint32_t lane = 0; lane < 32; lane++) {
+                uint32_t c = base + lane; t[lane] = 0.0;
+                if (c >= cnt) continue;
+                float a = cv.A(c);
+                if (!(a > 0.0f)) continue;
+                float off = sub32(T, a);
+                if (!(off > 0.0f)) continue;
+                todo |= 1u << lane;
+                t[lane] = chain_term(dT, cv.D(c), E);
+                if (2.0f < off) { cv.A(c) = -a; uint64_t sidx = rs + cv.J(c); v.arrive[sidx] = as_f32(sentinel); v.depol[sidx] = T; }
+            }
+            nVisits += __builtin_popcount(todo);
+            while (todo) {
+                const Binade b = binade_of(np);
+                const bool neg = np < 0.0f;
+                double r[32], pre[32]; bool flag[32];
+                for (uint32_t lane = 0; lane < 32; lane++) { r[lane] = 0.0; flag[lane] = false; if ((todo >> lane) & 1u) flag[lane] = !chain_lane(b, neg, t[lane], r[lane]); }
+                double run = 0.0;
+                for (uint32_t lane = 0; lane < 32; lane++) { run = run + r[lane]; pre[lane] = run; }
+                const double m = fabs((double)np);
+                uint32_t bad = 0;
+                for (uint32_t lane = 0; lane < 32; lane++) {
+                    double mi = m + pre[lane];
+                    if (((todo >> lane) & 1u) && !(mi > b.lo && mi < b.hi)) flag[lane] = true;
+                    if (flag[lane] && ((todo >> lane) & 1u)) bad |= 1u << lane;
+                }
+                if (!bad) { double mm = m + pre[31]; np = (float)(neg ? -mm : mm); todo = 0; }
+                else {
+                    int f = __builtin_ffs(bad) - 1;
+                    double acc = f > 0 ? pre[f - 1] : 0.0;
+                    double mm = m + acc;
+                    np = (float)(neg ? -mm : mm);
+                    np = (float)((double)np + t[f]);
+                    todo &= ~((2u << f) - 1u);
+                }
+            }
+        }
+    }
+    if (neuron_run_finish(n, np, T, dT)) { nFires++; emit_fire(v, q, T, rk1, k2); }
+}
+
 // serial restatement of k_neuron_pass
 static void model_pass1(nc_engine* e, const StepArgs& s) {
     View& v = e->v;
@@ -132,13 +185,13 @@ static void model_pass1(nc_engine* e, const StepArgs& s) {
                 }
                 if (bc == ~0ull) break;
                 uint32_t rank = (uint32_t)(bc >> 32), k = (uint32_t)bc;
-                if (rank == 0) neuron_fire(v, n, q, bt, k, q, nFires);
-                else if (rank == 1) { nDeliv++; neuron_run(v, n, cv, cnt, rs, q, bt, (1u << 30) | q, k, NC_SENT | (1u << 29) | cv.J(bsrc), nFires, nRuns, nVisits); }
-                else neuron_run(v, n, cv, cnt, rs, q, bt, (2u << 30) | q, 0u, NC_SENT | (2u << 29), nFires, nRuns, nVisits);
+                if (rank == 0) { n.lastFire = bt; n.firings++; nFires++; emit_fire(v, q, bt, k, q); }
+                else if (rank == 1) { nDeliv++; model_neuron_run(v, n, cv, cnt, rs, q, bt, (1u << 30) | q, k, NC_SENT | (1u << 29) | cv.J(bsrc), nFires, nRuns, nVisits); }
+                else model_neuron_run(v, n, cv, cnt, rs, q, bt, (2u << 30) | q, 0u, NC_SENT | (2u << 29), nFires, nRuns, nVisits);
                 curT = bt; curC = bc; first = false;
             }
         }
-        if (s.sweep & NC_SWEEP_END) neuron_run(v, n, cv, cnt, rs, q, s.t1, (3u << 30) | q, 0u, NC_SENT | (3u << 29), nFires, nRuns, nVisits);
+        if (s.sweep & NC_SWEEP_END) model_neuron_run(v, n, cv, cnt, rs, q, s.t1, (3u << 30) | q, 0u, NC_SENT | (3u << 29), nFires, nRuns, nVisits);
         v.potAct[row] = make_float2(n.pot, n.act); v.lastRan[row] = n.lastRan; v.lastFire[row] = n.lastFire; v.firings[row] = n.firings;
     }
     v.stats[0] += nFires; v.stats[1] += nDeliv; v.stats[6] += nRuns; v.stats[7] += nVisits;

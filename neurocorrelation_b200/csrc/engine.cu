@@ -38,7 +38,7 @@ using namespace ncm;
 using namespace ncs;
 
 #define NC_WARPS_PER_BLOCK 8
-#define NC_UNROLL 8          // independent coalesced row loads kept in flight per warp
+#define NC_UNROLL4 4         // independent 16-byte-per-lane (512 B per warp) row loads kept in flight per warp
 #define NC_P2_THREADS 1024   // synapse pass: one persistent block per SM, fire bitmask staged in its shared memory
 
 // ------------------------------------------------------------------------------------------------
@@ -126,7 +126,7 @@ __device__ __forceinline__ void warp_neuron_run(const View& v, NeuronState& n, C
     }
 }
 
-__global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32) k_neuron_pass(View v, StepArgs s) {
+__global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32, 4) k_neuron_pass(View v, StepArgs s) {
     extern __shared__ unsigned char smem[];
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     const uint32_t cap = s.candCap;
@@ -146,28 +146,41 @@ __global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32) k_neuron_pass(View v,
         }
         const uint64_t rs = v.rowptr[row], re = v.rowptr[row + 1];
         // ---- stage occupied slots (arrive != 0 && arrive <= t1), preserving row order ----
+        // Rows are walked in 128-slot groups aligned in the global slot index space: lane l owns slots 4l..4l+3 of a group, so
+        // every lane issues one 16-byte load per group; slots outside [rs, re) are masked. Per group the four ballots (one per
+        // sub-slot) are also written to the candidate bitmap that lets the synapse pass skip its own read of `arrive`.
         uint32_t cnt = 0;
-        for (uint64_t base = rs; base < re; base += 32 * NC_UNROLL) {
-            float av[NC_UNROLL];
+        const uint64_t g0 = rs >> 7, g1 = (re + 127) >> 7;
+        uint4* bm = reinterpret_cast<uint4*>(v.candBits) + (g0 + row);
+        for (uint64_t gb = g0; gb < g1; gb += NC_UNROLL4) {
+            float4 av[NC_UNROLL4];
 #pragma unroll
-            for (int u = 0; u < NC_UNROLL; u++) {  // NC_UNROLL independent 128-byte requests in flight per warp
-                uint64_t j = base + (uint64_t)u * 32 + lane;
-                av[u] = (j < re) ? __ldcs(&v.arrive[j]) : 0.0f;
-            }
+            for (int u = 0; u < NC_UNROLL4; u++)
+                av[u] = (gb + u < g1) ? __ldcs(reinterpret_cast<const float4*>(v.arrive) + ((gb + u) << 5) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int u = 0; u < NC_UNROLL; u++) {
-                float a = av[u];
-                bool is = (a != 0.0f) && (a <= s.t1);
-                uint32_t m = __ballot_sync(0xffffffffu, is);
-                if (m) {
-                    if (is) {
-                        uint64_t j = base + (uint64_t)u * 32 + lane;
-                        uint32_t pos = cnt + __popc(m & ((1u << lane) - 1u));
-                        cv.A(pos) = a;
-                        cv.D(pos) = v.depol[j];
-                        cv.J(pos) = (uint32_t)(j - rs);
-                    }
-                    cnt += __popc(m);
+            for (int u = 0; u < NC_UNROLL4; u++) {
+                if (gb + u >= g1) break;
+                const uint64_t j0 = ((gb + u) << 7) + 4 * lane;
+                const float a4[4] = {av[u].x, av[u].y, av[u].z, av[u].w};
+                bool is[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) is[k] = (a4[k] != 0.0f) && (a4[k] <= s.t1) && (j0 + k >= rs) && (j0 + k < re);
+                uint32_t m[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) m[k] = __ballot_sync(0xffffffffu, is[k]);
+                if (lane == 0) bm[gb + u - g0] = make_uint4(m[0], m[1], m[2], m[3]);
+                if (m[0] | m[1] | m[2] | m[3]) {
+                    const uint32_t lt = (1u << lane) - 1u;
+                    uint32_t pos = cnt + __popc(m[0] & lt) + __popc(m[1] & lt) + __popc(m[2] & lt) + __popc(m[3] & lt);
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (is[k]) {
+                            cv.A(pos) = a4[k];
+                            cv.D(pos) = v.depol[j0 + k];
+                            cv.J(pos) = (uint32_t)(j0 + k - rs);
+                            pos++;
+                        }
+                    cnt += __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
                 }
             }
         }
@@ -294,13 +307,13 @@ __global__ void k_index_reset(View v, StepArgs s) {
 // ------------------------------------------------------------------------------------------------
 // Synapse pass
 // ------------------------------------------------------------------------------------------------
-#define NC_P2_QUEUE 64  // per-warp queue of eventful slots (drained 32 at a time so that every lane resolves one)
+#define NC_P2_QUEUE 160  // per-warp queue of eventful slots (drained 32 at a time so that every lane resolves one)
 
 __global__ void __launch_bounds__(NC_P2_THREADS) k_synapse_pass(View v, StepArgs s, uint32_t maskWordsInSmem) {
     extern __shared__ uint32_t smem2[];
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     // the fire bitmask (1 bit per neuron of the whole network) is probed once per synapse: keep it in shared memory
-    uint32_t* smask = smem2 + (size_t)wpb * 3 * NC_P2_QUEUE;
+    uint32_t* smask = smem2 + (size_t)wpb * 2 * NC_P2_QUEUE;
     const uint32_t* mask = v.mask;
     if (maskWordsInSmem) {
         for (uint32_t i = threadIdx.x; i < maskWordsInSmem; i += blockDim.x) smask[i] = v.mask[i];
@@ -308,9 +321,8 @@ __global__ void __launch_bounds__(NC_P2_THREADS) k_synapse_pass(View v, StepArgs
         mask = smask;
     }
     // eventful slots are rare and scattered: queue them per warp and resolve 32 at a time instead of diverging in place
-    uint32_t* qJ = smem2 + (size_t)wib * 3 * NC_P2_QUEUE;
+    uint32_t* qJ = smem2 + (size_t)wib * 2 * NC_P2_QUEUE;
     uint32_t* qP = qJ + NC_P2_QUEUE;
-    uint32_t* qA = qP + NC_P2_QUEUE;
     const uint64_t gw = (uint64_t)blockIdx.x * wpb + wib, nW = (uint64_t)gridDim.x * wpb;
     uint32_t cnt[5] = {0, 0, 0, 0, 0};  // loads accepted, dropped, plasticity calls, hidden rand, deliveries
     for (uint64_t row = gw; row < v.nRows; row += nW) {
@@ -319,48 +331,65 @@ __global__ void __launch_bounds__(NC_P2_THREADS) k_synapse_pass(View v, StepArgs
         const bool qFired = (mask[q >> 5] >> (q & 31u)) & 1u;
         const float lfS = v.lfStart[row];
         uint32_t qn = 0;
-        for (uint64_t base = rs; base < re; base += 32 * NC_UNROLL) {
-            uint32_t pv[NC_UNROLL], abv[NC_UNROLL];
+        const uint64_t g0 = rs >> 7, g1 = (re + 127) >> 7;
+        const uint4* bm = reinterpret_cast<const uint4*>(v.candBits) + (g0 + row);
+        for (uint64_t gb = g0; gb < g1; gb += NC_UNROLL4) {
+            uint4 pv[NC_UNROLL4], cb[NC_UNROLL4];
 #pragma unroll
-            for (int u = 0; u < NC_UNROLL; u++) {
-                uint64_t j = base + (uint64_t)u * 32 + lane;
-                bool in = j < re;
-                pv[u] = in ? __ldcs(&v.pre[j]) : 0xffffffffu;
-                abv[u] = in ? __float_as_uint(__ldcs(&v.arrive[j])) : 0u;
+            for (int u = 0; u < NC_UNROLL4; u++) {
+                bool in = gb + u < g1;
+                pv[u] = in ? __ldcs(reinterpret_cast<const uint4*>(v.pre) + ((gb + u) << 5) + lane) : make_uint4(0u, 0u, 0u, 0u);
+                cb[u] = in ? __ldg(bm + (gb + u - g0)) : make_uint4(0u, 0u, 0u, 0u);  // candidate bits written by the neuron pass
             }
-            uint32_t evb = 0;  // bit u: my slot of sub-group u is eventful
 #pragma unroll
-            for (int u = 0; u < NC_UNROLL; u++) {
-                uint32_t pw = pv[u], ab = abv[u];
-                if (pw == 0xffffffffu) continue;  // past the end of the row
-                uint32_t p = pw & 0x7fffffffu;
-                bool pFired = (mask[p >> 5] >> (p & 31u)) & 1u;
-                float a = __uint_as_float(ab);
-                if (qFired || pFired || (ab & NC_SENT) || (ab != 0u && a > s.t0 && a <= s.t1)) evb |= 1u << u;
-            }
-            if (!__any_sync(0xffffffffu, evb != 0u)) continue;
+            for (int u = 0; u < NC_UNROLL4; u++) {
+                if (gb + u >= g1) break;
+                const uint64_t j0 = ((gb + u) << 7) + 4 * lane;
+                const uint32_t p4[4] = {pv[u].x, pv[u].y, pv[u].z, pv[u].w};
+                const uint32_t c4[4] = {cb[u].x, cb[u].y, cb[u].z, cb[u].w};
+                bool ev[4];
 #pragma unroll
-            for (int u = 0; u < NC_UNROLL; u++) {
-                bool ev = (evb >> u) & 1u;
-                uint32_t m = __ballot_sync(0xffffffffu, ev);
-                if (!m) continue;
-                if (ev) {
-                    uint32_t pos = qn + __popc(m & ((1u << lane) - 1u));
-                    qJ[pos] = (uint32_t)(base + (uint64_t)u * 32 + lane - rs);
-                    qP[pos] = pv[u];
-                    qA[pos] = abv[u];
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t p = p4[k] & 0x7fffffffu;
+                    const bool in = (j0 + k >= rs) && (j0 + k < re);
+                    const bool pFired = in && ((mask[p >> 5] >> (p & 31u)) & 1u);
+                    bool own = false;  // delivery in this window or cleared by the neuron pass: only occupied slots (candidates) can be
+                    if (in && ((c4[k] >> lane) & 1u)) {
+                        uint32_t ab = __float_as_uint(v.arrive[j0 + k]);
+                        float a = __uint_as_float(ab);
+                        own = (ab & NC_SENT) || (a > s.t0 && a <= s.t1);
+                    }
+                    ev[k] = in && (qFired || pFired || own);
                 }
-                qn += __popc(m);
-                if (qn >= 32) {
+                if (!__any_sync(0xffffffffu, ev[0] | ev[1] | ev[2] | ev[3])) continue;
+                uint32_t m[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) m[k] = __ballot_sync(0xffffffffu, ev[k]);
+                const uint32_t lt = (1u << lane) - 1u;
+                uint32_t pos = qn + __popc(m[0] & lt) + __popc(m[1] & lt) + __popc(m[2] & lt) + __popc(m[3] & lt);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (ev[k]) { qJ[pos] = (uint32_t)(j0 + k - rs); qP[pos] = p4[k]; pos++; }
+                qn += __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+                while (qn >= 32) {  // drain the oldest 32 entries: one per lane
                     __syncwarp();
-                    uint32_t jj = qJ[lane], pw = qP[lane], ab = qA[lane];
-                    uint32_t mv = (lane < qn - 32) ? 1u : 0u;
-                    uint32_t j2 = mv ? qJ[32 + lane] : 0u, p2 = mv ? qP[32 + lane] : 0u, a2 = mv ? qA[32 + lane] : 0u;
+                    uint32_t jj = qJ[lane], pw = qP[lane];
+                    uint32_t keepJ[4], keepP[4];
+                    const uint32_t rest = qn - 32;
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        uint32_t idx = 32 + t * 32 + lane;
+                        bool mv = t * 32 + lane < rest;
+                        keepJ[t] = mv ? qJ[idx] : 0u; keepP[t] = mv ? qP[idx] : 0u;
+                    }
                     __syncwarp();
-                    if (mv) { qJ[lane] = j2; qP[lane] = p2; qA[lane] = a2; }
-                    qn -= 32;
+#pragma unroll
+                    for (int t = 0; t < 4; t++)
+                        if (t * 32 + lane < rest) { qJ[t * 32 + lane] = keepJ[t]; qP[t * 32 + lane] = keepP[t]; }
+                    qn = rest;
                     uint32_t p = pw & 0x7fffffffu;
                     bool pFired = (mask[p >> 5] >> (p & 31u)) & 1u;
+                    uint32_t ab = __float_as_uint(v.arrive[rs + jj]);
                     resolve_slot(v, s, rs + jj, rs, q, p, (pw >> 31) != 0u, ab, pFired, qFired, lfS, cnt);
                     __syncwarp();
                 }
@@ -368,9 +397,10 @@ __global__ void __launch_bounds__(NC_P2_THREADS) k_synapse_pass(View v, StepArgs
         }
         __syncwarp();
         if (lane < qn) {
-            uint32_t jj = qJ[lane], pw = qP[lane], ab = qA[lane];
+            uint32_t jj = qJ[lane], pw = qP[lane];
             uint32_t p = pw & 0x7fffffffu;
             bool pFired = (mask[p >> 5] >> (p & 31u)) & 1u;
+            uint32_t ab = __float_as_uint(v.arrive[rs + jj]);
             resolve_slot(v, s, rs + jj, rs, q, p, (pw >> 31) != 0u, ab, pFired, qFired, lfS, cnt);
         }
         __syncwarp();
@@ -552,7 +582,7 @@ static void free_all(nc_engine* e) {
     View& v = e->v;
     cudaFree((void*)v.rowptr); cudaFree(v.pre); cudaFree(v.arrive); cudaFree(v.depol); cudaFree(v.weight); cudaFree(v.lastArr);
     cudaFree(v.lastStart); cudaFree(e->dDelay); cudaFree(v.potAct); cudaFree(v.lastRan); cudaFree(v.lastFire); cudaFree(v.lfStart);
-    cudaFree(v.actStart); cudaFree(v.firings); cudaFree(v.localHdr); cudaFree(v.head); cudaFree(v.next); cudaFree(v.mask); cudaFree(v.evMask);
+    cudaFree(v.actStart); cudaFree(v.firings); cudaFree(v.localHdr); cudaFree(v.head); cudaFree(v.next); cudaFree(v.mask); cudaFree(v.evMask); cudaFree(v.candBits);
     cudaFree(v.spillA); cudaFree(v.spillD); cudaFree(v.spillJ);
     if (!e->gatherBound) cudaFree(e->dGather);
     cudaFree(e->dEv); cudaFree(e->dTape);
@@ -612,7 +642,11 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
     v.nGlobal = nGlobal; v.row0 = row0; v.nRows = nRows; v.S = S;
     const uint64_t S1 = std::max<uint64_t>(S, 1), N1 = std::max<uint64_t>(nRows, 1), G1 = std::max<uint64_t>(nGlobal, 1);
     CK(cudaMalloc((void**)&v.rowptr, (nRows + 1) * 8));
-    CK(cudaMalloc(&v.pre, S1 * 4)); CK(cudaMalloc(&v.arrive, S1 * 4)); CK(cudaMalloc(&v.depol, S1 * 4));
+    const uint64_t SP = ((S1 + 127) / 128 + 1) * 128;  // 16-byte row loads may touch the rest of the last 128-slot group
+    CK(cudaMalloc(&v.pre, SP * 4)); CK(cudaMalloc(&v.arrive, SP * 4)); CK(cudaMalloc(&v.depol, S1 * 4));
+    CK(cudaMemsetAsync(v.pre, 0, SP * 4, e->stream)); CK(cudaMemsetAsync(v.arrive, 0, SP * 4, e->stream));
+    CK(cudaMalloc(&v.candBits, (SP / 128 + N1 + 1) * 16));
+    CK(cudaMemsetAsync(v.candBits, 0, (SP / 128 + N1 + 1) * 16, e->stream));
     CK(cudaMalloc(&v.weight, S1 * 4)); CK(cudaMalloc(&v.lastArr, S1 * 4)); CK(cudaMalloc(&v.lastStart, S1 * 4));
     CK(cudaMalloc(&e->dDelay, S1 * 4)); v.delay = e->dDelay;
     CK(cudaMalloc(&v.potAct, N1 * 8)); CK(cudaMalloc(&v.lastRan, N1 * 4)); CK(cudaMalloc(&v.lastFire, N1 * 4));
@@ -655,7 +689,7 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
     // synapse pass: the whole-network fire bitmask goes to shared memory when it fits (<= 200 KB, i.e. 1.6 M neurons)
     uint64_t maskWords = (G1 + 31) / 32;
     e->maskWordsSmem = maskWords * 4 <= 200 * 1024 ? (uint32_t)maskWords : 0u;
-    e->smem2 = (size_t)e->maskWordsSmem * 4 + (size_t)(NC_P2_THREADS / 32) * 3 * NC_P2_QUEUE * 4;
+    e->smem2 = (size_t)e->maskWordsSmem * 4 + (size_t)(NC_P2_THREADS / 32) * 2 * NC_P2_QUEUE * 4;
     CK(cudaFuncSetAttribute(k_synapse_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem2));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_synapse_pass, NC_P2_THREADS, e->smem2));
     uint64_t needBlocks = (nRows + NC_WARPS_PER_BLOCK - 1) / NC_WARPS_PER_BLOCK;

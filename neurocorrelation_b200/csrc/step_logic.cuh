@@ -80,6 +80,7 @@ struct View {
     int32_t* next;         // per record
     uint32_t* mask;        // one bit per global neuron: fired in this window
     uint32_t* evMask;      // one bit per row of this shard: has host events in this window
+    uint32_t* candBits;    // per row and 128-slot group: 4 ballot words marking the occupied slots staged by the neuron pass
     // spill area for rows with more occupied slots than fit in shared memory
     float* spillA;
     float* spillD;

@@ -18,6 +18,93 @@ namespace {
 inline float randomUnit() {  // NeuCor.cpp:12-14
     return static_cast<float>(rand()) / static_cast<float>(RAND_MAX);
 }
+
+// Bulk access to libc's rand() stream.  run() must draw once per neuron per call (NeuCor.cpp:604-607) from the very
+// generator the application seeds with srand() and shares with the core, and libc's rand() costs ~8 ns a call (lock +
+// PLT).  glibc's generator is the TYPE_3 additive feedback generator r[i] = r[i-31] + r[i-3], output r[i] >> 1; its state
+// array is reachable through the public setstate() API, so a window borrows the live state, advances it in place with
+// the same recurrence, and hands it back — every draw is exactly the value rand() would have returned, and rand()
+// continues from the right position afterwards.  A self-test at first use compares the two; on any mismatch (other
+// libc, other generator type) the window silently degrades to calling rand().
+class RandWindow {
+public:
+    RandWindow() {
+        if (!checked_) { checked_ = true; usable_ = selfTest(); }
+        if (usable_) open();
+    }
+    ~RandWindow() { close(); }
+    inline int next() {
+        if (!words_) return rand();
+        int32_t* st = words_ + 1;
+        st[f_] = (int32_t)((uint32_t)st[f_] + (uint32_t)st[r_]);
+        int out = (int)(((uint32_t)st[f_]) >> 1);
+        if (++f_ == 31) f_ = 0;
+        if (++r_ == 31) r_ = 0;
+        return out;
+    }
+    void skip(uint64_t n) { for (uint64_t k = 0; k < n; k++) (void)next(); }
+
+private:
+    void open() {
+        static int32_t parking[34];
+        static bool parked = false;
+        if (!parked) {  // a valid TYPE_3 state to park the global generator on while we hold the real one
+            parking[0] = 3;
+            for (int i = 1; i < 34; i++) parking[i] = (int32_t)((uint32_t)i * 1103515245u + 12345u);
+            parked = true;
+        }
+        parking[0] = 3;  // rear = 0, type 3
+        char* cur = setstate(reinterpret_cast<char*>(parking));  // saves the live positions into cur[0] and returns it
+        if (!cur) return;
+        int32_t* w = reinterpret_cast<int32_t*>(cur);
+        if (w[0] % 5 != 3) { setstate(cur); return; }  // not the TYPE_3 generator: leave it alone
+        words_ = w;
+        r_ = w[0] / 5;
+        f_ = (r_ + 3) % 31;
+    }
+    void close() {
+        if (!words_) return;
+        words_[0] = r_ * 5 + 3;
+        setstate(reinterpret_cast<char*>(words_));
+        words_ = nullptr;
+    }
+    static bool selfTest() {
+        // clone the live state, replay 64 draws on the clone with the recurrence, compare with rand(), then rewind
+        static int32_t parking2[34];
+        parking2[0] = 3;
+        for (int i = 1; i < 34; i++) parking2[i] = (int32_t)((uint32_t)i * 69069u + 1u);
+        char* cur = setstate(reinterpret_cast<char*>(parking2));
+        if (!cur) return false;
+        int32_t* w = reinterpret_cast<int32_t*>(cur);
+        int32_t saved[34];
+        for (int i = 0; i < 32; i++) saved[i] = w[i];
+        bool ok = (w[0] % 5 == 3);
+        setstate(cur);
+        if (!ok) return false;
+        int32_t clone[32];
+        for (int i = 0; i < 32; i++) clone[i] = saved[i];
+        int r = clone[0] / 5, f = (r + 3) % 31;
+        for (int k = 0; k < 64 && ok; k++) {
+            int32_t* st = clone + 1;
+            st[f] = (int32_t)((uint32_t)st[f] + (uint32_t)st[r]);
+            int expect = (int)(((uint32_t)st[f]) >> 1);
+            if (++f == 31) f = 0;
+            if (++r == 31) r = 0;
+            ok = (rand() == expect);
+        }
+        // rewind the live generator to where it was
+        cur = setstate(reinterpret_cast<char*>(parking2));
+        w = reinterpret_cast<int32_t*>(cur);
+        for (int i = 0; i < 32; i++) w[i] = saved[i];
+        setstate(cur);
+        return ok;
+    }
+    int32_t* words_ = nullptr;
+    int r_ = 0, f_ = 0;
+    static bool checked_, usable_;
+};
+bool RandWindow::checked_ = false;
+bool RandWindow::usable_ = false;
 }  // namespace
 
 NeuCor::NeuCor(int n_neurons) {  // NeuCor.cpp:17-42
@@ -273,7 +360,7 @@ float NeuCor::getDetectorVoltage(unsigned ID) {  // VoltageDetector::getVoltage,
     uint64_t hidden = 0;
     nc_step_stats st;
     check(nc_run_neurons(engine_, currentTime, d.near.data(), (uint32_t)d.near.size(), &hidden, &st), "nc_run_neurons");
-    for (uint64_t k = 0; k < hidden; k++) (void)rand();
+    if (hidden) { RandWindow rw; rw.skip(hidden); }
     float out = 0.0f;
     check(nc_detector_mean(engine_, d.near.data(), (uint32_t)d.near.size(), &out), "nc_detector_mean");
     return out;
@@ -307,7 +394,7 @@ void NeuCor::window(float t0, float t1, int flags, std::vector<nc_event>& ev) {
     h2dBytes_ += ev.size() * sizeof(nc_event);
     d2hBytes_ += 16 + 8 * sizeof(uint64_t);
     // the rand() calls hidden in synapticPlasticity's short-circuit (NeuCor.cpp:752): only their number matters
-    for (uint64_t k = 0; k < hidden; k++) (void)rand();
+    if (hidden) { RandWindow rw; rw.skip(hidden); }
     lastStats_.fires += st.fires; lastStats_.deliveries += st.deliveries; lastStats_.loadsAccepted += st.loads_accepted;
     lastStats_.loadsDropped += st.loads_dropped; lastStats_.plasticityCalls += st.plasticity_calls; lastStats_.hiddenRand += st.hidden_rand_calls;
     lastStats_.neuronRuns += st.neuron_runs; lastStats_.activeVisits += st.active_visits;
@@ -329,10 +416,11 @@ float NeuCor::stepInternal(bool sweep) {  // NeuCor::run, NeuCor.cpp:583-617
     const std::size_t bgBegin = events_.size();
     {
         const int backgroundFirePeriod = std::max(1, static_cast<int>(600.0f / runSpeed));
+        RandWindow rw;  // the same draws rand() would return, without its per-call cost
         for (std::size_t i = 0; i < N; ++i) {
-            if (rand() % backgroundFirePeriod == 0) {
-                uint32_t n = (uint32_t)(rand() % N);
-                float t = randomUnit() * runSpeed;
+            if (rw.next() % backgroundFirePeriod == 0) {
+                uint32_t n = (uint32_t)(rw.next() % N);
+                float t = (static_cast<float>(rw.next()) / static_cast<float>(RAND_MAX)) * runSpeed;
                 events_.push_back(nc_event{n, currentTime + t, 2u, 0u});  // Neuron::scheduleFire, NeuCor.cpp:658-661
             }
         }

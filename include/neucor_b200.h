@@ -136,24 +136,31 @@ int nc_tape_end(nc_engine* e);
 int nc_snapshot(nc_engine* e);
 int nc_restore(nc_engine* e);
 /* Replays taped steps [first, first+count); ms_total = CUDA-event time of the whole region,
- * ms_pass1 / ms_pass2 = summed per-kernel times (may be NULL). */
+ * ms_pass1 / ms_pass2 / ms_exchange = summed per-launch times of the neuron pass, the synapse pass and the
+ * fire exchange (may be NULL; asking for them adds event records between the launches). */
 int nc_tape_replay(nc_engine* e, uint32_t first, uint32_t count, float* ms_total, float* ms_pass1, float* ms_pass2,
-                   uint64_t* hidden_rand_calls, nc_step_stats* stats_or_null);
+                   float* ms_exchange, uint64_t* hidden_rand_calls, nc_step_stats* stats_or_null);
 /* Number of kernel launches issued by this engine since creation. */
 uint64_t nc_launch_count(const nc_engine* e);
 
-/* Multi-GPU: engines of one process group exchange fire records through caller-provided
- * callbacks is NOT done here — the exchange buffer is exposed so that the host (NCCL via
- * torch.distributed, or ncclAllGather directly) can all-gather it between the two passes. */
-int nc_step_begin(nc_engine* e, float t0, float t1, int sweep, const nc_event* events, uint32_t n_events);
-/* Device pointer and byte size of this shard's fire-record block: [count u32, pad u32 x3, records...]. */
-int nc_exchange_buffer(nc_engine* e, void** dev_ptr, uint64_t* bytes);
-/* Device pointer where the gathered blocks of all `world` shards must be placed (world * bytes). */
-int nc_gather_buffer(nc_engine* e, void** dev_ptr, uint64_t* bytes);
-int nc_step_end(nc_engine* e, uint64_t* hidden_rand_calls, nc_step_stats* stats_or_null);
-/* world > 1: per-shard record counts and the record stride used when placing the gathered blocks. */
-int nc_step_end_counts(nc_engine* e, const uint32_t* counts, uint32_t stride, uint64_t* hidden_rand_calls,
-                       nc_step_stats* stats_or_null);
+/* Multi-GPU: the network is partitioned by neuron-ID range, one engine (process, GPU) per
+ * shard, each owning the synapses incoming to its neurons.  The only data that crosses shards is the window's
+ * fire records — there is nothing like it in the single-threaded reference; it replaces the shared
+ * address space through which Neuron::fire reaches its outSynapses (NeuCor.cpp:646-649).  Inside nc_step
+ * (and nc_tape_replay) the shards' record blocks are all-gathered between the neuron pass and the synapse
+ * pass, and the per-window counters (incl. the hidden rand() count) are summed over shards, so every
+ * shard's nc_step reports network-wide numbers.  Transport: an NCCL communicator owned by the engine
+ * (in-stream ncclAllGather over NVLink; libnccl is bound at run time) or a caller-provided all-gather. */
+typedef struct nc_comm_id { char internal[128]; } nc_comm_id; /* = ncclUniqueId */
+/* Rank 0 creates the id, the caller distributes it to all ranks (any out-of-band channel). */
+int nc_comm_unique_id(nc_comm_id* out);
+/* Collective over all ranks of the job: creates this engine's communicator (rank/world from nc_config). */
+int nc_comm_init(nc_engine* e, const nc_comm_id* id);
+/* Alternative transport: fn(ctx, send, recv, bytes) must all-gather `bytes` bytes from every rank's `send`
+ * into `recv` (rank-major) and return 0; the engine drains its stream before calling it.  Pointers are in the
+ * engine's memory space (device memory for the CUDA engine). */
+typedef int (*nc_allgather_fn)(void* ctx, const void* send, void* recv, uint64_t bytes);
+int nc_set_exchange(nc_engine* e, nc_allgather_fn fn, void* ctx);
 
 /* Self-test: the device replicas of glibc's powf / exp (the libm calls at NeuCor.cpp:672,678,695,710-711,741)
  * evaluated on host arrays, for bit-for-bit comparison against the host libm. x > 0 normal for powf. */

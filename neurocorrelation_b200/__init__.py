@@ -21,6 +21,8 @@ u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
 u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
 u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
 
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64)
+
 STAT_NAMES = ("fires", "deliveries", "loads_accepted", "loads_dropped", "plasticity_calls", "hidden_rand",
               "neuron_runs", "active_visits")
 
@@ -58,6 +60,11 @@ def load_host_library(path=None):
     L.nch_make_connections.argtypes = [vp]
     L.nch_import_network.argtypes = [vp, C.c_uint64, u64p, u32p, f32p, f32p, u8p, vp]
     L.nch_import_network_device.argtypes = [vp, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp]
+    L.nch_import_shard_device.argtypes = [vp, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp, C.c_float]
+    L.nch_set_shard.argtypes = [vp, C.c_int, C.c_int]
+    L.nch_set_comm_id.argtypes = [vp, C.c_char_p]
+    L.nch_set_exchange.argtypes = [vp, ALLGATHER_FN, vp]
+    L.nch_shard_info.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.nch_set_sweep_mean.argtypes = [vp, C.c_int]
     L.nch_set_inputs.argtypes = [vp, vp, C.c_uint, vp, vp]
     L.nch_set_rate.argtypes = [vp, C.c_uint, C.c_float]
@@ -134,6 +141,33 @@ class NeuCor:
         b = cls(0, device, library)
         b._ck(b.L.nch_import_network_device(b.h, int(N), int(S), d_rowptr, d_pre, d_weight, d_length, d_flag))
         return b
+
+    @classmethod
+    def from_device_shard(cls, N, S_local, d_rowptr, d_pre, d_weight, d_length, d_flag, rank, world, global_min_delay, device=0, library=None):
+        """This rank's rows [N*rank/world, N*(rank+1)/world) of an N-neuron network, already on `device` (local rowptr from 0)."""
+        b = cls(0, device, library)
+        b.set_shard(rank, world)
+        b._ck(b.L.nch_import_shard_device(b.h, int(N), int(S_local), d_rowptr, d_pre, d_weight, d_length, d_flag, float(global_min_delay)))
+        return b
+
+    # ---- multi-GPU: one process per shard; call before the first step ----
+    def set_shard(self, rank, world):
+        self._ck(self.L.nch_set_shard(self.h, int(rank), int(world)))
+
+    def set_comm_id(self, unique_id):
+        """128-byte NCCL unique id created by rank 0 (engine.Engine.comm_unique_id()) and distributed by the caller."""
+        self._ck(self.L.nch_set_comm_id(self.h, bytes(unique_id)))
+
+    def set_exchange(self, fn):
+        """fn(send_ptr, recv_ptr, nbytes) -> 0: caller-provided all-gather over the job's ranks (tests / other transports)."""
+        self._xchg = ALLGATHER_FN(lambda ctx, a, b, n: int(fn(a, b, n)))
+        self._ck(self.L.nch_set_exchange(self.h, self._xchg, None))
+
+    def shard(self):
+        """(row0, rows, synapses) of this process's shard (the whole network for world 1)."""
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.L.nch_shard_info(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
 
     def set_sweep_mean(self, on):
         """step() in sweep mode returns the mean potential (a device->host read of every potential) only when on."""
@@ -265,13 +299,17 @@ class NeuCor:
         return out
 
     def read_neurons(self):
-        N, _ = self.counts()
+        """State of this shard's neurons (all neurons for world 1), in ID order from shard()[0]."""
+        self.finalize()
+        _, N, _ = self.shard()
         a = [np.zeros(max(N, 1), np.float32) for _ in range(4)]
         self._ck(self.L.nch_read_neurons(self.h, *a))
         return dict(pot=a[0][:N], act=a[1][:N], lastFire=a[2][:N], lastRan=a[3][:N])
 
     def read_synapses(self):
-        _, S = self.counts()
+        """State of this shard's synapses in CSR order (rows = its target neurons)."""
+        self.finalize()
+        _, _, S = self.shard()
         a = [np.zeros(max(S, 1), np.float32) for _ in range(5)]
         self._ck(self.L.nch_read_synapses(self.h, *a))
         return dict(weight=a[0][:S], arrive=a[1][:S], depol=a[2][:S], lastArr=a[3][:S], lastStart=a[4][:S])

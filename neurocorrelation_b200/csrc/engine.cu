@@ -10,9 +10,9 @@
 //       ordered accumulation over active slots in ascending presynaptic ID, passive decay, threshold /
 //       refractory check, AP waveform, activity.  Emits fire records (warp-aggregated append) and
 //       marks cleared slots in place.  Never touches weights.
-//   exchange     — fire records of all shards are made visible to every shard (NCCL all-gather by the
-//       host between nc_step_begin and nc_step_end; a no-op for world = 1), then k_index_build turns
-//       them into a per-neuron lookup (bitmask + linked records).
+//   exchange     — fire records of all shards are made visible to every shard (in-stream NCCL all-gather of
+//       the shards' record blocks; a no-op for world = 1), then k_index_build turns them into a per-neuron
+//       lookup (bitmask + linked records).
 //   synapse pass (k_synapse_pass) — one warp per row, one lane per slot: tests "did my presynaptic
 //       neuron fire" against the bitmask (the pull gather), and resolves each eventful slot's
 //       operations — load (Synapse::fire, NeuCor.cpp:727-738), clear (NeuCor.cpp:697), post-fire
@@ -22,6 +22,7 @@
 // Arithmetic mirrors the reference's float/double typing operator by operator with explicit-rounding
 // intrinsics (no FMA contraction; built with -fmad=false) and glibc-exact powf/exp (glibc_math.cuh).
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -286,22 +287,45 @@ __global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32, 4) k_neuron_pass(View
 // ------------------------------------------------------------------------------------------------
 // Fire index (bitmask + per-neuron record lists) over the gathered records of all shards
 // ------------------------------------------------------------------------------------------------
+// Block b of the gathered buffer starts with its header unit {count, overflow}; record i of block b is unit
+// b*gStride + 1 + i, and that unit index is what head[] / next[] hold.
+__device__ __forceinline__ uint32_t block_count(const View& v, const StepArgs& s, uint32_t b) {
+    const uint32_t* hdr = reinterpret_cast<const uint32_t*>(v.gRecs + (uint64_t)b * s.gStride);
+    return min(hdr[0], s.gStride - 1u);
+}
 __global__ void k_index_build(View v, StepArgs s) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t b = blockIdx.y;
-    if (b >= s.world || i >= s.counts[b]) return;
-    uint32_t idx = b * s.gStride + i;
-    uint32_t nrn = v.gRecs[idx].neuron;
-    v.next[idx] = atomicExch(&v.head[nrn], (int32_t)idx);
-    atomicOr(&v.mask[nrn >> 5], 1u << (nrn & 31u));
+    const uint32_t b = blockIdx.y;
+    const uint32_t n = block_count(v, s, b);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t idx = b * s.gStride + 1u + i;
+        const uint32_t nrn = v.gRecs[idx].neuron;
+        v.next[idx] = atomicExch(&v.head[nrn], (int32_t)idx);
+        atomicOr(&v.mask[nrn >> 5], 1u << (nrn & 31u));
+    }
 }
 __global__ void k_index_reset(View v, StepArgs s) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t b = blockIdx.y;
-    if (b >= s.world || i >= s.counts[b]) return;
-    uint32_t nrn = v.gRecs[b * s.gStride + i].neuron;
-    v.head[nrn] = -1;
-    v.mask[nrn >> 5] = 0u;
+    const uint32_t b = blockIdx.y;
+    const uint32_t n = block_count(v, s, b);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t nrn = v.gRecs[b * s.gStride + 1u + i].neuron;
+        v.head[nrn] = -1;
+        v.mask[nrn >> 5] = 0u;
+    }
+}
+// End of a window: publish (or, for replay, accumulate) the shard's counters and its exchange header into `out`
+// (10 x u64: the 8 nc_step_stats counters, fire count, overflow flag), then clear both for the next window.
+__global__ void k_finish_step(View v, unsigned long long* out, int accumulate) {
+    const uint32_t i = threadIdx.x;
+    if (i < 8) {
+        unsigned long long x = v.stats[i];
+        out[i] = accumulate ? out[i] + x : x;
+        v.stats[i] = 0ull;
+    } else if (i == 8) {
+        out[8] = v.localHdr[0];
+        out[9] = accumulate ? (out[9] | v.localHdr[1]) : v.localHdr[1];
+    }
+    __syncwarp();
+    if (i == 8) { v.localHdr[0] = 0u; v.localHdr[1] = 0u; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -497,7 +521,18 @@ __global__ void k_synapse_pots(View v, float now, float* prePot, float* postPot)
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 
-struct TapeStep { float t0, t1; int sweep; uint64_t evOff; uint32_t nEv; };
+struct TapeStep { float t0, t1; int sweep; uint64_t evOff; uint32_t nEv; uint32_t units; };
+
+// NCCL is bound at run time (dlopen) so that single-GPU users need no NCCL at all; only the five entry points below are used.
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, nc_comm_id, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
 
 struct nc_engine {
     nc_config cfg;
@@ -509,17 +544,22 @@ struct nc_engine {
     float* dDelay = nullptr;
     nc_event* dEv = nullptr; uint32_t evCap = 0;
     nc_event* hEvPinned = nullptr; uint32_t hEvCap = 0;
-    unsigned long long* hStats = nullptr;  // pinned, 8 + 2
-    uint32_t* hHdr = nullptr;              // pinned, 4
-    FireRec* dGather = nullptr;            // world * fireCap (own) or bound by the host
-    bool gatherBound = false;
+    // per-window result block: 10 x u64 per shard (8 counters, fire count, overflow flag)
+    unsigned long long* dOut = nullptr;     // this shard's block
+    unsigned long long* dOutAll = nullptr;  // world blocks (world > 1)
+    unsigned long long* hOut = nullptr;     // pinned, world blocks
+    uint32_t* hHdrAll = nullptr;            // pinned, world x 4: gathered exchange headers
+    FireRec* dGather = nullptr;             // world blocks of (fireCap + 1) units (world > 1)
+    // exchange transport (world > 1): NCCL communicator or caller-provided all-gather
+    void* comm = nullptr;
+    nc_allgather_fn xchgFn = nullptr; void* xchgCtx = nullptr;
+    uint32_t xchgUnits = 1u + 1024u;        // units per shard moved by the fire exchange; grows on demand
+    uint32_t lastCounts[NC_MAX_WORLD] = {0}; uint32_t lastStride = 0;
     float lr = 1.0f, preF = 0.13f, postF = 0.30f, preD = 0.75f, postD = 0.65f;
     float minDelay = INFINITY;
     uint32_t candCap = 512, grid1 = 0, grid2 = 0, maskWordsSmem = 0;
     size_t smem1 = 0, smem2 = 0;
     uint64_t launches = 0;
-    // in-flight step (nc_step_begin .. nc_step_end)
-    StepArgs cur; bool inStep = false;
     // tape
     bool taping = false; std::vector<TapeStep> tape; nc_event* dTape = nullptr; uint64_t tapeCap = 0, tapeUsed = 0; uint32_t tapeMaxSteps = 0;
     // snapshot
@@ -565,8 +605,11 @@ extern "C" int nc_create(const nc_config* cfg, nc_engine** out) {
     if (ce == cudaSuccess) ce = cudaMemcpyToSymbol(d_POWF_LOG2_TAB, NC_POWF_LOG2_TAB, sizeof(NC_POWF_LOG2_TAB));
     if (ce == cudaSuccess) ce = cudaMemcpyToSymbol(d_EXP2F_TAB, NC_EXP2F_TAB, sizeof(NC_EXP2F_TAB));
     if (ce == cudaSuccess) ce = cudaMemcpyToSymbol(d_EXP_TAB, NC_EXP_TAB, sizeof(NC_EXP_TAB));
-    if (ce == cudaSuccess) ce = cudaMallocHost(&e->hStats, 16 * sizeof(unsigned long long));
-    if (ce == cudaSuccess) ce = cudaMallocHost(&e->hHdr, 4 * sizeof(uint32_t));
+    if (ce == cudaSuccess) ce = cudaMallocHost(&e->hOut, (size_t)cfg->world * 10 * sizeof(unsigned long long));
+    if (ce == cudaSuccess) ce = cudaMallocHost(&e->hHdrAll, (size_t)cfg->world * 4 * sizeof(uint32_t));
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->dOut, 10 * sizeof(unsigned long long));
+    if (ce == cudaSuccess) ce = cudaMemset(e->dOut, 0, 10 * sizeof(unsigned long long));
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->dOutAll, (size_t)cfg->world * 10 * sizeof(unsigned long long));
     if (ce == cudaSuccess) ce = cudaMalloc(&e->v.stats, 8 * sizeof(unsigned long long));
     if (ce == cudaSuccess) ce = cudaMemset(e->v.stats, 0, 8 * sizeof(unsigned long long));
     cudaDeviceProp prop;
@@ -584,7 +627,7 @@ static void free_all(nc_engine* e) {
     cudaFree(v.lastStart); cudaFree(e->dDelay); cudaFree(v.potAct); cudaFree(v.lastRan); cudaFree(v.lastFire); cudaFree(v.lfStart);
     cudaFree(v.actStart); cudaFree(v.firings); cudaFree(v.localHdr); cudaFree(v.head); cudaFree(v.next); cudaFree(v.mask); cudaFree(v.evMask); cudaFree(v.candBits);
     cudaFree(v.spillA); cudaFree(v.spillD); cudaFree(v.spillJ);
-    if (!e->gatherBound) cudaFree(e->dGather);
+    cudaFree(e->dGather);
     cudaFree(e->dEv); cudaFree(e->dTape);
     auto& s = e->snap;
     cudaFree(s.arrive); cudaFree(s.depol); cudaFree(s.weight); cudaFree(s.lastArr); cudaFree(s.lastStart); cudaFree(s.lastRan);
@@ -596,8 +639,9 @@ extern "C" void nc_destroy(nc_engine* e) {
     cudaSetDevice(e->cfg.device);
     cudaStreamSynchronize(e->stream);
     free_all(e);
-    cudaFree(e->v.stats);
-    cudaFreeHost(e->hStats); cudaFreeHost(e->hHdr); cudaFreeHost(e->hEvPinned);
+    cudaFree(e->v.stats); cudaFree(e->dOut); cudaFree(e->dOutAll);
+    cudaFreeHost(e->hOut); cudaFreeHost(e->hHdrAll); cudaFreeHost(e->hEvPinned);
+    if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     if (e->ownStream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -651,13 +695,14 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
     CK(cudaMalloc(&e->dDelay, S1 * 4)); v.delay = e->dDelay;
     CK(cudaMalloc(&v.potAct, N1 * 8)); CK(cudaMalloc(&v.lastRan, N1 * 4)); CK(cudaMalloc(&v.lastFire, N1 * 4));
     CK(cudaMalloc(&v.lfStart, N1 * 4)); CK(cudaMalloc(&v.actStart, N1 * 4)); CK(cudaMalloc(&v.firings, N1 * 4));
-    v.fireCap = e->cfg.fire_capacity ? e->cfg.fire_capacity : (uint32_t)std::min<uint64_t>(4 * nRows + 1024, 1u << 28);
-    CK(cudaMalloc(&v.localHdr, 16 + (uint64_t)v.fireCap * sizeof(FireRec)));
-    v.localRecs = reinterpret_cast<FireRec*>(reinterpret_cast<unsigned char*>(v.localHdr) + 16);
+    v.fireCap = e->cfg.fire_capacity ? e->cfg.fire_capacity : (uint32_t)std::min<uint64_t>(4 * nRows + 1024, (1u << 28) / (uint32_t)e->cfg.world);
+    const uint64_t blockUnits = (uint64_t)v.fireCap + 1;  // header unit + records
+    CK(cudaMalloc(&v.localHdr, blockUnits * sizeof(FireRec)));
+    v.localRecs = reinterpret_cast<FireRec*>(v.localHdr) + 1;
     CK(cudaMemsetAsync(v.localHdr, 0, 16, e->stream));
-    if (e->cfg.world > 1) { CK(cudaMalloc(&e->dGather, (uint64_t)e->cfg.world * v.fireCap * sizeof(FireRec))); v.gRecs = e->dGather; }
-    else v.gRecs = v.localRecs;
-    CK(cudaMalloc(&v.head, G1 * 4)); CK(cudaMalloc(&v.next, (uint64_t)e->cfg.world * v.fireCap * 4));
+    if (e->cfg.world > 1) { CK(cudaMalloc(&e->dGather, (uint64_t)e->cfg.world * blockUnits * sizeof(FireRec))); v.gRecs = e->dGather; }
+    else v.gRecs = reinterpret_cast<FireRec*>(v.localHdr);
+    CK(cudaMalloc(&v.head, G1 * 4)); CK(cudaMalloc(&v.next, (uint64_t)e->cfg.world * blockUnits * 4));
     CK(cudaMalloc(&v.mask, ((G1 + 31) / 32) * 4));
     CK(cudaMemsetAsync(v.mask, 0, ((G1 + 31) / 32) * 4, e->stream));
     CK(cudaMalloc(&v.evMask, ((N1 + 31) / 32) * 4));
@@ -786,7 +831,8 @@ static void fill_args(nc_engine* e, StepArgs& a, float t0, float t1, int sweep, 
     memset(&a, 0, sizeof(a));
     a.t0 = t0; a.t1 = t1; a.sweep = sweep;
     a.lr = e->lr; a.preFactor = e->preF; a.postFactor = e->postF; a.preDecay = e->preD; a.postDecay = e->postD;
-    a.ev = dEv; a.nEv = nEv; a.candCap = e->candCap; a.gStride = e->v.fireCap; a.world = (uint32_t)e->cfg.world;
+    a.ev = dEv; a.nEv = nEv; a.candCap = e->candCap; a.world = (uint32_t)e->cfg.world;
+    a.gStride = e->cfg.world == 1 ? e->v.fireCap + 1u : e->xchgUnits;
 }
 
 static int launch_pass1(nc_engine* e, const StepArgs& a) {
@@ -797,16 +843,16 @@ static int launch_pass1(nc_engine* e, const StepArgs& a) {
     CK(cudaGetLastError());
     return NC_OK;
 }
-// `a.counts` / `a.gStride` must be final. Launches index build, synapse pass, index reset, header reset.
-static int launch_pass2(nc_engine* e, const StepArgs& a) {
-    uint32_t maxc = 0;
-    for (uint32_t b = 0; b < a.world; b++) maxc = std::max(maxc, a.counts[b]);
-    dim3 g((maxc + 255) / 256, a.world);
-    if (maxc) { k_index_build<<<g, 256, 0, e->stream>>>(e->v, a); e->launches++; }
+// Index build over the gathered blocks (counts are read from the block headers on the device), synapse pass, index reset,
+// and the end-of-window kernel that publishes the counters + exchange header into dOut and clears them.
+static int launch_pass2(nc_engine* e, const StepArgs& a, uint32_t expectMax, int accumulate) {
+    const uint32_t gx = std::min<uint32_t>(std::max<uint32_t>((expectMax + 255u) / 256u, 1u), 1024u);
+    dim3 g(gx, a.world);
+    k_index_build<<<g, 256, 0, e->stream>>>(e->v, a);
     k_synapse_pass<<<e->grid2, NC_P2_THREADS, e->smem2, e->stream>>>(e->v, a, e->maskWordsSmem);
-    e->launches++;
-    if (maxc) { k_index_reset<<<g, 256, 0, e->stream>>>(e->v, a); e->launches++; }
-    CK(cudaMemsetAsync(e->v.localHdr, 0, 16, e->stream));
+    k_index_reset<<<g, 256, 0, e->stream>>>(e->v, a);
+    k_finish_step<<<1, 32, 0, e->stream>>>(e->v, e->dOut, accumulate);
+    e->launches += 4;
     CK(cudaGetLastError());
     return NC_OK;
 }
@@ -816,105 +862,159 @@ static int upload_events(nc_engine* e, const nc_event* events, uint32_t nEv, con
     if (!nEv) return NC_OK;
     for (uint32_t i = 1; i < nEv; i++)
         if (events[i].neuron < events[i - 1].neuron) return fail(e, NC_ERR_INVALID, "step: events must be sorted by neuron");
+    if (nEv > e->hEvCap) { cudaFreeHost(e->hEvPinned); e->hEvCap = nEv * 2 + 1024; CK(cudaMallocHost(&e->hEvPinned, (size_t)e->hEvCap * sizeof(nc_event))); }
+    memcpy(e->hEvPinned, events, (size_t)nEv * sizeof(nc_event));
     if (e->taping) {
         if (e->tapeUsed + nEv > e->tapeCap) return fail(e, NC_ERR_CAPACITY, "tape: event capacity exceeded");
         nc_event* dst = e->dTape + e->tapeUsed;
-        if (nEv > e->hEvCap) { cudaFreeHost(e->hEvPinned); e->hEvCap = nEv * 2 + 1024; CK(cudaMallocHost(&e->hEvPinned, (size_t)e->hEvCap * sizeof(nc_event))); }
-        memcpy(e->hEvPinned, events, (size_t)nEv * sizeof(nc_event));
         CK(cudaMemcpyAsync(dst, e->hEvPinned, (size_t)nEv * sizeof(nc_event), cudaMemcpyHostToDevice, e->stream));
         *dOut = dst;
         return NC_OK;
     }
     if (nEv > e->evCap) { cudaFree(e->dEv); e->evCap = nEv * 2 + 1024; CK(cudaMalloc(&e->dEv, (size_t)e->evCap * sizeof(nc_event))); }
-    if (nEv > e->hEvCap) { cudaFreeHost(e->hEvPinned); e->hEvCap = nEv * 2 + 1024; CK(cudaMallocHost(&e->hEvPinned, (size_t)e->hEvCap * sizeof(nc_event))); }
-    memcpy(e->hEvPinned, events, (size_t)nEv * sizeof(nc_event));
     CK(cudaMemcpyAsync(e->dEv, e->hEvPinned, (size_t)nEv * sizeof(nc_event), cudaMemcpyHostToDevice, e->stream));
     *dOut = e->dEv;
     return NC_OK;
 }
 
-static int finish_counters(nc_engine* e, uint64_t* hidden, nc_step_stats* st) {
-    CK(cudaMemcpyAsync(e->hStats, e->v.stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaMemsetAsync(e->v.stats, 0, 8 * sizeof(unsigned long long), e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    if (hidden) *hidden = e->hStats[5];
-    if (st) {
-        st->fires = e->hStats[0]; st->deliveries = e->hStats[1]; st->loads_accepted = e->hStats[2]; st->loads_dropped = e->hStats[3];
-        st->plasticity_calls = e->hStats[4]; st->hidden_rand_calls = e->hStats[5]; st->neuron_runs = e->hStats[6]; st->active_visits = e->hStats[7];
+// ---- exchange transport (world > 1) ----
+static bool nccl_load(std::string& err) {
+    if (g_nccl.lib) return true;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { err = std::string("NCCL not loadable: ") + dlerror(); return false; }
+    NcclApi a;
+    a.lib = lib;
+    *(void**)&a.GetUniqueId = dlsym(lib, "ncclGetUniqueId");
+    *(void**)&a.CommInitRank = dlsym(lib, "ncclCommInitRank");
+    *(void**)&a.AllGather = dlsym(lib, "ncclAllGather");
+    *(void**)&a.CommDestroy = dlsym(lib, "ncclCommDestroy");
+    *(void**)&a.GetErrorString = dlsym(lib, "ncclGetErrorString");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.AllGather || !a.CommDestroy || !a.GetErrorString) { err = "NCCL: missing symbols"; return false; }
+    g_nccl = a;
+    return true;
+}
+extern "C" int nc_comm_unique_id(nc_comm_id* out) {
+    if (!out) { g_err = "nc_comm_unique_id: null argument"; return NC_ERR_INVALID; }
+    if (!nccl_load(g_err)) return NC_ERR_NO_DEVICE;
+    int rc = g_nccl.GetUniqueId(out);
+    if (rc) { g_err = std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(rc); return NC_ERR_CUDA; }
+    return NC_OK;
+}
+extern "C" int nc_comm_init(nc_engine* e, const nc_comm_id* id) {
+    if (!id) return fail(e, NC_ERR_INVALID, "nc_comm_init: null id");
+    if (e->comm) return fail(e, NC_ERR_STATE, "nc_comm_init: communicator already initialised");
+    if (!nccl_load(e->err)) return NC_ERR_NO_DEVICE;
+    cudaSetDevice(e->cfg.device);
+    int rc = g_nccl.CommInitRank(&e->comm, e->cfg.world, *id, e->cfg.rank);
+    if (rc) { e->comm = nullptr; return fail(e, NC_ERR_CUDA, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc)); }
+    return NC_OK;
+}
+extern "C" int nc_set_exchange(nc_engine* e, nc_allgather_fn fn, void* ctx) {
+    e->xchgFn = fn; e->xchgCtx = ctx;
+    return NC_OK;
+}
+// all-gather of `bytes` per shard, stream-ordered with NCCL; with a caller-provided transport the stream is drained first
+static int exchange(nc_engine* e, const void* send, void* recv, size_t bytes) {
+    if (e->comm) {
+        int rc = g_nccl.AllGather(send, recv, bytes, /*ncclChar*/ 0, e->comm, e->stream);
+        if (rc) return fail(e, NC_ERR_CUDA, std::string("ncclAllGather: ") + g_nccl.GetErrorString(rc));
+        return NC_OK;
     }
+    if (e->xchgFn) {
+        CK(cudaStreamSynchronize(e->stream));
+        if (e->xchgFn(e->xchgCtx, send, recv, (uint64_t)bytes)) return fail(e, NC_ERR_CUDA, "exchange: the caller's all-gather failed");
+        return NC_OK;
+    }
+    return fail(e, NC_ERR_STATE, "exchange: world > 1 needs nc_comm_init or nc_set_exchange");
+}
+
+static void sum_out(nc_engine* e, uint64_t* hidden, nc_step_stats* st) {
+    unsigned long long t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int b = 0; b < e->cfg.world; b++)
+        for (int i = 0; i < 8; i++) t[i] += e->hOut[b * 10 + i];
+    if (hidden) *hidden = t[5];
+    if (st) {
+        st->fires = t[0]; st->deliveries = t[1]; st->loads_accepted = t[2]; st->loads_dropped = t[3];
+        st->plasticity_calls = t[4]; st->hidden_rand_calls = t[5]; st->neuron_runs = t[6]; st->active_visits = t[7];
+    }
+}
+// Reads the per-window result blocks (own, or all shards' after an all-gather) and reports the network-wide counters.
+static int finish_counters(nc_engine* e, uint64_t* hidden, nc_step_stats* st) {
+    const int W = e->cfg.world;
+    if (W == 1) {
+        CK(cudaMemcpyAsync(e->hOut, e->dOut, 10 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    } else {
+        int rc = exchange(e, e->dOut, e->dOutAll, 10 * sizeof(unsigned long long));
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(e->hOut, e->dOutAll, (size_t)W * 10 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    sum_out(e, hidden, st);
+    for (int b = 0; b < W; b++)
+        if (e->hOut[b * 10 + 9]) return fail(e, NC_ERR_CAPACITY, "step: fire-record capacity exceeded (raise nc_config.fire_capacity)");
     return NC_OK;
 }
 
-extern "C" int nc_step_begin(nc_engine* e, float t0, float t1, int sweep, const nc_event* events, uint32_t nEv) {
-    if (e->inStep) return fail(e, NC_ERR_STATE, "nc_step_begin: previous step not ended");
+// The fire exchange of a live window (world > 1): all-gather of the first xchgUnits units of every shard's block, then a
+// look at the gathered headers; when a shard fired more than that the size is raised and the all-gather repeated.
+static int exchange_fires(nc_engine* e, StepArgs& a, uint32_t* maxCount) {
+    const int W = e->cfg.world;
+    for (;;) {
+        int rc = exchange(e, e->v.localHdr, e->dGather, (size_t)e->xchgUnits * sizeof(FireRec));
+        if (rc) return rc;
+        CK(cudaMemcpy2DAsync(e->hHdrAll, 16, e->dGather, (size_t)e->xchgUnits * sizeof(FireRec), 16, W, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        uint32_t mx = 0;
+        for (int b = 0; b < W; b++) {
+            if (e->hHdrAll[4 * b + 1]) return fail(e, NC_ERR_CAPACITY, "step: fire-record capacity exceeded (raise nc_config.fire_capacity)");
+            mx = std::max(mx, e->hHdrAll[4 * b]);
+        }
+        if (mx + 1u <= e->xchgUnits) {
+            for (int b = 0; b < W; b++) e->lastCounts[b] = e->hHdrAll[4 * b];
+            e->lastStride = e->xchgUnits;
+            a.gStride = e->xchgUnits;
+            *maxCount = mx;
+            return NC_OK;
+        }
+        uint64_t want = 1;
+        while (want < 2ull * mx) want <<= 1;
+        e->xchgUnits = (uint32_t)std::min<uint64_t>(want + 1, (uint64_t)e->v.fireCap + 1);
+    }
+}
+
+extern "C" int nc_step(nc_engine* e, float t0, float t1, int sweep, const nc_event* events, uint32_t nEv, uint64_t* hidden,
+                       nc_step_stats* st) {
     int rc = check_window(e, t0, t1);
     if (rc) return rc;
     cudaSetDevice(e->cfg.device);
     const nc_event* dEv = nullptr;
     rc = upload_events(e, events, nEv, &dEv);
     if (rc) return rc;
+    if (e->taping && e->tape.size() >= e->tapeMaxSteps) return fail(e, NC_ERR_CAPACITY, "tape: step capacity exceeded");
+    StepArgs a;
+    fill_args(e, a, t0, t1, sweep, dEv, nEv);
+    rc = launch_pass1(e, a);
+    if (rc) return rc;
+    uint32_t expect = std::max<uint32_t>(e->lastCounts[0], 256u);
+    if (e->cfg.world > 1) {
+        rc = exchange_fires(e, a, &expect);
+        if (rc) return rc;
+    }
     if (e->taping) {
-        if (e->tape.size() >= e->tapeMaxSteps) return fail(e, NC_ERR_CAPACITY, "tape: step capacity exceeded");
-        e->tape.push_back({t0, t1, sweep, e->tapeUsed, nEv});
+        e->tape.push_back({t0, t1, sweep, e->tapeUsed, nEv, a.gStride});
         e->tapeUsed += nEv;
     }
-    fill_args(e, e->cur, t0, t1, sweep, dEv, nEv);
-    rc = launch_pass1(e, e->cur);
+    rc = launch_pass2(e, a, expect, 0);
     if (rc) return rc;
-    // fire count of this shard (needed by the host to size the exchange and by the index kernels)
-    CK(cudaMemcpyAsync(e->hHdr, e->v.localHdr, 16, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    if (e->hHdr[1]) return fail(e, NC_ERR_CAPACITY, "step: fire-record capacity exceeded (raise nc_config.fire_capacity)");
-    e->inStep = true;
-    return NC_OK;
-}
-
-extern "C" int nc_exchange_buffer(nc_engine* e, void** p, uint64_t* bytes) {
-    if (!e->uploaded) return NC_ERR_STATE;
-    *p = e->v.localRecs;
-    *bytes = (uint64_t)e->hHdr[0] * sizeof(FireRec);
-    return NC_OK;
-}
-extern "C" int nc_gather_buffer(nc_engine* e, void** p, uint64_t* bytes) {
-    if (!e->uploaded) return NC_ERR_STATE;
-    *p = (void*)e->v.gRecs;
-    *bytes = (uint64_t)e->cfg.world * e->v.fireCap * sizeof(FireRec);
-    return NC_OK;
-}
-// For world > 1 the host passes the per-shard record counts and the record stride it used when placing the
-// gathered blocks into nc_gather_buffer (counts == NULL: world 1).
-extern "C" int nc_step_end_counts(nc_engine* e, const uint32_t* counts, uint32_t stride, uint64_t* hidden, nc_step_stats* st) {
-    if (!e->inStep) return fail(e, NC_ERR_STATE, "nc_step_end: no step in flight");
-    cudaSetDevice(e->cfg.device);
-    e->inStep = false;
-    if (e->cfg.world == 1) { e->cur.counts[0] = e->hHdr[0]; e->cur.gStride = e->v.fireCap; }
-    else {
-        if (!counts) return fail(e, NC_ERR_INVALID, "nc_step_end: counts required for world > 1");
-        for (int b = 0; b < e->cfg.world; b++) {
-            if (counts[b] > stride) return fail(e, NC_ERR_INVALID, "nc_step_end: count exceeds stride");
-            e->cur.counts[b] = counts[b];
-        }
-        if ((uint64_t)stride * e->cfg.world > (uint64_t)e->v.fireCap * e->cfg.world) return fail(e, NC_ERR_INVALID, "nc_step_end: stride too large");
-        e->cur.gStride = stride;
-    }
-    int rc = launch_pass2(e, e->cur);
-    if (rc) return rc;
-    return finish_counters(e, hidden, st);
-}
-extern "C" int nc_step_end(nc_engine* e, uint64_t* hidden, nc_step_stats* st) { return nc_step_end_counts(e, nullptr, 0, hidden, st); }
-
-extern "C" int nc_step(nc_engine* e, float t0, float t1, int sweep, const nc_event* events, uint32_t nEv, uint64_t* hidden,
-                       nc_step_stats* st) {
-    if (e->cfg.world != 1) return fail(e, NC_ERR_STATE, "nc_step: sharded engines use nc_step_begin / exchange / nc_step_end");
-    int rc = nc_step_begin(e, t0, t1, sweep, events, nEv);
-    if (rc) return rc;
-    return nc_step_end(e, hidden, st);
+    rc = finish_counters(e, hidden, st);
+    if (e->cfg.world == 1) { e->lastCounts[0] = (uint32_t)std::min<unsigned long long>(e->hOut[8], e->v.fireCap); e->lastStride = e->v.fireCap + 1u; }
+    return rc;
 }
 
 extern "C" int nc_run_neurons(nc_engine* e, float now, const uint32_t* ids, uint32_t nIds, uint64_t* hidden, nc_step_stats* st) {
     if (e->cfg.world != 1) return fail(e, NC_ERR_STATE, "nc_run_neurons: single-shard engines only");
     if (!e->uploaded) return fail(e, NC_ERR_STATE, "nc_run_neurons: no network uploaded");
-    if (e->inStep) return fail(e, NC_ERR_STATE, "nc_run_neurons: a step is in flight");
     cudaSetDevice(e->cfg.device);
     uint32_t* dIds = nullptr;
     if (ids) {
@@ -930,14 +1030,9 @@ extern "C" int nc_run_neurons(nc_engine* e, float now, const uint32_t* ids, uint
     fill_args(e, a, now, now, NC_SWEEP_END, nullptr, 0);
     a.subset = dIds; a.nSubset = nIds;
     int rc = launch_pass1(e, a);
-    if (!rc) {
-        cudaError_t ce = cudaMemcpyAsync(e->hHdr, e->v.localHdr, 16, cudaMemcpyDeviceToHost, e->stream);
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
-        if (ce != cudaSuccess) { e->err = cudaGetErrorString(ce); rc = NC_ERR_CUDA; }
-    }
-    if (!rc && e->hHdr[1]) rc = fail(e, NC_ERR_CAPACITY, "nc_run_neurons: fire-record capacity exceeded");
-    if (!rc) { a.counts[0] = e->hHdr[0]; e->cur = a; rc = launch_pass2(e, a); }
+    if (!rc) rc = launch_pass2(e, a, std::max<uint32_t>(e->lastCounts[0], 256u), 0);
     if (!rc) rc = finish_counters(e, hidden, st);
+    if (!rc) { e->lastCounts[0] = (uint32_t)std::min<unsigned long long>(e->hOut[8], e->v.fireCap); e->lastStride = e->v.fireCap + 1u; }
     cudaFree(dIds);
     return rc;
 }
@@ -970,10 +1065,10 @@ extern "C" int nc_read_fires(nc_engine* e, uint32_t capacity, uint32_t* neuron, 
     uint32_t total = 0;
     std::vector<FireRec> tmp;
     for (uint32_t b = 0; b < (uint32_t)e->cfg.world; b++) {
-        uint32_t c = e->cur.counts[b];
+        uint32_t c = e->lastCounts[b];
         if (!c) continue;
         tmp.resize(c);
-        CK(cudaMemcpy(tmp.data(), e->v.gRecs + (uint64_t)b * e->cur.gStride, (uint64_t)c * sizeof(FireRec), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(tmp.data(), e->v.gRecs + (uint64_t)b * e->lastStride + 1, (uint64_t)c * sizeof(FireRec), cudaMemcpyDeviceToHost));
         for (uint32_t i = 0; i < c; i++, total++)
             if (total < capacity) { if (neuron) neuron[total] = tmp[i].neuron; if (time) time[total] = tmp[i].time; }
     }
@@ -1061,81 +1156,66 @@ extern "C" int nc_restore(nc_engine* e) {
     return snap_all(e, false);
 }
 
-// Device-side copy of the shard's fire count into a StepArgs-free path is avoided by reading the header
-// in the index kernels through a second, count-agnostic pair of kernels used only by replay.
-__global__ void k_index_build_dev(View v, StepArgs s) {
-    uint32_t n = min(v.localHdr[0], v.fireCap);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        uint32_t nrn = v.gRecs[i].neuron;
-        v.next[i] = atomicExch(&v.head[nrn], (int32_t)i);
-        atomicOr(&v.mask[nrn >> 5], 1u << (nrn & 31u));
-    }
-}
-__global__ void k_index_reset_dev(View v, StepArgs s) {
-    uint32_t n = min(v.localHdr[0], v.fireCap);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        uint32_t nrn = v.gRecs[i].neuron;
-        v.head[nrn] = -1;
-        v.mask[nrn >> 5] = 0u;
-    }
-}
-__global__ void k_hdr_reset(View v, uint32_t* overflowAccum) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        if (v.localHdr[1]) *overflowAccum = 1u;
-        v.localHdr[0] = 0u; v.localHdr[1] = 0u;
-    }
-}
-
-extern "C" int nc_tape_replay(nc_engine* e, uint32_t first, uint32_t count, float* msTotal, float* msP1, float* msP2,
+// Replays taped windows back to back with no host<->device traffic and no host synchronisation inside the timed region:
+// the index kernels read the fire counts from the block headers on the device, and for world > 1 the fire exchange is an
+// in-stream NCCL all-gather of the size the live run settled on for that window.
+extern "C" int nc_tape_replay(nc_engine* e, uint32_t first, uint32_t count, float* msTotal, float* msP1, float* msP2, float* msXchg,
                               uint64_t* hidden, nc_step_stats* st) {
-    if (e->cfg.world != 1) return fail(e, NC_ERR_STATE, "replay: single-shard engines only");
     if ((uint64_t)first + count > e->tape.size()) return fail(e, NC_ERR_INVALID, "replay: step range outside the tape");
+    if (e->cfg.world > 1 && !e->comm) return fail(e, NC_ERR_STATE, "replay: world > 1 needs the NCCL communicator (nc_comm_init)");
     cudaSetDevice(e->cfg.device);
-    uint32_t* dOvf; CK(cudaMalloc(&dOvf, 4)); CK(cudaMemsetAsync(dOvf, 0, 4, e->stream));
     CK(cudaMemsetAsync(e->v.stats, 0, 8 * sizeof(unsigned long long), e->stream));
-    const bool perKernel = msP1 || msP2;
+    CK(cudaMemsetAsync(e->dOut, 0, 10 * sizeof(unsigned long long), e->stream));
+    const bool perKernel = msP1 || msP2 || msXchg;
     std::vector<cudaEvent_t> evs;
-    if (perKernel) { evs.resize((size_t)count * 4); for (auto& x : evs) CK(cudaEventCreate(&x)); }
+    if (perKernel) { evs.resize((size_t)count * 5); for (auto& x : evs) CK(cudaEventCreate(&x)); }
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    const uint32_t idxGrid = (uint32_t)std::min<uint64_t>(std::max<uint64_t>((e->v.nRows / 64 + 255) / 256, 1), 1024);
+    const uint32_t gx = (uint32_t)std::min<uint64_t>(std::max<uint64_t>((e->v.nRows / 64 + 255) / 256, 1), 1024);
     CK(cudaEventRecord(e0, e->stream));
     for (uint32_t k = 0; k < count; k++) {
         const TapeStep& ts = e->tape[first + k];
         StepArgs a;
         fill_args(e, a, ts.t0, ts.t1, ts.sweep, e->dTape + ts.evOff, ts.nEv);
+        a.gStride = ts.units;
         if (a.nEv) { k_mark_events<<<(a.nEv + 255) / 256, 256, 0, e->stream>>>(e->v, a.ev, a.nEv, 1); e->launches++; }
-        if (perKernel) CK(cudaEventRecord(evs[4 * k], e->stream));
+        if (perKernel) CK(cudaEventRecord(evs[5 * k], e->stream));
         k_neuron_pass<<<e->grid1, NC_WARPS_PER_BLOCK * 32, e->smem1, e->stream>>>(e->v, a);
-        if (perKernel) CK(cudaEventRecord(evs[4 * k + 1], e->stream));
+        e->launches++;
+        if (perKernel) CK(cudaEventRecord(evs[5 * k + 1], e->stream));
+        if (e->cfg.world > 1) {
+            int rc = exchange(e, e->v.localHdr, e->dGather, (size_t)ts.units * sizeof(FireRec));
+            if (rc) return rc;
+        }
+        if (perKernel) CK(cudaEventRecord(evs[5 * k + 2], e->stream));
         if (a.nEv) { k_mark_events<<<(a.nEv + 255) / 256, 256, 0, e->stream>>>(e->v, a.ev, a.nEv, 0); e->launches++; }
-        k_index_build_dev<<<idxGrid, 256, 0, e->stream>>>(e->v, a);
-        if (perKernel) CK(cudaEventRecord(evs[4 * k + 2], e->stream));
+        dim3 g(gx, a.world);
+        k_index_build<<<g, 256, 0, e->stream>>>(e->v, a);
+        if (perKernel) CK(cudaEventRecord(evs[5 * k + 3], e->stream));
         k_synapse_pass<<<e->grid2, NC_P2_THREADS, e->smem2, e->stream>>>(e->v, a, e->maskWordsSmem);
-        if (perKernel) CK(cudaEventRecord(evs[4 * k + 3], e->stream));
-        k_index_reset_dev<<<idxGrid, 256, 0, e->stream>>>(e->v, a);
-        k_hdr_reset<<<1, 32, 0, e->stream>>>(e->v, dOvf);
-        e->launches += 5;
+        if (perKernel) CK(cudaEventRecord(evs[5 * k + 4], e->stream));
+        k_index_reset<<<g, 256, 0, e->stream>>>(e->v, a);
+        k_finish_step<<<1, 32, 0, e->stream>>>(e->v, e->dOut, 1);
+        e->launches += 4;
     }
     CK(cudaEventRecord(e1, e->stream));
     CK(cudaGetLastError());
-    uint32_t ovf = 0;
-    CK(cudaMemcpyAsync(&ovf, dOvf, 4, cudaMemcpyDeviceToHost, e->stream));
     int rc = finish_counters(e, hidden, st);
-    if (rc) return rc;
+    CK(cudaMemsetAsync(e->dOut, 0, 10 * sizeof(unsigned long long), e->stream));
     if (msTotal) CK(cudaEventElapsedTime(msTotal, e0, e1));
     if (perKernel) {
-        float s1 = 0, s2 = 0, x;
+        float s1 = 0, s2 = 0, sx = 0, x;
         for (uint32_t k = 0; k < count; k++) {
-            CK(cudaEventElapsedTime(&x, evs[4 * k], evs[4 * k + 1])); s1 += x;
-            CK(cudaEventElapsedTime(&x, evs[4 * k + 2], evs[4 * k + 3])); s2 += x;
+            CK(cudaEventElapsedTime(&x, evs[5 * k], evs[5 * k + 1])); s1 += x;
+            CK(cudaEventElapsedTime(&x, evs[5 * k + 1], evs[5 * k + 2])); sx += x;
+            CK(cudaEventElapsedTime(&x, evs[5 * k + 3], evs[5 * k + 4])); s2 += x;
         }
         if (msP1) *msP1 = s1;
         if (msP2) *msP2 = s2;
+        if (msXchg) *msXchg = sx;
         for (auto& x2 : evs) cudaEventDestroy(x2);
     }
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(dOvf);
-    if (ovf) return fail(e, NC_ERR_CAPACITY, "replay: fire-record capacity exceeded");
-    return NC_OK;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------

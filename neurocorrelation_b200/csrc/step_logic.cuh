@@ -74,10 +74,11 @@ struct View {
     uint32_t* localHdr;  // [0] = fire count of this shard, [1] = overflow flag
     FireRec* localRecs;
     uint32_t fireCap;
-    // gathered fire index
-    const FireRec* gRecs;  // `world` blocks of `gStride` records
-    int32_t* head;         // per global neuron: first record index or -1
-    int32_t* next;         // per record
+    // gathered fire index.  A shard's exchange block is a run of 16-byte units: unit 0 is the header
+    // {count, overflow, 0, 0}, units 1..count are the records; localHdr/localRecs are this shard's own block.
+    const FireRec* gRecs;  // `world` blocks of `gStride` units each (world 1: the local block itself)
+    int32_t* head;         // per global neuron: unit index of its first record or -1
+    int32_t* next;         // per unit
     uint32_t* mask;        // one bit per global neuron: fired in this window
     uint32_t* evMask;      // one bit per row of this shard: has host events in this window
     uint32_t* candBits;    // per row and 128-slot group: 4 ballot words marking the occupied slots staged by the neuron pass
@@ -98,9 +99,8 @@ struct StepArgs {
     const uint32_t* subset;  // nc_run_neurons: ascending IDs that take part in the sweep (NULL = all)
     uint32_t nSubset;
     uint32_t candCap;
-    uint32_t gStride;
+    uint32_t gStride;  // units per gathered block (header included)
     uint32_t world;
-    uint32_t counts[NC_MAX_WORLD];
 };
 
 struct NeuronState {

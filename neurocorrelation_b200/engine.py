@@ -25,8 +25,8 @@ ABI_SYMBOLS = (
     "nc_upload_network_device", "nc_min_delay",
     "nc_set_plasticity", "nc_step", "nc_run_neurons", "nc_read_neurons", "nc_read_synapses", "nc_read_fires",
     "nc_read_synapse_pots", "nc_reset_activities", "nc_detector_mean", "nc_tape_begin", "nc_tape_end", "nc_snapshot",
-    "nc_restore", "nc_tape_replay", "nc_launch_count", "nc_step_begin", "nc_exchange_buffer", "nc_gather_buffer",
-    "nc_step_end", "nc_step_end_counts", "nc_selftest_powf", "nc_selftest_exp",
+    "nc_restore", "nc_tape_replay", "nc_launch_count", "nc_comm_unique_id", "nc_comm_init", "nc_set_exchange",
+    "nc_selftest_powf", "nc_selftest_exp",
 )
 
 
@@ -46,6 +46,8 @@ class StepStats(C.Structure):
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64)
 
 EVENT_DTYPE = np.dtype([("neuron", np.uint32), ("time", np.float32), ("kind", np.uint32), ("index_or_flags", np.uint32)])
 
@@ -85,14 +87,12 @@ def load(path=None):
     L.nc_snapshot.argtypes = [vp]
     L.nc_restore.argtypes = [vp]
     L.nc_tape_replay.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
-                                 C.POINTER(C.c_uint64), C.POINTER(StepStats)]
+                                 C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.POINTER(StepStats)]
     L.nc_launch_count.argtypes = [vp]
     L.nc_launch_count.restype = C.c_uint64
-    L.nc_step_begin.argtypes = [vp, C.c_float, C.c_float, C.c_int, vp, C.c_uint32]
-    L.nc_exchange_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
-    L.nc_gather_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
-    L.nc_step_end.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(StepStats)]
-    L.nc_step_end_counts.argtypes = [vp, u32p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(StepStats)]
+    L.nc_comm_unique_id.argtypes = [vp]
+    L.nc_comm_init.argtypes = [vp, vp]
+    L.nc_set_exchange.argtypes = [vp, ALLGATHER_FN, vp]
     L.nc_selftest_powf.argtypes = [vp, f32p, f32p, f32p, C.c_uint64]
     L.nc_selftest_exp.argtypes = [vp, f64p, f64p, C.c_uint64]
     if path == _build.ENGINE_SO:
@@ -227,39 +227,36 @@ class Engine:
         self._ck(self.L.nc_restore(self.h))
 
     def tape_replay(self, first, count, per_kernel=False):
-        ms, m1, m2 = C.c_float(), C.c_float(), C.c_float()
+        ms, m1, m2, mx = C.c_float(), C.c_float(), C.c_float(), C.c_float()
         hidden = C.c_uint64()
         st = StepStats()
         self._ck(self.L.nc_tape_replay(self.h, first, count, C.byref(ms), C.byref(m1) if per_kernel else None,
-                                       C.byref(m2) if per_kernel else None, C.byref(hidden), C.byref(st)))
-        return dict(ms_total=ms.value, ms_pass1=m1.value, ms_pass2=m2.value, hidden=hidden.value, stats=st.as_dict())
+                                       C.byref(m2) if per_kernel else None, C.byref(mx) if per_kernel else None,
+                                       C.byref(hidden), C.byref(st)))
+        return dict(ms_total=ms.value, ms_pass1=m1.value, ms_pass2=m2.value, ms_exchange=mx.value, hidden=hidden.value,
+                    stats=st.as_dict())
 
     def launch_count(self):
         return int(self.L.nc_launch_count(self.h))
 
-    # ---- sharded stepping (world > 1): begin -> host all-gathers fire records -> end ----
-    def step_begin(self, t0, t1, sweep, events=None):
-        p, n, keep = self._events(events)
-        self._ck(self.L.nc_step_begin(self.h, t0, t1, sweep, p, n))
+    # ---- sharded engines (world > 1): the fire exchange lives inside nc_step / nc_tape_replay ----
+    @staticmethod
+    def comm_unique_id(library=None):
+        """128-byte NCCL unique id (create on rank 0, distribute to all ranks, pass to comm_init)."""
+        L = load(library)
+        buf = C.create_string_buffer(128)
+        rc = L.nc_comm_unique_id(buf)
+        if rc != 0:
+            raise EngineError("nc_comm_unique_id failed (%d): %s" % (rc, L.nc_global_error().decode()))
+        return buf.raw
 
-    def exchange_buffer(self):
-        p, b = C.c_void_p(), C.c_uint64()
-        self._ck(self.L.nc_exchange_buffer(self.h, C.byref(p), C.byref(b)))
-        return p.value, b.value
+    def comm_init(self, unique_id):
+        self._ck(self.L.nc_comm_init(self.h, C.create_string_buffer(bytes(unique_id), 128)))
 
-    def gather_buffer(self):
-        p, b = C.c_void_p(), C.c_uint64()
-        self._ck(self.L.nc_gather_buffer(self.h, C.byref(p), C.byref(b)))
-        return p.value, b.value
-
-    def step_end(self, counts=None, stride=0):
-        hidden = C.c_uint64()
-        st = StepStats()
-        if counts is None:
-            self._ck(self.L.nc_step_end(self.h, C.byref(hidden), C.byref(st)))
-        else:
-            self._ck(self.L.nc_step_end_counts(self.h, np.ascontiguousarray(counts, np.uint32), int(stride), C.byref(hidden), C.byref(st)))
-        return hidden.value, st.as_dict()
+    def set_exchange(self, fn):
+        """fn(send_ptr, recv_ptr, nbytes) -> 0: caller-provided all-gather (tests; other transports)."""
+        self._xchg = ALLGATHER_FN(lambda ctx, a, b, n: int(fn(a, b, n)))
+        self._ck(self.L.nc_set_exchange(self.h, self._xchg, None))
 
     # ---- self-tests ----
     def selftest_powf(self, x, y):

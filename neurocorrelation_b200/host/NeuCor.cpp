@@ -5,6 +5,7 @@
 #include "NeuCor.h"
 
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <cassert>
@@ -265,9 +266,25 @@ void NeuCor::importNetworkDevice(std::size_t n, uint64_t synapses, const uint64_
     imported_ = true;
 }
 
+void NeuCor::setShard(int rank, int world) {
+    if (engine_) throw std::logic_error("NeuCor::setShard: the network is already on the device");
+    if (world < 1 || rank < 0 || rank >= world) throw std::out_of_range("NeuCor::setShard: bad rank/world");
+    rank_ = rank; world_ = world;
+}
+void NeuCor::setCommId(const void* commId128) { memcpy(commId_, commId128, 128); haveCommId_ = true; }
+void NeuCor::setExchange(int (*allgather)(void*, const void*, void*, uint64_t), void* ctx) { xchgFn_ = allgather; xchgCtx_ = ctx; }
+
+void NeuCor::importShardDevice(std::size_t n, uint64_t localSynapses, const uint64_t* d_rowptr, const uint32_t* d_pre, const float* d_weight,
+                               const float* d_length, const uint8_t* d_inhibitory) {
+    importNetworkDevice(n, localSynapses, d_rowptr, d_pre, d_weight, d_length, d_inhibitory);
+    shardImport_ = true;
+}
+
 void NeuCor::finalize() {
     if (engine_) return;
     const std::size_t N = positions.size();
+    row0_ = (std::size_t)((uint64_t)N * (uint64_t)rank_ / (uint64_t)world_);
+    nRows_ = (std::size_t)((uint64_t)N * (uint64_t)(rank_ + 1) / (uint64_t)world_) - row0_;
     if (!imported_) {  // rows = target, in-row ascending presynaptic ID: Neuron::inSynapses' std::map order (NeuCor.h:212)
         rowptr_.assign(N + 1, 0);
         for (auto& outs : out_)
@@ -284,21 +301,45 @@ void NeuCor::finalize() {
     }
     nc_config cfg = {};
     cfg.device = deviceOrdinal;
-    cfg.rank = 0;
-    cfg.world = 1;
+    cfg.rank = rank_;
+    cfg.world = world_;
     cfg.cand_smem = candidateSmem;
     nc_engine* e = nullptr;
     int rc = nc_create(&cfg, &e);
     if (rc != NC_OK) throw std::runtime_error(std::string("NeuCor: cannot create the CUDA engine: ") + nc_global_error());
     engine_ = e;
     if (dev_.set) {
-        check(nc_upload_network_device(engine_, N, 0, N, dev_.rowptr, dev_.pre, dev_.weight, dev_.length, dev_.inh), "nc_upload_network_device");
-    } else {
+        if (world_ > 1 && !shardImport_) throw std::logic_error("NeuCor: a sharded run takes its device-resident rows through importShardDevice");
+        check(nc_upload_network_device(engine_, N, row0_, nRows_, dev_.rowptr, dev_.pre, dev_.weight, dev_.length, dev_.inh), "nc_upload_network_device");
+        sLocal_ = dev_.S;
+    } else if (world_ == 1) {
         check(nc_upload_network(engine_, N, 0, N, rowptr_.data(), pre_.data(), weight_.data(), length_.data(), flag_.data()), "nc_upload_network");
+        sLocal_ = pre_.size();
         h2dBytes_ += (N + 1) * 8 + pre_.size() * 13;
+    } else {  // this shard's rows of the host CSR, re-based to start at 0
+        const uint64_t lo = rowptr_[row0_], hi = rowptr_[row0_ + nRows_];
+        std::vector<uint64_t> rp(nRows_ + 1);
+        for (std::size_t r = 0; r <= nRows_; r++) rp[r] = rowptr_[row0_ + r] - lo;
+        check(nc_upload_network(engine_, N, row0_, nRows_, rp.data(), pre_.data() + lo, weight_.data() + lo, length_.data() + lo, flag_.data() + lo), "nc_upload_network");
+        sLocal_ = hi - lo;
+        h2dBytes_ += (nRows_ + 1) * 8 + sLocal_ * 13;
     }
+    if (world_ > 1) {
+        if (haveCommId_) check(nc_comm_init(engine_, reinterpret_cast<const nc_comm_id*>(commId_)), "nc_comm_init");
+        else if (xchgFn_) check(nc_set_exchange(engine_, xchgFn_, xchgCtx_), "nc_set_exchange");
+        else throw std::logic_error("NeuCor: a sharded run needs setCommId or setExchange before the first run()");
+    }
+    // the smallest delay of the WHOLE network bounds the window (every shard must split windows identically)
     minDelay_ = INFINITY;
-    if (synapseCount()) check(nc_min_delay(engine_, &minDelay_), "nc_min_delay");
+    if (sLocal_) check(nc_min_delay(engine_, &minDelay_), "nc_min_delay");
+    if (world_ > 1) {
+        if (dev_.set) {
+            if (!(globalMinDelay > 0.0f)) throw std::logic_error("NeuCor: set globalMinDelay (smallest 2*length over all shards) for device-resident shards");
+            minDelay_ = globalMinDelay;
+        } else {
+            for (float l : length_) minDelay_ = std::min(minDelay_, l * 2.0f);
+        }
+    }
     lastFireMirror_.assign(N, NAN);
 }
 
@@ -357,6 +398,7 @@ void NeuCor::setDetectors(unsigned detectorNumber, coord3 detectorPositions[], f
 float NeuCor::getDetectorVoltage(unsigned ID) {  // VoltageDetector::getVoltage, NeuCor.cpp:359-366
     VoltageDetector& d = voltageDetectors.at(ID);
     finalize();
+    if (world_ > 1) throw std::logic_error("NeuCor::getDetectorVoltage: not available on a sharded network (use runSwept)");
     uint64_t hidden = 0;
     nc_step_stats st;
     check(nc_run_neurons(engine_, currentTime, d.near.data(), (uint32_t)d.near.size(), &hidden, &st), "nc_run_neurons");
@@ -390,6 +432,12 @@ void NeuCor::scheduleInput(unsigned i, float deltaT, float frequency, std::vecto
 void NeuCor::window(float t0, float t1, int flags, std::vector<nc_event>& ev) {
     uint64_t hidden = 0;
     nc_step_stats st;
+    if (world_ > 1) {  // every process schedules the whole network's events (same rand() stream); a shard takes those of its rows
+        std::size_t k = 0;
+        for (auto& x : ev)
+            if (x.neuron >= row0_ && x.neuron < row0_ + nRows_) ev[k++] = x;
+        ev.resize(k);
+    }
     check(nc_step(engine_, t0, t1, flags, ev.data(), (uint32_t)ev.size(), &hidden, &st), "nc_step");
     h2dBytes_ += ev.size() * sizeof(nc_event);
     d2hBytes_ += 16 + 8 * sizeof(uint64_t);
@@ -465,7 +513,7 @@ void NeuCor::run() { stepInternal(false); }
 
 float NeuCor::runSwept() {
     stepInternal(true);
-    if (!sweepReturnsMean) return 0.0f;
+    if (!sweepReturnsMean || world_ > 1) return 0.0f;
     // mean potential of all neurons, summed in ID order in float — VoltageDetector::getVoltage, NeuCor.cpp:360-365
     syncState();
     d2hBytes_ += potAct.size() * 4;
@@ -478,15 +526,15 @@ float NeuCor::runSwept() {
 // ---- state read-back --------------------------------------------------------------------------------------
 void NeuCor::syncState() {
     if (!engine_) return;
-    check(nc_read_neurons(engine_, potAct.data(), lastFireMirror_.data(), nullptr), "nc_read_neurons");
+    check(nc_read_neurons(engine_, potAct.data() + 2 * row0_, lastFireMirror_.data() + row0_, nullptr), "nc_read_neurons");
 }
 void NeuCor::readNeurons(float* pot, float* act, float* lastFire, float* lastRan) {
     finalize();
-    const std::size_t N = positions.size();
-    check(nc_read_neurons(engine_, potAct.data(), lastFire, lastRan), "nc_read_neurons");
-    for (std::size_t i = 0; i < N; i++) {
-        if (pot) pot[i] = potAct[2 * i];
-        if (act) act[i] = potAct[2 * i + 1];
+    // this shard's rows (all of them for world 1), in ID order starting at shardRow0()
+    check(nc_read_neurons(engine_, potAct.data() + 2 * row0_, lastFire, lastRan), "nc_read_neurons");
+    for (std::size_t i = 0; i < nRows_; i++) {
+        if (pot) pot[i] = potAct[2 * (row0_ + i)];
+        if (act) act[i] = potAct[2 * (row0_ + i) + 1];
     }
 }
 void NeuCor::readSynapses(float* weight, float* arrive, float* depol, float* lastArrival, float* lastStart) {

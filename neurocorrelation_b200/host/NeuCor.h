@@ -96,6 +96,20 @@ public:
     // Same with the CSR already resident on the device `deviceOrdinal` (device pointers; copied at finalize()).
     void importNetworkDevice(std::size_t n, uint64_t synapses, const uint64_t* d_rowptr, const uint32_t* d_pre, const float* d_weight,
                              const float* d_length, const uint8_t* d_inhibitory);
+    // Multi-GPU: this process simulates the neuron-ID range [N*rank/world, N*(rank+1)/world) and the
+    // synapses incoming to it; every process makes the same calls in the same order with the same libc rand() state.
+    // Call before the first run().  The fire exchange runs inside run(): over an NCCL communicator created from `commId`
+    // (a 128-byte ncclUniqueId made by rank 0, see nc_comm_unique_id) or through a caller-provided all-gather.
+    void setShard(int rank, int world);
+    void setCommId(const void* commId128);
+    void setExchange(int (*allgather)(void* ctx, const void* send, void* recv, uint64_t bytes), void* ctx);
+    float globalMinDelay = 0.0f;    // device-resident shards only: smallest 2*length over ALL shards (bounds the window)
+    std::size_t shardRow0() const { return row0_; }
+    std::size_t shardRows() const { return engine_ ? nRows_ : positions.size(); }
+    std::size_t shardSynapses() const { return engine_ ? sLocal_ : synapseCount(); }
+    // The shard's rows of a network of `n` neurons, already resident on the device (local rowptr starting at 0).
+    void importShardDevice(std::size_t n, uint64_t localSynapses, const uint64_t* d_rowptr, const uint32_t* d_pre, const float* d_weight,
+                           const float* d_length, const uint8_t* d_inhibitory);
     void setInputNear(unsigned inputID, const uint32_t* ids, std::size_t n);  // overrides an input's `near` list
     void setInputLastFire(unsigned inputID, float t);
     float runSwept();               // run() + "run every neuron at the new time, ascending ID"; returns the mean potential
@@ -149,6 +163,11 @@ private:
     bool imported_ = false;
     struct { const uint64_t* rowptr; const uint32_t* pre; const float *weight, *length; const uint8_t* inh; uint64_t S; bool set; } dev_ = {};
     nc_engine* engine_ = nullptr;
+    int rank_ = 0, world_ = 1;
+    std::size_t row0_ = 0, nRows_ = 0, sLocal_ = 0;
+    bool shardImport_ = false;
+    char commId_[128]; bool haveCommId_ = false;
+    int (*xchgFn_)(void*, const void*, void*, uint64_t) = nullptr; void* xchgCtx_ = nullptr;
     float minDelay_ = 0.0f;
     std::vector<float> lastFireMirror_;
     std::vector<nc_event> events_, winEvents_;

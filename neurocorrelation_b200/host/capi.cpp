@@ -53,6 +53,16 @@ int nch_import_network(void* hv, uint64_t n, const uint64_t* rowptr, const uint3
 int nch_import_network_device(void* hv, uint64_t n, uint64_t S, const void* rowptr, const void* pre, const void* weight, const void* length, const void* flag) {
     return guard([&] { B->importNetworkDevice(n, S, (const uint64_t*)rowptr, (const uint32_t*)pre, (const float*)weight, (const float*)length, (const uint8_t*)flag); });
 }
+int nch_import_shard_device(void* hv, uint64_t n, uint64_t S, const void* rowptr, const void* pre, const void* weight, const void* length, const void* flag, float globalMinDelay) {
+    return guard([&] {
+        B->importShardDevice(n, S, (const uint64_t*)rowptr, (const uint32_t*)pre, (const float*)weight, (const float*)length, (const uint8_t*)flag);
+        B->globalMinDelay = globalMinDelay;
+    });
+}
+int nch_set_shard(void* hv, int rank, int world) { return guard([&] { B->setShard(rank, world); }); }
+int nch_set_comm_id(void* hv, const void* id128) { return guard([&] { B->setCommId(id128); }); }
+int nch_set_exchange(void* hv, int (*fn)(void*, const void*, void*, uint64_t), void* ctx) { return guard([&] { B->setExchange(fn, ctx); }); }
+void nch_shard_info(void* hv, uint64_t* row0, uint64_t* rows, uint64_t* synapses) { *row0 = B->shardRow0(); *rows = B->shardRows(); *synapses = B->shardSynapses(); }
 int nch_set_sweep_mean(void* hv, int on) { return guard([&] { B->sweepReturnsMean = on != 0; }); }
 int nch_set_inputs(void* hv, const float* rates, unsigned n, const float* pos_xyz, const float* radius) {
     return guard([&] {

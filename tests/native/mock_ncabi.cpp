@@ -26,13 +26,16 @@ struct nc_engine {
     std::vector<uint32_t> pre, firings, hdr, mask, spillJ;
     std::vector<float> arrive, depol, weight, lastArr, lastStart, delay, lastRan, lastFire, lfStart, actStart, spillA, spillD;
     std::vector<float2> potAct;
-    std::vector<FireRec> recs;
+    std::vector<FireRec> units, gather;  // exchange block (header unit + records) and the gathered blocks of all shards
     std::vector<int32_t> head, next;
+    int rank = 0, world = 1;
+    nc_allgather_fn xchgFn = nullptr; void* xchgCtx = nullptr;
+    uint32_t xchgUnits = 1u + 4u;  // deliberately tiny so that the grow-and-repeat path of the exchange is exercised
+    uint32_t counts[NC_MAX_WORLD] = {0}; uint32_t stride = 0;
     unsigned long long stats[8];
     float lr = 1.0f, preF = 0.13f, postF = 0.30f, preD = 0.75f, postD = 0.65f, minDelay = INFINITY;
     uint32_t candCap = 8;  // deliberately tiny so that the spill path is exercised
     bool uploaded = false;
-    uint32_t lastCount = 0;
 };
 static std::string g_err;
 static int fail(nc_engine* e, int code, const char* m) { e->err = m; return code; }
@@ -47,6 +50,7 @@ int nc_create(const nc_config* cfg, nc_engine** out) {
     memset(&e->v, 0, sizeof(View));
     memset(e->stats, 0, sizeof(e->stats));
     if (cfg->cand_smem) e->candCap = cfg->cand_smem;
+    e->rank = cfg->rank; e->world = cfg->world;
     *out = e;
     return NC_OK;
 }
@@ -65,14 +69,15 @@ int nc_upload_network(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t nR
     e->potAct.assign(nRows, make_float2(-70.0f, 0.0f)); e->lastRan.assign(nRows, 0.0f); e->lastFire.assign(nRows, NAN);
     e->lfStart.assign(nRows, NAN); e->actStart.assign(nRows, 0.0f); e->firings.assign(nRows, 0u);
     uint32_t cap = (uint32_t)(4 * nRows + 1024);
-    e->hdr.assign(4, 0u); e->recs.resize(cap); e->head.assign(nGlobal, -1); e->next.assign(cap, -1); e->mask.assign((nGlobal + 31) / 32 + 1, 0u);
+    e->units.assign((size_t)cap + 1, FireRec{0, 0, 0, 0}); e->gather.assign((size_t)e->world * (cap + 1), FireRec{0, 0, 0, 0});
+    e->head.assign(nGlobal, -1); e->next.assign((size_t)e->world * (cap + 1), -1); e->mask.assign((nGlobal + 31) / 32 + 1, 0u);
     e->spillA.resize(maxRow + 1); e->spillD.resize(maxRow + 1); e->spillJ.resize(maxRow + 1);
     View& v = e->v;
     v.nGlobal = nGlobal; v.row0 = row0; v.nRows = nRows; v.S = S; v.rowptr = e->rowptr.data(); v.pre = e->pre.data();
     v.arrive = e->arrive.data(); v.depol = e->depol.data(); v.weight = e->weight.data(); v.lastArr = e->lastArr.data(); v.lastStart = e->lastStart.data();
     v.delay = e->delay.data(); v.potAct = e->potAct.data(); v.lastRan = e->lastRan.data(); v.lastFire = e->lastFire.data(); v.lfStart = e->lfStart.data();
-    v.actStart = e->actStart.data(); v.firings = e->firings.data(); v.localHdr = e->hdr.data(); v.localRecs = e->recs.data(); v.fireCap = cap;
-    v.gRecs = e->recs.data(); v.head = e->head.data(); v.next = e->next.data(); v.mask = e->mask.data();
+    v.actStart = e->actStart.data(); v.firings = e->firings.data(); v.localHdr = reinterpret_cast<uint32_t*>(e->units.data()); v.localRecs = e->units.data() + 1; v.fireCap = cap;
+    v.gRecs = e->world > 1 ? e->gather.data() : e->units.data(); v.head = e->head.data(); v.next = e->next.data(); v.mask = e->mask.data();
     v.spillA = e->spillA.data(); v.spillD = e->spillD.data(); v.spillJ = e->spillJ.data(); v.spillPerWarp = (uint32_t)maxRow; v.stats = e->stats;
     e->uploaded = true;
     return NC_OK;
@@ -196,13 +201,23 @@ static void model_pass1(nc_engine* e, const StepArgs& s) {
     }
     v.stats[0] += nFires; v.stats[1] += nDeliv; v.stats[6] += nRuns; v.stats[7] += nVisits;
 }
-// serial restatement of k_index_build / k_synapse_pass / k_index_reset
+// serial restatement of k_index_build / k_synapse_pass / k_index_reset / k_finish_step
 static void model_pass2(nc_engine* e, const StepArgs& s) {
     View& v = e->v;
-    uint32_t count = v.localHdr[0];
-    // records were appended in row order here; on the device the order is arbitrary — shuffle to make sure nothing depends on it
-    for (uint32_t i = 0; i + 1 < count; i += 2) std::swap(e->recs[i], e->recs[i + 1]);
-    for (uint32_t i = 0; i < count; i++) { uint32_t nrn = v.gRecs[i].neuron; v.next[i] = v.head[nrn]; v.head[nrn] = (int32_t)i; v.mask[nrn >> 5] |= 1u << (nrn & 31u); }
+    if (s.world == 1) {
+        // records were appended in row order here; on the device the order is arbitrary — shuffle to make sure nothing depends on it
+        uint32_t count = v.localHdr[0];
+        for (uint32_t i = 0; i + 1 < count; i += 2) std::swap(v.localRecs[i], v.localRecs[i + 1]);
+    }
+    for (uint32_t b = 0; b < s.world; b++) {
+        uint32_t count = std::min(reinterpret_cast<const uint32_t*>(v.gRecs + (uint64_t)b * s.gStride)[0], s.gStride - 1u);
+        e->counts[b] = count;
+        for (uint32_t i = 0; i < count; i++) {
+            uint32_t idx = b * s.gStride + 1u + i, nrn = v.gRecs[idx].neuron;
+            v.next[idx] = v.head[nrn]; v.head[nrn] = (int32_t)idx; v.mask[nrn >> 5] |= 1u << (nrn & 31u);
+        }
+    }
+    e->stride = s.gStride;
     uint32_t cnt[5] = {0, 0, 0, 0, 0};
     for (uint64_t row = 0; row < v.nRows; row++) {
         const uint32_t q = (uint32_t)(v.row0 + row);
@@ -218,21 +233,50 @@ static void model_pass2(nc_engine* e, const StepArgs& s) {
         }
     }
     v.stats[2] += cnt[0]; v.stats[3] += cnt[1]; v.stats[4] += cnt[2]; v.stats[5] += cnt[3];
-    for (uint32_t i = 0; i < count; i++) { uint32_t nrn = v.gRecs[i].neuron; v.head[nrn] = -1; v.mask[nrn >> 5] = 0u; }
-    e->lastCount = count;
+    for (uint32_t b = 0; b < s.world; b++)
+        for (uint32_t i = 0; i < e->counts[b]; i++) { uint32_t nrn = v.gRecs[b * s.gStride + 1u + i].neuron; v.head[nrn] = -1; v.mask[nrn >> 5] = 0u; }
     v.localHdr[0] = 0; v.localHdr[1] = 0;
 }
 static void fill(nc_engine* e, StepArgs& a, float t0, float t1, int sweep, const nc_event* ev, uint32_t nEv) {
     memset(&a, 0, sizeof(a));
     a.t0 = t0; a.t1 = t1; a.sweep = sweep; a.lr = e->lr; a.preFactor = e->preF; a.postFactor = e->postF; a.preDecay = e->preD; a.postDecay = e->postD;
-    a.ev = ev; a.nEv = nEv; a.candCap = e->candCap; a.gStride = e->v.fireCap; a.world = 1;
+    a.ev = ev; a.nEv = nEv; a.candCap = e->candCap; a.gStride = e->v.fireCap + 1u; a.world = (uint32_t)e->world;
 }
-static void finish(nc_engine* e, uint64_t* hidden, nc_step_stats* st) {
-    if (hidden) *hidden = e->stats[5];
-    if (st) { st->fires = e->stats[0]; st->deliveries = e->stats[1]; st->loads_accepted = e->stats[2]; st->loads_dropped = e->stats[3];
-              st->plasticity_calls = e->stats[4]; st->hidden_rand_calls = e->stats[5]; st->neuron_runs = e->stats[6]; st->active_visits = e->stats[7]; }
+static int finish(nc_engine* e, uint64_t* hidden, nc_step_stats* st) {
+    unsigned long long t[8];
+    memcpy(t, e->stats, sizeof(t));
+    if (e->world > 1) {  // network-wide counters: all-gather the shards' blocks and add them up
+        std::vector<unsigned long long> all((size_t)e->world * 8);
+        if (!e->xchgFn || e->xchgFn(e->xchgCtx, e->stats, all.data(), sizeof(t))) return fail(e, NC_ERR_STATE, "exchange failed");
+        memset(t, 0, sizeof(t));
+        for (int b = 0; b < e->world; b++) for (int i = 0; i < 8; i++) t[i] += all[(size_t)b * 8 + i];
+    }
+    if (hidden) *hidden = t[5];
+    if (st) { st->fires = t[0]; st->deliveries = t[1]; st->loads_accepted = t[2]; st->loads_dropped = t[3];
+              st->plasticity_calls = t[4]; st->hidden_rand_calls = t[5]; st->neuron_runs = t[6]; st->active_visits = t[7]; }
     memset(e->stats, 0, sizeof(e->stats));
+    return NC_OK;
 }
+// the live fire exchange of engine.cu (exchange_fires): all-gather the first xchgUnits units, look at the headers, grow and repeat
+static int exchange_fires(nc_engine* e, StepArgs& a) {
+    if (!e->xchgFn) return fail(e, NC_ERR_STATE, "exchange: world > 1 needs nc_set_exchange");
+    for (;;) {
+        if (e->xchgFn(e->xchgCtx, e->units.data(), e->gather.data(), (uint64_t)e->xchgUnits * sizeof(FireRec))) return fail(e, NC_ERR_STATE, "exchange failed");
+        uint32_t mx = 0;
+        for (int b = 0; b < e->world; b++) {
+            const uint32_t* hdr = reinterpret_cast<const uint32_t*>(e->gather.data() + (size_t)b * e->xchgUnits);
+            if (hdr[1]) return fail(e, NC_ERR_CAPACITY, "fire capacity (gathered header)");
+            mx = std::max(mx, hdr[0]);
+        }
+        if (mx + 1u <= e->xchgUnits) { a.gStride = e->xchgUnits; return NC_OK; }
+        uint64_t want = 1;
+        while (want < 2ull * mx) want <<= 1;
+        e->xchgUnits = (uint32_t)std::min<uint64_t>(want + 1, (uint64_t)e->v.fireCap + 1);
+    }
+}
+int nc_set_exchange(nc_engine* e, nc_allgather_fn fn, void* ctx) { e->xchgFn = fn; e->xchgCtx = ctx; return NC_OK; }
+int nc_comm_unique_id(nc_comm_id*) { g_err = "the CPU test double has no NCCL"; return NC_ERR_NO_DEVICE; }
+int nc_comm_init(nc_engine* e, const nc_comm_id*) { return fail(e, NC_ERR_NO_DEVICE, "the CPU test double has no NCCL"); }
 int nc_step(nc_engine* e, float t0, float t1, int sweep, const nc_event* ev, uint32_t nEv, uint64_t* hidden, nc_step_stats* st) {
     if (!e->uploaded) return fail(e, NC_ERR_STATE, "step: no network uploaded");
     if (!(t1 > t0)) return fail(e, NC_ERR_INVALID, "step: window must have t1 > t0");
@@ -240,18 +284,18 @@ int nc_step(nc_engine* e, float t0, float t1, int sweep, const nc_event* ev, uin
     StepArgs a; fill(e, a, t0, t1, sweep, ev, nEv);
     model_pass1(e, a);
     if (e->v.localHdr[1]) return fail(e, NC_ERR_CAPACITY, "fire capacity");
+    if (e->world > 1) { int rc = exchange_fires(e, a); if (rc) return rc; }
     model_pass2(e, a);
-    finish(e, hidden, st);
-    return NC_OK;
+    return finish(e, hidden, st);
 }
 int nc_run_neurons(nc_engine* e, float now, const uint32_t* ids, uint32_t n, uint64_t* hidden, nc_step_stats* st) {
     if (ids && !n) return NC_OK;
     StepArgs a; fill(e, a, now, now, NC_SWEEP_END, nullptr, 0);
     a.subset = ids; a.nSubset = n;
+    if (e->world > 1) return fail(e, NC_ERR_STATE, "nc_run_neurons: single-shard engines only");
     model_pass1(e, a);
     model_pass2(e, a);
-    finish(e, hidden, st);
-    return NC_OK;
+    return finish(e, hidden, st);
 }
 int nc_read_neurons(nc_engine* e, float* potAct, float* lastFire, float* lastRan) {
     uint64_t N = e->v.nRows;
@@ -270,8 +314,11 @@ int nc_read_synapses(nc_engine* e, float* w, float* a, float* d, float* la, floa
     return NC_OK;
 }
 int nc_read_fires(nc_engine* e, uint32_t cap, uint32_t* neuron, float* time, uint32_t* count) {
-    for (uint32_t i = 0; i < e->lastCount && i < cap; i++) { if (neuron) neuron[i] = e->recs[i].neuron; if (time) time[i] = e->recs[i].time; }
-    *count = e->lastCount;
+    uint32_t total = 0;
+    for (int b = 0; b < e->world; b++)
+        for (uint32_t i = 0; i < e->counts[b]; i++, total++)
+            if (total < cap) { const FireRec& r = e->v.gRecs[(size_t)b * e->stride + 1u + i]; if (neuron) neuron[total] = r.neuron; if (time) time[total] = r.time; }
+    *count = total;
     return NC_OK;
 }
 int nc_read_synapse_pots(nc_engine* e, float, float* pre, float* post) {

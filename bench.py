@@ -1,20 +1,25 @@
 #!/usr/bin/env python3
 """bench.py — the hot path (one window of NeuCor::run, sweep mode, STDP on) on N B200s of one node.
 
-  python bench.py --gpus N --steps K --warmup W [--workload c2|c3|c1] [--impl reference]
+  python bench.py --gpus N --steps K --warmup W [--workload c2|c3|m100|c1] [--impl reference]
+  N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one pass of the hot path over the whole network: host scheduling (input firers, background
-rand() draws) -> neuron pass -> fire exchange -> synapse pass, dt = 0.0625 ms.
-  value  device-resident throughput: the K timed steps are first run live (that run is the `e2e` number:
-         through the host NeuCor class, host event lists copied to the device and counters read back every
-         step), recorded on a device-side tape, the state is restored from a device snapshot, and the same K
-         steps are replayed back to back with no host<->device traffic, timed with CUDA events on the launching
-         stream. Replay is bit-identical to the live run (tests/test_gpu_parity.py).
-  e2e    the same K steps through the reference-facing API (host class -> C ABI) with host buffers.
-  roofline  the dominant kernel's algorithmic bytes per launch / its mean launch time (CUDA events around
-         every launch of the replay) against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
-  cpu_baseline  the reference's own NeuCor.cpp (oracle/_ref, kind "reference"; else the oracle port) on one
-         host core (the reference is single-threaded), on a bounded sample of the same recipe.
+A "step" is one pass of the hot path over the whole network: host scheduling (input firers, background rand()
+draws) -> neuron pass -> fire exchange -> synapse pass, dt = 0.0625 ms.  Weak scaling: every GPU owns the workload's
+neuron count (rows of the post-sorted CSR); the network of an N-GPU run has N times the neurons and synapses.
+The network is first spun up (untimed) for `spinup_ms` of simulated time so that the timed steps see the recipe's
+running regime (mean rate, deliveries and drops per step are printed), not the silent first milliseconds.
+  value  device-resident throughput: the K timed steps are first run live (that run is the `e2e` number: through the
+         host NeuCor class, host event lists copied to the device and counters read back every step), recorded on a
+         device-side tape, the state is restored from a device snapshot, and the same K steps are replayed back to back
+         with no host<->device traffic (the fire exchange is an in-stream NCCL all-gather), timed with CUDA events on
+         the launching stream, max over ranks.  Replay is bit-identical to the live run (tests/test_gpu_parity.py).
+  e2e    the same K steps through the reference-facing API (host class -> C ABI) with host buffers, wall clock between
+         barriers, max over ranks.
+  roofline  the dominant kernel's algorithmic bytes per launch / its mean launch time (CUDA events around every launch of
+         a second replay) against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline  the reference's own NeuCor.cpp (oracle/_ref, kind "reference"; else the oracle port) on one host core
+         (the reference is single-threaded), on a bounded sample of the same recipe, spun up the same way.
 `--impl reference` times only that CPU implementation and prints the same line shape.
 """
 import argparse
@@ -33,11 +38,11 @@ import numpy as np  # noqa: E402
 
 DT = 0.0625
 WORKLOADS = {
-    # name: (N, K, description)
-    "c1": (750, None, "default main.cpp network (750 neurons, ~20.7k synapses), C1"),
-    "c2": (100_000, 100, "100k neurons x 100 synapses (10M synapses), C2"),
-    "c3": (1_000_000, 1000, "1M neurons x 1000 synapses (1B synapses), C3"),
-    "m100": (100_000, 1000, "100k neurons x 1000 synapses (100M synapses), profiling-sized slice of C3"),
+    # name: (neurons per GPU, in-degree K, default spin-up [simulated ms], description)
+    "c1": (750, None, 0.0, "default main.cpp network (750 neurons, ~20.7k synapses), C1"),
+    "c2": (100_000, 100, 50.0, "100k neurons x 100 synapses (10M synapses) per GPU, C2"),
+    "c3": (1_000_000, 1000, 12.5, "1M neurons x 1000 synapses (1B synapses) per GPU, C3"),
+    "m100": (100_000, 1000, 12.5, "100k neurons x 1000 synapses (100M synapses) per GPU, profiling-sized slice of C3"),
 }
 
 
@@ -93,135 +98,170 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_brain(workload, dev, seed=1):
-    """Returns (host-class brain, network description). C2: spatial recipe built on the host (numpy) and uploaded;
-    C3: stratified stand-in built directly in device memory (torch) and handed over as device pointers."""
+def drive_setup(brain, net, keyword_near, phase=True):
+    """Sweep-mode drive of a synthetic network: fixed random rates in [0, 75) Hz (helpers.synthetic_drive) and — so that
+    the firers do not all start one full period after t = 0 — a random phase per firer through the reference's own
+    NeuCor::addInputOffset (NeuCor.cpp:66-68).  Leaves libc's generator at srand(777)."""
+    from helpers import libc, synthetic_drive
+    from neurocorrelation_b200.presets import F, random_unit
+    rates = synthetic_drive(brain, net, keyword_near)
+    if phase:
+        libc.srand(6)
+        for i, f in enumerate(rates):
+            if f > 0:
+                brain.add_input_offset(i, float(-random_unit(libc.rand) * F(1000.0) / F(f)))
+        libc.srand(777)
+    return rates
+
+
+def build_brain(workload, dev, rank=0, world=1, seed=1, weight_scale=1.0, comm_id=None):
+    """Returns (host-class brain, network description).  C1: the reference constructor.  Everything else: this rank's
+    rows of the stratified stand-in, built directly in device memory (torch) and handed over as device pointers."""
     import neurocorrelation_b200 as nb
-    from neurocorrelation_b200.networks import stratified_network_torch, synthetic_network
-    N, K, _ = WORKLOADS[workload]
-    if workload in ("c3", "m100"):
-        import torch
-        net = stratified_network_torch(N, K, "cuda:%d" % dev, seed=seed)
-        torch.cuda.synchronize()
-        g = nb.NeuCor.from_device_network(net["N"], net["S"], net["rowptr"].data_ptr(), net["pre"].data_ptr(), net["weight"].data_ptr(),
-                                          net["length"].data_ptr(), net["flag"].data_ptr(), device=dev)
-        g._keepalive = net
-        return g, net
-    net = synthetic_network(N if K else 750, K if K else 28, seed=seed)
-    return nb.NeuCor.from_network(net, device=dev), net
+    N, K, _, _ = WORKLOADS[workload]
+    if workload == "c1":
+        from helpers import libc
+        libc.srand(seed)
+        return nb.NeuCor(750, device=dev), None
+    import torch
+    from neurocorrelation_b200.networks import stratified_shard_torch
+    net = stratified_shard_torch(N * world, K, N * rank, N, "cuda:%d" % dev, seed=seed, weight_scale=weight_scale)
+    torch.cuda.synchronize()
+    md = net["min_delay"]
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([md], device="cuda:%d" % dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        md = float(t.item())
+    ptrs = [net[k].data_ptr() for k in ("rowptr", "pre", "weight", "length", "flag")]
+    if world == 1:
+        g = nb.NeuCor.from_device_network(net["N"], net["S"], *ptrs, device=dev)
+    else:
+        g = nb.NeuCor.from_device_shard(net["N"], net["S"], *ptrs, rank=rank, world=world, global_min_delay=md, device=dev)
+        g.set_comm_id(comm_id)
+    g._keepalive = net
+    return g, net
 
 
-def sample_network(workload, seed=1):
+def sample_network(workload, seed=1, weight_scale=1.0):
     """Bounded sample of the workload's recipe for the single-core CPU reference (cost ~ S * K_out per step)."""
     from neurocorrelation_b200.networks import synthetic_network
-    _, K, _ = WORKLOADS[workload]
-    n = 2500 if (K or 28) <= 100 else 800
-    return synthetic_network(n, K if K else 28, seed=seed)
+    _, K, _, _ = WORKLOADS[workload]
+    n = 500 if (K or 28) <= 100 else 300
+    net = synthetic_network(n, min(K if K else 28, n - 1), seed=seed)
+    if weight_scale != 1.0:
+        net["weight"] = (net["weight"] * np.float32(weight_scale)).astype(np.float32)
+    return net
 
 
-def drive_setup(brain, net, keyword_near, libc):
-    from helpers import synthetic_drive
-    return synthetic_drive(brain, net, keyword_near)
-
-
-def cpu_reference_run(workload, steps, warmup, budget_s=25.0):
+def cpu_reference_run(workload, steps, warmup, spinup_ms, budget_s=25.0, weight_scale=1.0):
     """Times the reference's own CPU implementation (oracle/_ref) — or the oracle port when _ref is absent — on one
-    core. Returns (events/s, sim-ms/wall-s, synapse-updates/s, kind, sample description, steps done, ms/step)."""
+    core: spin-up (untimed, same simulated time as the GPU arm but at most half the budget), `warmup` steps, then up to
+    `steps` timed steps within the budget."""
     from helpers import libc
     from oracle import refbind
-    if workload == "c1":
-        net = None
-    else:
-        net = sample_network(workload)
+    from oracle.orcbind import OracleBrain
     kind = "reference" if refbind.available("ref") else "port"
-    if kind == "reference":
-        from oracle.refbind import RefBrain
+    events_brain = None
+    if workload == "c1":
         libc.srand(1)
-        if net is None:
-            b = RefBrain(750, "ref")
+        if kind == "reference":
             from neurocorrelation_b200.presets import StandardDriver
+            b = refbind.RefBrain(750, "ref")
             drv = StandardDriver(b, libc.rand)
+            libc.srand(777)
+            step = drv.step
+            N, S = b.counts()
             desc = "NeuCor(750) STANDARD preset, full network"
         else:
-            b = RefBrain(0, "ref")
+            raise SystemExit("c1 reference arm needs oracle/_ref")
+    else:
+        net = sample_network(workload, weight_scale=weight_scale)
+        N, S = net["N"], net["S"]
+        if kind == "reference":
+            b = refbind.RefBrain(0, "ref")
             for p in net["positions"]:
                 b.create_neuron(float(p[0]), float(p[1]), float(p[2]))
             rp = net["rowptr"]
-            for q in range(net["N"]):
+            for q in range(N):
                 for k in range(int(rp[q]), int(rp[q + 1])):
                     b.create_synapse(q, int(net["pre"][k]), float(net["weight"][k]))
-            from neurocorrelation_b200.presets import F, random_unit
-            libc.srand(5)
-            rates = np.array([random_unit(libc.rand) * F(75) for _ in range(net["inputs"]["G"])], np.float32)
-            b.set_inputs(rates, net["inputs"]["positions"], net["inputs"]["radius"])
-            b.enable_sweep()
-            b.set_params(DT, 1.0, False)
-            desc = "same recipe shrunk to N=%d, S=%d (reference cost grows ~S*K per step)" % (net["N"], net["S"])
-        libc.srand(777)
-        N, S = b.counts()
-        stepper = b
-    else:
-        from oracle.orcbind import OracleBrain
-        if net is None:
-            net = sample_network("c2")
-        b = OracleBrain(net)
-        drive_setup(b, net, False, libc)
-        N, S = net["N"], net["S"]
-        desc = "oracle port (oracle/_ref absent) on N=%d, S=%d" % (N, S)
-        stepper = b
-    # deliveries are not observable through the reference's API; count them with the oracle port on the same network
-    t_w = time.perf_counter()
-    done_w = 0
-    while done_w < warmup and time.perf_counter() - t_w < budget_s * 0.3:
-        stepper.step() if net is not None or kind != "reference" else drv.step()
-        done_w += 1
+
+            class PosInputs:  # the reference builds its `near` lists from positions (NeuCor.cpp:319-323)
+                def __init__(self, inner):
+                    self.inner = inner
+
+                def set_inputs(self, rates, near=None):
+                    self.inner.set_inputs(rates, net["inputs"]["positions"], net["inputs"]["radius"])
+
+                def __getattr__(self, k):
+                    return getattr(self.inner, k)
+            drive_setup(PosInputs(b), net, True)
+            desc = "reference NeuCor.cpp, same recipe shrunk to N=%d, S=%d (its cost grows ~S*K per step)" % (N, S)
+        else:
+            b = OracleBrain(net)
+            drive_setup(b, net, False)
+            desc = "oracle port (oracle/_ref absent), same recipe shrunk to N=%d, S=%d" % (N, S)
+        step = b.step
+        # deliveries are not observable through the reference's API: count them with the oracle port on the same network
+        events_brain = OracleBrain(net)
+        drive_setup(events_brain, net, False)
+    spin = int(round(spinup_ms / DT))
+    t_s = time.perf_counter()
+    done_spin = 0
+    while done_spin < spin and time.perf_counter() - t_s < budget_s * 0.5:
+        step()
+        done_spin += 1
+    for _ in range(warmup):
+        step()
     t0 = time.perf_counter()
     done = 0
-    while done < steps and time.perf_counter() - t0 < budget_s:
-        stepper.step() if net is not None or kind != "reference" else drv.step()
+    while done < steps and time.perf_counter() - t0 < budget_s * 0.5:
+        step()
         done += 1
     wall = time.perf_counter() - t0
-    # event count of the same steps from the oracle port (bit-identical dynamics, tests/test_oracle_pinned.py)
     events = None
-    try:
-        from oracle.orcbind import OracleBrain
-        if net is not None:
-            o = OracleBrain(net)
-            drive_setup(o, net, False, libc)
-            for _ in range(done_w):
-                o.step()
-            s0 = o.stats()["deliveries"]
-            for _ in range(done):
-                o.step()
-            events = o.stats()["deliveries"] - s0
-    except Exception:
-        events = None
-    ms_step = wall / max(done, 1) * 1e3
+    if events_brain is not None:
+        for _ in range(done_spin + warmup):
+            events_brain.step()
+        s0 = events_brain.stats()["deliveries"]
+        for _ in range(done):
+            events_brain.step()
+        events = events_brain.stats()["deliveries"] - s0
     return dict(events_per_s=(events / wall) if events is not None else None, sim_ms_per_wall_s=done * DT / wall,
-                synapse_updates_per_s=S * done / wall, kind=kind, sample=desc, steps=done, ms_per_step=ms_step, N=N, S=S)
+                synapse_updates_per_s=S * done / wall, kind=kind,
+                sample=desc + "; spin-up %d steps (%.1f ms simulated), %d timed steps" % (done_spin, done_spin * DT, done),
+                steps=done, ms_per_step=wall / max(done, 1) * 1e3, N=N, S=S)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--workload", default=os.environ.get("NC_WORKLOAD", "c2"), choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--spinup-ms", type=float, default=None, help="simulated ms run (untimed) before warm-up; default per workload")
+    ap.add_argument("--weight-scale", type=float, default=1.0, help="multiplies the recipe's initial weights (experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    N, K, wl_desc = WORKLOADS[args.workload]
-    config = {"workload": wl_desc, "dt_ms": DT, "mode": "sweep (run() + full detector read), STDP on, background firing on",
-              "l2": "inputs larger than L2" if args.workload in ("c3", "m100") else "state (%.0f MB) fits the 126 MB L2: HBM fraction is an upper-bound exercise, see DESIGN.md" % (N * (K or 28) * 24 / 1e6)}
+    Nper, K, spin_default, wl_desc = WORKLOADS[args.workload]
+    spinup_ms = spin_default if args.spinup_ms is None else args.spinup_ms
+    warmup = max(args.warmup, 3)
+    state_mb = Nper * (K or 28) * 28 / 1e6
+    config = {"workload": wl_desc, "dt_ms": DT, "mode": "sweep (run() + full detector read), STDP on (learningRate 1), background firing on",
+              "network": "stratified random stand-in (in-degree exactly K, lengths ~ r^2 in a ball, weights U(0.2,1)*%g, 20%% inhibitory), %d input firers with random phase" % (args.weight_scale, max(1, Nper * world // 250)) if K else "NeuCor(750)",
+              "spinup_ms": spinup_ms,
+              "l2": "per-GPU state %.0f MB: larger than the 126 MB L2 (no flush needed)" % state_mb if state_mb > 126 * 2 else "per-GPU state %.0f MB vs 126 MB L2: partly L2-resident" % state_mb}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        r = cpu_reference_run(args.workload, args.steps, max(args.warmup, 3))
+        r = cpu_reference_run(args.workload, args.steps, warmup, spinup_ms, budget_s=60.0, weight_scale=args.weight_scale)
         line = {"impl": "reference", "metric": "synaptic_events_per_s", "value": r["events_per_s"], "unit": "delivered synaptic events/s",
-                "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "n_gpus": args.gpus, "steps": r["steps"], "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 state, f64 intermediates", "data": "synthetic", "config": config,
                 "sim_ms_per_wall_s": r["sim_ms_per_wall_s"], "synapse_updates_per_s": r["synapse_updates_per_s"],
                 "cpu_baseline": {"value": r["events_per_s"], "unit": "delivered synaptic events/s", "cores": 1, "kind": r["kind"], "sample": r["sample"]},
@@ -231,49 +271,76 @@ def main():
         return
 
     import torch
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
     dev = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(dev)
-
-    import neurocorrelation_b200 as nb
-    from helpers import libc
-    from neurocorrelation_b200 import engine
-
+    dist = None
+    comm_id = None
     if world > 1:
-        raise SystemExit("multi-GPU bench path: see bench_multi in a later round")
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+    from neurocorrelation_b200 import engine
+    if world > 1:
+        box = [engine.Engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        comm_id = box[0]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda:%d" % dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     t_build = time.perf_counter()
-    g, net = build_brain(args.workload, dev)
-    S = net["S"]
-    drive_setup(g, net, True, libc)
+    g, net = build_brain(args.workload, dev, rank, world, weight_scale=args.weight_scale, comm_id=comm_id)
+    if args.workload == "c1":
+        from helpers import libc
+        from neurocorrelation_b200.presets import StandardDriver
+        drv = StandardDriver(g, libc.rand)
+        libc.srand(777)
+        step = drv.step
+    else:
+        drive_setup(g, net, True)
+        step = g.step
     g.set_sweep_mean(False)  # the per-step device->host result is the counter block (hidden rand() count, fires, ...)
     g.finalize()
-    if args.workload in ("c3", "m100"):
+    Nglob, S_glob = g.counts()[0], (net["S"] * world if net else g.counts()[1])
+    if net:
         g._keepalive = None
         for k in ("pre", "weight", "length", "flag", "rowptr"):
             net[k] = None
         torch.cuda.empty_cache()
     t_build = time.perf_counter() - t_build
     E = engine.Engine(borrowed=g.engine_handle())
-    E.N, E.S, E.row0, E.n_rows = net["N"], S, 0, net["N"]
 
-    for _ in range(max(args.warmup, 3)):
-        g.step()
+    t_spin = time.perf_counter()
+    spin_steps = int(round(spinup_ms / DT))
+    for _ in range(spin_steps):
+        step()
+    for _ in range(warmup):
+        step()
+    barrier()
+    t_spin = time.perf_counter() - t_spin
     E.snapshot()
-    E.tape_begin(args.steps + 1, max(1 << 16, 64 * args.steps * (net["N"] // 1000 + 64)))
+    ev_cap = max(1 << 16, 64 * args.steps * (Nglob // 1000 + 64))
+    E.tape_begin(args.steps + 1, ev_cap)
     launches0 = E.launch_count()
     h2d0, d2h0 = g.traffic()
     stats0 = g.stats()
     sampler = ClockSampler(dev)
-    sampler.start()
-    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        g.step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+        step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
     E.tape_end()
     h2d1, d2h1 = g.traffic()
     stats1 = g.stats()
@@ -285,22 +352,35 @@ def main():
     E.tape_replay(0, min(args.steps, 3))  # warm the replay path
     E.restore()
     launches1 = E.launch_count()
+    barrier()
     rep = E.tape_replay(0, args.steps, per_kernel=False)
     replay_launches = E.launch_count() - launches1
-    clocks = sampler.stop()
+    ms_total = max_over_ranks(rep["ms_total"])
+    clocks = sampler.stop() if rank == 0 else None
     E.restore()
+    barrier()
     repk = E.tape_replay(0, args.steps, per_kernel=True)
     assert rep["stats"]["deliveries"] == d["deliveries"], "replay is not the same computation as the live run"
+    p1 = max_over_ranks(repk["ms_pass1"]) / args.steps
+    p2 = max_over_ranks(repk["ms_pass2"]) / args.steps
+    px = max_over_ranks(repk["ms_exchange"]) / args.steps
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
-    ms_step = rep["ms_total"] / args.steps
-    events = d["deliveries"]
-    value = events / (rep["ms_total"] * 1e-3)
+    ms_step = ms_total / args.steps
+    events = d["deliveries"]  # network-wide (summed over shards inside nc_step)
+    value = events / (ms_total * 1e-3)
     peak, peak_src = hbm_peak()
-    p1, p2 = repk["ms_pass1"] / args.steps, repk["ms_pass2"] / args.steps
-    nL = (d["loads_accepted"] + d["loads_dropped"]) / args.steps
-    nPD = d["plasticity_calls"] / args.steps
-    bytes_p1 = 4.0 * S + 28.0 * net["N"]
-    bytes_p2 = 4.0 * S + 16.0 * nL + 12.0 * nPD
+    # algorithmic bytes PER GPU and launch: counters are network-wide, shards are equal-sized
+    S_gpu, N_gpu = S_glob / world, Nglob / world
+    nL = (d["loads_accepted"] + d["loads_dropped"]) / args.steps / world
+    nPD = d["plasticity_calls"] / args.steps / world
+    nAct = d["active_visits"] / max(d["neuron_runs"], 1) * N_gpu  # active slots staged per row scan (average over runs)
+    bytes_p1 = 4.0 * S_gpu + 28.0 * N_gpu + 4.0 * nAct
+    bytes_p2 = 4.0 * S_gpu + 16.0 * nL + 12.0 * nPD
     if p1 >= p2:
         dom, dom_ms, dom_bytes = "k_neuron_pass", p1, bytes_p1
     else:
@@ -308,13 +388,14 @@ def main():
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     step_bytes = bytes_p1 + bytes_p2
     line = {
-        "metric": "synaptic_events_per_s", "value": value, "unit": "delivered synaptic events/s", "n_gpus": 1, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": "synaptic_events_per_s", "value": value, "unit": "delivered synaptic events/s", "n_gpus": world, "steps": args.steps,
+        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 state, f64 intermediates", "data": "synthetic", "config": config,
-        "sim_ms_per_wall_s": DT / (ms_step * 1e-3), "synapse_updates_per_s": S / (ms_step * 1e-3),
-        "neurons": net["N"], "synapses": S, "build_s": t_build, "mean_rate_hz": d["fires"] / args.steps / net["N"] / DT * 1e3,
+        "sim_ms_per_wall_s": DT / (ms_step * 1e-3), "synapse_updates_per_s": S_glob / (ms_step * 1e-3),
+        "neurons": Nglob, "synapses": S_glob, "build_s": t_build, "spinup_s": t_spin, "sim_time_ms": g.time(),
+        "mean_rate_hz": d["fires"] / args.steps / Nglob / DT * 1e3,
         "per_step": {k: v / args.steps for k, v in d.items()},
-        "kernel_ms": {"k_neuron_pass": p1, "k_synapse_pass": p2, "step_total": ms_step},
+        "kernel_ms": {"k_neuron_pass": p1, "k_synapse_pass": p2, "fire_exchange": px, "step_total": ms_step},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
                      "step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9, "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak}},
@@ -323,11 +404,14 @@ def main():
                 "sim_ms_per_wall_s": DT * args.steps / e2e_s},
         "gpu_launches": replay_launches, "gpu_launches_e2e": live_launches, "clocks": clocks,
     }
-    if not args.no_cpu_baseline:
-        r = cpu_reference_run(args.workload, 10_000, 2, budget_s=20.0)
-        line["cpu_baseline"] = {"value": r["events_per_s"], "unit": "delivered synaptic events/s", "cores": 1, "kind": r["kind"], "sample": r["sample"] + "; %d steps" % r["steps"],
+    if not args.no_cpu_baseline and world == 1:
+        r = cpu_reference_run(args.workload, 10_000, 2, spinup_ms, budget_s=24.0, weight_scale=args.weight_scale)
+        line["cpu_baseline"] = {"value": r["events_per_s"], "unit": "delivered synaptic events/s", "cores": 1, "kind": r["kind"], "sample": r["sample"],
                                 "sim_ms_per_wall_s": r["sim_ms_per_wall_s"], "synapse_updates_per_s": r["synapse_updates_per_s"], "ms_per_step": r["ms_per_step"]}
     print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

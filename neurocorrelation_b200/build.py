@@ -41,7 +41,7 @@ def build_engine(force=False, verbose=False):
     srcs.append(os.path.join(ROOT, "..", "include", "neucor_b200.h"))
     if force or _newer(ENGINE_SO, srcs):
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", ENGINE_SO, srcs[0]]
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", ENGINE_SO, srcs[0], "-ldl"]
         r = _run(cmd)
         if verbose:
             print(r.stderr)

@@ -140,43 +140,54 @@ def uniform_random_network(N, K, seed=1, max_length=None):
                 inputs=dict(G=G, positions=None, radius=np.full(G, 0.8, np.float32), near=near))
 
 
-def stratified_network_torch(N, K, device, seed=1, chunk_rows=32768):
-    """C3-scale stand-in built directly in device memory with torch (plumbing only): every neuron gets K distinct
-    presynaptic partners, one drawn uniformly from each of K equal strata of the ID range (so rows are sorted by
-    construction and in-degree is exactly K), lengths from the distance distribution of uniform points in a ball
-    of radius radius_for(K) (pdf ~ r^2) truncated to >= MIN_LENGTH, weights U(0.2, 1) with 20 % negated.
-    Returns device tensors (rowptr int64, pre int32, weight f32, length f32, flag uint8) and host `near` lists."""
+def stratified_network_torch(N, K, device, seed=1, chunk_rows=32768, weight_scale=1.0):
+    """Whole network of stratified_shard_torch (one shard holding every row)."""
+    return stratified_shard_torch(N, K, 0, N, device, seed=seed, chunk_rows=chunk_rows, weight_scale=weight_scale)
+
+
+def stratified_shard_torch(N, K, row0, n_rows, device, seed=1, chunk_rows=32768, weight_scale=1.0):
+    """Rows [row0, row0+n_rows) of the C3-scale stand-in, built directly in device memory with torch (plumbing only):
+    every neuron gets K distinct presynaptic partners, one drawn uniformly from each of K equal strata of the GLOBAL ID
+    range (so rows are sorted by construction and in-degree is exactly K), lengths from the distance distribution of
+    uniform points in a ball of radius radius_for(K) (pdf ~ r^2) truncated to >= MIN_LENGTH, weights
+    U(0.2, 1) * weight_scale with 20 % negated.  Returns device tensors (local rowptr int64 from 0, pre int32, weight
+    f32, length f32, flag uint8), the host `near` lists of the WHOLE network's input firers (identical on every shard)
+    and `min_delay` of this shard."""
     import torch
     gen = torch.Generator(device=device)
-    gen.manual_seed(seed)
-    N, K = int(N), int(K)
-    S = N * K
+    gen.manual_seed(seed * 1000003 + row0)
+    N, K, row0, n_rows = int(N), int(K), int(row0), int(n_rows)
+    S = n_rows * K
     R = radius_for(K)
     pre = torch.empty(S, dtype=torch.int32, device=device)
     weight = torch.empty(S, dtype=torch.float32, device=device)
     length = torch.empty(S, dtype=torch.float32, device=device)
     bounds = (torch.arange(K + 1, device=device, dtype=torch.int64) * N) // K
     lo, width = bounds[:-1], (bounds[1:] - bounds[:-1])
-    for q0 in range(0, N, chunk_rows):
-        q1 = min(N, q0 + chunk_rows)
+    for q0 in range(0, n_rows, chunk_rows):
+        q1 = min(n_rows, q0 + chunk_rows)
         n = q1 - q0
         u = torch.rand((n, K), device=device, generator=gen, dtype=torch.float64)
         off = torch.minimum((u * width).to(torch.int64), width - 1)
         p = lo + off
-        rows = torch.arange(q0, q1, device=device, dtype=torch.int64)[:, None]
+        rows = torch.arange(row0 + q0, row0 + q1, device=device, dtype=torch.int64)[:, None]
         clash = p == rows
         p = torch.where(clash, lo + (off + 1) % width, p)
         pre[q0 * K:q1 * K] = p.reshape(-1).to(torch.int32)
         ul = torch.rand(n * K, device=device, generator=gen)
         length[q0 * K:q1 * K] = torch.clamp(R * ul.pow(1.0 / 3.0), min=MIN_LENGTH)
-        w = torch.rand(n * K, device=device, generator=gen) * 0.8 + 0.2
+        w = (torch.rand(n * K, device=device, generator=gen) * 0.8 + 0.2) * float(weight_scale)
         neg = torch.rand(n * K, device=device, generator=gen) < 0.2
         weight[q0 * K:q1 * K] = torch.where(neg, -w, w)
         del u, off, p, clash, ul, w, neg
     flag = (weight < 0).to(torch.uint8)
-    rowptr = torch.arange(N + 1, device=device, dtype=torch.int64) * K
+    rowptr = torch.arange(n_rows + 1, device=device, dtype=torch.int64) * K
     rng = np.random.default_rng(seed)
     G = max(1, N // 250)
-    near = [np.sort(rng.choice(N, size=min(N, 17), replace=False)).astype(np.uint32) for _ in range(G)]
-    return dict(N=N, S=S, rowptr=rowptr, pre=pre, weight=weight, length=length, flag=flag,
+    if N <= 4_000_000:
+        near = [np.sort(rng.choice(N, size=min(N, 17), replace=False)).astype(np.uint32) for _ in range(G)]
+    else:  # rng.choice without replacement is O(N) per call: draw with replacement and de-duplicate instead
+        near = [np.unique(rng.integers(0, N, size=17)).astype(np.uint32) for _ in range(G)]
+    return dict(N=N, S=S, row0=row0, n_rows=n_rows, rowptr=rowptr, pre=pre, weight=weight, length=length, flag=flag,
+                min_delay=float(length.min().item()) * 2.0 if S else float("inf"),
                 inputs=dict(G=G, positions=None, radius=np.full(G, 0.8, np.float32), near=near))

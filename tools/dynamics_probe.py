@@ -9,8 +9,9 @@ import bench
 from helpers import libc
 
 wl, steps, blk = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
-g, net = bench.build_brain(wl, 0)
-bench.drive_setup(g, net, True, libc)
+ws = float(sys.argv[4]) if len(sys.argv) > 4 else 1.0
+g, net = bench.build_brain(wl, 0, weight_scale=ws)
+bench.drive_setup(g, net, True)
 g.set_sweep_mean(False)
 g.finalize()
 prev = g.stats()

@@ -127,160 +127,337 @@ __device__ __forceinline__ void warp_neuron_run(const View& v, NeuronState& n, C
     }
 }
 
+// ---- staging ------------------------------------------------------------------------------------------------
+// Occupied slots (arrive != 0 && arrive <= t1) of one row, compacted in row order (= ascending presynaptic ID).
+// Rows are walked in 128-slot groups aligned in the global slot index space: lane l owns slots 4l..4l+3 of a group, so every
+// lane issues one 16-byte load per group; slots outside [rs, re) are masked.  Per group the four ballots (one per sub-slot)
+// are also written to the candidate bitmap that lets the synapse pass skip its own read of `arrive`.
+//   SPILL = true : entries go to the CandView (shared memory first, per-warp global spill area after) — warp-per-row path
+//   SPILL = false: entries go to pa/pd/pj while they fit in `room`; the returned count tells the caller whether they did
+// hasEv: some staged slot delivers (t0 < arrive) or re-queues its target (t0 < arrive + 2 <= t1) in this window.
+template <bool SPILL>
+__device__ __forceinline__ uint32_t stage_row(const View& v, const StepArgs& s, uint64_t row, uint64_t rs, uint64_t re, CandView& cv,
+                                              float* pa, float* pd, uint32_t* pj, uint32_t room, uint32_t lane, bool& hasEv) {
+    uint32_t cnt = 0;
+    bool ev = false;
+    const uint32_t len = (uint32_t)(re - rs);
+    const uint32_t t1b = __float_as_uint(s.t1);
+    const uint64_t g0 = rs >> 7, g1 = (re + 127) >> 7;
+    uint4* bm = reinterpret_cast<uint4*>(v.candBits) + (g0 + row);
+    const float4* src = reinterpret_cast<const float4*>(v.arrive) + lane;
+    for (uint64_t gb = g0; gb < g1; gb += NC_UNROLL4) {
+        float4 av[NC_UNROLL4];
+#pragma unroll
+        for (int u = 0; u < NC_UNROLL4; u++)
+            av[u] = (gb + u < g1) ? __ldcs(src + ((gb + u) << 5)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < NC_UNROLL4; u++) {
+            if (gb + u >= g1) break;
+            // slot index relative to the row start; one unsigned compare against the row length masks both ends
+            const uint32_t rel0 = (uint32_t)(int32_t)((int64_t)((gb + u) << 7) - (int64_t)rs) + 4u * lane;
+            const float a4[4] = {av[u].x, av[u].y, av[u].z, av[u].w};
+            bool is[4];
+            // arrive times are positive floats (0 = idle): as unsigned integers, (bits - 1) < bits(t1)  <=>  0 < arrive <= t1
+#pragma unroll
+            for (int k = 0; k < 4; k++) is[k] = (__float_as_uint(a4[k]) - 1u < t1b) && (rel0 + k < len);
+            if (!__any_sync(0xffffffffu, is[0] | is[1] | is[2] | is[3])) {
+                if (lane == 0) bm[gb + u - g0] = make_uint4(0u, 0u, 0u, 0u);
+                continue;
+            }
+            uint32_t m[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) m[k] = __ballot_sync(0xffffffffu, is[k]);
+            if (lane == 0) bm[gb + u - g0] = make_uint4(m[0], m[1], m[2], m[3]);
+            const uint32_t lt = (1u << lane) - 1u;
+            uint32_t pos = cnt + __popc(m[0] & lt) + __popc(m[1] & lt) + __popc(m[2] & lt) + __popc(m[3] & lt);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (is[k]) {
+                    const float a = a4[k];
+                    const float tR = add32(a, 2.0f);
+                    ev |= (a > s.t0) || (tR > s.t0 && tR <= s.t1);
+                    const uint32_t jr = rel0 + k;  // (32-bit wrap intended: rel0 is "negative" left of the row start)
+                    const float d = v.depol[rs + jr];
+                    if (SPILL) { cv.A(pos) = a; cv.D(pos) = d; cv.J(pos) = jr; }
+                    else if (pos < room) { pa[pos] = a; pd[pos] = d; pj[pos] = jr; }
+                    pos++;
+                }
+            cnt += __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+        }
+    }
+    hasEv = __any_sync(0xffffffffu, ev);
+    return cnt;
+}
+
+// host events of neuron q: [evLo, evHi) in the (neuron, time)-sorted list (bit set by k_mark_events for rows that have any)
+__device__ __forceinline__ void host_event_range(const View& v, const StepArgs& s, uint64_t row, uint32_t q, uint32_t& evLo, uint32_t& evHi) {
+    evLo = 0; evHi = 0;
+    if (s.nEv && ((v.evMask[row >> 5] >> (row & 31u)) & 1u)) {
+        uint32_t lo = 0, hi = s.nEv;
+        while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (s.ev[mid].neuron < q) lo = mid + 1; else hi = mid; }
+        evLo = lo; hi = s.nEv;
+        while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (s.ev[mid].neuron <= q) lo = mid + 1; else hi = mid; }
+        evHi = lo;
+    }
+}
+__device__ __forceinline__ bool in_subset(const StepArgs& s, uint32_t q) {  // nc_run_neurons: only the listed neurons are run
+    uint32_t lo = 0, hi = s.nSubset;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (s.subset[mid] < q) lo = mid + 1; else hi = mid; }
+    return lo < s.nSubset && s.subset[lo] == q;
+}
+
+// ---- warp-per-row path: rows whose occupied slots do not fit the warp's shared-memory pool ---------------------------
+__device__ void warp_row(const View& v, const StepArgs& s, uint64_t row, CandView& cv, uint32_t lane, P1Counters& ctr) {
+    const uint32_t q = (uint32_t)(v.row0 + row);
+    const uint64_t rs = v.rowptr[row], re = v.rowptr[row + 1];
+    bool hasEv;
+    const uint32_t cnt = stage_row<true>(v, s, row, rs, re, cv, nullptr, nullptr, nullptr, 0u, lane, hasEv);
+    __syncwarp();
+    uint32_t evLo, evHi;
+    host_event_range(v, s, row, q, evLo, evHi);
+    NeuronState n;
+    {
+        float2 pa = v.potAct[row];
+        n.pot = pa.x; n.act = pa.y;
+        n.lastRan = v.lastRan[row]; n.lastFire = v.lastFire[row]; n.actStart = v.actStart[row];
+        n.firings = v.firings[row];
+        n.sched = __uint_as_float(0x7fc00000u);
+        for (uint32_t e = evLo; e < evHi; e++)
+            if (s.ev[e].kind == 2u && (s.ev[e].index_or_flags & 1u)) n.sched = s.ev[e].time;
+        if (lane == 0) v.lfStart[row] = n.lastFire;
+    }
+    // ---- replay in-window events in canonical order ----
+    if (hasEv || evHi > evLo || (s.sweep & NC_SWEEP_START)) {
+        float curT = s.t0;
+        unsigned long long curC = 0;
+        bool first = true;  // events at exactly t0 are allowed for host events only
+        for (;;) {
+            EvPick best;
+            best.t = INFINITY; best.code = ~0ull; best.src = 0xffffffffu;
+            for (uint32_t c = lane; c < cnt; c += 32) {
+                float a = fabsf(cv.A(c));
+                if (a > s.t0) {  // delivery in this window (a <= t1 by staging)
+                    uint32_t p = v.pre[rs + cv.J(c)] & 0x7fffffffu;
+                    unsigned long long code = (1ull << 32) | p;
+                    if ((first || pick_less(curT, curC, a, code)) && pick_less(a, code, best.t, best.code)) {
+                        best.t = a; best.code = code; best.src = c;
+                    }
+                }
+                float tR = add32(a, 2.0f);  // Neuron::transfer's requeue (NeuCor.cpp:665)
+                if (tR > s.t0 && tR <= s.t1) {
+                    unsigned long long code = (2ull << 32);
+                    if ((first || pick_less(curT, curC, tR, code)) && pick_less(tR, code, best.t, best.code)) {
+                        best.t = tR; best.code = code; best.src = c;
+                    }
+                }
+            }
+            if ((s.sweep & NC_SWEEP_START) && lane == 0 && (first || pick_less(curT, curC, s.t0, 2ull << 32)) &&
+                pick_less(s.t0, 2ull << 32, best.t, best.code)) {
+                best.t = s.t0; best.code = 2ull << 32; best.src = 0xfffffffeu;  // runAll: queued at t0 (NeuCor.cpp:596)
+            }
+            for (uint32_t e = evLo + lane; e < evHi; e += 32) {
+                nc_event ev = s.ev[e];
+                unsigned long long code = ev.kind == 0u ? (unsigned long long)ev.index_or_flags : (2ull << 32);
+                bool after = first ? (ev.time >= s.t0) : pick_less(curT, curC, ev.time, code);
+                if (after && ev.time <= s.t1 && pick_less(ev.time, code, best.t, best.code)) {
+                    best.t = ev.time; best.code = code; best.src = 0x80000000u | e;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                float ot = __shfl_xor_sync(0xffffffffu, best.t, o);
+                unsigned long long oc = __shfl_xor_sync(0xffffffffu, best.code, o);
+                uint32_t os = __shfl_xor_sync(0xffffffffu, best.src, o);
+                if (pick_less(ot, oc, best.t, best.code)) { best.t = ot; best.code = oc; best.src = os; }
+            }
+            if (best.code == ~0ull) break;
+            {
+                uint32_t rank = (uint32_t)(best.code >> 32), k = (uint32_t)best.code;
+                if (rank == 0) {  // InputFirer::run → Neuron::fire, no update, ignores refractory (NeuCor.cpp:326-331,643-645)
+                    n.lastFire = best.t;
+                    n.firings++;
+                    ctr.fires++;
+                    if (lane == 0) emit_fire(v, q, best.t, k, q);
+                } else if (rank == 1) {  // Synapse::run → Neuron::transfer (NeuCor.cpp:718-726,663-666)
+                    ctr.deliveries++;
+                    warp_neuron_run(v, n, cv, cnt, rs, q, best.t, (1u << 30) | q, k, NC_SENT | (1u << 29) | cv.J(best.src), lane, ctr);
+                } else {
+                    warp_neuron_run(v, n, cv, cnt, rs, q, best.t, (2u << 30) | q, 0u, NC_SENT | (2u << 29), lane, ctr);
+                }
+            }
+            __syncwarp();
+            curT = best.t; curC = best.code; first = false;
+        }
+    }
+    if (s.sweep & NC_SWEEP_END) warp_neuron_run(v, n, cv, cnt, rs, q, s.t1, (3u << 30) | q, 0u, NC_SENT | (3u << 29), lane, ctr);
+    if (lane == 0) {
+        v.potAct[row] = make_float2(n.pot, n.act);
+        v.lastRan[row] = n.lastRan; v.lastFire[row] = n.lastFire; v.firings[row] = n.firings;
+    }
+    __syncwarp();
+}
+
+// ---- lane-per-row path: one lane replays one neuron; its occupied slots sit in a slice of the warp's pool ------------------
+struct ActMark { float T; uint32_t firings; bool ran; };
+
+// Neuron::run (NeuCor.cpp:619-641) by a single lane: the ordered accumulation is the reference's own loop, one slot after
+// the other in ascending presynaptic ID with a double -> float rounding per addition (NeuCor.cpp:688-700).
+__device__ __forceinline__ void lane_neuron_run(const View& v, NeuronState& n, float* A, const float* D, const uint32_t* J, uint32_t cnt,
+                                                uint64_t rs, uint32_t q, float T, uint32_t rk1, uint32_t k2, uint32_t sentinel, P1Counters& ctr,
+                                                ActMark& am) {
+    float dT;
+    if (!neuron_run_begin(n, T, dT)) return;
+    ctr.runs++;
+    float np = n.pot;
+    double E = 0.0;
+    bool haveE = false;
+    for (uint32_t c = 0; c < cnt; c++) {
+        const float a = A[c];
+        if (a > 0.0f) {                    // not cleared earlier in this window
+            const float off = sub32(T, a);
+            if (off > 0.0f) {              // arrived
+                if (!haveE) { E = exp_glibc(mul64(0.3702, (double)dT)); haveE = true; }
+                ctr.visits++;
+                np = (float)add64((double)np, chain_term(dT, D[c], E));
+                if (2.0f < off) {          // NeuCor.cpp:697 — the slot becomes idle; leave the when-and-why for the synapse pass
+                    A[c] = -a;
+                    const uint64_t sidx = rs + J[c];
+                    v.arrive[sidx] = __uint_as_float(sentinel);
+                    v.depol[sidx] = T;
+                }
+            }
+        }
+    }
+    const bool fired = neuron_run_finish(n, np, T, dT, false);
+    am.T = T; am.firings = n.firings; am.ran = true;
+    if (fired) { ctr.fires++; emit_fire(v, q, T, rk1, k2); }
+}
+
+__device__ void lane_row(const View& v, const StepArgs& s, uint64_t row, float* A, const float* D, const uint32_t* J, uint32_t cnt, bool hasEv,
+                         P1Counters& ctr) {
+    const uint32_t q = (uint32_t)(v.row0 + row);
+    const uint64_t rs = v.rowptr[row];
+    uint32_t evLo, evHi;
+    host_event_range(v, s, row, q, evLo, evHi);
+    NeuronState n;
+    {
+        float2 pa = v.potAct[row];
+        n.pot = pa.x; n.act = pa.y;
+        n.lastRan = v.lastRan[row]; n.lastFire = v.lastFire[row]; n.actStart = v.actStart[row];
+        n.firings = v.firings[row];
+        n.sched = __uint_as_float(0x7fc00000u);
+        for (uint32_t e = evLo; e < evHi; e++)
+            if (s.ev[e].kind == 2u && (s.ev[e].index_or_flags & 1u)) n.sched = s.ev[e].time;
+        v.lfStart[row] = n.lastFire;
+    }
+    ActMark am;
+    am.T = 0.0f; am.firings = 0u; am.ran = false;
+    if (hasEv || evHi > evLo || (s.sweep & NC_SWEEP_START)) {
+        float curT = s.t0;
+        unsigned long long curC = 0;
+        bool first = true;
+        for (;;) {
+            float bt = INFINITY;
+            unsigned long long bc = ~0ull;
+            uint32_t bsrc = 0xffffffffu;
+            if (hasEv)
+                for (uint32_t c = 0; c < cnt; c++) {
+                    const float a = fabsf(A[c]);
+                    if (a > s.t0) {
+                        const uint32_t p = v.pre[rs + J[c]] & 0x7fffffffu;
+                        const unsigned long long code = (1ull << 32) | p;
+                        if ((first || pick_less(curT, curC, a, code)) && pick_less(a, code, bt, bc)) { bt = a; bc = code; bsrc = c; }
+                    }
+                    const float tR = add32(a, 2.0f);
+                    if (tR > s.t0 && tR <= s.t1) {
+                        const unsigned long long code = (2ull << 32);
+                        if ((first || pick_less(curT, curC, tR, code)) && pick_less(tR, code, bt, bc)) { bt = tR; bc = code; bsrc = c; }
+                    }
+                }
+            if ((s.sweep & NC_SWEEP_START) && (first || pick_less(curT, curC, s.t0, 2ull << 32)) && pick_less(s.t0, 2ull << 32, bt, bc)) {
+                bt = s.t0; bc = 2ull << 32; bsrc = 0xfffffffeu;
+            }
+            for (uint32_t e = evLo; e < evHi; e++) {
+                const nc_event ev = s.ev[e];
+                const unsigned long long code = ev.kind == 0u ? (unsigned long long)ev.index_or_flags : (2ull << 32);
+                const bool after = first ? (ev.time >= s.t0) : pick_less(curT, curC, ev.time, code);
+                if (after && ev.time <= s.t1 && pick_less(ev.time, code, bt, bc)) { bt = ev.time; bc = code; bsrc = 0x80000000u | e; }
+            }
+            if (bc == ~0ull) break;
+            const uint32_t rank = (uint32_t)(bc >> 32), k = (uint32_t)bc;
+            if (rank == 0) {
+                n.lastFire = bt;
+                n.firings++;
+                ctr.fires++;
+                emit_fire(v, q, bt, k, q);
+            } else if (rank == 1) {
+                ctr.deliveries++;
+                lane_neuron_run(v, n, A, D, J, cnt, rs, q, bt, (1u << 30) | q, k, NC_SENT | (1u << 29) | J[bsrc], ctr, am);
+            } else {
+                lane_neuron_run(v, n, A, D, J, cnt, rs, q, bt, (2u << 30) | q, 0u, NC_SENT | (2u << 29), ctr, am);
+            }
+            curT = bt; curC = bc; first = false;
+        }
+    }
+    if (s.sweep & NC_SWEEP_END) lane_neuron_run(v, n, A, D, J, cnt, rs, q, s.t1, (3u << 30) | q, 0u, NC_SENT | (3u << 29), ctr, am);
+    if (am.ran) n.act = neuron_activity(am.firings, am.T, n.actStart);
+    v.potAct[row] = make_float2(n.pot, n.act);
+    v.lastRan[row] = n.lastRan; v.lastFire[row] = n.lastFire; v.firings[row] = n.firings;
+}
+
+// Neuron pass.  A warp takes tiles of 32 consecutive rows.  It stages the occupied slots of as many rows as fit its
+// shared-memory pool (cooperative, coalesced row scans), then every lane replays ONE of those neurons on its own
+// (lane-per-row: the per-neuron math — ordered accumulation, powf/exp, threshold, AP — is not replicated across lanes);
+// a row that alone exceeds the pool takes the warp-per-row path with the global spill area.
 __global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32, 4) k_neuron_pass(View v, StepArgs s) {
     extern __shared__ unsigned char smem[];
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     const uint32_t cap = s.candCap;
     float* sA = reinterpret_cast<float*>(smem) + (size_t)wib * 3 * cap;
+    float* sD = sA + cap;
+    uint32_t* sJ = reinterpret_cast<uint32_t*>(sA + 2 * cap);
     CandView cv;
-    cv.a = sA; cv.d = sA + cap; cv.j = reinterpret_cast<uint32_t*>(sA + 2 * cap); cv.cap = cap;
+    cv.a = sA; cv.d = sD; cv.j = sJ; cv.cap = cap;
     const uint64_t gw = (uint64_t)blockIdx.x * NC_WARPS_PER_BLOCK + wib, nW = (uint64_t)gridDim.x * NC_WARPS_PER_BLOCK;
     cv.sa = v.spillA + gw * v.spillPerWarp; cv.sd = v.spillD + gw * v.spillPerWarp; cv.sj = v.spillJ + gw * v.spillPerWarp;
-    P1Counters ctr = {0, 0, 0, 0};
+    P1Counters ctrW = {0, 0, 0, 0};  // warp-uniform counts of the warp-per-row path
+    P1Counters ctrL = {0, 0, 0, 0};  // this lane's counts of the lane-per-row path
+    const uint64_t nTiles = (v.nRows + 31) >> 5;
 
-    for (uint64_t row = gw; row < v.nRows; row += nW) {
-        const uint32_t q = (uint32_t)(v.row0 + row);
-        if (s.subset) {  // nc_run_neurons: zero-length window, only the listed neurons are run
-            uint32_t lo = 0, hi = s.nSubset;
-            while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (s.subset[mid] < q) lo = mid + 1; else hi = mid; }
-            if (lo >= s.nSubset || s.subset[lo] != q) continue;
-        }
-        const uint64_t rs = v.rowptr[row], re = v.rowptr[row + 1];
-        // ---- stage occupied slots (arrive != 0 && arrive <= t1), preserving row order ----
-        // Rows are walked in 128-slot groups aligned in the global slot index space: lane l owns slots 4l..4l+3 of a group, so
-        // every lane issues one 16-byte load per group; slots outside [rs, re) are masked. Per group the four ballots (one per
-        // sub-slot) are also written to the candidate bitmap that lets the synapse pass skip its own read of `arrive`.
-        uint32_t cnt = 0;
-        const uint64_t g0 = rs >> 7, g1 = (re + 127) >> 7;
-        uint4* bm = reinterpret_cast<uint4*>(v.candBits) + (g0 + row);
-        for (uint64_t gb = g0; gb < g1; gb += NC_UNROLL4) {
-            float4 av[NC_UNROLL4];
-#pragma unroll
-            for (int u = 0; u < NC_UNROLL4; u++)
-                av[u] = (gb + u < g1) ? __ldcs(reinterpret_cast<const float4*>(v.arrive) + ((gb + u) << 5) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int u = 0; u < NC_UNROLL4; u++) {
-                if (gb + u >= g1) break;
-                const uint64_t j0 = ((gb + u) << 7) + 4 * lane;
-                const float a4[4] = {av[u].x, av[u].y, av[u].z, av[u].w};
-                bool is[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) is[k] = (a4[k] != 0.0f) && (a4[k] <= s.t1) && (j0 + k >= rs) && (j0 + k < re);
-                uint32_t m[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) m[k] = __ballot_sync(0xffffffffu, is[k]);
-                if (lane == 0) bm[gb + u - g0] = make_uint4(m[0], m[1], m[2], m[3]);
-                if (m[0] | m[1] | m[2] | m[3]) {
-                    const uint32_t lt = (1u << lane) - 1u;
-                    uint32_t pos = cnt + __popc(m[0] & lt) + __popc(m[1] & lt) + __popc(m[2] & lt) + __popc(m[3] & lt);
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        if (is[k]) {
-                            cv.A(pos) = a4[k];
-                            cv.D(pos) = v.depol[j0 + k];
-                            cv.J(pos) = (uint32_t)(j0 + k - rs);
-                            pos++;
-                        }
-                    cnt += __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
-                }
+    for (uint64_t tile = gw; tile < nTiles; tile += nW) {
+        const uint64_t rowBase = tile << 5;
+        const uint32_t nr = (uint32_t)min((uint64_t)32, v.nRows - rowBase);
+        uint32_t r = 0;
+        while (r < nr) {
+            // ---- batch: stage rows r, r+1, ... while their occupied slots fit the pool; the i-th staged row goes to lane i ----
+            uint32_t used = 0, nb = 0, myRow = 0, myOff = 0, myCnt = 0;
+            bool myEv = false, heavy = false;
+            while (r < nr) {
+                const uint64_t row = rowBase + r;
+                if (s.subset && !in_subset(s, (uint32_t)(v.row0 + row))) { r++; continue; }
+                const uint64_t rs = v.rowptr[row], re = v.rowptr[row + 1];
+                bool ev;
+                const uint32_t c = stage_row<false>(v, s, row, rs, re, cv, sA + used, sD + used, sJ + used, cap - used, lane, ev);
+                if (c > cap - used) { heavy = (nb == 0); break; }  // does not fit: close the batch (an over-long row goes alone)
+                if (lane == nb) { myRow = r; myOff = used; myCnt = c; myEv = ev; }
+                used += c; nb++; r++;
             }
+            __syncwarp();
+            if (heavy) { warp_row(v, s, rowBase + r, cv, lane, ctrW); r++; continue; }
+            if (lane < nb) lane_row(v, s, rowBase + myRow, sA + myOff, sD + myOff, sJ + myOff, myCnt, myEv, ctrL);
+            __syncwarp();
         }
-        __syncwarp();
-        // ---- host events of this neuron: [evLo, evHi) in the (neuron, time)-sorted list ----
-        uint32_t evLo = 0, evHi = 0;
-        if (s.nEv && ((v.evMask[row >> 5] >> (row & 31u)) & 1u)) {  // bit set by k_mark_events for rows that have host events
-            uint32_t lo = 0, hi = s.nEv;
-            while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (s.ev[mid].neuron < q) lo = mid + 1; else hi = mid; }
-            evLo = lo; hi = s.nEv;
-            while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (s.ev[mid].neuron <= q) lo = mid + 1; else hi = mid; }
-            evHi = lo;
-        }
-        NeuronState n;
-        {
-            float2 pa = v.potAct[row];
-            n.pot = pa.x; n.act = pa.y;
-            n.lastRan = v.lastRan[row]; n.lastFire = v.lastFire[row]; n.actStart = v.actStart[row];
-            n.firings = v.firings[row];
-            n.sched = __uint_as_float(0x7fc00000u);
-            for (uint32_t e = evLo; e < evHi; e++)
-                if (s.ev[e].kind == 2u && (s.ev[e].index_or_flags & 1u)) n.sched = s.ev[e].time;
-            if (lane == 0) v.lfStart[row] = n.lastFire;
-        }
-        // ---- replay in-window events in canonical order ----
-        if (cnt || evHi > evLo || (s.sweep & NC_SWEEP_START)) {
-            float curT = s.t0;
-            unsigned long long curC = 0;
-            bool first = true;  // events at exactly t0 are allowed for host events only
-            for (;;) {
-                EvPick best;
-                best.t = INFINITY; best.code = ~0ull; best.src = 0xffffffffu;
-                for (uint32_t c = lane; c < cnt; c += 32) {
-                    float a = fabsf(cv.A(c));
-                    if (a > s.t0) {  // delivery in this window (a <= t1 by staging)
-                        uint32_t p = v.pre[rs + cv.J(c)] & 0x7fffffffu;
-                        unsigned long long code = (1ull << 32) | p;
-                        if ((first || pick_less(curT, curC, a, code)) && pick_less(a, code, best.t, best.code)) {
-                            best.t = a; best.code = code; best.src = c;
-                        }
-                    }
-                    float tR = add32(a, 2.0f);  // Neuron::transfer's requeue (NeuCor.cpp:665)
-                    if (tR > s.t0 && tR <= s.t1) {
-                        unsigned long long code = (2ull << 32);
-                        if ((first || pick_less(curT, curC, tR, code)) && pick_less(tR, code, best.t, best.code)) {
-                            best.t = tR; best.code = code; best.src = c;
-                        }
-                    }
-                }
-                if ((s.sweep & NC_SWEEP_START) && lane == 0 && (first || pick_less(curT, curC, s.t0, 2ull << 32)) &&
-                    pick_less(s.t0, 2ull << 32, best.t, best.code)) {
-                    best.t = s.t0; best.code = 2ull << 32; best.src = 0xfffffffeu;  // runAll: queued at t0 (NeuCor.cpp:596)
-                }
-                for (uint32_t e = evLo + lane; e < evHi; e += 32) {
-                    nc_event ev = s.ev[e];
-                    unsigned long long code = ev.kind == 0u ? (unsigned long long)ev.index_or_flags : (2ull << 32);
-                    bool after = first ? (ev.time >= s.t0) : pick_less(curT, curC, ev.time, code);
-                    if (after && ev.time <= s.t1 && pick_less(ev.time, code, best.t, best.code)) {
-                        best.t = ev.time; best.code = code; best.src = 0x80000000u | e;
-                    }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    float ot = __shfl_xor_sync(0xffffffffu, best.t, o);
-                    unsigned long long oc = __shfl_xor_sync(0xffffffffu, best.code, o);
-                    uint32_t os = __shfl_xor_sync(0xffffffffu, best.src, o);
-                    if (pick_less(ot, oc, best.t, best.code)) { best.t = ot; best.code = oc; best.src = os; }
-                }
-                if (best.code == ~0ull) break;
-                {
-                    uint32_t rank = (uint32_t)(best.code >> 32), k = (uint32_t)best.code;
-                    if (rank == 0) {  // InputFirer::run → Neuron::fire, no update, ignores refractory (NeuCor.cpp:326-331,643-645)
-                        n.lastFire = best.t;
-                        n.firings++;
-                        ctr.fires++;
-                        if (lane == 0) emit_fire(v, q, best.t, k, q);
-                    } else if (rank == 1) {  // Synapse::run → Neuron::transfer (NeuCor.cpp:718-726,663-666)
-                        ctr.deliveries++;
-                        warp_neuron_run(v, n, cv, cnt, rs, q, best.t, (1u << 30) | q, k, NC_SENT | (1u << 29) | cv.J(best.src), lane, ctr);
-                    } else {
-                        warp_neuron_run(v, n, cv, cnt, rs, q, best.t, (2u << 30) | q, 0u, NC_SENT | (2u << 29), lane, ctr);
-                    }
-                }
-                __syncwarp();
-                curT = best.t; curC = best.code; first = false;
-            }
-        }
-        if (s.sweep & NC_SWEEP_END) warp_neuron_run(v, n, cv, cnt, rs, q, s.t1, (3u << 30) | q, 0u, NC_SENT | (3u << 29), lane, ctr);
-        if (lane == 0) {
-            v.potAct[row] = make_float2(n.pot, n.act);
-            v.lastRan[row] = n.lastRan; v.lastFire[row] = n.lastFire; v.firings[row] = n.firings;
-        }
-        __syncwarp();
     }
-    if (lane == 0) {  // every lane counted the same (warp-uniform) events
-        if (ctr.fires) atomicAdd(&v.stats[0], ctr.fires);
-        if (ctr.deliveries) atomicAdd(&v.stats[1], ctr.deliveries);
-        if (ctr.runs) atomicAdd(&v.stats[6], ctr.runs);
-        if (ctr.visits) atomicAdd(&v.stats[7], ctr.visits);
+    unsigned long long c4[4] = {ctrL.fires, ctrL.deliveries, ctrL.runs, ctrL.visits};
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        for (int o = 16; o > 0; o >>= 1) c4[i] += __shfl_xor_sync(0xffffffffu, c4[i], o);
+    if (lane == 0) {  // the warp-per-row path counted the same (warp-uniform) events in every lane
+        c4[0] += ctrW.fires; c4[1] += ctrW.deliveries; c4[2] += ctrW.runs; c4[3] += ctrW.visits;
+        if (c4[0]) atomicAdd(&v.stats[0], c4[0]);
+        if (c4[1]) atomicAdd(&v.stats[1], c4[1]);
+        if (c4[2]) atomicAdd(&v.stats[6], c4[2]);
+        if (c4[3]) atomicAdd(&v.stats[7], c4[3]);
     }
 }
 
@@ -726,7 +903,8 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
     k_fill_i32<<<(unsigned)((G1 + 255) / 256), 256, 0, e->stream>>>(v.head, G1, -1); e->launches++;
     CK(cudaGetLastError());
     // launch geometry: persistent grids sized to the SM count x resident blocks per SM
-    e->candCap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(std::min<uint64_t>(e->candCap, maxRow), 32), 1024);
+    // the warp's shared-memory pool of staged slots: shared by the rows of a lane-per-row batch, so not tied to the row length
+    e->candCap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(e->candCap, 32), 1024);
     e->smem1 = (size_t)NC_WARPS_PER_BLOCK * 3 * e->candCap * 4;
     CK(cudaFuncSetAttribute(k_neuron_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem1));
     int occ1 = 1, occ2 = 1;

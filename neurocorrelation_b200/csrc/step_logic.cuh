@@ -190,7 +190,12 @@ NC_HD bool neuron_run_begin(NeuronState& n, float T, float& dT) {
 }
 // Neuron::run, part 3 (after charge_insynapses produced `np`): passive decay, threshold check, AP waveform, activity.
 // Returns true when the neuron fired; the caller emits the fire record.
-NC_HD bool neuron_run_finish(NeuronState& n, float np, float T, float dT) {
+NC_HD float neuron_activity(uint32_t firings, float T, float actStart) {  // NeuCor.cpp:640
+    return (float)div64((double)firings, div64((double)sub32(T, actStart), 10.0));
+}
+// withAct = false: the caller evaluates neuron_activity() once, for the last run of the window (activity is only ever read
+// back, never fed into the dynamics, so intermediate values are dead).
+NC_HD bool neuron_run_finish(NeuronState& n, float np, float T, float dT, bool withAct = true) {
     const float baselevel = -70.0f, threshold = -55.0f, recharge = 0.5f, AP_cutoff = 2.0f;
     // charge_passive (NeuCor.cpp:677-680)
     np = add32(mul32(sub32(np, baselevel), powf_pos(recharge, dT)), baselevel);
@@ -217,7 +222,7 @@ NC_HD bool neuron_run_finish(NeuronState& n, float np, float T, float dT) {
         n.pot = (float)add64(add64(wave, (double)baselevel), tail);
     }
     // activity (NeuCor.cpp:640)
-    n.act = (float)div64((double)n.firings, div64((double)sub32(T, n.actStart), 10.0));
+    if (withAct) n.act = neuron_activity(n.firings, T, n.actStart);
     return fired;
 }
 

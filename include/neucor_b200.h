@@ -40,7 +40,7 @@ typedef struct nc_config {
     int32_t device;            /* CUDA device ordinal */
     int32_t rank, world;       /* neuron-range shard of this engine (world = 1: whole network) */
     uint32_t fire_capacity;    /* max fire records per step (0 = default: 4*N_global + 1024) */
-    uint32_t cand_smem;        /* per-row candidate slots staged in shared memory (0 = default 512) */
+    uint32_t cand_smem;        /* staged-slot pool per warp in shared memory, shared by the rows of a batch (0 = default 1024) */
     void* stream;              /* cudaStream_t to launch on (NULL = the engine creates its own) */
     uint32_t reserved[2];
 } nc_config;

@@ -38,7 +38,7 @@
 using namespace ncm;
 using namespace ncs;
 
-#define NC_WARPS_PER_BLOCK 8
+#define NC_WARPS_PER_BLOCK 4
 #define NC_UNROLL4 4         // independent 16-byte-per-lane (512 B per warp) row loads kept in flight per warp
 #define NC_P2_THREADS 1024   // synapse pass: one persistent block per SM, fire bitmask staged in its shared memory
 
@@ -298,111 +298,135 @@ __device__ void warp_row(const View& v, const StepArgs& s, uint64_t row, CandVie
 }
 
 // ---- lane-per-row path: one lane replays one neuron; its occupied slots sit in a slice of the warp's pool ------------------
-struct ActMark { float T; uint32_t firings; bool ran; };
+// All 32 lanes run this together and stay converged: the replay proceeds in ROUNDS, in every round each lane executes the
+// next event of its own neuron (or idles once it has none left), and the loops over the staged slots run to the largest
+// count of the batch.  The end-of-window sweep run is simply every lane's last event, so lanes with few events sweep while
+// others are still delivering.  One pass over a lane's slots does two things at once: it adds the active slots'
+// contributions for the event being executed — the reference's own loop, one slot after the other in ascending presynaptic
+// ID with a double -> float rounding per addition (NeuCor.cpp:688-700) — and it finds the neuron's next event.
+struct LanePick { float t; unsigned long long code; uint32_t src; };
 
-// Neuron::run (NeuCor.cpp:619-641) by a single lane: the ordered accumulation is the reference's own loop, one slot after
-// the other in ascending presynaptic ID with a double -> float rounding per addition (NeuCor.cpp:688-700).
-__device__ __forceinline__ void lane_neuron_run(const View& v, NeuronState& n, float* A, const float* D, const uint32_t* J, uint32_t cnt,
-                                                uint64_t rs, uint32_t q, float T, uint32_t rk1, uint32_t k2, uint32_t sentinel, P1Counters& ctr,
-                                                ActMark& am) {
-    float dT;
-    if (!neuron_run_begin(n, T, dT)) return;
-    ctr.runs++;
-    float np = n.pot;
-    double E = 0.0;
-    bool haveE = false;
-    for (uint32_t c = 0; c < cnt; c++) {
-        const float a = A[c];
-        if (a > 0.0f) {                    // not cleared earlier in this window
-            const float off = sub32(T, a);
-            if (off > 0.0f) {              // arrived
-                if (!haveE) { E = exp_glibc(mul64(0.3702, (double)dT)); haveE = true; }
-                ctr.visits++;
-                np = (float)add64((double)np, chain_term(dT, D[c], E));
-                if (2.0f < off) {          // NeuCor.cpp:697 — the slot becomes idle; leave the when-and-why for the synapse pass
-                    A[c] = -a;
-                    const uint64_t sidx = rs + J[c];
-                    v.arrive[sidx] = __uint_as_float(sentinel);
-                    v.depol[sidx] = T;
-                }
-            }
-        }
+__device__ __forceinline__ void pick_from_slot(const View& v, const StepArgs& s, uint64_t rs, const uint32_t* J, uint32_t c, float a,
+                                               bool first, float curT, unsigned long long curC, LanePick& nx) {
+    if (a > s.t0) {  // delivery in this window (a <= t1 by staging)
+        const uint32_t p = v.pre[rs + J[c]] & 0x7fffffffu;
+        const unsigned long long code = (1ull << 32) | p;
+        if ((first || pick_less(curT, curC, a, code)) && pick_less(a, code, nx.t, nx.code)) { nx.t = a; nx.code = code; nx.src = c; }
     }
-    const bool fired = neuron_run_finish(n, np, T, dT, false);
-    am.T = T; am.firings = n.firings; am.ran = true;
-    if (fired) { ctr.fires++; emit_fire(v, q, T, rk1, k2); }
+    const float tR = add32(a, 2.0f);  // Neuron::transfer's requeue (NeuCor.cpp:665)
+    if (tR > s.t0 && tR <= s.t1) {
+        const unsigned long long code = (2ull << 32);
+        if ((first || pick_less(curT, curC, tR, code)) && pick_less(tR, code, nx.t, nx.code)) { nx.t = tR; nx.code = code; nx.src = c; }
+    }
+}
+__device__ __forceinline__ void pick_from_host(const StepArgs& s, uint32_t evLo, uint32_t evHi, bool first, float curT, unsigned long long curC,
+                                               LanePick& nx) {
+    if (s.sweep & NC_SWEEP_START)  // runAll: queued at t0 (NeuCor.cpp:596)
+        if ((first || pick_less(curT, curC, s.t0, 2ull << 32)) && pick_less(s.t0, 2ull << 32, nx.t, nx.code)) { nx.t = s.t0; nx.code = 2ull << 32; nx.src = 0xfffffffeu; }
+    for (uint32_t e = evLo; e < evHi; e++) {
+        const nc_event ev = s.ev[e];
+        const unsigned long long code = ev.kind == 0u ? (unsigned long long)ev.index_or_flags : (2ull << 32);
+        const bool after = first ? (ev.time >= s.t0) : pick_less(curT, curC, ev.time, code);
+        if (after && ev.time <= s.t1 && pick_less(ev.time, code, nx.t, nx.code)) { nx.t = ev.time; nx.code = code; nx.src = 0x80000000u | e; }
+    }
 }
 
-__device__ void lane_row(const View& v, const StepArgs& s, uint64_t row, float* A, const float* D, const uint32_t* J, uint32_t cnt, bool hasEv,
-                         P1Counters& ctr) {
+__device__ void lanes_replay(const View& v, const StepArgs& s, bool valid, uint64_t row, float* A, const float* D, const uint32_t* J, uint32_t cnt,
+                             bool hasEv, P1Counters& ctr) {
+    const uint32_t FULL = 0xffffffffu;
+    const unsigned long long NONE = ~0ull, SWEEP = 3ull << 32;
+    if (!valid) { cnt = 0; hasEv = false; row = 0; }
     const uint32_t q = (uint32_t)(v.row0 + row);
-    const uint64_t rs = v.rowptr[row];
-    uint32_t evLo, evHi;
-    host_event_range(v, s, row, q, evLo, evHi);
+    const uint64_t rs = valid ? v.rowptr[row] : 0;
+    uint32_t evLo = 0, evHi = 0;
     NeuronState n;
-    {
+    n.pot = 0.f; n.act = 0.f; n.lastRan = 0.f; n.lastFire = 0.f; n.actStart = 0.f; n.firings = 0u; n.sched = __uint_as_float(0x7fc00000u);
+    if (valid) {
+        host_event_range(v, s, row, q, evLo, evHi);
         float2 pa = v.potAct[row];
         n.pot = pa.x; n.act = pa.y;
         n.lastRan = v.lastRan[row]; n.lastFire = v.lastFire[row]; n.actStart = v.actStart[row];
         n.firings = v.firings[row];
-        n.sched = __uint_as_float(0x7fc00000u);
         for (uint32_t e = evLo; e < evHi; e++)
             if (s.ev[e].kind == 2u && (s.ev[e].index_or_flags & 1u)) n.sched = s.ev[e].time;
         v.lfStart[row] = n.lastFire;
     }
-    ActMark am;
-    am.T = 0.0f; am.firings = 0u; am.ran = false;
-    if (hasEv || evHi > evLo || (s.sweep & NC_SWEEP_START)) {
-        float curT = s.t0;
-        unsigned long long curC = 0;
-        bool first = true;
-        for (;;) {
-            float bt = INFINITY;
-            unsigned long long bc = ~0ull;
-            uint32_t bsrc = 0xffffffffu;
-            if (hasEv)
-                for (uint32_t c = 0; c < cnt; c++) {
-                    const float a = fabsf(A[c]);
-                    if (a > s.t0) {
-                        const uint32_t p = v.pre[rs + J[c]] & 0x7fffffffu;
-                        const unsigned long long code = (1ull << 32) | p;
-                        if ((first || pick_less(curT, curC, a, code)) && pick_less(a, code, bt, bc)) { bt = a; bc = code; bsrc = c; }
-                    }
-                    const float tR = add32(a, 2.0f);
-                    if (tR > s.t0 && tR <= s.t1) {
-                        const unsigned long long code = (2ull << 32);
-                        if ((first || pick_less(curT, curC, tR, code)) && pick_less(tR, code, bt, bc)) { bt = tR; bc = code; bsrc = c; }
-                    }
-                }
-            if ((s.sweep & NC_SWEEP_START) && (first || pick_less(curT, curC, s.t0, 2ull << 32)) && pick_less(s.t0, 2ull << 32, bt, bc)) {
-                bt = s.t0; bc = 2ull << 32; bsrc = 0xfffffffeu;
-            }
-            for (uint32_t e = evLo; e < evHi; e++) {
-                const nc_event ev = s.ev[e];
-                const unsigned long long code = ev.kind == 0u ? (unsigned long long)ev.index_or_flags : (2ull << 32);
-                const bool after = first ? (ev.time >= s.t0) : pick_less(curT, curC, ev.time, code);
-                if (after && ev.time <= s.t1 && pick_less(ev.time, code, bt, bc)) { bt = ev.time; bc = code; bsrc = 0x80000000u | e; }
-            }
-            if (bc == ~0ull) break;
-            const uint32_t rank = (uint32_t)(bc >> 32), k = (uint32_t)bc;
-            if (rank == 0) {
-                n.lastFire = bt;
+    const uint32_t maxCnt = __reduce_max_sync(FULL, cnt);
+    const bool sweepEnd = (s.sweep & NC_SWEEP_END) != 0;
+    float actT = 0.0f; uint32_t actF = 0u; bool ran = false;
+    // ---- first event of every lane ----
+    LanePick nx;
+    nx.t = INFINITY; nx.code = NONE; nx.src = 0xffffffffu;
+    if (__any_sync(FULL, hasEv))
+        for (uint32_t c = 0; c < maxCnt; c++)
+            if (hasEv && c < cnt) pick_from_slot(v, s, rs, J, c, A[c], true, s.t0, 0ull, nx);
+    if (valid) pick_from_host(s, evLo, evHi, true, s.t0, 0ull, nx);
+    bool swept = !sweepEnd || !valid;
+    if (nx.code == NONE && !swept) { nx.t = s.t1; nx.code = SWEEP; swept = true; }
+    // ---- rounds ----
+    while (__any_sync(FULL, nx.code != NONE)) {
+        const LanePick cur = nx;
+        nx.t = INFINITY; nx.code = NONE; nx.src = 0xffffffffu;
+        const bool act = cur.code != NONE;
+        const uint32_t rank = (uint32_t)(cur.code >> 32), k = (uint32_t)cur.code;
+        const float T = cur.t;
+        bool running = false;
+        float dT = 0.0f;
+        uint32_t rk1 = 0u, k2 = 0u, sentinel = 0u;
+        if (act) {
+            if (rank == 0u) {  // InputFirer::run → Neuron::fire, no update, ignores refractory (NeuCor.cpp:326-331,643-645)
+                n.lastFire = T;
                 n.firings++;
                 ctr.fires++;
-                emit_fire(v, q, bt, k, q);
-            } else if (rank == 1) {
-                ctr.deliveries++;
-                lane_neuron_run(v, n, A, D, J, cnt, rs, q, bt, (1u << 30) | q, k, NC_SENT | (1u << 29) | J[bsrc], ctr, am);
+                emit_fire(v, q, T, k, q);
             } else {
-                lane_neuron_run(v, n, A, D, J, cnt, rs, q, bt, (2u << 30) | q, 0u, NC_SENT | (2u << 29), ctr, am);
+                if (rank == 1u) {  // Synapse::run → Neuron::transfer (NeuCor.cpp:718-726,663-666)
+                    ctr.deliveries++;
+                    rk1 = (1u << 30) | q; k2 = k; sentinel = NC_SENT | (1u << 29) | J[cur.src];
+                } else {           // rank 2: queued Neuron::run; rank 3: end-of-window sweep
+                    rk1 = (rank << 30) | q; k2 = 0u; sentinel = NC_SENT | (rank << 29);
+                }
+                running = neuron_run_begin(n, T, dT);  // false when no time has passed (NeuCor.cpp:626)
+                if (running) ctr.runs++;
             }
-            curT = bt; curC = bc; first = false;
         }
+        const bool pickMore = act && rank != 3u;  // the sweep is a lane's last event
+        float np = n.pot;
+        double E = 0.0;
+        if (running && cnt) E = exp_glibc(mul64(0.3702, (double)dT));
+        if (__any_sync(FULL, (running && cnt) || (pickMore && hasEv)))
+            for (uint32_t c = 0; c < maxCnt; c++) {
+                if (c < cnt && act) {
+                    const float araw = A[c];
+                    if (running && araw > 0.0f) {       // not cleared earlier in this window
+                        const float off = sub32(T, araw);
+                        if (off > 0.0f) {               // arrived
+                            ctr.visits++;
+                            np = (float)add64((double)np, chain_term(dT, D[c], E));
+                            if (2.0f < off) {           // NeuCor.cpp:697 — the slot becomes idle; leave the when-and-why for the synapse pass
+                                A[c] = -araw;
+                                const uint64_t sidx = rs + J[c];
+                                v.arrive[sidx] = __uint_as_float(sentinel);
+                                v.depol[sidx] = T;
+                            }
+                        }
+                    }
+                    if (pickMore && hasEv) pick_from_slot(v, s, rs, J, c, fabsf(araw), false, cur.t, cur.code, nx);
+                }
+            }
+        if (pickMore) pick_from_host(s, evLo, evHi, false, cur.t, cur.code, nx);
+        if (running) {
+            const bool fired = neuron_run_finish(n, np, T, dT, false);
+            actT = T; actF = n.firings; ran = true;
+            if (fired) { ctr.fires++; emit_fire(v, q, T, rk1, k2); }
+        }
+        if (act && nx.code == NONE && !swept) { nx.t = s.t1; nx.code = SWEEP; swept = true; }
     }
-    if (s.sweep & NC_SWEEP_END) lane_neuron_run(v, n, A, D, J, cnt, rs, q, s.t1, (3u << 30) | q, 0u, NC_SENT | (3u << 29), ctr, am);
-    if (am.ran) n.act = neuron_activity(am.firings, am.T, n.actStart);
-    v.potAct[row] = make_float2(n.pot, n.act);
-    v.lastRan[row] = n.lastRan; v.lastFire[row] = n.lastFire; v.firings[row] = n.firings;
+    if (valid) {
+        if (ran) n.act = neuron_activity(actF, actT, n.actStart);
+        v.potAct[row] = make_float2(n.pot, n.act);
+        v.lastRan[row] = n.lastRan; v.lastFire[row] = n.lastFire; v.firings[row] = n.firings;
+    }
 }
 
 // Neuron pass.  A warp takes tiles of 32 consecutive rows.  It stages the occupied slots of as many rows as fit its
@@ -411,6 +435,7 @@ __device__ void lane_row(const View& v, const StepArgs& s, uint64_t row, float* 
 // a row that alone exceeds the pool takes the warp-per-row path with the global spill area.
 __global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32, 4) k_neuron_pass(View v, StepArgs s) {
     extern __shared__ unsigned char smem[];
+    math_tables_to_shared();
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     const uint32_t cap = s.candCap;
     float* sA = reinterpret_cast<float*>(smem) + (size_t)wib * 3 * cap;
@@ -418,13 +443,17 @@ __global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32, 4) k_neuron_pass(View
     uint32_t* sJ = reinterpret_cast<uint32_t*>(sA + 2 * cap);
     CandView cv;
     cv.a = sA; cv.d = sD; cv.j = sJ; cv.cap = cap;
-    const uint64_t gw = (uint64_t)blockIdx.x * NC_WARPS_PER_BLOCK + wib, nW = (uint64_t)gridDim.x * NC_WARPS_PER_BLOCK;
+    const uint64_t gw = (uint64_t)blockIdx.x * NC_WARPS_PER_BLOCK + wib;
     cv.sa = v.spillA + gw * v.spillPerWarp; cv.sd = v.spillD + gw * v.spillPerWarp; cv.sj = v.spillJ + gw * v.spillPerWarp;
     P1Counters ctrW = {0, 0, 0, 0};  // warp-uniform counts of the warp-per-row path
     P1Counters ctrL = {0, 0, 0, 0};  // this lane's counts of the lane-per-row path
     const uint64_t nTiles = (v.nRows + 31) >> 5;
 
-    for (uint64_t tile = gw; tile < nTiles; tile += nW) {
+    for (;;) {  // tiles are claimed dynamically: their cost varies with the activity of their neurons
+        uint32_t t32 = 0;
+        if (lane == 0) t32 = atomicAdd(&v.tileCtr[0], 1u);
+        const uint64_t tile = __shfl_sync(0xffffffffu, t32, 0);
+        if (tile >= nTiles) break;
         const uint64_t rowBase = tile << 5;
         const uint32_t nr = (uint32_t)min((uint64_t)32, v.nRows - rowBase);
         uint32_t r = 0;
@@ -444,7 +473,7 @@ __global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32, 4) k_neuron_pass(View
             }
             __syncwarp();
             if (heavy) { warp_row(v, s, rowBase + r, cv, lane, ctrW); r++; continue; }
-            if (lane < nb) lane_row(v, s, rowBase + myRow, sA + myOff, sD + myOff, sJ + myOff, myCnt, myEv, ctrL);
+            lanes_replay(v, s, lane < nb, rowBase + myRow, sA + myOff, sD + myOff, sJ + myOff, myCnt, myEv, ctrL);
             __syncwarp();
         }
     }
@@ -502,7 +531,7 @@ __global__ void k_finish_step(View v, unsigned long long* out, int accumulate) {
         out[9] = accumulate ? (out[9] | v.localHdr[1]) : v.localHdr[1];
     }
     __syncwarp();
-    if (i == 8) { v.localHdr[0] = 0u; v.localHdr[1] = 0u; }
+    if (i == 8) { v.localHdr[0] = 0u; v.localHdr[1] = 0u; v.tileCtr[0] = 0u; v.tileCtr[1] = 0u; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -512,6 +541,7 @@ __global__ void k_finish_step(View v, unsigned long long* out, int accumulate) {
 
 __global__ void __launch_bounds__(NC_P2_THREADS) k_synapse_pass(View v, StepArgs s, uint32_t maskWordsInSmem) {
     extern __shared__ uint32_t smem2[];
+    math_tables_to_shared();
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     // the fire bitmask (1 bit per neuron of the whole network) is probed once per synapse: keep it in shared memory
     uint32_t* smask = smem2 + (size_t)wpb * 2 * NC_P2_QUEUE;
@@ -681,6 +711,7 @@ __device__ __forceinline__ float render_behaviour(float valf) {  // AP_RENDER_BE
     return (float)mul64(8.0, (double)mul32(x, x));
 }
 __global__ void k_synapse_pots(View v, float now, float* prePot, float* postPot) {
+    math_tables_to_shared();
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= v.S) return;
     float a = v.arrive[i], w = v.weight[i], dl = v.delay[i];
@@ -734,7 +765,7 @@ struct nc_engine {
     uint32_t lastCounts[NC_MAX_WORLD] = {0}; uint32_t lastStride = 0;
     float lr = 1.0f, preF = 0.13f, postF = 0.30f, preD = 0.75f, postD = 0.65f;
     float minDelay = INFINITY;
-    uint32_t candCap = 512, grid1 = 0, grid2 = 0, maskWordsSmem = 0;
+    uint32_t candCap = 1024, grid1 = 0, grid2 = 0, maskWordsSmem = 0;
     size_t smem1 = 0, smem2 = 0;
     uint64_t launches = 0;
     // tape
@@ -789,6 +820,8 @@ extern "C" int nc_create(const nc_config* cfg, nc_engine** out) {
     if (ce == cudaSuccess) ce = cudaMalloc(&e->dOutAll, (size_t)cfg->world * 10 * sizeof(unsigned long long));
     if (ce == cudaSuccess) ce = cudaMalloc(&e->v.stats, 8 * sizeof(unsigned long long));
     if (ce == cudaSuccess) ce = cudaMemset(e->v.stats, 0, 8 * sizeof(unsigned long long));
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->v.tileCtr, 2 * sizeof(uint32_t));
+    if (ce == cudaSuccess) ce = cudaMemset(e->v.tileCtr, 0, 2 * sizeof(uint32_t));
     cudaDeviceProp prop;
     if (ce == cudaSuccess) ce = cudaGetDeviceProperties(&prop, cfg->device);
     if (ce != cudaSuccess) { g_err = std::string("nc_create: ") + cudaGetErrorString(ce); delete e; return NC_ERR_CUDA; }
@@ -816,7 +849,7 @@ extern "C" void nc_destroy(nc_engine* e) {
     cudaSetDevice(e->cfg.device);
     cudaStreamSynchronize(e->stream);
     free_all(e);
-    cudaFree(e->v.stats); cudaFree(e->dOut); cudaFree(e->dOutAll);
+    cudaFree(e->v.stats); cudaFree(e->v.tileCtr); cudaFree(e->dOut); cudaFree(e->dOutAll);
     cudaFreeHost(e->hOut); cudaFreeHost(e->hHdrAll); cudaFreeHost(e->hEvPinned);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     if (e->ownStream) cudaStreamDestroy(e->stream);
@@ -915,7 +948,7 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
     e->smem2 = (size_t)e->maskWordsSmem * 4 + (size_t)(NC_P2_THREADS / 32) * 2 * NC_P2_QUEUE * 4;
     CK(cudaFuncSetAttribute(k_synapse_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem2));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_synapse_pass, NC_P2_THREADS, e->smem2));
-    uint64_t needBlocks = (nRows + NC_WARPS_PER_BLOCK - 1) / NC_WARPS_PER_BLOCK;
+    uint64_t needBlocks = ((nRows + 31) / 32 + NC_WARPS_PER_BLOCK - 1) / NC_WARPS_PER_BLOCK;  // one tile of 32 rows per warp at a time
     uint64_t needBlocks2 = (nRows + NC_P2_THREADS / 32 - 1) / (NC_P2_THREADS / 32);
     e->grid1 = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(needBlocks, (uint64_t)e->smCount * std::max(occ1, 1)));
     e->grid2 = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(needBlocks2, (uint64_t)e->smCount * std::max(occ2, 1)));
@@ -1401,10 +1434,12 @@ extern "C" int nc_tape_replay(nc_engine* e, uint32_t first, uint32_t count, floa
 // compare them bit-for-bit with the host libm the reference uses (SURVEY.md hard part #1).
 // ------------------------------------------------------------------------------------------------
 __global__ void k_selftest_powf(const float* x, const float* y, float* out, uint64_t n) {
+    math_tables_to_shared();
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = powf_pos(x[i], y[i]);
 }
 __global__ void k_selftest_exp(const double* x, double* out, uint64_t n) {
+    math_tables_to_shared();
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = exp_glibc(x[i]);
 }

@@ -58,30 +58,43 @@ NC_HD double div64(double a, double b) { return a / b; }
 NC_HD float div32(float a, float b) { return a / b; }
 #endif
 
-// Tables live in __constant__ memory on the device (indexed loads, 2.8 KB in total).
+// Tables (2.5 KB in total) are uploaded to __constant__ memory once and copied to shared memory at the start of every
+// kernel that evaluates powf/exp (math_tables_to_shared): the lanes of a warp index them with DIFFERENT values, which the
+// constant cache would serialise.
 #if defined(__CUDACC__)
 __device__ __constant__ unsigned long long d_POWF_LOG2_TAB[32];
 __device__ __constant__ unsigned long long d_EXP2F_TAB[32];
 __device__ __constant__ unsigned long long d_EXP_TAB[256];
+__shared__ unsigned long long s_POWF_LOG2_TAB[32];
+__shared__ unsigned long long s_EXP2F_TAB[32];
+__shared__ unsigned long long s_EXP_TAB[256];
+// every thread of the block must call this before the first powf_pos / exp_glibc
+__device__ __forceinline__ void math_tables_to_shared() {
+    for (unsigned i = threadIdx.x; i < 256u; i += blockDim.x) {
+        s_EXP_TAB[i] = d_EXP_TAB[i];
+        if (i < 32u) { s_POWF_LOG2_TAB[i] = d_POWF_LOG2_TAB[i]; s_EXP2F_TAB[i] = d_EXP2F_TAB[i]; }
+    }
+    __syncthreads();
+}
 #endif
 
 NC_HD unsigned long long tab_powf_log2(int i) {
 #if defined(__CUDA_ARCH__)
-    return d_POWF_LOG2_TAB[i];
+    return s_POWF_LOG2_TAB[i];
 #else
     return NC_POWF_LOG2_TAB[i];
 #endif
 }
 NC_HD unsigned long long tab_exp2f(int i) {
 #if defined(__CUDA_ARCH__)
-    return d_EXP2F_TAB[i];
+    return s_EXP2F_TAB[i];
 #else
     return NC_EXP2F_TAB[i];
 #endif
 }
 NC_HD unsigned long long tab_exp(int i) {
 #if defined(__CUDA_ARCH__)
-    return d_EXP_TAB[i];
+    return s_EXP_TAB[i];
 #else
     return NC_EXP_TAB[i];
 #endif

@@ -88,6 +88,7 @@ struct View {
     uint32_t* spillJ;
     uint32_t spillPerWarp;
     unsigned long long* stats;  // 8 counters (nc_step_stats order)
+    uint32_t* tileCtr;          // [0] neuron pass, [1] synapse pass: next unclaimed tile of the window (dynamic scheduling)
 };
 
 struct StepArgs {

@@ -138,12 +138,12 @@ __device__ __forceinline__ void warp_neuron_run(const View& v, NeuronState& n, C
 template <bool SPILL>
 __device__ __forceinline__ uint32_t stage_row(const View& v, const StepArgs& s, uint64_t row, uint64_t rs, uint64_t re, CandView& cv,
                                               float* pa, float* pd, uint32_t* pj, uint32_t room, uint32_t lane, bool& hasEv) {
-    uint32_t cnt = 0;
+    uint32_t cnt = 0, summ = 0;
     bool ev = false;
     const uint32_t len = (uint32_t)(re - rs);
     const uint32_t t1b = __float_as_uint(s.t1);
     const uint64_t g0 = rs >> 7, g1 = (re + 127) >> 7;
-    uint4* bm = reinterpret_cast<uint4*>(v.candBits) + (g0 + row);
+    uint4* bm = reinterpret_cast<uint4*>(v.ownBits) + (g0 + row);
     const float4* src = reinterpret_cast<const float4*>(v.arrive) + lane;
     for (uint64_t gb = g0; gb < g1; gb += NC_UNROLL4) {
         float4 av[NC_UNROLL4];
@@ -153,6 +153,7 @@ __device__ __forceinline__ uint32_t stage_row(const View& v, const StepArgs& s, 
 #pragma unroll
         for (int u = 0; u < NC_UNROLL4; u++) {
             if (gb + u >= g1) break;
+            const uint32_t gi = (uint32_t)(gb + u - g0);
             // slot index relative to the row start; one unsigned compare against the row length masks both ends
             const uint32_t rel0 = (uint32_t)(int32_t)((int64_t)((gb + u) << 7) - (int64_t)rs) + 4u * lane;
             const float a4[4] = {av[u].x, av[u].y, av[u].z, av[u].w};
@@ -161,13 +162,26 @@ __device__ __forceinline__ uint32_t stage_row(const View& v, const StepArgs& s, 
 #pragma unroll
             for (int k = 0; k < 4; k++) is[k] = (__float_as_uint(a4[k]) - 1u < t1b) && (rel0 + k < len);
             if (!__any_sync(0xffffffffu, is[0] | is[1] | is[2] | is[3])) {
-                if (lane == 0) bm[gb + u - g0] = make_uint4(0u, 0u, 0u, 0u);
+                if (gi >= 31u && lane == 0) bm[gi] = make_uint4(0u, 0u, 0u, 0u);
                 continue;
+            }
+            // "own" bits for the synapse pass: the slot delivers in this window, or is old enough to be cleared by one of this
+            // window's runs (2 < T - arrive needs 2 < t1 - arrive); everything else about an occupied slot stays put
+            bool own[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) own[k] = is[k] && (a4[k] > s.t0 || sub32(s.t1, a4[k]) > 2.0f);
+            if (__any_sync(0xffffffffu, own[0] | own[1] | own[2] | own[3])) {
+                uint32_t o[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) o[k] = __ballot_sync(0xffffffffu, own[k]);
+                if (lane == 0) bm[gi] = make_uint4(o[0], o[1], o[2], o[3]);
+                summ |= 1u << min(gi, 31u);
+            } else if (gi >= 31u && lane == 0) {
+                bm[gi] = make_uint4(0u, 0u, 0u, 0u);
             }
             uint32_t m[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) m[k] = __ballot_sync(0xffffffffu, is[k]);
-            if (lane == 0) bm[gb + u - g0] = make_uint4(m[0], m[1], m[2], m[3]);
             const uint32_t lt = (1u << lane) - 1u;
             uint32_t pos = cnt + __popc(m[0] & lt) + __popc(m[1] & lt) + __popc(m[2] & lt) + __popc(m[3] & lt);
 #pragma unroll
@@ -185,6 +199,7 @@ __device__ __forceinline__ uint32_t stage_row(const View& v, const StepArgs& s, 
             cnt += __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
         }
     }
+    if (lane == 0) v.ownSumm[row] = summ;
     hasEv = __any_sync(0xffffffffu, ev);
     return cnt;
 }
@@ -538,104 +553,118 @@ __global__ void k_finish_step(View v, unsigned long long* out, int accumulate) {
 // Synapse pass
 // ------------------------------------------------------------------------------------------------
 #define NC_P2_QUEUE 160  // per-warp queue of eventful slots (drained 32 at a time so that every lane resolves one)
+#define NC_P2_CHUNK 16   // rows claimed at a time by a warp
+
+// one queued slot per lane: fetch its row's context and apply all of the window's operations on it
+__device__ __forceinline__ void resolve_queued(const View& v, const StepArgs& s, const uint32_t* mask, uint32_t row, uint32_t rel, uint32_t pw, uint32_t* cnt) {
+    const uint32_t q = (uint32_t)(v.row0 + row);
+    const uint64_t rs = v.rowptr[row];
+    const bool qFired = (mask[q >> 5] >> (q & 31u)) & 1u;
+    const float lfS = v.lfStart[row];
+    const uint32_t p = pw & 0x7fffffffu;
+    const bool pFired = (mask[p >> 5] >> (p & 31u)) & 1u;
+    const uint32_t ab = __float_as_uint(v.arrive[rs + rel]);
+    resolve_slot(v, s, rs + rel, rs, q, p, (pw >> 31) != 0u, ab, pFired, qFired, lfS, cnt);
+}
 
 __global__ void __launch_bounds__(NC_P2_THREADS) k_synapse_pass(View v, StepArgs s, uint32_t maskWordsInSmem) {
     extern __shared__ uint32_t smem2[];
     math_tables_to_shared();
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     // the fire bitmask (1 bit per neuron of the whole network) is probed once per synapse: keep it in shared memory
-    uint32_t* smask = smem2 + (size_t)wpb * 2 * NC_P2_QUEUE;
+    uint32_t* smask = smem2 + (size_t)wpb * 3 * NC_P2_QUEUE;
     const uint32_t* mask = v.mask;
     if (maskWordsInSmem) {
         for (uint32_t i = threadIdx.x; i < maskWordsInSmem; i += blockDim.x) smask[i] = v.mask[i];
         __syncthreads();
         mask = smask;
     }
-    // eventful slots are rare and scattered: queue them per warp and resolve 32 at a time instead of diverging in place
-    uint32_t* qJ = smem2 + (size_t)wib * 2 * NC_P2_QUEUE;
+    // eventful slots are rare and scattered: queue them per warp — across rows — and resolve 32 at a time instead of
+    // diverging in place
+    uint32_t* qJ = smem2 + (size_t)wib * 3 * NC_P2_QUEUE;
     uint32_t* qP = qJ + NC_P2_QUEUE;
-    const uint64_t gw = (uint64_t)blockIdx.x * wpb + wib, nW = (uint64_t)gridDim.x * wpb;
+    uint32_t* qR = qP + NC_P2_QUEUE;
     uint32_t cnt[5] = {0, 0, 0, 0, 0};  // loads accepted, dropped, plasticity calls, hidden rand, deliveries
-    for (uint64_t row = gw; row < v.nRows; row += nW) {
-        const uint32_t q = (uint32_t)(v.row0 + row);
-        const uint64_t rs = v.rowptr[row], re = v.rowptr[row + 1];
-        const bool qFired = (mask[q >> 5] >> (q & 31u)) & 1u;
-        const float lfS = v.lfStart[row];
-        uint32_t qn = 0;
-        const uint64_t g0 = rs >> 7, g1 = (re + 127) >> 7;
-        const uint4* bm = reinterpret_cast<const uint4*>(v.candBits) + (g0 + row);
-        for (uint64_t gb = g0; gb < g1; gb += NC_UNROLL4) {
-            uint4 pv[NC_UNROLL4], cb[NC_UNROLL4];
+    uint32_t qn = 0;
+    const uint64_t nChunks = (v.nRows + NC_P2_CHUNK - 1) / NC_P2_CHUNK;
+    for (;;) {
+        uint32_t c32 = 0;
+        if (lane == 0) c32 = atomicAdd(&v.tileCtr[1], 1u);
+        const uint64_t chunk = __shfl_sync(0xffffffffu, c32, 0);
+        if (chunk >= nChunks) break;
+        const uint64_t rowEnd = min(v.nRows, (chunk + 1) * NC_P2_CHUNK);
+        for (uint64_t row = chunk * NC_P2_CHUNK; row < rowEnd; row++) {
+            const uint32_t q = (uint32_t)(v.row0 + row);
+            const uint64_t rs = v.rowptr[row], re = v.rowptr[row + 1];
+            const uint32_t len = (uint32_t)(re - rs);
+            const bool qFired = (mask[q >> 5] >> (q & 31u)) & 1u;
+            const uint32_t summ = v.ownSumm[row];  // groups in which the neuron pass saw slots that may deliver or have been cleared
+            const uint64_t g0 = rs >> 7, g1 = (re + 127) >> 7;
+            const uint4* bm = reinterpret_cast<const uint4*>(v.ownBits) + (g0 + row);
+            const uint4* src = reinterpret_cast<const uint4*>(v.pre) + lane;
+            for (uint64_t gb = g0; gb < g1; gb += NC_UNROLL4) {
+                uint4 pv[NC_UNROLL4];
 #pragma unroll
-            for (int u = 0; u < NC_UNROLL4; u++) {
-                bool in = gb + u < g1;
-                pv[u] = in ? __ldcs(reinterpret_cast<const uint4*>(v.pre) + ((gb + u) << 5) + lane) : make_uint4(0u, 0u, 0u, 0u);
-                cb[u] = in ? __ldg(bm + (gb + u - g0)) : make_uint4(0u, 0u, 0u, 0u);  // candidate bits written by the neuron pass
-            }
+                for (int u = 0; u < NC_UNROLL4; u++)
+                    pv[u] = (gb + u < g1) ? __ldcs(src + ((gb + u) << 5)) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-            for (int u = 0; u < NC_UNROLL4; u++) {
-                if (gb + u >= g1) break;
-                const uint64_t j0 = ((gb + u) << 7) + 4 * lane;
-                const uint32_t p4[4] = {pv[u].x, pv[u].y, pv[u].z, pv[u].w};
-                const uint32_t c4[4] = {cb[u].x, cb[u].y, cb[u].z, cb[u].w};
-                bool ev[4];
+                for (int u = 0; u < NC_UNROLL4; u++) {
+                    if (gb + u >= g1) break;
+                    const uint32_t gi = (uint32_t)(gb + u - g0);
+                    const uint32_t rel0 = (uint32_t)(int32_t)((int64_t)((gb + u) << 7) - (int64_t)rs) + 4u * lane;
+                    const uint32_t p4[4] = {pv[u].x, pv[u].y, pv[u].z, pv[u].w};
+                    const bool flagged = (summ >> min(gi, 31u)) & 1u;
+                    uint32_t c4[4] = {0u, 0u, 0u, 0u};
+                    if (flagged) { const uint4 cb = __ldg(bm + gi); c4[0] = cb.x; c4[1] = cb.y; c4[2] = cb.z; c4[3] = cb.w; }
+                    bool ev[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t p = p4[k] & 0x7fffffffu;
-                    const bool in = (j0 + k >= rs) && (j0 + k < re);
-                    const bool pFired = in && ((mask[p >> 5] >> (p & 31u)) & 1u);
-                    bool own = false;  // delivery in this window or cleared by the neuron pass: only occupied slots (candidates) can be
-                    if (in && ((c4[k] >> lane) & 1u)) {
-                        uint32_t ab = __float_as_uint(v.arrive[j0 + k]);
-                        float a = __uint_as_float(ab);
-                        own = (ab & NC_SENT) || (a > s.t0 && a <= s.t1);
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t p = p4[k] & 0x7fffffffu;
+                        const bool in = rel0 + k < len;
+                        bool hit = qFired || ((mask[p >> 5] >> (p & 31u)) & 1u);
+                        if (flagged && in && ((c4[k] >> lane) & 1u)) {  // delivery in this window or cleared by the neuron pass
+                            const uint32_t ab = __float_as_uint(v.arrive[rs + (uint32_t)(rel0 + k)]);
+                            const float a = __uint_as_float(ab);
+                            hit = hit || (ab & NC_SENT) || (a > s.t0 && a <= s.t1);
+                        }
+                        ev[k] = in && hit;
                     }
-                    ev[k] = in && (qFired || pFired || own);
-                }
-                if (!__any_sync(0xffffffffu, ev[0] | ev[1] | ev[2] | ev[3])) continue;
-                uint32_t m[4];
+                    if (!__any_sync(0xffffffffu, ev[0] | ev[1] | ev[2] | ev[3])) continue;
+                    uint32_t m[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++) m[k] = __ballot_sync(0xffffffffu, ev[k]);
-                const uint32_t lt = (1u << lane) - 1u;
-                uint32_t pos = qn + __popc(m[0] & lt) + __popc(m[1] & lt) + __popc(m[2] & lt) + __popc(m[3] & lt);
+                    for (int k = 0; k < 4; k++) m[k] = __ballot_sync(0xffffffffu, ev[k]);
+                    const uint32_t lt = (1u << lane) - 1u;
+                    uint32_t pos = qn + __popc(m[0] & lt) + __popc(m[1] & lt) + __popc(m[2] & lt) + __popc(m[3] & lt);
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (ev[k]) { qJ[pos] = (uint32_t)(j0 + k - rs); qP[pos] = p4[k]; pos++; }
-                qn += __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
-                while (qn >= 32) {  // drain the oldest 32 entries: one per lane
-                    __syncwarp();
-                    uint32_t jj = qJ[lane], pw = qP[lane];
-                    uint32_t keepJ[4], keepP[4];
-                    const uint32_t rest = qn - 32;
+                    for (int k = 0; k < 4; k++)
+                        if (ev[k]) { qJ[pos] = rel0 + k; qP[pos] = p4[k]; qR[pos] = (uint32_t)row; pos++; }
+                    qn += __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+                    while (qn >= 32) {  // drain the oldest 32 entries: one per lane
+                        __syncwarp();
+                        const uint32_t jj = qJ[lane], pw = qP[lane], rr = qR[lane];
+                        uint32_t keepJ[4], keepP[4], keepR[4];
+                        const uint32_t rest = qn - 32;
 #pragma unroll
-                    for (int t = 0; t < 4; t++) {
-                        uint32_t idx = 32 + t * 32 + lane;
-                        bool mv = t * 32 + lane < rest;
-                        keepJ[t] = mv ? qJ[idx] : 0u; keepP[t] = mv ? qP[idx] : 0u;
+                        for (int t = 0; t < 4; t++) {
+                            const uint32_t idx = 32 + t * 32 + lane;
+                            const bool mv = t * 32 + lane < rest;
+                            keepJ[t] = mv ? qJ[idx] : 0u; keepP[t] = mv ? qP[idx] : 0u; keepR[t] = mv ? qR[idx] : 0u;
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int t = 0; t < 4; t++)
+                            if (t * 32 + lane < rest) { qJ[t * 32 + lane] = keepJ[t]; qP[t * 32 + lane] = keepP[t]; qR[t * 32 + lane] = keepR[t]; }
+                        qn = rest;
+                        resolve_queued(v, s, mask, rr, jj, pw, cnt);
+                        __syncwarp();
                     }
-                    __syncwarp();
-#pragma unroll
-                    for (int t = 0; t < 4; t++)
-                        if (t * 32 + lane < rest) { qJ[t * 32 + lane] = keepJ[t]; qP[t * 32 + lane] = keepP[t]; }
-                    qn = rest;
-                    uint32_t p = pw & 0x7fffffffu;
-                    bool pFired = (mask[p >> 5] >> (p & 31u)) & 1u;
-                    uint32_t ab = __float_as_uint(v.arrive[rs + jj]);
-                    resolve_slot(v, s, rs + jj, rs, q, p, (pw >> 31) != 0u, ab, pFired, qFired, lfS, cnt);
-                    __syncwarp();
                 }
             }
         }
-        __syncwarp();
-        if (lane < qn) {
-            uint32_t jj = qJ[lane], pw = qP[lane];
-            uint32_t p = pw & 0x7fffffffu;
-            bool pFired = (mask[p >> 5] >> (p & 31u)) & 1u;
-            uint32_t ab = __float_as_uint(v.arrive[rs + jj]);
-            resolve_slot(v, s, rs + jj, rs, q, p, (pw >> 31) != 0u, ab, pFired, qFired, lfS, cnt);
-        }
-        __syncwarp();
     }
+    __syncwarp();
+    if (lane < qn) resolve_queued(v, s, mask, qR[lane], qJ[lane], qP[lane], cnt);
+    __syncwarp();
 #pragma unroll
     for (int i = 0; i < 5; i++) {
         uint32_t x = cnt[i];
@@ -835,7 +864,7 @@ static void free_all(nc_engine* e) {
     View& v = e->v;
     cudaFree((void*)v.rowptr); cudaFree(v.pre); cudaFree(v.arrive); cudaFree(v.depol); cudaFree(v.weight); cudaFree(v.lastArr);
     cudaFree(v.lastStart); cudaFree(e->dDelay); cudaFree(v.potAct); cudaFree(v.lastRan); cudaFree(v.lastFire); cudaFree(v.lfStart);
-    cudaFree(v.actStart); cudaFree(v.firings); cudaFree(v.localHdr); cudaFree(v.head); cudaFree(v.next); cudaFree(v.mask); cudaFree(v.evMask); cudaFree(v.candBits);
+    cudaFree(v.actStart); cudaFree(v.firings); cudaFree(v.localHdr); cudaFree(v.head); cudaFree(v.next); cudaFree(v.mask); cudaFree(v.evMask); cudaFree(v.ownBits); cudaFree(v.ownSumm);
     cudaFree(v.spillA); cudaFree(v.spillD); cudaFree(v.spillJ);
     cudaFree(e->dGather);
     cudaFree(e->dEv); cudaFree(e->dTape);
@@ -899,8 +928,10 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
     const uint64_t SP = ((S1 + 127) / 128 + 1) * 128;  // 16-byte row loads may touch the rest of the last 128-slot group
     CK(cudaMalloc(&v.pre, SP * 4)); CK(cudaMalloc(&v.arrive, SP * 4)); CK(cudaMalloc(&v.depol, S1 * 4));
     CK(cudaMemsetAsync(v.pre, 0, SP * 4, e->stream)); CK(cudaMemsetAsync(v.arrive, 0, SP * 4, e->stream));
-    CK(cudaMalloc(&v.candBits, (SP / 128 + N1 + 1) * 16));
-    CK(cudaMemsetAsync(v.candBits, 0, (SP / 128 + N1 + 1) * 16, e->stream));
+    CK(cudaMalloc(&v.ownBits, (SP / 128 + N1 + 1) * 16));
+    CK(cudaMemsetAsync(v.ownBits, 0, (SP / 128 + N1 + 1) * 16, e->stream));
+    CK(cudaMalloc(&v.ownSumm, N1 * 4));
+    CK(cudaMemsetAsync(v.ownSumm, 0, N1 * 4, e->stream));
     CK(cudaMalloc(&v.weight, S1 * 4)); CK(cudaMalloc(&v.lastArr, S1 * 4)); CK(cudaMalloc(&v.lastStart, S1 * 4));
     CK(cudaMalloc(&e->dDelay, S1 * 4)); v.delay = e->dDelay;
     CK(cudaMalloc(&v.potAct, N1 * 8)); CK(cudaMalloc(&v.lastRan, N1 * 4)); CK(cudaMalloc(&v.lastFire, N1 * 4));
@@ -942,10 +973,10 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
     CK(cudaFuncSetAttribute(k_neuron_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem1));
     int occ1 = 1, occ2 = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_neuron_pass, NC_WARPS_PER_BLOCK * 32, e->smem1));
-    // synapse pass: the whole-network fire bitmask goes to shared memory when it fits (<= 200 KB, i.e. 1.6 M neurons)
+    // synapse pass: the whole-network fire bitmask goes to shared memory when it fits (<= 160 KB, i.e. 1.3 M neurons)
     uint64_t maskWords = (G1 + 31) / 32;
-    e->maskWordsSmem = maskWords * 4 <= 200 * 1024 ? (uint32_t)maskWords : 0u;
-    e->smem2 = (size_t)e->maskWordsSmem * 4 + (size_t)(NC_P2_THREADS / 32) * 2 * NC_P2_QUEUE * 4;
+    e->maskWordsSmem = maskWords * 4 <= 160 * 1024 ? (uint32_t)maskWords : 0u;
+    e->smem2 = (size_t)e->maskWordsSmem * 4 + (size_t)(NC_P2_THREADS / 32) * 3 * NC_P2_QUEUE * 4;
     CK(cudaFuncSetAttribute(k_synapse_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem2));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_synapse_pass, NC_P2_THREADS, e->smem2));
     uint64_t needBlocks = ((nRows + 31) / 32 + NC_WARPS_PER_BLOCK - 1) / NC_WARPS_PER_BLOCK;  // one tile of 32 rows per warp at a time

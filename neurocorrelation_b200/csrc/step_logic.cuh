@@ -81,7 +81,8 @@ struct View {
     int32_t* next;         // per unit
     uint32_t* mask;        // one bit per global neuron: fired in this window
     uint32_t* evMask;      // one bit per row of this shard: has host events in this window
-    uint32_t* candBits;    // per row and 128-slot group: 4 ballot words marking the occupied slots staged by the neuron pass
+    uint32_t* ownBits;     // per row and 128-slot group: 4 ballot words marking the slots that may deliver / be cleared in this window
+    uint32_t* ownSumm;     // per row: bit min(g, 31) set when group g of the row has any such slot (groups >= 31 are always written)
     // spill area for rows with more occupied slots than fit in shared memory
     float* spillA;
     float* spillD;

@@ -142,20 +142,22 @@ __device__ __forceinline__ uint32_t stage_row(const View& v, const StepArgs& s, 
     bool ev = false;
     const uint32_t len = (uint32_t)(re - rs);
     const uint32_t t1b = __float_as_uint(s.t1);
-    const uint64_t g0 = rs >> 7, g1 = (re + 127) >> 7;
+    const uint64_t g0 = rs >> 7;
+    const uint32_t ng = (uint32_t)(((re + 127) >> 7) - g0);
     uint4* bm = reinterpret_cast<uint4*>(v.ownBits) + (g0 + row);
-    const float4* src = reinterpret_cast<const float4*>(v.arrive) + lane;
-    for (uint64_t gb = g0; gb < g1; gb += NC_UNROLL4) {
+    const float4* src = reinterpret_cast<const float4*>(v.arrive) + (g0 << 5) + lane;
+    const uint32_t relBase = 4u * lane - (uint32_t)(rs & 127u);  // row-relative index of this lane's first slot in group 0
+    for (uint32_t g = 0; g < ng; g += NC_UNROLL4) {
         float4 av[NC_UNROLL4];
 #pragma unroll
         for (int u = 0; u < NC_UNROLL4; u++)
-            av[u] = (gb + u < g1) ? __ldcs(src + ((gb + u) << 5)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            av[u] = (g + u < ng) ? __ldcs(src + ((g + u) << 5)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int u = 0; u < NC_UNROLL4; u++) {
-            if (gb + u >= g1) break;
-            const uint32_t gi = (uint32_t)(gb + u - g0);
+            if (g + u >= ng) break;
+            const uint32_t gi = g + u;
             // slot index relative to the row start; one unsigned compare against the row length masks both ends
-            const uint32_t rel0 = (uint32_t)(int32_t)((int64_t)((gb + u) << 7) - (int64_t)rs) + 4u * lane;
+            const uint32_t rel0 = relBase + (gi << 7);
             const float a4[4] = {av[u].x, av[u].y, av[u].z, av[u].w};
             bool is[4];
             // arrive times are positive floats (0 = idle): as unsigned integers, (bits - 1) < bits(t1)  <=>  0 < arrive <= t1
@@ -567,18 +569,21 @@ __device__ __forceinline__ void resolve_queued(const View& v, const StepArgs& s,
     resolve_slot(v, s, rs + rel, rs, q, p, (pw >> 31) != 0u, ab, pFired, qFired, lfS, cnt);
 }
 
+// MASK_SMEM: the whole-network fire bitmask (1 bit per neuron), probed once per synapse, is staged in shared memory
+// (a compile-time choice so that the probe is a plain 32-bit-addressed LDS); otherwise it is read through L1/L2.
+template <bool MASK_SMEM>
 __global__ void __launch_bounds__(NC_P2_THREADS) k_synapse_pass(View v, StepArgs s, uint32_t maskWordsInSmem) {
     extern __shared__ uint32_t smem2[];
     math_tables_to_shared();
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    // the fire bitmask (1 bit per neuron of the whole network) is probed once per synapse: keep it in shared memory
     uint32_t* smask = smem2 + (size_t)wpb * 3 * NC_P2_QUEUE;
-    const uint32_t* mask = v.mask;
-    if (maskWordsInSmem) {
-        for (uint32_t i = threadIdx.x; i < maskWordsInSmem; i += blockDim.x) smask[i] = v.mask[i];
+    const uint32_t* __restrict__ gmask = v.mask;
+    if (MASK_SMEM) {
+        for (uint32_t i = threadIdx.x; i < maskWordsInSmem; i += blockDim.x) smask[i] = gmask[i];
         __syncthreads();
-        mask = smask;
     }
+    const uint32_t* mask = MASK_SMEM ? smask : gmask;  // for the (rare) per-entry probes of the resolve step
+    auto fired = [&](uint32_t n) -> bool { return ((MASK_SMEM ? smask[n >> 5] : __ldg(gmask + (n >> 5))) >> (n & 31u)) & 1u; };
     // eventful slots are rare and scattered: queue them per warp — across rows — and resolve 32 at a time instead of
     // diverging in place
     uint32_t* qJ = smem2 + (size_t)wib * 3 * NC_P2_QUEUE;
@@ -597,37 +602,38 @@ __global__ void __launch_bounds__(NC_P2_THREADS) k_synapse_pass(View v, StepArgs
             const uint32_t q = (uint32_t)(v.row0 + row);
             const uint64_t rs = v.rowptr[row], re = v.rowptr[row + 1];
             const uint32_t len = (uint32_t)(re - rs);
-            const bool qFired = (mask[q >> 5] >> (q & 31u)) & 1u;
+            const bool qFired = fired(q);
             const uint32_t summ = v.ownSumm[row];  // groups in which the neuron pass saw slots that may deliver or have been cleared
-            const uint64_t g0 = rs >> 7, g1 = (re + 127) >> 7;
+            const uint64_t g0 = rs >> 7;
+            const uint32_t ng = (uint32_t)(((re + 127) >> 7) - g0);
             const uint4* bm = reinterpret_cast<const uint4*>(v.ownBits) + (g0 + row);
-            const uint4* src = reinterpret_cast<const uint4*>(v.pre) + lane;
-            for (uint64_t gb = g0; gb < g1; gb += NC_UNROLL4) {
+            const uint4* src = reinterpret_cast<const uint4*>(v.pre) + (g0 << 5) + lane;
+            const uint32_t relBase = 4u * lane - (uint32_t)(rs & 127u);  // row-relative index of this lane's first slot in group 0
+            for (uint32_t g = 0; g < ng; g += NC_UNROLL4) {
                 uint4 pv[NC_UNROLL4];
 #pragma unroll
                 for (int u = 0; u < NC_UNROLL4; u++)
-                    pv[u] = (gb + u < g1) ? __ldcs(src + ((gb + u) << 5)) : make_uint4(0u, 0u, 0u, 0u);
+                    pv[u] = (g + u < ng) ? __ldcs(src + ((g + u) << 5)) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                 for (int u = 0; u < NC_UNROLL4; u++) {
-                    if (gb + u >= g1) break;
-                    const uint32_t gi = (uint32_t)(gb + u - g0);
-                    const uint32_t rel0 = (uint32_t)(int32_t)((int64_t)((gb + u) << 7) - (int64_t)rs) + 4u * lane;
+                    if (g + u >= ng) break;
+                    const uint32_t gi = g + u;
+                    const uint32_t rel0 = relBase + (gi << 7);  // one unsigned compare against the row length masks both ends
                     const uint32_t p4[4] = {pv[u].x, pv[u].y, pv[u].z, pv[u].w};
-                    const bool flagged = (summ >> min(gi, 31u)) & 1u;
-                    uint32_t c4[4] = {0u, 0u, 0u, 0u};
-                    if (flagged) { const uint4 cb = __ldg(bm + gi); c4[0] = cb.x; c4[1] = cb.y; c4[2] = cb.z; c4[3] = cb.w; }
+                    // common case, branch-free: "did my presynaptic neuron (or my row's neuron) fire"
                     bool ev[4];
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const uint32_t p = p4[k] & 0x7fffffffu;
-                        const bool in = rel0 + k < len;
-                        bool hit = qFired || ((mask[p >> 5] >> (p & 31u)) & 1u);
-                        if (flagged && in && ((c4[k] >> lane) & 1u)) {  // delivery in this window or cleared by the neuron pass
-                            const uint32_t ab = __float_as_uint(v.arrive[rs + (uint32_t)(rel0 + k)]);
-                            const float a = __uint_as_float(ab);
-                            hit = hit || (ab & NC_SENT) || (a > s.t0 && a <= s.t1);
-                        }
-                        ev[k] = in && hit;
+                    for (int k = 0; k < 4; k++) ev[k] = (rel0 + k < len) && (qFired | fired(p4[k] & 0x7fffffffu));
+                    if ((summ >> min(gi, 31u)) & 1u) {  // (warp-uniform) the neuron pass flagged slots of this group
+                        const uint4 cb = __ldg(bm + gi);
+                        const uint32_t c4[4] = {cb.x, cb.y, cb.z, cb.w};
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            if ((rel0 + k < len) && ((c4[k] >> lane) & 1u)) {  // may deliver in this window / may have been cleared
+                                const uint32_t ab = __float_as_uint(v.arrive[rs + (uint32_t)(rel0 + k)]);
+                                const float a = __uint_as_float(ab);
+                                ev[k] = ev[k] || (ab & NC_SENT) || (a > s.t0 && a <= s.t1);
+                            }
                     }
                     if (!__any_sync(0xffffffffu, ev[0] | ev[1] | ev[2] | ev[3])) continue;
                     uint32_t m[4];
@@ -977,8 +983,13 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
     uint64_t maskWords = (G1 + 31) / 32;
     e->maskWordsSmem = maskWords * 4 <= 160 * 1024 ? (uint32_t)maskWords : 0u;
     e->smem2 = (size_t)e->maskWordsSmem * 4 + (size_t)(NC_P2_THREADS / 32) * 3 * NC_P2_QUEUE * 4;
-    CK(cudaFuncSetAttribute(k_synapse_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem2));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_synapse_pass, NC_P2_THREADS, e->smem2));
+    if (e->maskWordsSmem) {
+        CK(cudaFuncSetAttribute(k_synapse_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem2));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_synapse_pass<true>, NC_P2_THREADS, e->smem2));
+    } else {
+        CK(cudaFuncSetAttribute(k_synapse_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem2));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_synapse_pass<false>, NC_P2_THREADS, e->smem2));
+    }
     uint64_t needBlocks = ((nRows + 31) / 32 + NC_WARPS_PER_BLOCK - 1) / NC_WARPS_PER_BLOCK;  // one tile of 32 rows per warp at a time
     uint64_t needBlocks2 = (nRows + NC_P2_THREADS / 32 - 1) / (NC_P2_THREADS / 32);
     e->grid1 = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(needBlocks, (uint64_t)e->smCount * std::max(occ1, 1)));
@@ -1077,6 +1088,10 @@ static void fill_args(nc_engine* e, StepArgs& a, float t0, float t1, int sweep, 
     a.gStride = e->cfg.world == 1 ? e->v.fireCap + 1u : e->xchgUnits;
 }
 
+static void launch_synapse_pass(nc_engine* e, const StepArgs& a) {
+    if (e->maskWordsSmem) k_synapse_pass<true><<<e->grid2, NC_P2_THREADS, e->smem2, e->stream>>>(e->v, a, e->maskWordsSmem);
+    else k_synapse_pass<false><<<e->grid2, NC_P2_THREADS, e->smem2, e->stream>>>(e->v, a, 0u);
+}
 static int launch_pass1(nc_engine* e, const StepArgs& a) {
     if (a.nEv) { k_mark_events<<<(a.nEv + 255) / 256, 256, 0, e->stream>>>(e->v, a.ev, a.nEv, 1); e->launches++; }
     k_neuron_pass<<<e->grid1, NC_WARPS_PER_BLOCK * 32, e->smem1, e->stream>>>(e->v, a);
@@ -1091,7 +1106,7 @@ static int launch_pass2(nc_engine* e, const StepArgs& a, uint32_t expectMax, int
     const uint32_t gx = std::min<uint32_t>(std::max<uint32_t>((expectMax + 255u) / 256u, 1u), 1024u);
     dim3 g(gx, a.world);
     k_index_build<<<g, 256, 0, e->stream>>>(e->v, a);
-    k_synapse_pass<<<e->grid2, NC_P2_THREADS, e->smem2, e->stream>>>(e->v, a, e->maskWordsSmem);
+    launch_synapse_pass(e, a);
     k_index_reset<<<g, 256, 0, e->stream>>>(e->v, a);
     k_finish_step<<<1, 32, 0, e->stream>>>(e->v, e->dOut, accumulate);
     e->launches += 4;
@@ -1433,7 +1448,7 @@ extern "C" int nc_tape_replay(nc_engine* e, uint32_t first, uint32_t count, floa
         dim3 g(gx, a.world);
         k_index_build<<<g, 256, 0, e->stream>>>(e->v, a);
         if (perKernel) CK(cudaEventRecord(evs[5 * k + 3], e->stream));
-        k_synapse_pass<<<e->grid2, NC_P2_THREADS, e->smem2, e->stream>>>(e->v, a, e->maskWordsSmem);
+        launch_synapse_pass(e, a);
         if (perKernel) CK(cudaEventRecord(evs[5 * k + 4], e->stream));
         k_index_reset<<<g, 256, 0, e->stream>>>(e->v, a);
         k_finish_step<<<1, 32, 0, e->stream>>>(e->v, e->dOut, 1);

@@ -133,11 +133,12 @@ __device__ __forceinline__ void warp_neuron_run(const View& v, NeuronState& n, C
 // lane issues one 16-byte load per group; slots outside [rs, re) are masked.  Per group the four ballots (one per sub-slot)
 // are also written to the candidate bitmap that lets the synapse pass skip its own read of `arrive`.
 //   SPILL = true : entries go to the CandView (shared memory first, per-warp global spill area after) — warp-per-row path
-//   SPILL = false: entries go to pa/pd/pj while they fit in `room`; the returned count tells the caller whether they did
+//   SPILL = false: arrive times and slot indices (jbase + index in the row) go to pa/pj while they fit in `room`; the returned
+//                  count tells the caller whether they did; the caller gathers depol for the whole batch in one go
 // hasEv: some staged slot delivers (t0 < arrive) or re-queues its target (t0 < arrive + 2 <= t1) in this window.
 template <bool SPILL>
 __device__ __forceinline__ uint32_t stage_row(const View& v, const StepArgs& s, uint64_t row, uint64_t rs, uint64_t re, CandView& cv,
-                                              float* pa, float* pd, uint32_t* pj, uint32_t room, uint32_t lane, bool& hasEv) {
+                                              float* pa, uint32_t* pj, uint32_t jbase, uint32_t room, uint32_t lane, bool& hasEv) {
     uint32_t cnt = 0, summ = 0;
     bool ev = false;
     const uint32_t len = (uint32_t)(re - rs);
@@ -193,9 +194,8 @@ __device__ __forceinline__ uint32_t stage_row(const View& v, const StepArgs& s, 
                     const float tR = add32(a, 2.0f);
                     ev |= (a > s.t0) || (tR > s.t0 && tR <= s.t1);
                     const uint32_t jr = rel0 + k;  // (32-bit wrap intended: rel0 is "negative" left of the row start)
-                    const float d = v.depol[rs + jr];
-                    if (SPILL) { cv.A(pos) = a; cv.D(pos) = d; cv.J(pos) = jr; }
-                    else if (pos < room) { pa[pos] = a; pd[pos] = d; pj[pos] = jr; }
+                    if (SPILL) { cv.A(pos) = a; cv.D(pos) = v.depol[rs + jr]; cv.J(pos) = jr; }
+                    else if (pos < room) { pa[pos] = a; pj[pos] = jbase + jr; }  // depol is gathered for the whole batch afterwards
                     pos++;
                 }
             cnt += __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
@@ -228,7 +228,7 @@ __device__ void warp_row(const View& v, const StepArgs& s, uint64_t row, CandVie
     const uint32_t q = (uint32_t)(v.row0 + row);
     const uint64_t rs = v.rowptr[row], re = v.rowptr[row + 1];
     bool hasEv;
-    const uint32_t cnt = stage_row<true>(v, s, row, rs, re, cv, nullptr, nullptr, nullptr, 0u, lane, hasEv);
+    const uint32_t cnt = stage_row<true>(v, s, row, rs, re, cv, nullptr, nullptr, 0u, 0u, lane, hasEv);
     __syncwarp();
     uint32_t evLo, evHi;
     host_event_range(v, s, row, q, evLo, evHi);
@@ -323,10 +323,10 @@ __device__ void warp_row(const View& v, const StepArgs& s, uint64_t row, CandVie
 // ID with a double -> float rounding per addition (NeuCor.cpp:688-700) — and it finds the neuron's next event.
 struct LanePick { float t; unsigned long long code; uint32_t src; };
 
-__device__ __forceinline__ void pick_from_slot(const View& v, const StepArgs& s, uint64_t rs, const uint32_t* J, uint32_t c, float a,
+__device__ __forceinline__ void pick_from_slot(const View& v, const StepArgs& s, uint64_t tb, const uint32_t* J, uint32_t c, float a,
                                                bool first, float curT, unsigned long long curC, LanePick& nx) {
     if (a > s.t0) {  // delivery in this window (a <= t1 by staging)
-        const uint32_t p = v.pre[rs + J[c]] & 0x7fffffffu;
+        const uint32_t p = v.pre[tb + J[c]] & 0x7fffffffu;
         const unsigned long long code = (1ull << 32) | p;
         if ((first || pick_less(curT, curC, a, code)) && pick_less(a, code, nx.t, nx.code)) { nx.t = a; nx.code = code; nx.src = c; }
     }
@@ -348,13 +348,14 @@ __device__ __forceinline__ void pick_from_host(const StepArgs& s, uint32_t evLo,
     }
 }
 
-__device__ void lanes_replay(const View& v, const StepArgs& s, bool valid, uint64_t row, float* A, const float* D, const uint32_t* J, uint32_t cnt,
-                             bool hasEv, P1Counters& ctr) {
+// J holds slot indices relative to `tb`, the first slot of the tile's first row.
+__device__ void lanes_replay(const View& v, const StepArgs& s, bool valid, uint64_t row, uint64_t tb, float* A, const float* D, const uint32_t* J,
+                             uint32_t cnt, bool hasEv, P1Counters& ctr) {
     const uint32_t FULL = 0xffffffffu;
     const unsigned long long NONE = ~0ull, SWEEP = 3ull << 32;
     if (!valid) { cnt = 0; hasEv = false; row = 0; }
     const uint32_t q = (uint32_t)(v.row0 + row);
-    const uint64_t rs = valid ? v.rowptr[row] : 0;
+    const uint32_t rowOff = valid ? (uint32_t)(v.rowptr[row] - tb) : 0u;  // J - rowOff = index within the row
     uint32_t evLo = 0, evHi = 0;
     NeuronState n;
     n.pot = 0.f; n.act = 0.f; n.lastRan = 0.f; n.lastFire = 0.f; n.actStart = 0.f; n.firings = 0u; n.sched = __uint_as_float(0x7fc00000u);
@@ -376,7 +377,7 @@ __device__ void lanes_replay(const View& v, const StepArgs& s, bool valid, uint6
     nx.t = INFINITY; nx.code = NONE; nx.src = 0xffffffffu;
     if (__any_sync(FULL, hasEv))
         for (uint32_t c = 0; c < maxCnt; c++)
-            if (hasEv && c < cnt) pick_from_slot(v, s, rs, J, c, A[c], true, s.t0, 0ull, nx);
+            if (hasEv && c < cnt) pick_from_slot(v, s, tb, J, c, A[c], true, s.t0, 0ull, nx);
     if (valid) pick_from_host(s, evLo, evHi, true, s.t0, 0ull, nx);
     bool swept = !sweepEnd || !valid;
     if (nx.code == NONE && !swept) { nx.t = s.t1; nx.code = SWEEP; swept = true; }
@@ -399,7 +400,7 @@ __device__ void lanes_replay(const View& v, const StepArgs& s, bool valid, uint6
             } else {
                 if (rank == 1u) {  // Synapse::run → Neuron::transfer (NeuCor.cpp:718-726,663-666)
                     ctr.deliveries++;
-                    rk1 = (1u << 30) | q; k2 = k; sentinel = NC_SENT | (1u << 29) | J[cur.src];
+                    rk1 = (1u << 30) | q; k2 = k; sentinel = NC_SENT | (1u << 29) | (J[cur.src] - rowOff);
                 } else {           // rank 2: queued Neuron::run; rank 3: end-of-window sweep
                     rk1 = (rank << 30) | q; k2 = 0u; sentinel = NC_SENT | (rank << 29);
                 }
@@ -422,13 +423,13 @@ __device__ void lanes_replay(const View& v, const StepArgs& s, bool valid, uint6
                             np = (float)add64((double)np, chain_term(dT, D[c], E));
                             if (2.0f < off) {           // NeuCor.cpp:697 — the slot becomes idle; leave the when-and-why for the synapse pass
                                 A[c] = -araw;
-                                const uint64_t sidx = rs + J[c];
+                                const uint64_t sidx = tb + J[c];
                                 v.arrive[sidx] = __uint_as_float(sentinel);
                                 v.depol[sidx] = T;
                             }
                         }
                     }
-                    if (pickMore && hasEv) pick_from_slot(v, s, rs, J, c, fabsf(araw), false, cur.t, cur.code, nx);
+                    if (pickMore && hasEv) pick_from_slot(v, s, tb, J, c, fabsf(araw), false, cur.t, cur.code, nx);
                 }
             }
         if (pickMore) pick_from_host(s, evLo, evHi, false, cur.t, cur.code, nx);
@@ -473,6 +474,7 @@ __global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32, 4) k_neuron_pass(View
         if (tile >= nTiles) break;
         const uint64_t rowBase = tile << 5;
         const uint32_t nr = (uint32_t)min((uint64_t)32, v.nRows - rowBase);
+        const uint64_t tb = v.rowptr[rowBase];  // staged slot indices are relative to the tile's first slot (rows < 2^27 slots)
         uint32_t r = 0;
         while (r < nr) {
             // ---- batch: stage rows r, r+1, ... while their occupied slots fit the pool; the i-th staged row goes to lane i ----
@@ -483,14 +485,18 @@ __global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32, 4) k_neuron_pass(View
                 if (s.subset && !in_subset(s, (uint32_t)(v.row0 + row))) { r++; continue; }
                 const uint64_t rs = v.rowptr[row], re = v.rowptr[row + 1];
                 bool ev;
-                const uint32_t c = stage_row<false>(v, s, row, rs, re, cv, sA + used, sD + used, sJ + used, cap - used, lane, ev);
+                const uint32_t c = stage_row<false>(v, s, row, rs, re, cv, sA + used, sJ + used, (uint32_t)(rs - tb), cap - used, lane, ev);
                 if (c > cap - used) { heavy = (nb == 0); break; }  // does not fit: close the batch (an over-long row goes alone)
                 if (lane == nb) { myRow = r; myOff = used; myCnt = c; myEv = ev; }
                 used += c; nb++; r++;
             }
             __syncwarp();
             if (heavy) { warp_row(v, s, rowBase + r, cv, lane, ctrW); r++; continue; }
-            lanes_replay(v, s, lane < nb, rowBase + myRow, sA + myOff, sD + myOff, sJ + myOff, myCnt, myEv, ctrL);
+            // depolarisation factors of all staged slots of the batch: one round of independent gathers instead of a dependent
+            // load per 128-slot group during staging
+            for (uint32_t i = lane; i < used; i += 32) sD[i] = v.depol[tb + sJ[i]];
+            __syncwarp();
+            lanes_replay(v, s, lane < nb, rowBase + myRow, tb, sA + myOff, sD + myOff, sJ + myOff, myCnt, myEv, ctrL);
             __syncwarp();
         }
     }
@@ -908,7 +914,7 @@ __global__ void k_validate_csr(uint64_t nGlobal, uint64_t nRows, const uint64_t*
     for (uint64_t row = gw; row < nRows; row += nW) {
         uint64_t rs = rowptr[row], re = rowptr[row + 1];
         if (re < rs) { err |= 1u; continue; }
-        if (re - rs >= (1ull << 29)) { err |= 2u; continue; }
+        if (re - rs >= (1ull << 27)) { err |= 2u; continue; }
         maxRow = max(maxRow, (unsigned int)(re - rs));
         for (uint64_t j = rs + lane; j < re; j += 32) {
             uint32_t p = pre[j];
@@ -1024,7 +1030,7 @@ extern "C" int nc_upload_network(nc_engine* e, uint64_t nGlobal, uint64_t row0, 
         if (rowptr[r + 1] < rowptr[r]) return fail(e, NC_ERR_INVALID, "nc_upload_network: rowptr not monotone");
         uint64_t len = rowptr[r + 1] - rowptr[r];
         maxRow = std::max(maxRow, len);
-        if (len >= (1ull << 29)) return fail(e, NC_ERR_INVALID, "nc_upload_network: row longer than 2^29-1");
+        if (len >= (1ull << 27)) return fail(e, NC_ERR_INVALID, "nc_upload_network: row longer than 2^27-1");
         for (uint64_t j = rowptr[r]; j < rowptr[r + 1]; j++) {
             if (pre[j] >= nGlobal) return fail(e, NC_ERR_INVALID, "nc_upload_network: presynaptic ID out of range");
             if (j > rowptr[r] && pre[j] <= pre[j - 1]) return fail(e, NC_ERR_INVALID, "nc_upload_network: row not strictly ascending in presynaptic ID");
@@ -1057,7 +1063,7 @@ extern "C" int nc_upload_network_device(nc_engine* e, uint64_t nGlobal, uint64_t
     CK(cudaMemcpy(hOut, dOut, 12, cudaMemcpyDeviceToHost));
     cudaFree(dOut);
     if (hOut[0] & 1u) return fail(e, NC_ERR_INVALID, "nc_upload_network: rowptr not monotone");
-    if (hOut[0] & 2u) return fail(e, NC_ERR_INVALID, "nc_upload_network: row longer than 2^29-1");
+    if (hOut[0] & 2u) return fail(e, NC_ERR_INVALID, "nc_upload_network: row longer than 2^27-1");
     if (hOut[0] & 4u) return fail(e, NC_ERR_INVALID, "nc_upload_network: presynaptic ID out of range");
     if (hOut[0] & 8u) return fail(e, NC_ERR_INVALID, "nc_upload_network: row not strictly ascending in presynaptic ID");
     if (hOut[0] & 16u) return fail(e, NC_ERR_INVALID, "nc_upload_network: synapse length must be positive");

@@ -315,6 +315,8 @@ def main():
     else:
         drive_setup(g, net, True)
         step = g.step
+    if os.environ.get("NC_CAND_SMEM"):  # tuning knob: slots in the neuron pass's per-warp shared-memory pool
+        g.set_candidate_smem(int(os.environ["NC_CAND_SMEM"]))
     g.set_sweep_mean(False)  # the per-step device->host result is the counter block (hidden rand() count, fires, ...)
     g.finalize()
     Nglob, S_glob = g.counts()[0], (net["S"] * world if net else g.counts()[1])

@@ -109,6 +109,11 @@ int nc_set_plasticity(nc_engine* e, float learning_rate, float pre_factor, float
 int nc_step(nc_engine* e, float t0, float t1, int sweep, const nc_event* events, uint32_t n_events,
             uint64_t* hidden_rand_calls, nc_step_stats* stats_or_null);
 
+/* The same window in two halves, so that the host can work while the device runs: nc_step_launch enqueues everything
+ * (for world > 1 it blocks briefly inside the fire exchange) and returns; nc_step_collect waits and reports. */
+int nc_step_launch(nc_engine* e, float t0, float t1, int sweep, const nc_event* events, uint32_t n_events);
+int nc_step_collect(nc_engine* e, uint64_t* hidden_rand_calls, nc_step_stats* stats_or_null);
+
 /* The side effect of VoltageDetector::getVoltage (NeuCor.cpp:361-362): run the listed neurons
  * (ascending IDs of this shard; NULL = all) at time `now`, including any fires this causes. */
 int nc_run_neurons(nc_engine* e, float now, const uint32_t* ids, uint32_t n_ids, uint64_t* hidden_rand_calls,

@@ -804,6 +804,7 @@ struct nc_engine {
     nc_allgather_fn xchgFn = nullptr; void* xchgCtx = nullptr;
     uint32_t xchgUnits = 1u + 1024u;        // units per shard moved by the fire exchange; grows on demand
     uint32_t lastCounts[NC_MAX_WORLD] = {0}; uint32_t lastStride = 0;
+    bool pending = false;                   // nc_step_launch issued, nc_step_collect outstanding
     float lr = 1.0f, preF = 0.13f, postF = 0.30f, preD = 0.75f, postD = 0.65f;
     float minDelay = INFINITY;
     uint32_t candCap = 1024, grid1 = 0, grid2 = 0, maskWordsSmem = 0;
@@ -1202,8 +1203,8 @@ static void sum_out(nc_engine* e, uint64_t* hidden, nc_step_stats* st) {
         st->plasticity_calls = t[4]; st->hidden_rand_calls = t[5]; st->neuron_runs = t[6]; st->active_visits = t[7];
     }
 }
-// Reads the per-window result blocks (own, or all shards' after an all-gather) and reports the network-wide counters.
-static int finish_counters(nc_engine* e, uint64_t* hidden, nc_step_stats* st) {
+// Per-window result blocks (own, or all shards' after an all-gather): enqueue the read-back ...
+static int enqueue_counters(nc_engine* e) {
     const int W = e->cfg.world;
     if (W == 1) {
         CK(cudaMemcpyAsync(e->hOut, e->dOut, 10 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
@@ -1212,11 +1213,21 @@ static int finish_counters(nc_engine* e, uint64_t* hidden, nc_step_stats* st) {
         if (rc) return rc;
         CK(cudaMemcpyAsync(e->hOut, e->dOutAll, (size_t)W * 10 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
     }
+    return NC_OK;
+}
+// ... and wait for it: reports the network-wide counters.
+static int wait_counters(nc_engine* e, uint64_t* hidden, nc_step_stats* st) {
+    const int W = e->cfg.world;
     CK(cudaStreamSynchronize(e->stream));
     sum_out(e, hidden, st);
     for (int b = 0; b < W; b++)
         if (e->hOut[b * 10 + 9]) return fail(e, NC_ERR_CAPACITY, "step: fire-record capacity exceeded (raise nc_config.fire_capacity)");
     return NC_OK;
+}
+static int finish_counters(nc_engine* e, uint64_t* hidden, nc_step_stats* st) {
+    int rc = enqueue_counters(e);
+    if (rc) return rc;
+    return wait_counters(e, hidden, st);
 }
 
 // The fire exchange of a live window (world > 1): all-gather of the first xchgUnits units of every shard's block, then a
@@ -1246,8 +1257,8 @@ static int exchange_fires(nc_engine* e, StepArgs& a, uint32_t* maxCount) {
     }
 }
 
-extern "C" int nc_step(nc_engine* e, float t0, float t1, int sweep, const nc_event* events, uint32_t nEv, uint64_t* hidden,
-                       nc_step_stats* st) {
+extern "C" int nc_step_launch(nc_engine* e, float t0, float t1, int sweep, const nc_event* events, uint32_t nEv) {
+    if (e->pending) return fail(e, NC_ERR_STATE, "nc_step_launch: the previous window has not been collected");
     int rc = check_window(e, t0, t1);
     if (rc) return rc;
     cudaSetDevice(e->cfg.device);
@@ -1270,9 +1281,24 @@ extern "C" int nc_step(nc_engine* e, float t0, float t1, int sweep, const nc_eve
     }
     rc = launch_pass2(e, a, expect, 0);
     if (rc) return rc;
-    rc = finish_counters(e, hidden, st);
+    rc = enqueue_counters(e);
+    if (rc) return rc;
+    e->pending = true;
+    return NC_OK;
+}
+extern "C" int nc_step_collect(nc_engine* e, uint64_t* hidden, nc_step_stats* st) {
+    if (!e->pending) return fail(e, NC_ERR_STATE, "nc_step_collect: no window in flight");
+    cudaSetDevice(e->cfg.device);
+    e->pending = false;
+    int rc = wait_counters(e, hidden, st);
     if (e->cfg.world == 1) { e->lastCounts[0] = (uint32_t)std::min<unsigned long long>(e->hOut[8], e->v.fireCap); e->lastStride = e->v.fireCap + 1u; }
     return rc;
+}
+extern "C" int nc_step(nc_engine* e, float t0, float t1, int sweep, const nc_event* events, uint32_t nEv, uint64_t* hidden,
+                       nc_step_stats* st) {
+    int rc = nc_step_launch(e, t0, t1, sweep, events, nEv);
+    if (rc) return rc;
+    return nc_step_collect(e, hidden, st);
 }
 
 extern "C" int nc_run_neurons(nc_engine* e, float now, const uint32_t* ids, uint32_t nIds, uint64_t* hidden, nc_step_stats* st) {

@@ -23,7 +23,7 @@ NC_SWEEP_START = 2
 ABI_SYMBOLS = (
     "nc_global_error", "nc_device_count", "nc_create", "nc_destroy", "nc_last_error", "nc_upload_network",
     "nc_upload_network_device", "nc_min_delay",
-    "nc_set_plasticity", "nc_step", "nc_run_neurons", "nc_read_neurons", "nc_read_synapses", "nc_read_fires",
+    "nc_set_plasticity", "nc_step", "nc_step_launch", "nc_step_collect", "nc_run_neurons", "nc_read_neurons", "nc_read_synapses", "nc_read_fires",
     "nc_read_synapse_pots", "nc_reset_activities", "nc_detector_mean", "nc_tape_begin", "nc_tape_end", "nc_snapshot",
     "nc_restore", "nc_tape_replay", "nc_launch_count", "nc_comm_unique_id", "nc_comm_init", "nc_set_exchange",
     "nc_selftest_powf", "nc_selftest_exp",

@@ -44,6 +44,31 @@ public:
         return out;
     }
     void skip(uint64_t n) { for (uint64_t k = 0; k < n; k++) (void)next(); }
+    bool bulk() const { return words_ != nullptr; }
+    // Bulk draws: out[0..n) = the next n values of rand().  The recurrence r[i] = r[i-31] + r[i-3] has a dependency distance of
+    // 3, so a straight loop over the state array pipelines well once the index wrap is taken out of it.
+    void fill(int32_t* out, std::size_t n) {
+        if (!words_) { for (std::size_t k = 0; k < n; k++) out[k] = rand(); return; }
+        uint32_t* st = reinterpret_cast<uint32_t*>(words_ + 1);
+        std::size_t k = 0;
+        while (k < n && r_ != 0) out[k++] = next();
+        while (n - k >= 31) {  // r_ == 0, f_ == 3: one full turn of the 31-word state
+            for (int i = 0; i < 28; i++) { st[i + 3] += st[i]; out[k + i] = (int32_t)(st[i + 3] >> 1); }
+            for (int i = 28; i < 31; i++) { st[i - 28] += st[i]; out[k + i] = (int32_t)(st[i - 28] >> 1); }
+            k += 31;
+        }
+        while (k < n) out[k++] = next();
+    }
+    // Takes back the last n draws (the recurrence is reversible: r[i-31] = r[i] - r[i-3]).
+    void unnext(std::size_t n) {
+        if (!words_) return;  // (never used without the bulk path)
+        uint32_t* st = reinterpret_cast<uint32_t*>(words_ + 1);
+        for (std::size_t k = 0; k < n; k++) {
+            f_ = f_ == 0 ? 30 : f_ - 1;
+            r_ = r_ == 0 ? 30 : r_ - 1;
+            st[f_] -= st[r_];
+        }
+    }
 
 private:
     void open() {
@@ -108,6 +133,96 @@ bool RandWindow::checked_ = false;
 bool RandWindow::usable_ = false;
 }  // namespace
 
+// ---- RandStream: look-ahead view of libc's rand() stream -------------------------------------------------------
+// run() draws once per neuron per call from libc's generator (NeuCor.cpp:604-607), and where that stream continues
+// depends on a count only the device knows at the end of the window (the hidden rand() calls, NeuCor.cpp:752).  The
+// VALUES of the stream do not depend on that count, only the position does — so the raw stream and the positions whose
+// draw is a background hit (draw % period == 0) are generated ahead, while the device is busy, and the per-window work on
+// the critical path shrinks to walking the (rare) hits.  glibc's TYPE_3 generator is x[n] = x[n-31] + x[n-3] (mod 2^32),
+// rand() = x[n] >> 1; its 31-word state is borrowed through setstate() for the duration of run() and handed back at the
+// position actually consumed, so the application's own rand() calls continue exactly where the reference's would.  If the
+// application drew from (or re-seeded) the generator in between, the look-ahead no longer matches and is rebuilt.
+struct NeuCor::RandStream {
+    std::vector<uint32_t> raw;    // raw[k + 31] = x of draw k (k counted from `base`); raw[0..31) = the 31 values before draw 0
+    std::size_t pos = 0;          // next unconsumed draw
+    std::vector<uint64_t> hits;   // ascending draw numbers whose rand() value is divisible by `period`
+    std::size_t hitHead = 0;      // hits[0..hitHead) are known to lie before pos
+    std::size_t scanned = 0;      // draws [0, scanned) have been tested
+    int period = 0;
+    uint64_t magic = 0;
+    bool attached = false, usable = true, valid = false;
+    int32_t* words = nullptr;     // libc's state block while attached
+
+    bool attach() {
+        static int32_t parking[34];
+        parking[0] = 3;
+        for (int i = 1; i < 34; i++) parking[i] = (int32_t)((uint32_t)i * 1103515245u + 12345u);
+        { RandWindow probe; if (!probe.bulk()) { usable = false; return false; } }  // self-test of the recurrence against rand()
+        char* cur = setstate(reinterpret_cast<char*>(parking));  // saves the live positions into cur[0] and returns it
+        if (!cur) { usable = false; return false; }
+        int32_t* w = reinterpret_cast<int32_t*>(cur);
+        if (w[0] % 5 != 3) { setstate(cur); usable = false; return false; }
+        words = w;
+        const int r = w[0] / 5, f = (r + 3) % 31;
+        uint32_t h[31];  // ring order from the oldest value: x[n-31] .. x[n-1]
+        for (int i = 0; i < 31; i++) h[i] = (uint32_t)w[1 + (f + i) % 31];
+        bool same = valid && raw.size() >= pos + 31;
+        for (int i = 0; i < 31 && same; i++) same = raw[pos + i] == h[i];
+        if (!same) {
+            raw.assign(h, h + 31);
+            pos = 0; hits.clear(); hitHead = 0; scanned = 0; valid = true;
+        }
+        attached = true;
+        return true;
+    }
+    void detach() {
+        if (!attached) return;
+        // libc continues at `pos`: oldest value at ring position 3, rear index 0
+        for (int i = 0; i < 31; i++) words[1 + (3 + i) % 31] = (int32_t)raw[pos + i];
+        words[0] = 3;
+        setstate(reinterpret_cast<char*>(words));
+        words = nullptr; attached = false;
+        if (pos > (1u << 22)) {  // drop the consumed part
+            raw.erase(raw.begin(), raw.begin() + pos);
+            std::size_t k = 0;
+            for (std::size_t i = hitHead; i < hits.size(); i++) if (hits[i] >= pos) hits[k++] = hits[i] - pos;
+            hits.resize(k); hitHead = 0;
+            scanned = scanned > pos ? scanned - pos : 0;
+            pos = 0;
+        }
+    }
+    void setPeriod(int p) {
+        if (p == period) return;
+        period = p; magic = ~0ull / (uint64_t)p + 1ull;
+        hits.clear(); hitHead = 0; scanned = pos;
+    }
+    // draws [0, upto) generated and tested for hits
+    void generate(std::size_t upto) {
+        std::size_t n = raw.size();
+        if (n < upto + 31) {
+            raw.resize(upto + 31);
+            uint32_t* x = raw.data();
+            for (; n < upto + 31; n++) x[n] = x[n - 31] + x[n - 3];
+        }
+        if (period > 1 && scanned < upto) {
+            const uint32_t* x = raw.data() + 31;
+            const uint64_t M = magic;
+            for (std::size_t k = scanned; k < upto; k++)  // (v * ceil(2^64/P)) wraps below ceil(2^64/P) exactly for multiples of P
+                if ((uint64_t)(x[k] >> 1) * M < M) hits.push_back(k);
+            scanned = upto;
+        }
+    }
+    void prefetch(std::size_t ahead) { generate(pos + ahead); }
+    int32_t value(std::size_t k) { if (raw.size() < k + 32) generate(k + 1 + 4096); return (int32_t)(raw[k + 31] >> 1); }
+    void advance(uint64_t n) { pos += n; if (raw.size() < pos + 31) generate(pos); }
+    // first hit at or after draw `from` and before `limit`, or `limit`
+    std::size_t nextHit(std::size_t from, std::size_t limit) {
+        if (scanned < limit) generate(limit);
+        while (hitHead < hits.size() && hits[hitHead] < from) hitHead++;
+        return (hitHead < hits.size() && hits[hitHead] < limit) ? (std::size_t)hits[hitHead] : limit;
+    }
+};
+
 NeuCor::NeuCor(int n_neurons) {  // NeuCor.cpp:17-42
     runSpeed = 1.0;
     runAll = false;
@@ -129,6 +244,7 @@ NeuCor::NeuCor(int n_neurons) {  // NeuCor.cpp:17-42
 
 NeuCor::~NeuCor() {
     if (engine_) nc_destroy(engine_);
+    delete rs_;
 }
 
 void NeuCor::check(int rc, const char* what) {
@@ -438,11 +554,19 @@ void NeuCor::window(float t0, float t1, int flags, std::vector<nc_event>& ev) {
             if (x.neuron >= row0_ && x.neuron < row0_ + nRows_) ev[k++] = x;
         ev.resize(k);
     }
-    check(nc_step(engine_, t0, t1, flags, ev.data(), (uint32_t)ev.size(), &hidden, &st), "nc_step");
+    check(nc_step_launch(engine_, t0, t1, flags, ev.data(), (uint32_t)ev.size()), "nc_step");
+    // while the device runs: extend the look-ahead of the rand() stream to cover this window's hidden calls (a guess from
+    // the last window) and the next run()'s per-neuron draws
+    if (rs_ && rs_->attached) rs_->prefetch((std::size_t)(2 * lastHidden_ + positions.size() + positions.size() / 64 + 8192));
+    check(nc_step_collect(engine_, &hidden, &st), "nc_step");
     h2dBytes_ += ev.size() * sizeof(nc_event);
     d2hBytes_ += 16 + 8 * sizeof(uint64_t);
     // the rand() calls hidden in synapticPlasticity's short-circuit (NeuCor.cpp:752): only their number matters
-    if (hidden) { RandWindow rw; rw.skip(hidden); }
+    lastHidden_ = hidden;
+    if (hidden) {
+        if (rs_ && rs_->attached) rs_->advance(hidden);
+        else { RandWindow rw; rw.skip(hidden); }
+    }
     lastStats_.fires += st.fires; lastStats_.deliveries += st.deliveries; lastStats_.loadsAccepted += st.loads_accepted;
     lastStats_.loadsDropped += st.loads_dropped; lastStats_.plasticityCalls += st.plasticity_calls; lastStats_.hiddenRand += st.hidden_rand_calls;
     lastStats_.neuronRuns += st.neuron_runs; lastStats_.activeVisits += st.active_visits;
@@ -455,6 +579,12 @@ float NeuCor::stepInternal(bool sweep) {  // NeuCor::run, NeuCor.cpp:583-617
     check(nc_set_plasticity(engine_, learningRate, presynapticFactor, postsynapticFactor, presynapticTraceDecay, postsynapticTraceDecay), "nc_set_plasticity");
     lastStats_ = StepStats{};
     const std::size_t N = positions.size();
+    // borrow libc's generator for the duration of this call (handed back, at the position consumed, on every exit path)
+    if (!rs_) rs_ = new RandStream();
+    struct Borrow {
+        RandStream* r;
+        ~Borrow() { if (r) r->detach(); }
+    } borrow{(rs_->usable && static_cast<int>(600.0f / runSpeed) > 1 && rs_->attach()) ? rs_ : nullptr};
     events_.clear();
     for (unsigned i = 0; i < inputHandler.size(); i++) {
         const float inputFrequency = inputArray != nullptr && i < inputArraySize ? inputArray[i] : 0.0f;
@@ -464,12 +594,30 @@ float NeuCor::stepInternal(bool sweep) {  // NeuCor::run, NeuCor.cpp:583-617
     const std::size_t bgBegin = events_.size();
     {
         const int backgroundFirePeriod = std::max(1, static_cast<int>(600.0f / runSpeed));
-        RandWindow rw;  // the same draws rand() would return, without its per-call cost
-        for (std::size_t i = 0; i < N; ++i) {
-            if (rw.next() % backgroundFirePeriod == 0) {
-                uint32_t n = (uint32_t)(rw.next() % N);
-                float t = (static_cast<float>(rw.next()) / static_cast<float>(RAND_MAX)) * runSpeed;
+        if (rs_ && rs_->attached && backgroundFirePeriod > 1) {
+            // neuron i tests draw number p + i + 2 * (hits before it); a hit consumes the next two draws (NeuCor.cpp:606)
+            RandStream& rs = *rs_;
+            rs.setPeriod(backgroundFirePeriod);
+            std::size_t p = rs.pos, i = 0;
+            while (i < N) {
+                const std::size_t j = rs.nextHit(p, p + (N - i));
+                if (j >= p + (N - i)) { p += N - i; break; }
+                i += j - p;
+                uint32_t n = (uint32_t)(rs.value(j + 1) % N);
+                float t = (static_cast<float>(rs.value(j + 2)) / static_cast<float>(RAND_MAX)) * runSpeed;
                 events_.push_back(nc_event{n, currentTime + t, 2u, 0u});  // Neuron::scheduleFire, NeuCor.cpp:658-661
+                p = j + 3;
+                i += 1;
+            }
+            rs.advance(p - rs.pos);
+        } else {
+            RandWindow rw;  // the same draws rand() would return, without its per-call cost
+            for (std::size_t i = 0; i < N; ++i) {
+                if (rw.next() % backgroundFirePeriod == 0) {
+                    uint32_t n = (uint32_t)(rw.next() % N);
+                    float t = (static_cast<float>(rw.next()) / static_cast<float>(RAND_MAX)) * runSpeed;
+                    events_.push_back(nc_event{n, currentTime + t, 2u, 0u});  // Neuron::scheduleFire, NeuCor.cpp:658-661
+                }
             }
         }
         // scheduledFireTime keeps the LAST value drawn for a neuron

@@ -172,6 +172,9 @@ private:
     std::vector<float> lastFireMirror_;
     std::vector<nc_event> events_, winEvents_;
     std::vector<float> schedScratch_;
+    struct RandStream;              // look-ahead view of libc's rand() stream (NeuCor.cpp)
+    RandStream* rs_ = nullptr;
+    uint64_t lastHidden_ = 0;
     StepStats lastStats_ = {}, totalStats_ = {};
     uint64_t h2dBytes_ = 0, d2hBytes_ = 0;
 };

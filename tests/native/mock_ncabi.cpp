@@ -288,6 +288,19 @@ int nc_step(nc_engine* e, float t0, float t1, int sweep, const nc_event* ev, uin
     model_pass2(e, a);
     return finish(e, hidden, st);
 }
+// the two-halves form of nc_step: the test double does the work in the first half and hands the result over in the second
+static uint64_t g_pendingHidden; static nc_step_stats g_pendingStats; static int g_pendingRc = NC_ERR_STATE;
+int nc_step_launch(nc_engine* e, float t0, float t1, int sweep, const nc_event* ev, uint32_t nEv) {
+    g_pendingRc = nc_step(e, t0, t1, sweep, ev, nEv, &g_pendingHidden, &g_pendingStats);
+    return g_pendingRc;
+}
+int nc_step_collect(nc_engine* e, uint64_t* hidden, nc_step_stats* st) {
+    if (g_pendingRc != NC_OK) return fail(e, NC_ERR_STATE, "nc_step_collect: no window in flight");
+    if (hidden) *hidden = g_pendingHidden;
+    if (st) *st = g_pendingStats;
+    g_pendingRc = NC_ERR_STATE;
+    return NC_OK;
+}
 int nc_run_neurons(nc_engine* e, float now, const uint32_t* ids, uint32_t n, uint64_t* hidden, nc_step_stats* st) {
     if (ids && !n) return NC_OK;
     StepArgs a; fill(e, a, now, now, NC_SWEEP_END, nullptr, 0);

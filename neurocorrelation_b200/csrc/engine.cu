@@ -318,9 +318,9 @@ __device__ void warp_row(const View& v, const StepArgs& s, uint64_t row, CandVie
 // All 32 lanes run this together and stay converged: the replay proceeds in ROUNDS, in every round each lane executes the
 // next event of its own neuron (or idles once it has none left), and the loops over the staged slots run to the largest
 // count of the batch.  The end-of-window sweep run is simply every lane's last event, so lanes with few events sweep while
-// others are still delivering.  One pass over a lane's slots does two things at once: it adds the active slots'
-// contributions for the event being executed — the reference's own loop, one slot after the other in ascending presynaptic
-// ID with a double -> float rounding per addition (NeuCor.cpp:688-700) — and it finds the neuron's next event.
+// others are still delivering.  The pass over a lane's slots adds the active slots' contributions for the event being
+// executed — the reference's own loop, one slot after the other in ascending presynaptic ID with a double -> float rounding
+// per addition (NeuCor.cpp:688-700); the neuron's next event is then picked among the few slots that carry one.
 struct LanePick { float t; unsigned long long code; uint32_t src; };
 
 __device__ __forceinline__ void pick_from_slot(const View& v, const StepArgs& s, uint64_t tb, const uint32_t* J, uint32_t c, float a,
@@ -373,11 +373,33 @@ __device__ void lanes_replay(const View& v, const StepArgs& s, bool valid, uint6
     const bool sweepEnd = (s.sweep & NC_SWEEP_END) != 0;
     float actT = 0.0f; uint32_t actF = 0u; bool ran = false;
     // ---- first event of every lane ----
-    LanePick nx;
-    nx.t = INFINITY; nx.code = NONE; nx.src = 0xffffffffu;
+    // which of this lane's staged slots carry an event in this window (delivery or requeue): usually one or two of dozens, so
+    // they are remembered as a bit mask (first 64 slots; beyond that the tail is scanned) and only those are looked at when
+    // the neuron's next event is picked
+    unsigned long long em = 0ull;
+    bool evTail = false;
     if (__any_sync(FULL, hasEv))
         for (uint32_t c = 0; c < maxCnt; c++)
-            if (hasEv && c < cnt) pick_from_slot(v, s, tb, J, c, A[c], true, s.t0, 0ull, nx);
+            if (hasEv && c < cnt) {
+                const float a = A[c];
+                const float tR = add32(a, 2.0f);
+                if ((a > s.t0) || (tR > s.t0 && tR <= s.t1)) {
+                    if (c < 64u) em |= 1ull << c; else evTail = true;
+                }
+            }
+    auto pick_slots = [&](bool first, float curT, unsigned long long curC, LanePick& out) {
+        unsigned long long m = em;
+        while (m) {
+            const uint32_t c = (uint32_t)__ffsll((long long)m) - 1u;
+            m &= m - 1ull;
+            pick_from_slot(v, s, tb, J, c, fabsf(A[c]), first, curT, curC, out);
+        }
+        if (evTail)
+            for (uint32_t c = 64u; c < cnt; c++) pick_from_slot(v, s, tb, J, c, fabsf(A[c]), first, curT, curC, out);
+    };
+    LanePick nx;
+    nx.t = INFINITY; nx.code = NONE; nx.src = 0xffffffffu;
+    pick_slots(true, s.t0, 0ull, nx);
     if (valid) pick_from_host(s, evLo, evHi, true, s.t0, 0ull, nx);
     bool swept = !sweepEnd || !valid;
     if (nx.code == NONE && !swept) { nx.t = s.t1; nx.code = SWEEP; swept = true; }
@@ -412,11 +434,11 @@ __device__ void lanes_replay(const View& v, const StepArgs& s, bool valid, uint6
         float np = n.pot;
         double E = 0.0;
         if (running && cnt) E = exp_glibc(mul64(0.3702, (double)dT));
-        if (__any_sync(FULL, (running && cnt) || (pickMore && hasEv)))
+        if (__any_sync(FULL, running && cnt))
             for (uint32_t c = 0; c < maxCnt; c++) {
-                if (c < cnt && act) {
+                if (c < cnt && running) {
                     const float araw = A[c];
-                    if (running && araw > 0.0f) {       // not cleared earlier in this window
+                    if (araw > 0.0f) {                  // not cleared earlier in this window
                         const float off = sub32(T, araw);
                         if (off > 0.0f) {               // arrived
                             ctr.visits++;
@@ -429,10 +451,12 @@ __device__ void lanes_replay(const View& v, const StepArgs& s, bool valid, uint6
                             }
                         }
                     }
-                    if (pickMore && hasEv) pick_from_slot(v, s, tb, J, c, fabsf(araw), false, cur.t, cur.code, nx);
                 }
             }
-        if (pickMore) pick_from_host(s, evLo, evHi, false, cur.t, cur.code, nx);
+        if (pickMore) {
+            pick_slots(false, cur.t, cur.code, nx);
+            pick_from_host(s, evLo, evHi, false, cur.t, cur.code, nx);
+        }
         if (running) {
             const bool fired = neuron_run_finish(n, np, T, dT, false);
             actT = T; actF = n.firings; ran = true;

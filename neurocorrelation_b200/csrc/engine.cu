@@ -39,6 +39,7 @@ using namespace ncm;
 using namespace ncs;
 
 #define NC_WARPS_PER_BLOCK 4
+#define NC_UNROLL_N 4         // neuron pass: independent 16-byte-per-lane row loads in flight per warp (8 was faster in the quiet regime, 30 % slower in the running one)
 #define NC_UNROLL4 4         // independent 16-byte-per-lane (512 B per warp) row loads kept in flight per warp
 #define NC_P2_THREADS 1024   // synapse pass: one persistent block per SM, fire bitmask staged in its shared memory
 
@@ -142,19 +143,19 @@ __device__ __forceinline__ uint32_t stage_row(const View& v, const StepArgs& s, 
     uint32_t cnt = 0, summ = 0;
     bool ev = false;
     const uint32_t len = (uint32_t)(re - rs);
-    const uint32_t t1b = __float_as_uint(s.t1);
+    const uint32_t t1b = __float_as_uint(s.t1), t0b = __float_as_uint(s.t0);
     const uint64_t g0 = rs >> 7;
     const uint32_t ng = (uint32_t)(((re + 127) >> 7) - g0);
     uint4* bm = reinterpret_cast<uint4*>(v.ownBits) + (g0 + row);
     const float4* src = reinterpret_cast<const float4*>(v.arrive) + (g0 << 5) + lane;
     const uint32_t relBase = 4u * lane - (uint32_t)(rs & 127u);  // row-relative index of this lane's first slot in group 0
-    for (uint32_t g = 0; g < ng; g += NC_UNROLL4) {
-        float4 av[NC_UNROLL4];
+    for (uint32_t g = 0; g < ng; g += NC_UNROLL_N) {
+        float4 av[NC_UNROLL_N];
 #pragma unroll
-        for (int u = 0; u < NC_UNROLL4; u++)
+        for (int u = 0; u < NC_UNROLL_N; u++)
             av[u] = (g + u < ng) ? __ldcs(src + ((g + u) << 5)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int u = 0; u < NC_UNROLL4; u++) {
+        for (int u = 0; u < NC_UNROLL_N; u++) {
             if (g + u >= ng) break;
             const uint32_t gi = g + u;
             // slot index relative to the row start; one unsigned compare against the row length masks both ends
@@ -172,7 +173,7 @@ __device__ __forceinline__ uint32_t stage_row(const View& v, const StepArgs& s, 
             // window's runs (2 < T - arrive needs 2 < t1 - arrive); everything else about an occupied slot stays put
             bool own[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) own[k] = is[k] && (a4[k] > s.t0 || sub32(s.t1, a4[k]) > 2.0f);
+            for (int k = 0; k < 4; k++) own[k] = is[k] && (__float_as_uint(a4[k]) > t0b || __float_as_uint(a4[k]) <= s.clrB);
             if (__any_sync(0xffffffffu, own[0] | own[1] | own[2] | own[3])) {
                 uint32_t o[4];
 #pragma unroll
@@ -191,8 +192,8 @@ __device__ __forceinline__ uint32_t stage_row(const View& v, const StepArgs& s, 
             for (int k = 0; k < 4; k++)
                 if (is[k]) {
                     const float a = a4[k];
-                    const float tR = add32(a, 2.0f);
-                    ev |= (a > s.t0) || (tR > s.t0 && tR <= s.t1);
+                    const uint32_t ab = __float_as_uint(a);
+                    ev |= (ab > t0b) || (ab > s.reqLoB && ab <= s.reqHiB);
                     const uint32_t jr = rel0 + k;  // (32-bit wrap intended: rel0 is "negative" left of the row start)
                     if (SPILL) { cv.A(pos) = a; cv.D(pos) = v.depol[rs + jr]; cv.J(pos) = jr; }
                     else if (pos < room) { pa[pos] = a; pj[pos] = jbase + jr; }  // depol is gathered for the whole batch afterwards
@@ -1111,8 +1112,28 @@ static int check_window(nc_engine* e, float t0, float t1) {
     return NC_OK;
 }
 
+// Largest positive-float bit pattern b (1 <= b <= hi) for which pred(float(b)) holds, 0 if none; pred must be monotone
+// (true for small values, false for large ones).  Evaluated with the same fp32 operations the kernels would use.
+template <typename P>
+static uint32_t last_true_bits(uint32_t hi, P pred) {
+    auto f = [](uint32_t b) { float x; memcpy(&x, &b, 4); return x; };
+    if (hi == 0 || !pred(f(1u))) return 0u;
+    uint32_t lo = 1u;  // pred(lo) holds
+    while (lo < hi) {
+        uint32_t mid = lo + (hi - lo + 1u) / 2u;
+        if (pred(f(mid))) lo = mid; else hi = mid - 1u;
+    }
+    return lo;
+}
 static void fill_args(nc_engine* e, StepArgs& a, float t0, float t1, int sweep, const nc_event* dEv, uint32_t nEv) {
     memset(&a, 0, sizeof(a));
+    {
+        uint32_t t1b; memcpy(&t1b, &t1, 4);
+        const volatile float two = 2.0f;
+        a.clrB = last_true_bits(t1b, [&](float x) { volatile float d = t1 - x; return d > two; });
+        a.reqHiB = last_true_bits(t1b, [&](float x) { volatile float r = x + two; return r <= t1; });
+        a.reqLoB = last_true_bits(t1b, [&](float x) { volatile float r = x + two; return r <= t0; });
+    }
     a.t0 = t0; a.t1 = t1; a.sweep = sweep;
     a.lr = e->lr; a.preFactor = e->preF; a.postFactor = e->postF; a.preDecay = e->preD; a.postDecay = e->postD;
     a.ev = dEv; a.nEv = nEv; a.candCap = e->candCap; a.world = (uint32_t)e->cfg.world;

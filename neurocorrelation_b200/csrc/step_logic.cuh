@@ -103,6 +103,9 @@ struct StepArgs {
     uint32_t candCap;
     uint32_t gStride;  // units per gathered block (header included)
     uint32_t world;
+    // float comparisons of the row scan as integer compares on the bit patterns of (positive) arrival times, fixed per window:
+    //   t1 - a > 2  (old enough to be cleared)  <=>  bits(a) <= clrB;     t0 < a + 2 <= t1 (requeue)  <=>  reqLoB < bits(a) <= reqHiB
+    uint32_t clrB, reqLoB, reqHiB;
 };
 
 struct NeuronState {

@@ -26,6 +26,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -555,6 +556,7 @@ __global__ void k_index_build(View v, StepArgs s) {
         const uint32_t nrn = v.gRecs[idx].neuron;
         v.next[idx] = atomicExch(&v.head[nrn], (int32_t)idx);
         atomicOr(&v.mask[nrn >> 5], 1u << (nrn & 31u));
+        atomicOr(&v.coarse[nrn >> 10], 1u << ((nrn >> 5) & 31u));
     }
 }
 __global__ void k_index_reset(View v, StepArgs s) {
@@ -564,6 +566,7 @@ __global__ void k_index_reset(View v, StepArgs s) {
         const uint32_t nrn = v.gRecs[b * s.gStride + 1u + i].neuron;
         v.head[nrn] = -1;
         v.mask[nrn >> 5] = 0u;
+        v.coarse[nrn >> 10] = 0u;
     }
 }
 // End of a window: publish (or, for replay, accumulate) the shard's counters and its exchange header into `out`
@@ -601,7 +604,9 @@ __device__ __forceinline__ void resolve_queued(const View& v, const StepArgs& s,
 }
 
 // MASK_SMEM: the whole-network fire bitmask (1 bit per neuron), probed once per synapse, is staged in shared memory
-// (a compile-time choice so that the probe is a plain 32-bit-addressed LDS); otherwise it is read through L1/L2.
+// (a compile-time choice so that the probe is a plain 32-bit-addressed LDS).  Networks too large for that (> 1.3 M neurons,
+// i.e. multi-GPU runs) stage the 32x smaller COARSE bitmask instead (1 bit per word of the fire mask) and go to the fire
+// mask in L2 only where the coarse bit is set — with a few thousand fires among millions of neurons that is < 1 % of probes.
 template <bool MASK_SMEM>
 __global__ void __launch_bounds__(NC_P2_THREADS) k_synapse_pass(View v, StepArgs s, uint32_t maskWordsInSmem) {
     extern __shared__ uint32_t smem2[];
@@ -609,12 +614,17 @@ __global__ void __launch_bounds__(NC_P2_THREADS) k_synapse_pass(View v, StepArgs
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     uint32_t* smask = smem2 + (size_t)wpb * 3 * NC_P2_QUEUE;
     const uint32_t* __restrict__ gmask = v.mask;
-    if (MASK_SMEM) {
-        for (uint32_t i = threadIdx.x; i < maskWordsInSmem; i += blockDim.x) smask[i] = gmask[i];
+    {   // maskWordsInSmem words of the fire mask (MASK_SMEM) or of the coarse mask
+        const uint32_t* __restrict__ srcm = MASK_SMEM ? gmask : v.coarse;
+        for (uint32_t i = threadIdx.x; i < maskWordsInSmem; i += blockDim.x) smask[i] = srcm[i];
         __syncthreads();
     }
     const uint32_t* mask = MASK_SMEM ? smask : gmask;  // for the (rare) per-entry probes of the resolve step
-    auto fired = [&](uint32_t n) -> bool { return ((MASK_SMEM ? smask[n >> 5] : __ldg(gmask + (n >> 5))) >> (n & 31u)) & 1u; };
+    auto fired = [&](uint32_t n) -> bool {
+        if (MASK_SMEM) return (smask[n >> 5] >> (n & 31u)) & 1u;
+        if (!((smask[n >> 10] >> ((n >> 5) & 31u)) & 1u)) return false;
+        return (__ldg(gmask + (n >> 5)) >> (n & 31u)) & 1u;
+    };
     // eventful slots are rare and scattered: queue them per warp — across rows — and resolve 32 at a time instead of
     // diverging in place
     uint32_t* qJ = smem2 + (size_t)wib * 3 * NC_P2_QUEUE;
@@ -830,9 +840,11 @@ struct nc_engine {
     uint32_t xchgUnits = 1u + 1024u;        // units per shard moved by the fire exchange; grows on demand
     uint32_t lastCounts[NC_MAX_WORLD] = {0}; uint32_t lastStride = 0;
     bool pending = false;                   // nc_step_launch issued, nc_step_collect outstanding
+    StepArgs pendingArgs;
     float lr = 1.0f, preF = 0.13f, postF = 0.30f, preD = 0.75f, postD = 0.65f;
     float minDelay = INFINITY;
     uint32_t candCap = 1024, grid1 = 0, grid2 = 0, maskWordsSmem = 0;
+    bool maskInSmem = true;
     size_t smem1 = 0, smem2 = 0;
     uint64_t launches = 0;
     // tape
@@ -902,7 +914,7 @@ static void free_all(nc_engine* e) {
     View& v = e->v;
     cudaFree((void*)v.rowptr); cudaFree(v.pre); cudaFree(v.arrive); cudaFree(v.depol); cudaFree(v.weight); cudaFree(v.lastArr);
     cudaFree(v.lastStart); cudaFree(e->dDelay); cudaFree(v.potAct); cudaFree(v.lastRan); cudaFree(v.lastFire); cudaFree(v.lfStart);
-    cudaFree(v.actStart); cudaFree(v.firings); cudaFree(v.localHdr); cudaFree(v.head); cudaFree(v.next); cudaFree(v.mask); cudaFree(v.evMask); cudaFree(v.ownBits); cudaFree(v.ownSumm);
+    cudaFree(v.actStart); cudaFree(v.firings); cudaFree(v.localHdr); cudaFree(v.head); cudaFree(v.next); cudaFree(v.mask); cudaFree(v.coarse); cudaFree(v.evMask); cudaFree(v.ownBits); cudaFree(v.ownSumm);
     cudaFree(v.spillA); cudaFree(v.spillD); cudaFree(v.spillJ);
     cudaFree(e->dGather);
     cudaFree(e->dEv); cudaFree(e->dTape);
@@ -984,6 +996,8 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
     CK(cudaMalloc(&v.head, G1 * 4)); CK(cudaMalloc(&v.next, (uint64_t)e->cfg.world * blockUnits * 4));
     CK(cudaMalloc(&v.mask, ((G1 + 31) / 32) * 4));
     CK(cudaMemsetAsync(v.mask, 0, ((G1 + 31) / 32) * 4, e->stream));
+    CK(cudaMalloc(&v.coarse, ((G1 + 1023) / 1024) * 4));
+    CK(cudaMemsetAsync(v.coarse, 0, ((G1 + 1023) / 1024) * 4, e->stream));
     CK(cudaMalloc(&v.evMask, ((N1 + 31) / 32) * 4));
     CK(cudaMemsetAsync(v.evMask, 0, ((N1 + 31) / 32) * 4, e->stream));
     const float* dLen = length; const unsigned char* dInh = inh;
@@ -1011,11 +1025,13 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
     CK(cudaFuncSetAttribute(k_neuron_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem1));
     int occ1 = 1, occ2 = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_neuron_pass, NC_WARPS_PER_BLOCK * 32, e->smem1));
-    // synapse pass: the whole-network fire bitmask goes to shared memory when it fits (<= 160 KB, i.e. 1.3 M neurons)
+    // synapse pass: the whole-network fire bitmask goes to shared memory when it fits (<= 160 KB, i.e. 1.3 M neurons),
+    // otherwise the 32x smaller coarse mask does (2^30 neurons -> 128 KB).  NC_FORCE_COARSE_MASK=1 forces the latter (tests).
     uint64_t maskWords = (G1 + 31) / 32;
-    e->maskWordsSmem = maskWords * 4 <= 160 * 1024 ? (uint32_t)maskWords : 0u;
+    e->maskInSmem = maskWords * 4 <= 160 * 1024 && !getenv("NC_FORCE_COARSE_MASK");
+    e->maskWordsSmem = e->maskInSmem ? (uint32_t)maskWords : (uint32_t)((G1 + 1023) / 1024);
     e->smem2 = (size_t)e->maskWordsSmem * 4 + (size_t)(NC_P2_THREADS / 32) * 3 * NC_P2_QUEUE * 4;
-    if (e->maskWordsSmem) {
+    if (e->maskInSmem) {
         CK(cudaFuncSetAttribute(k_synapse_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem2));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_synapse_pass<true>, NC_P2_THREADS, e->smem2));
     } else {
@@ -1141,8 +1157,8 @@ static void fill_args(nc_engine* e, StepArgs& a, float t0, float t1, int sweep, 
 }
 
 static void launch_synapse_pass(nc_engine* e, const StepArgs& a) {
-    if (e->maskWordsSmem) k_synapse_pass<true><<<e->grid2, NC_P2_THREADS, e->smem2, e->stream>>>(e->v, a, e->maskWordsSmem);
-    else k_synapse_pass<false><<<e->grid2, NC_P2_THREADS, e->smem2, e->stream>>>(e->v, a, 0u);
+    if (e->maskInSmem) k_synapse_pass<true><<<e->grid2, NC_P2_THREADS, e->smem2, e->stream>>>(e->v, a, e->maskWordsSmem);
+    else k_synapse_pass<false><<<e->grid2, NC_P2_THREADS, e->smem2, e->stream>>>(e->v, a, e->maskWordsSmem);
 }
 static int launch_pass1(nc_engine* e, const StepArgs& a) {
     if (a.nEv) { k_mark_events<<<(a.nEv + 255) / 256, 256, 0, e->stream>>>(e->v, a.ev, a.nEv, 1); e->launches++; }
@@ -1302,6 +1318,22 @@ static int exchange_fires(nc_engine* e, StepArgs& a, uint32_t* maxCount) {
     }
 }
 
+// exchange (world > 1), index build, synapse pass, end-of-window kernel, counter read-back enqueued
+static int step_second_half(nc_engine* e) {
+    StepArgs& a = e->pendingArgs;
+    uint32_t expect = std::max<uint32_t>(e->lastCounts[0], 256u);
+    if (e->cfg.world > 1) {
+        int rc = exchange_fires(e, a, &expect);
+        if (rc) return rc;
+    }
+    if (e->taping) {
+        e->tape.push_back({a.t0, a.t1, a.sweep, e->tapeUsed, a.nEv, a.gStride});
+        e->tapeUsed += a.nEv;
+    }
+    int rc = launch_pass2(e, a, expect, 0);
+    if (rc) return rc;
+    return enqueue_counters(e);
+}
 extern "C" int nc_step_launch(nc_engine* e, float t0, float t1, int sweep, const nc_event* events, uint32_t nEv) {
     if (e->pending) return fail(e, NC_ERR_STATE, "nc_step_launch: the previous window has not been collected");
     int rc = check_window(e, t0, t1);
@@ -1315,26 +1347,24 @@ extern "C" int nc_step_launch(nc_engine* e, float t0, float t1, int sweep, const
     fill_args(e, a, t0, t1, sweep, dEv, nEv);
     rc = launch_pass1(e, a);
     if (rc) return rc;
-    uint32_t expect = std::max<uint32_t>(e->lastCounts[0], 256u);
-    if (e->cfg.world > 1) {
-        rc = exchange_fires(e, a, &expect);
-        if (rc) return rc;
-    }
-    if (e->taping) {
-        e->tape.push_back({t0, t1, sweep, e->tapeUsed, nEv, a.gStride});
-        e->tapeUsed += nEv;
-    }
-    rc = launch_pass2(e, a, expect, 0);
-    if (rc) return rc;
-    rc = enqueue_counters(e);
-    if (rc) return rc;
+    e->pendingArgs = a;
     e->pending = true;
+    // a single shard needs nothing from the host between the passes: enqueue the rest of the window right away
+    if (e->cfg.world == 1) {
+        rc = step_second_half(e);
+        if (rc) e->pending = false;
+        return rc;
+    }
     return NC_OK;
 }
 extern "C" int nc_step_collect(nc_engine* e, uint64_t* hidden, nc_step_stats* st) {
     if (!e->pending) return fail(e, NC_ERR_STATE, "nc_step_collect: no window in flight");
     cudaSetDevice(e->cfg.device);
     e->pending = false;
+    if (e->cfg.world > 1) {  // the fire exchange looks at the gathered headers on the host (blocks until the neuron pass is done)
+        int rc = step_second_half(e);
+        if (rc) return rc;
+    }
     int rc = wait_counters(e, hidden, st);
     if (e->cfg.world == 1) { e->lastCounts[0] = (uint32_t)std::min<unsigned long long>(e->hOut[8], e->v.fireCap); e->lastStride = e->v.fireCap + 1u; }
     return rc;

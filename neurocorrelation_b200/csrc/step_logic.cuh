@@ -80,6 +80,7 @@ struct View {
     int32_t* head;         // per global neuron: unit index of its first record or -1
     int32_t* next;         // per unit
     uint32_t* mask;        // one bit per global neuron: fired in this window
+    uint32_t* coarse;      // one bit per word of `mask`: the word is non-zero (first level of the probe when `mask` stays in L2)
     uint32_t* evMask;      // one bit per row of this shard: has host events in this window
     uint32_t* ownBits;     // per row and 128-slot group: 4 ballot words marking the slots that may deliver / be cleared in this window
     uint32_t* ownSumm;     // per row: bit min(g, 31) set when group g of the row has any such slot (groups >= 31 are always written)

@@ -143,16 +143,28 @@ bool RandWindow::usable_ = false;
 // position actually consumed, so the application's own rand() calls continue exactly where the reference's would.  If the
 // application drew from (or re-seeded) the generator in between, the look-ahead no longer matches and is rebuilt.
 struct NeuCor::RandStream {
-    std::vector<uint32_t> raw;    // raw[k + 31] = x of draw k (k counted from `base`); raw[0..31) = the 31 values before draw 0
-    std::size_t pos = 0;          // next unconsumed draw
-    std::vector<uint64_t> hits;   // ascending draw numbers whose rand() value is divisible by `period`
-    std::size_t hitHead = 0;      // hits[0..hitHead) are known to lie before pos
-    std::size_t scanned = 0;      // draws [0, scanned) have been tested
+    // x[k + 31] = raw value of draw k (k counted from the buffer's origin); x[0..31) = the 31 values before draw 0.
+    // A plain array (no zero-fill on growth), compacted at every hand-back so that it stays cache-resident.
+    uint32_t* x = nullptr;
+    std::size_t len = 0, cap = 0;  // values held / allocated (incl. the 31 history values)
+    std::size_t pos = 0;           // next unconsumed draw
+    std::vector<uint64_t> hits;    // ascending draw numbers whose rand() value is divisible by `period`
+    std::size_t hitHead = 0;       // hits[0..hitHead) are known to lie before pos
+    std::size_t scanned = 0;       // draws [0, scanned) have been tested
     int period = 0;
     uint64_t magic = 0;
     bool attached = false, usable = true, valid = false;
-    int32_t* words = nullptr;     // libc's state block while attached
+    int32_t* words = nullptr;      // libc's state block while attached
 
+    ~RandStream() { delete[] x; }
+    void reserve(std::size_t n) {
+        if (n <= cap) return;
+        std::size_t c = std::max<std::size_t>(n + n / 2, 1u << 16);
+        uint32_t* y = new uint32_t[c];
+        if (len) memcpy(y, x, len * sizeof(uint32_t));
+        delete[] x;
+        x = y; cap = c;
+    }
     bool attach() {
         static int32_t parking[34];
         parking[0] = 3;
@@ -166,11 +178,12 @@ struct NeuCor::RandStream {
         const int r = w[0] / 5, f = (r + 3) % 31;
         uint32_t h[31];  // ring order from the oldest value: x[n-31] .. x[n-1]
         for (int i = 0; i < 31; i++) h[i] = (uint32_t)w[1 + (f + i) % 31];
-        bool same = valid && raw.size() >= pos + 31;
-        for (int i = 0; i < 31 && same; i++) same = raw[pos + i] == h[i];
+        bool same = valid && len >= pos + 31;
+        for (int i = 0; i < 31 && same; i++) same = x[pos + i] == h[i];
         if (!same) {
-            raw.assign(h, h + 31);
-            pos = 0; hits.clear(); hitHead = 0; scanned = 0; valid = true;
+            reserve(31);
+            memcpy(x, h, sizeof(h));
+            len = 31; pos = 0; hits.clear(); hitHead = 0; scanned = 0; valid = true;
         }
         attached = true;
         return true;
@@ -178,12 +191,13 @@ struct NeuCor::RandStream {
     void detach() {
         if (!attached) return;
         // libc continues at `pos`: oldest value at ring position 3, rear index 0
-        for (int i = 0; i < 31; i++) words[1 + (3 + i) % 31] = (int32_t)raw[pos + i];
+        for (int i = 0; i < 31; i++) words[1 + (3 + i) % 31] = (int32_t)x[pos + i];
         words[0] = 3;
         setstate(reinterpret_cast<char*>(words));
         words = nullptr; attached = false;
-        if (pos > (1u << 22)) {  // drop the consumed part
-            raw.erase(raw.begin(), raw.begin() + pos);
+        if (pos > (1u << 16)) {  // drop the consumed part
+            memmove(x, x + pos, (len - pos) * sizeof(uint32_t));
+            len -= pos;
             std::size_t k = 0;
             for (std::size_t i = hitHead; i < hits.size(); i++) if (hits[i] >= pos) hits[k++] = hits[i] - pos;
             hits.resize(k); hitHead = 0;
@@ -198,23 +212,38 @@ struct NeuCor::RandStream {
     }
     // draws [0, upto) generated and tested for hits
     void generate(std::size_t upto) {
-        std::size_t n = raw.size();
-        if (n < upto + 31) {
-            raw.resize(upto + 31);
-            uint32_t* x = raw.data();
-            for (; n < upto + 31; n++) x[n] = x[n - 31] + x[n - 3];
+        if (len < upto + 31) {
+            reserve(upto + 31);
+            uint32_t* y = x;
+            for (std::size_t n = len; n < upto + 31; n++) y[n] = y[n - 31] + y[n - 3];  // (dependency distance 3: ~0.7 ns a draw)
+            len = upto + 31;
         }
         if (period > 1 && scanned < upto) {
-            const uint32_t* x = raw.data() + 31;
+            const uint32_t* d = x + 31;
             const uint64_t M = magic;
-            for (std::size_t k = scanned; k < upto; k++)  // (v * ceil(2^64/P)) wraps below ceil(2^64/P) exactly for multiples of P
-                if ((uint64_t)(x[k] >> 1) * M < M) hits.push_back(k);
+            // rand() = x >> 1 is a multiple of P only if its low ctz(P) bits are zero.  Blocks of 32 draws are screened for that
+            // with a branch-free (vectorisable) reduction — (z - 1) has its top bit set only for z = 0 — and only blocks that
+            // hold such a draw are looked at one by one: (v * ceil(2^64/P)) wraps below ceil(2^64/P) exactly for multiples of P
+            const int tz = __builtin_ctz((unsigned)period);
+            const uint32_t low = ((1u << (tz > 8 ? 8 : tz)) - 1u) << 1;
+            std::size_t k = scanned;
+            if (low) {
+                for (; k + 32 <= upto; k += 32) {
+                    uint32_t flag = 0u;
+                    for (int j = 0; j < 32; j++) flag |= (d[k + j] & low) - 1u;
+                    if (flag & 0x80000000u)
+                        for (int j = 0; j < 32; j++)
+                            if ((d[k + j] & low) == 0u && (uint64_t)(d[k + j] >> 1) * M < M) hits.push_back(k + j);
+                }
+            }
+            for (; k < upto; k++)
+                if ((uint64_t)(d[k] >> 1) * M < M) hits.push_back(k);
             scanned = upto;
         }
     }
     void prefetch(std::size_t ahead) { generate(pos + ahead); }
-    int32_t value(std::size_t k) { if (raw.size() < k + 32) generate(k + 1 + 4096); return (int32_t)(raw[k + 31] >> 1); }
-    void advance(uint64_t n) { pos += n; if (raw.size() < pos + 31) generate(pos); }
+    int32_t value(std::size_t k) { if (len < k + 32) generate(k + 1 + 4096); return (int32_t)(x[k + 31] >> 1); }
+    void advance(uint64_t n) { pos += n; if (len < pos + 31) generate(pos); }
     // first hit at or after draw `from` and before `limit`, or `limit`
     std::size_t nextHit(std::size_t from, std::size_t limit) {
         if (scanned < limit) generate(limit);

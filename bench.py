@@ -52,6 +52,14 @@ WORKLOADS = {
 WEIGHT_SCALE = {"c1": 1.0, "c2": 1.0, "c3": K_REF / 1000, "m100": K_REF / 1000}
 
 
+def measured_traffic(workload, kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture of this workload (profiles/traffic.json), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[workload][kernel]
+    except Exception:
+        return None
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -406,7 +414,7 @@ def main():
         "mean_rate_hz": d["fires"] / args.steps / Nglob / DT * 1e3,
         "per_step": {k: v / args.steps for k, v in d.items()},
         "kernel_ms": {"k_neuron_pass": p1, "k_synapse_pass": p2, "fire_exchange": px, "step_total": ms_step},
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(args.workload, dom) if world == 1 else None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
                      "step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9, "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak}},
         "e2e": {"value": events / e2e_s, "unit": "delivered synaptic events/s", "h2d_bytes_per_step": (h2d1 - h2d0) / args.steps,

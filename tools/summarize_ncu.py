@@ -22,7 +22,7 @@ def launches(path, only_ours=True):
     k, v, u = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
     agg = defaultdict(lambda: [0, 0.0])
     for r in rows[1:]:
-        name = r[k].split("(")[0]
+        name = r[k].split("(")[0].replace("void ", "").split("<")[0]
         val = float(r[v].replace(",", ""))
         if r[u] == "ns":
             val /= 1e3
@@ -47,7 +47,7 @@ def rep(path):
     for r in rows[2:]:
         if len(r) < len(hdr):
             continue
-        d = {"kernel": r[hdr.index("Kernel Name")].split("(")[0]}
+        d = {"kernel": r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "")}
         for key in KEYS:
             if key in hdr:
                 i = hdr.index(key)

@@ -328,7 +328,7 @@ struct LanePick { float t; unsigned long long code; uint32_t src; };
 __device__ __forceinline__ void pick_from_slot(const View& v, const StepArgs& s, uint64_t tb, const uint32_t* J, uint32_t c, float a,
                                                bool first, float curT, unsigned long long curC, LanePick& nx) {
     if (a > s.t0) {  // delivery in this window (a <= t1 by staging)
-        const uint32_t p = v.pre[tb + J[c]] & 0x7fffffffu;
+        const uint32_t p = v.pre[tb + __ldcg(J + c)] & 0x7fffffffu;
         const unsigned long long code = (1ull << 32) | p;
         if ((first || pick_less(curT, curC, a, code)) && pick_less(a, code, nx.t, nx.code)) { nx.t = a; nx.code = code; nx.src = c; }
     }
@@ -424,7 +424,7 @@ __device__ void lanes_replay(const View& v, const StepArgs& s, bool valid, uint6
             } else {
                 if (rank == 1u) {  // Synapse::run → Neuron::transfer (NeuCor.cpp:718-726,663-666)
                     ctr.deliveries++;
-                    rk1 = (1u << 30) | q; k2 = k; sentinel = NC_SENT | (1u << 29) | (J[cur.src] - rowOff);
+                    rk1 = (1u << 30) | q; k2 = k; sentinel = NC_SENT | (1u << 29) | (__ldcg(J + cur.src) - rowOff);
                 } else {           // rank 2: queued Neuron::run; rank 3: end-of-window sweep
                     rk1 = (rank << 30) | q; k2 = 0u; sentinel = NC_SENT | (rank << 29);
                 }
@@ -447,7 +447,7 @@ __device__ void lanes_replay(const View& v, const StepArgs& s, bool valid, uint6
                             np = (float)add64((double)np, chain_term(dT, D[c], E));
                             if (2.0f < off) {           // NeuCor.cpp:697 — the slot becomes idle; leave the when-and-why for the synapse pass
                                 A[c] = -araw;
-                                const uint64_t sidx = tb + J[c];
+                                const uint64_t sidx = tb + __ldcg(J + c);
                                 v.arrive[sidx] = __uint_as_float(sentinel);
                                 v.depol[sidx] = T;
                             }
@@ -477,17 +477,20 @@ __device__ void lanes_replay(const View& v, const StepArgs& s, bool valid, uint6
 // shared-memory pool (cooperative, coalesced row scans), then every lane replays ONE of those neurons on its own
 // (lane-per-row: the per-neuron math — ordered accumulation, powf/exp, threshold, AP — is not replicated across lanes);
 // a row that alone exceeds the pool takes the warp-per-row path with the global spill area.
-__global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32, 4) k_neuron_pass(View v, StepArgs s) {
+__global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32, 6) k_neuron_pass(View v, StepArgs s) {
     extern __shared__ unsigned char smem[];
     math_tables_to_shared();
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     const uint32_t cap = s.candCap;
-    float* sA = reinterpret_cast<float*>(smem) + (size_t)wib * 3 * cap;
+    // pool of staged slots: arrival time and depolarisation factor (touched on every visit) in shared memory, the slot index
+    // (needed only where a slot delivers or is cleared) in an L2-resident per-warp scratch — 8 instead of 12 bytes of shared
+    // memory per staged slot buys two more resident blocks per SM
+    float* sA = reinterpret_cast<float*>(smem) + (size_t)wib * 2 * cap;
     float* sD = sA + cap;
-    uint32_t* sJ = reinterpret_cast<uint32_t*>(sA + 2 * cap);
+    const uint64_t gw = (uint64_t)blockIdx.x * NC_WARPS_PER_BLOCK + wib;
+    uint32_t* sJ = v.poolJ + gw * cap;
     CandView cv;
     cv.a = sA; cv.d = sD; cv.j = sJ; cv.cap = cap;
-    const uint64_t gw = (uint64_t)blockIdx.x * NC_WARPS_PER_BLOCK + wib;
     cv.sa = v.spillA + gw * v.spillPerWarp; cv.sd = v.spillD + gw * v.spillPerWarp; cv.sj = v.spillJ + gw * v.spillPerWarp;
     P1Counters ctrW = {0, 0, 0, 0};  // warp-uniform counts of the warp-per-row path
     P1Counters ctrL = {0, 0, 0, 0};  // this lane's counts of the lane-per-row path
@@ -520,7 +523,7 @@ __global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32, 4) k_neuron_pass(View
             if (heavy) { warp_row(v, s, rowBase + r, cv, lane, ctrW); r++; continue; }
             // depolarisation factors of all staged slots of the batch: one round of independent gathers instead of a dependent
             // load per 128-slot group during staging
-            for (uint32_t i = lane; i < used; i += 32) sD[i] = v.depol[tb + sJ[i]];
+            for (uint32_t i = lane; i < used; i += 32) sD[i] = v.depol[tb + __ldcg(sJ + i)];
             __syncwarp();
             lanes_replay(v, s, lane < nb, rowBase + myRow, tb, sA + myOff, sD + myOff, sJ + myOff, myCnt, myEv, ctrL);
             __syncwarp();
@@ -915,7 +918,7 @@ static void free_all(nc_engine* e) {
     cudaFree((void*)v.rowptr); cudaFree(v.pre); cudaFree(v.arrive); cudaFree(v.depol); cudaFree(v.weight); cudaFree(v.lastArr);
     cudaFree(v.lastStart); cudaFree(e->dDelay); cudaFree(v.potAct); cudaFree(v.lastRan); cudaFree(v.lastFire); cudaFree(v.lfStart);
     cudaFree(v.actStart); cudaFree(v.firings); cudaFree(v.localHdr); cudaFree(v.head); cudaFree(v.next); cudaFree(v.mask); cudaFree(v.coarse); cudaFree(v.evMask); cudaFree(v.ownBits); cudaFree(v.ownSumm);
-    cudaFree(v.spillA); cudaFree(v.spillD); cudaFree(v.spillJ);
+    cudaFree(v.spillA); cudaFree(v.spillD); cudaFree(v.spillJ); cudaFree(v.poolJ);
     cudaFree(e->dGather);
     cudaFree(e->dEv); cudaFree(e->dTape);
     auto& s = e->snap;
@@ -1021,7 +1024,7 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
     // launch geometry: persistent grids sized to the SM count x resident blocks per SM
     // the warp's shared-memory pool of staged slots: shared by the rows of a lane-per-row batch, so not tied to the row length
     e->candCap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(e->candCap, 32), 1024);
-    e->smem1 = (size_t)NC_WARPS_PER_BLOCK * 3 * e->candCap * 4;
+    e->smem1 = (size_t)NC_WARPS_PER_BLOCK * 2 * e->candCap * 4;
     CK(cudaFuncSetAttribute(k_neuron_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem1));
     int occ1 = 1, occ2 = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_neuron_pass, NC_WARPS_PER_BLOCK * 32, e->smem1));
@@ -1045,6 +1048,7 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
     v.spillPerWarp = (uint32_t)(maxRow > e->candCap ? maxRow - e->candCap : 0);
     uint64_t spillN = std::max<uint64_t>(1, (uint64_t)e->grid1 * NC_WARPS_PER_BLOCK * v.spillPerWarp);
     CK(cudaMalloc(&v.spillA, spillN * 4)); CK(cudaMalloc(&v.spillD, spillN * 4)); CK(cudaMalloc(&v.spillJ, spillN * 4));
+    CK(cudaMalloc(&v.poolJ, (uint64_t)e->grid1 * NC_WARPS_PER_BLOCK * e->candCap * 4));
     CK(cudaStreamSynchronize(e->stream));
     cudaFree(tmpLen); cudaFree(tmpInh);
     e->minDelay = minDelay;

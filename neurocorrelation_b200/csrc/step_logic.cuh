@@ -89,6 +89,7 @@ struct View {
     float* spillD;
     uint32_t* spillJ;
     uint32_t spillPerWarp;
+    uint32_t* poolJ;            // per warp of the neuron pass: slot indices of the staged slots (L2-resident scratch; rarely read)
     unsigned long long* stats;  // 8 counters (nc_step_stats order)
     uint32_t* tileCtr;          // [0] neuron pass, [1] synapse pass: next unclaimed tile of the window (dynamic scheduling)
 };

@@ -152,9 +152,10 @@ __device__ __forceinline__ uint32_t stage_row(const View& v, const StepArgs& s, 
     const uint32_t relBase = 4u * lane - (uint32_t)(rs & 127u);  // row-relative index of this lane's first slot in group 0
     for (uint32_t g = 0; g < ng; g += NC_UNROLL_N) {
         float4 av[NC_UNROLL_N];
+        const float4* sp = src + ((uint64_t)g << 5);  // (one 64-bit address per batch; the unrolled loads use immediate offsets)
 #pragma unroll
         for (int u = 0; u < NC_UNROLL_N; u++)
-            av[u] = (g + u < ng) ? __ldcs(src + ((g + u) << 5)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            av[u] = (g + u < ng) ? __ldcs(sp + (u << 5)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int u = 0; u < NC_UNROLL_N; u++) {
             if (g + u >= ng) break;
@@ -628,6 +629,11 @@ __global__ void __launch_bounds__(NC_P2_THREADS) k_synapse_pass(View v, StepArgs
         if (!((smask[n >> 10] >> ((n >> 5) & 31u)) & 1u)) return false;
         return (__ldg(gmask + (n >> 5)) >> (n & 31u)) & 1u;
     };
+    auto fired_word = [&](uint32_t n) -> uint32_t {  // bit 0 = fired(n); the other bits are junk
+        if (MASK_SMEM) return __funnelshift_r(smask[n >> 5], 0u, n);
+        if (!((smask[n >> 10] >> ((n >> 5) & 31u)) & 1u)) return 0u;
+        return __funnelshift_r(__ldg(gmask + (n >> 5)), 0u, n);
+    };
     // eventful slots are rare and scattered: queue them per warp — across rows — and resolve 32 at a time instead of
     // diverging in place
     uint32_t* qJ = smem2 + (size_t)wib * 3 * NC_P2_QUEUE;
@@ -655,20 +661,31 @@ __global__ void __launch_bounds__(NC_P2_THREADS) k_synapse_pass(View v, StepArgs
             const uint32_t relBase = 4u * lane - (uint32_t)(rs & 127u);  // row-relative index of this lane's first slot in group 0
             for (uint32_t g = 0; g < ng; g += NC_UNROLL4) {
                 uint4 pv[NC_UNROLL4];
+                const uint4* sp = src + ((uint64_t)g << 5);  // (one 64-bit address per batch; the unrolled loads use immediate offsets)
 #pragma unroll
                 for (int u = 0; u < NC_UNROLL4; u++)
-                    pv[u] = (g + u < ng) ? __ldcs(src + ((g + u) << 5)) : make_uint4(0u, 0u, 0u, 0u);
+                    pv[u] = (g + u < ng) ? __ldcs(sp + (u << 5)) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                 for (int u = 0; u < NC_UNROLL4; u++) {
                     if (g + u >= ng) break;
                     const uint32_t gi = g + u;
                     const uint32_t rel0 = relBase + (gi << 7);  // one unsigned compare against the row length masks both ends
                     const uint32_t p4[4] = {pv[u].x, pv[u].y, pv[u].z, pv[u].w};
-                    // common case, branch-free: "did my presynaptic neuron (or my row's neuron) fire"
+                    // common case — nothing happened to any of the warp's 128 slots — decided with four raw probes per lane
+                    // (bit 0 of the shifted mask word; slots outside the row probe a neighbour's presynaptic ID, which can only
+                    // send the group down the exact path below for nothing)
+                    const bool flagged = (summ >> min(gi, 31u)) & 1u;  // (warp-uniform) the neuron pass flagged slots of this group
+                    if (s.sparseFires && !qFired && !flagged) {
+                        uint32_t anyb = 0u;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) anyb |= fired_word(p4[k] & 0x7fffffffu);
+                        if (!__any_sync(0xffffffffu, anyb & 1u)) continue;
+                    }
+                    // exact per-slot evaluation: "did my presynaptic neuron (or my row's neuron) fire"
                     bool ev[4];
 #pragma unroll
                     for (int k = 0; k < 4; k++) ev[k] = (rel0 + k < len) && (qFired | fired(p4[k] & 0x7fffffffu));
-                    if ((summ >> min(gi, 31u)) & 1u) {  // (warp-uniform) the neuron pass flagged slots of this group
+                    if (flagged) {
                         const uint4 cb = __ldg(bm + gi);
                         const uint32_t c4[4] = {cb.x, cb.y, cb.z, cb.w};
 #pragma unroll
@@ -1157,6 +1174,11 @@ static void fill_args(nc_engine* e, StepArgs& a, float t0, float t1, int sweep, 
     a.t0 = t0; a.t1 = t1; a.sweep = sweep;
     a.lr = e->lr; a.preFactor = e->preF; a.postFactor = e->postF; a.preDecay = e->preD; a.postDecay = e->postD;
     a.ev = dEv; a.nEv = nEv; a.candCap = e->candCap; a.world = (uint32_t)e->cfg.world;
+    {   // expected fired presynaptic IDs per 128-slot group, from the last window's network-wide fire count
+        uint64_t fires = 0;
+        for (int b = 0; b < e->cfg.world; b++) fires += e->lastCounts[b];
+        a.sparseFires = (double)fires * 128.0 < 0.5 * (double)std::max<uint64_t>(e->v.nGlobal, 1);
+    }
     a.gStride = e->cfg.world == 1 ? e->v.fireCap + 1u : e->xchgUnits;
 }
 

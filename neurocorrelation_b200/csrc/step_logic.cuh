@@ -108,6 +108,7 @@ struct StepArgs {
     // float comparisons of the row scan as integer compares on the bit patterns of (positive) arrival times, fixed per window:
     //   t1 - a > 2  (old enough to be cleared)  <=>  bits(a) <= clrB;     t0 < a + 2 <= t1 (requeue)  <=>  reqLoB < bits(a) <= reqHiB
     uint32_t clrB, reqLoB, reqHiB;
+    uint32_t sparseFires;  // few enough neurons fired last window that most 128-slot groups see none: worth a cheap group-level pre-test
 };
 
 struct NeuronState {

@@ -18,7 +18,7 @@ MATH_SO = os.path.join(CSRC, "libnc_mathhost.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-fmad=false",  # no FMA contraction anywhere: the reference's float/double typing is kept operator by operator
               "-Xcompiler", "-fPIC", "-shared"]
-HOST_FLAGS = ["-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared"]
+HOST_FLAGS = ["-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-pthread"]
 
 
 def _newer(target, sources):

@@ -10,6 +10,9 @@
 #include <algorithm>
 #include <cassert>
 #include <cmath>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <stdexcept>
 #include <unordered_map>
 
@@ -155,8 +158,34 @@ struct NeuCor::RandStream {
     uint64_t magic = 0;
     bool attached = false, usable = true, valid = false;
     int32_t* words = nullptr;      // libc's state block while attached
+    // Optional generator thread (large networks): keeps the look-ahead `want` draws ahead of the consumer, in chunks, under
+    // one mutex that every method below takes; the consumer generates for itself whatever is still missing when it asks.
+    std::mutex mu;
+    std::condition_variable cv;
+    std::thread worker;
+    bool workerOn = false, stop = false;
+    std::size_t want = 0;          // draws [0, want) are wanted ahead of time
 
-    ~RandStream() { delete[] x; }
+    ~RandStream() {
+        if (workerOn) {
+            { std::lock_guard<std::mutex> g(mu); stop = true; }
+            cv.notify_all();
+            worker.join();
+        }
+        delete[] x;
+    }
+    std::size_t ready() const { return period > 1 ? std::min(len >= 31 ? len - 31 : 0, scanned) : (len >= 31 ? len - 31 : 0); }
+    void run_worker() {
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            cv.wait(lk, [&] { return stop || (valid && ready() < want); });
+            if (stop) return;
+            generate_l(std::min(want, ready() + (std::size_t)(1u << 15)));
+            lk.unlock();  // let the consumer in between chunks
+            std::this_thread::yield();
+            lk.lock();
+        }
+    }
     void reserve(std::size_t n) {
         if (n <= cap) return;
         std::size_t c = std::max<std::size_t>(n + n / 2, 1u << 16);
@@ -166,6 +195,7 @@ struct NeuCor::RandStream {
         x = y; cap = c;
     }
     bool attach() {
+        std::lock_guard<std::mutex> g(mu);
         static int32_t parking[34];
         parking[0] = 3;
         for (int i = 1; i < 34; i++) parking[i] = (int32_t)((uint32_t)i * 1103515245u + 12345u);
@@ -183,12 +213,13 @@ struct NeuCor::RandStream {
         if (!same) {
             reserve(31);
             memcpy(x, h, sizeof(h));
-            len = 31; pos = 0; hits.clear(); hitHead = 0; scanned = 0; valid = true;
+            len = 31; pos = 0; hits.clear(); hitHead = 0; scanned = 0; valid = true; want = 0;
         }
         attached = true;
         return true;
     }
     void detach() {
+        std::lock_guard<std::mutex> g(mu);
         if (!attached) return;
         // libc continues at `pos`: oldest value at ring position 3, rear index 0
         for (int i = 0; i < 31; i++) words[1 + (3 + i) % 31] = (int32_t)x[pos + i];
@@ -202,16 +233,18 @@ struct NeuCor::RandStream {
             for (std::size_t i = hitHead; i < hits.size(); i++) if (hits[i] >= pos) hits[k++] = hits[i] - pos;
             hits.resize(k); hitHead = 0;
             scanned = scanned > pos ? scanned - pos : 0;
+            want = want > pos ? want - pos : 0;
             pos = 0;
         }
     }
     void setPeriod(int p) {
+        std::lock_guard<std::mutex> g(mu);
         if (p == period) return;
         period = p; magic = ~0ull / (uint64_t)p + 1ull;
         hits.clear(); hitHead = 0; scanned = pos;
     }
     // draws [0, upto) generated and tested for hits
-    void generate(std::size_t upto) {
+    void generate_l(std::size_t upto) {  // (mu held)
         if (len < upto + 31) {
             reserve(upto + 31);
             uint32_t* y = x;
@@ -241,12 +274,29 @@ struct NeuCor::RandStream {
             scanned = upto;
         }
     }
-    void prefetch(std::size_t ahead) { generate(pos + ahead); }
-    int32_t value(std::size_t k) { if (len < k + 32) generate(k + 1 + 4096); return (int32_t)(x[k + 31] >> 1); }
-    void advance(uint64_t n) { pos += n; if (len < pos + 31) generate(pos); }
+    // Asks for `ahead` draws beyond the current position.  With the generator thread this only posts the request.
+    void prefetch(std::size_t ahead, bool threaded) {
+        std::unique_lock<std::mutex> lk(mu);
+        want = std::max(want, pos + ahead);
+        if (!threaded) { generate_l(want); return; }
+        if (!workerOn) { workerOn = true; worker = std::thread([this] { run_worker(); }); }
+        lk.unlock();
+        cv.notify_one();
+    }
+    int32_t value(std::size_t k) {
+        std::lock_guard<std::mutex> g(mu);
+        if (len < k + 32) generate_l(k + 1 + 4096);
+        return (int32_t)(x[k + 31] >> 1);
+    }
+    void advance(uint64_t n) {
+        std::lock_guard<std::mutex> g(mu);
+        pos += n;
+        if (len < pos + 31) generate_l(pos);
+    }
     // first hit at or after draw `from` and before `limit`, or `limit`
     std::size_t nextHit(std::size_t from, std::size_t limit) {
-        if (scanned < limit) generate(limit);
+        std::lock_guard<std::mutex> g(mu);
+        if (scanned < limit) generate_l(limit);
         while (hitHead < hits.size() && hits[hitHead] < from) hitHead++;
         return (hitHead < hits.size() && hits[hitHead] < limit) ? (std::size_t)hits[hitHead] : limit;
     }
@@ -586,7 +636,7 @@ void NeuCor::window(float t0, float t1, int flags, std::vector<nc_event>& ev) {
     check(nc_step_launch(engine_, t0, t1, flags, ev.data(), (uint32_t)ev.size()), "nc_step");
     // while the device runs: extend the look-ahead of the rand() stream to cover this window's hidden calls (a guess from
     // the last window) and the next run()'s per-neuron draws
-    if (rs_ && rs_->attached) rs_->prefetch((std::size_t)(2 * lastHidden_ + positions.size() + positions.size() / 64 + 8192));
+    if (rs_ && rs_->attached) rs_->prefetch((std::size_t)(2 * lastHidden_ + positions.size() + positions.size() / 64 + 8192), randThread_);
     check(nc_step_collect(engine_, &hidden, &st), "nc_step");
     h2dBytes_ += ev.size() * sizeof(nc_event);
     d2hBytes_ += 16 + 8 * sizeof(uint64_t);
@@ -609,7 +659,12 @@ float NeuCor::stepInternal(bool sweep) {  // NeuCor::run, NeuCor.cpp:583-617
     lastStats_ = StepStats{};
     const std::size_t N = positions.size();
     // borrow libc's generator for the duration of this call (handed back, at the position consumed, on every exit path)
-    if (!rs_) rs_ = new RandStream();
+    if (!rs_) {
+        rs_ = new RandStream();
+        // a generator thread pays once the per-call draws (one per neuron) take longer than a window on the device
+        const char* env = getenv("NC_RAND_THREAD");
+        randThread_ = env ? atoi(env) != 0 : N >= 200000;
+    }
     struct Borrow {
         RandStream* r;
         ~Borrow() { if (r) r->detach(); }

@@ -175,6 +175,7 @@ private:
     struct RandStream;              // look-ahead view of libc's rand() stream (NeuCor.cpp)
     RandStream* rs_ = nullptr;
     uint64_t lastHidden_ = 0;
+    bool randThread_ = false;
     StepStats lastStats_ = {}, totalStats_ = {};
     uint64_t h2dBytes_ = 0, d2hBytes_ = 0;
 };

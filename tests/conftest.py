@@ -34,7 +34,7 @@ def mock_host_lib():
             os.path.join(ROOT, "neurocorrelation_b200", "host", "capi.cpp")]
     deps = srcs + [os.path.join(ROOT, "neurocorrelation_b200", "csrc", f) for f in ("step_logic.cuh", "glibc_math.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-mfma", "-ffp-contract=off", "-fPIC", "-shared", "-I" + ROOT] + srcs + ["-o", out])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-mfma", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I" + ROOT] + srcs + ["-o", out])
     return out
 
 

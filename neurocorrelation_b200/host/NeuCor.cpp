@@ -661,9 +661,10 @@ float NeuCor::stepInternal(bool sweep) {  // NeuCor::run, NeuCor.cpp:583-617
     // borrow libc's generator for the duration of this call (handed back, at the position consumed, on every exit path)
     if (!rs_) {
         rs_ = new RandStream();
-        // a generator thread pays once the per-call draws (one per neuron) take longer than a window on the device
+        // NC_RAND_THREAD=1 moves the look-ahead generation to a helper thread.  Off by default: on the B200 box it did not beat
+        // generating under the device's shadow in the calling thread (C3 e2e 3.94 vs 3.72 ms per step), see profiles/README.md.
         const char* env = getenv("NC_RAND_THREAD");
-        randThread_ = env ? atoi(env) != 0 : N >= 200000;
+        randThread_ = env ? atoi(env) != 0 : false;
     }
     struct Borrow {
         RandStream* r;

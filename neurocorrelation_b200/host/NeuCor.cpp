@@ -245,32 +245,32 @@ struct NeuCor::RandStream {
     }
     // draws [0, upto) generated and tested for hits
     void generate_l(std::size_t upto) {  // (mu held)
+        const uint64_t M = magic;
+        // rand() = x >> 1 is a multiple of P only if its low ctz(P) bits are zero — a one-instruction screen that lets all but
+        // 1 in 2^ctz(P) draws through; then (v * ceil(2^64/P)) wraps below ceil(2^64/P) exactly for the multiples of P
+        const int tz = period > 1 ? __builtin_ctz((unsigned)period) : 0;
+        const uint32_t low = ((1u << (tz > 8 ? 8 : tz)) - 1u) << 1;
         if (len < upto + 31) {
             reserve(upto + 31);
             uint32_t* y = x;
-            for (std::size_t n = len; n < upto + 31; n++) y[n] = y[n - 31] + y[n - 3];  // (dependency distance 3: ~0.7 ns a draw)
+            std::size_t n = len;
+            if (period > 1 && scanned + 31 == len) {
+                // generate and test in one pass while the value is in a register (dependency distance 3: ~1 ns a draw)
+                for (; n < upto + 31; n++) {
+                    const uint32_t v = y[n - 31] + y[n - 3];
+                    y[n] = v;
+                    if (__builtin_expect((v & low) == 0u, 0) && (uint64_t)(v >> 1) * M < M) hits.push_back(n - 31);
+                }
+                scanned = upto;
+            } else {
+                for (; n < upto + 31; n++) y[n] = y[n - 31] + y[n - 3];
+            }
             len = upto + 31;
         }
-        if (period > 1 && scanned < upto) {
+        if (period > 1 && scanned < upto) {  // draws generated earlier (another period, or ahead of the scan)
             const uint32_t* d = x + 31;
-            const uint64_t M = magic;
-            // rand() = x >> 1 is a multiple of P only if its low ctz(P) bits are zero.  Blocks of 32 draws are screened for that
-            // with a branch-free (vectorisable) reduction — (z - 1) has its top bit set only for z = 0 — and only blocks that
-            // hold such a draw are looked at one by one: (v * ceil(2^64/P)) wraps below ceil(2^64/P) exactly for multiples of P
-            const int tz = __builtin_ctz((unsigned)period);
-            const uint32_t low = ((1u << (tz > 8 ? 8 : tz)) - 1u) << 1;
-            std::size_t k = scanned;
-            if (low) {
-                for (; k + 32 <= upto; k += 32) {
-                    uint32_t flag = 0u;
-                    for (int j = 0; j < 32; j++) flag |= (d[k + j] & low) - 1u;
-                    if (flag & 0x80000000u)
-                        for (int j = 0; j < 32; j++)
-                            if ((d[k + j] & low) == 0u && (uint64_t)(d[k + j] >> 1) * M < M) hits.push_back(k + j);
-                }
-            }
-            for (; k < upto; k++)
-                if ((uint64_t)(d[k] >> 1) * M < M) hits.push_back(k);
+            for (std::size_t k = scanned; k < upto; k++)
+                if ((d[k] & low) == 0u && (uint64_t)(d[k] >> 1) * M < M) hits.push_back(k);
             scanned = upto;
         }
     }

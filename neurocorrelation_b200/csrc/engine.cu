@@ -1,23 +1,24 @@
 // libneucor_b200.so — the device engine behind include/neucor_b200.h.
 //
 // One window (t0, t1] of the reference's event loop (NeuCor::run, /root/reference/src/NeuCor.cpp:583-617)
-// is executed as two data-parallel passes over a post-synaptic-sorted CSR (DESIGN.md §3):
+// is executed as two data-parallel passes over a post-synaptic-sorted CSR (DESIGN.md §3-4):
 //
-//   neuron pass  (k_neuron_pass)  — one warp per target neuron q.  Stages the row's occupied slots
-//       (arrive != 0 && arrive <= t1) from HBM into shared memory with ballot compaction, derives q's
-//       in-window events (deliveries, +2 ms requeues, host-scheduled input/background events), and
-//       replays them in the canonical order with Neuron::run / fire semantics (NeuCor.cpp:619-714):
-//       ordered accumulation over active slots in ascending presynaptic ID, passive decay, threshold /
-//       refractory check, AP waveform, activity.  Emits fire records (warp-aggregated append) and
-//       marks cleared slots in place.  Never touches weights.
+//   neuron pass  (k_neuron_pass)  — warps claim tiles of 32 target neurons.  STAGING (warp-cooperative, coalesced): the
+//       row's `arrive` is streamed in 128-slot groups, the occupied slots (0 < arrive <= t1) of as many rows as fit the
+//       warp's pool are ballot-compacted in row order, the slots that may deliver / be cleared are flagged for the synapse
+//       pass.  REPLAY (lane-per-row): every lane replays one neuron's in-window events (deliveries, +2 ms requeues,
+//       host-scheduled input/background events, the end-of-window sweep) in the canonical order with Neuron::run / fire
+//       semantics (NeuCor.cpp:619-714): ordered accumulation over active slots in ascending presynaptic ID, passive decay,
+//       threshold / refractory check, AP waveform, activity.  Emits fire records (atomic append) and marks cleared slots in
+//       place.  Never touches weights.  Rows whose occupied slots exceed the pool take a warp-per-row path with a spill area.
 //   exchange     — fire records of all shards are made visible to every shard (in-stream NCCL all-gather of
 //       the shards' record blocks; a no-op for world = 1), then k_index_build turns them into a per-neuron
-//       lookup (bitmask + linked records).
-//   synapse pass (k_synapse_pass) — one warp per row, one lane per slot: tests "did my presynaptic
-//       neuron fire" against the bitmask (the pull gather), and resolves each eventful slot's
-//       operations — load (Synapse::fire, NeuCor.cpp:727-738), clear (NeuCor.cpp:697), post-fire
-//       plasticity and delivery plasticity (Synapse::run / synapticPlasticity, NeuCor.cpp:718-764) — in
-//       the canonical event order.
+//       lookup (bitmask + coarse bitmask + linked records).
+//   synapse pass (k_synapse_pass) — warps claim chunks of rows and stream `pre`: "did my presynaptic neuron fire" is a
+//       probe of the fire bitmask in shared memory (the pull gather); eventful slots — fired parent, fired row, flagged
+//       delivery/clear — are queued per warp and resolved 32 at a time: load (Synapse::fire, NeuCor.cpp:727-738), clear
+//       (NeuCor.cpp:697), post-fire plasticity and delivery plasticity (Synapse::run / synapticPlasticity,
+//       NeuCor.cpp:718-764) in the canonical event order.
 //
 // Arithmetic mirrors the reference's float/double typing operator by operator with explicit-rounding
 // intrinsics (no FMA contraction; built with -fmad=false) and glibc-exact powf/exp (glibc_math.cuh).

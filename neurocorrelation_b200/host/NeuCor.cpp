@@ -48,30 +48,6 @@ public:
     }
     void skip(uint64_t n) { for (uint64_t k = 0; k < n; k++) (void)next(); }
     bool bulk() const { return words_ != nullptr; }
-    // Bulk draws: out[0..n) = the next n values of rand().  The recurrence r[i] = r[i-31] + r[i-3] has a dependency distance of
-    // 3, so a straight loop over the state array pipelines well once the index wrap is taken out of it.
-    void fill(int32_t* out, std::size_t n) {
-        if (!words_) { for (std::size_t k = 0; k < n; k++) out[k] = rand(); return; }
-        uint32_t* st = reinterpret_cast<uint32_t*>(words_ + 1);
-        std::size_t k = 0;
-        while (k < n && r_ != 0) out[k++] = next();
-        while (n - k >= 31) {  // r_ == 0, f_ == 3: one full turn of the 31-word state
-            for (int i = 0; i < 28; i++) { st[i + 3] += st[i]; out[k + i] = (int32_t)(st[i + 3] >> 1); }
-            for (int i = 28; i < 31; i++) { st[i - 28] += st[i]; out[k + i] = (int32_t)(st[i - 28] >> 1); }
-            k += 31;
-        }
-        while (k < n) out[k++] = next();
-    }
-    // Takes back the last n draws (the recurrence is reversible: r[i-31] = r[i] - r[i-3]).
-    void unnext(std::size_t n) {
-        if (!words_) return;  // (never used without the bulk path)
-        uint32_t* st = reinterpret_cast<uint32_t*>(words_ + 1);
-        for (std::size_t k = 0; k < n; k++) {
-            f_ = f_ == 0 ? 30 : f_ - 1;
-            r_ = r_ == 0 ? 30 : r_ - 1;
-            st[f_] -= st[r_];
-        }
-    }
 
 private:
     void open() {

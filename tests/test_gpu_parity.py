@@ -36,6 +36,20 @@ def test_synthetic_c2_recipe_10k(native_libs):
     scenarios.synthetic_vs_oracle(None, 10_000, 100, 150)
 
 
+def test_coarse_mask_path(native_libs, monkeypatch):
+    """Networks beyond 1.3 M neurons probe a coarse mask in shared memory and the fire mask in L2 (two-level probe, used by
+    every multi-GPU C3/C4-sized run); forced here on a small network: same results."""
+    monkeypatch.setenv("NC_FORCE_COARSE_MASK", "1")
+    st = scenarios.synthetic_vs_oracle(None, 1500, 60, 400)
+    assert st["deliveries"] > 50_000 and st["loads_dropped"] > 0
+
+
+def test_long_rows_take_the_warp_per_row_path(native_libs):
+    """A pool of 32 staged slots per warp: busy rows exceed it on their own and go through warp_row (spill area, exact
+    prefix-sum accumulation), the others are batched a few rows at a time."""
+    scenarios.synthetic_vs_oracle(None, 600, 120, 300, cand_smem=32)
+
+
 def test_synthetic_small_dt_and_run_all(native_libs):
     scenarios.synthetic_vs_oracle(None, 300, 30, 400, dt=0.03125, run_all=True)
 

@@ -187,6 +187,7 @@ def cpu_reference_run(workload, steps, warmup, spinup_ms, budget_s=25.0, weight_
             step = drv.step
             N, S = b.counts()
             desc = "NeuCor(750) STANDARD preset, full network"
+            c1_net, c1_ins, c1_rates0 = b.export_network(), b.export_inputs(), drv.rates.copy()
         else:
             raise SystemExit("c1 reference arm needs oracle/_ref")
     else:
@@ -235,6 +236,28 @@ def cpu_reference_run(workload, steps, warmup, spinup_ms, budget_s=25.0, weight_
         done += 1
     wall = time.perf_counter() - t0
     events = None
+    if workload == "c1":
+        # deliveries of the same steps, counted by the oracle port driven through the same preset with the same seeds
+        from helpers import NearInputs
+        from neurocorrelation_b200.presets import standard_on_frame
+        o = OracleBrain(c1_net)
+        NearInputs(o, [i["near"] for i in c1_ins], False).set_inputs(c1_rates0.copy())
+        o.enable_sweep()
+        o.set_params(DT, 1.0, False)
+        rates = c1_rates0.copy()
+        libc.srand(777)
+
+        def ostep():
+            standard_on_frame(rates, libc.rand)
+            for i, v in enumerate(rates):
+                o.set_rate(i, v)
+            o.step()
+        for _ in range(done_spin + warmup):
+            ostep()
+        s0 = o.stats()["deliveries"]
+        for _ in range(done):
+            ostep()
+        events = o.stats()["deliveries"] - s0
     if events_brain is not None:
         for _ in range(done_spin + warmup):
             events_brain.step()

@@ -17,4 +17,4 @@ def test_reference_arm_line(have_ref):
         assert k in line, k
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] == 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
-    assert line["steps"] > 0 and line["ms_per_step"] > 0
+    assert line["steps"] > 0 and line["ms_per_step"] > 0 and line["value"] is not None

@@ -176,6 +176,13 @@ class RefBrain:
         self.L.ref_read_synapses(self.h, *a)
         return dict(weight=a[0], arrive=a[1], depol=a[2], lastArr=a[3], lastStart=a[4])
 
+    def read_synapse_pots(self):
+        """Synapse::getPrePot / getPostPot of every synapse at the current time (CSR order)."""
+        _, S = self.counts() if self._S is None else (self._N, self._S)
+        a = [np.zeros(S, np.float32) for _ in range(2)]
+        self.L.ref_read_synapse_pots(self.h, *a)
+        return a[0], a[1]
+
     def state_hash(self):
         out = np.zeros(6, np.uint64)
         self.L.ref_state_hash(self.h, out)

@@ -21,6 +21,33 @@ def test_c1_golden_seed2_raw_flags(native_libs):
     scenarios.c1_golden(None, "c1_seed2_raw.npz", 2000, check_every=5)
 
 
+def test_renderer_readback_golden(native_libs):
+    """Synapse::getPrePot / getPostPot (NeuCor.cpp:547-567; what NeuCor_Renderer draws, Renderer.cpp:655-699) evaluated on the
+    device for every synapse, against values recorded from the reference at four points of the C1 golden run."""
+    import neurocorrelation_b200 as nb
+    from helpers import load_golden, run_c1_golden, GOLDEN
+    from neurocorrelation_b200 import engine
+    import os
+    zp = np.load(os.path.join(GOLDEN, "c1_seed1_pots.npz"))
+    z, net, near = load_golden("c1_seed1_normalised.npz")
+    g = nb.NeuCor.from_network(net)
+    checked = []
+
+    def on_step(k):
+        if k in zp["steps"]:
+            E = engine.Engine(borrowed=g.engine_handle())
+            E.S = net["S"]
+            assert np.float32(g.time()).view(np.uint32) == zp["time_%d" % k].view(np.uint32)
+            pre, post = E.read_synapse_pots(g.time())
+            assert same_bits(pre, zp["pre_%d" % k]), "prePot differs at step %d" % k
+            assert same_bits(post, zp["post_%d" % k]), "postPot differs at step %d" % k
+            checked.append(k)
+    bad, fields = run_c1_golden(g, z, near, 600, keyword_near=True, check_every=50, on_step=on_step)
+    assert bad == -1, (bad, fields)
+    assert checked == list(zp["steps"])
+    g.close()
+
+
 def test_c1_golden_tiny_shared_memory_spill(native_libs):
     """Rows with more occupied slots than staged in shared memory take the spill path: same results."""
     scenarios.c1_golden(None, "c1_seed1_normalised.npz", 800, check_every=1, cand_smem=32)

@@ -417,6 +417,7 @@ void NeuCor::importNetwork(std::size_t n, const uint64_t* rowptr, const uint32_t
         potAct[2 * i] = -70.0f;
     }
     out_.clear();
+    gridN_ = 0;
     rowptr_.assign(rowptr, rowptr + n + 1);
     uint64_t S = rowptr[n];
     pre_.assign(pre, pre + S);
@@ -515,6 +516,57 @@ void NeuCor::finalize() {
 }
 
 // ---- inputs and detectors ---------------------------------------------------------------------------------
+// Neurons within `radius` of `c`, ascending ID — what InputFirer / VoltageDetector collect with a loop over all neurons
+// (NeuCor.cpp:319-323, 352-356).  Large networks with many firers (C2-C4: N/250 of them) go through a uniform grid of
+// unit cells instead of N distance evaluations per firer; the distance test itself is the same float expression.
+void NeuCor::nearList(coord3 c, float radius, std::vector<uint32_t>& out) {
+    const std::size_t N = positions.size();
+    out.clear();
+    bool finite = std::isfinite(c.x) && std::isfinite(c.y) && std::isfinite(c.z) && std::isfinite(radius);
+    if (N < 4096 || !finite) {
+        for (std::size_t n = 0; n < N; n++)
+            if (positions[n].getDist(c) < radius) out.push_back((uint32_t)n);
+        return;
+    }
+    if (gridN_ != N) {  // (re)build: neurons are only ever appended
+        gridCells_.clear();
+        gridLo_[0] = gridLo_[1] = gridLo_[2] = INFINITY;
+        bool ok = true;
+        for (auto& p : positions) {
+            ok = ok && std::isfinite(p.x) && std::isfinite(p.y) && std::isfinite(p.z);
+            gridLo_[0] = std::min(gridLo_[0], p.x); gridLo_[1] = std::min(gridLo_[1], p.y); gridLo_[2] = std::min(gridLo_[2], p.z);
+        }
+        gridOk_ = ok;
+        if (ok)
+            for (std::size_t i = 0; i < N; i++) gridCells_[cellKey(positions[i].x, positions[i].y, positions[i].z)].push_back((uint32_t)i);
+        gridN_ = N;
+    }
+    if (!gridOk_) {  // imported networks may carry no positions (NaN): nothing is near anything, as in the reference
+        for (std::size_t n = 0; n < N; n++)
+            if (positions[n].getDist(c) < radius) out.push_back((uint32_t)n);
+        return;
+    }
+    const double r = (double)radius + 1e-3;  // cells that can hold a neuron within the radius (with slack for float rounding)
+    const long x0 = (long)std::floor((double)c.x - r - gridLo_[0]), x1 = (long)std::floor((double)c.x + r - gridLo_[0]);
+    const long y0 = (long)std::floor((double)c.y - r - gridLo_[1]), y1 = (long)std::floor((double)c.y + r - gridLo_[1]);
+    const long z0 = (long)std::floor((double)c.z - r - gridLo_[2]), z1 = (long)std::floor((double)c.z + r - gridLo_[2]);
+    for (long x = x0; x <= x1; x++)
+        for (long y = y0; y <= y1; y++)
+            for (long z = z0; z <= z1; z++) {
+                auto it = gridCells_.find(packKey(x, y, z));
+                if (it == gridCells_.end()) continue;
+                for (uint32_t n : it->second)
+                    if (positions[n].getDist(c) < radius) out.push_back(n);
+            }
+    std::sort(out.begin(), out.end());
+}
+uint64_t NeuCor::packKey(long x, long y, long z) {
+    return ((uint64_t)(x + (1L << 20)) << 42) ^ ((uint64_t)(y + (1L << 20)) << 21) ^ (uint64_t)(z + (1L << 20));
+}
+uint64_t NeuCor::cellKey(float x, float y, float z) const {
+    return packKey((long)std::floor((double)x - gridLo_[0]), (long)std::floor((double)y - gridLo_[1]), (long)std::floor((double)z - gridLo_[2]));
+}
+
 void NeuCor::setInputRateArray(float inputs[], unsigned inputCount, coord3 inputPositions[], float inputRadius[]) {  // NeuCor.cpp:46-64
     inputArray = inputs;
     inputArraySize = inputCount;
@@ -529,8 +581,7 @@ void NeuCor::setInputRateArray(float inputs[], unsigned inputCount, coord3 input
             if (!(f.a.x == f.a.x)) {
                 f.a.x = (randomUnit() - 0.5f) * 5.f; f.a.y = (randomUnit() - 0.5f) * 5.f; f.a.z = (randomUnit() - 0.5f) * 5.f;
             }
-            for (std::size_t n = 0; n < positions.size(); n++)
-                if (positions[n].getDist(f.a) < f.radius) f.near.push_back((uint32_t)n);
+            nearList(f.a, f.radius, f.near);
             inputHandler.push_back(std::move(f));
         }
     } else if (change < 0) {
@@ -560,8 +611,7 @@ void NeuCor::setDetectors(unsigned detectorNumber, coord3 detectorPositions[], f
         if (!(d.a.x == d.a.x)) {
             d.a.x = (randomUnit() - 0.5f) * 3.f; d.a.y = (randomUnit() - 0.5f) * 3.f; d.a.z = (randomUnit() - 0.5f) * 3.f;
         }
-        for (std::size_t n = 0; n < positions.size(); n++)
-            if (positions[n].getDist(d.a) < d.radius) d.near.push_back((uint32_t)n);
+        nearList(d.a, d.radius, d.near);
         voltageDetectors.push_back(std::move(d));
     }
 }

@@ -22,6 +22,7 @@
 
 #include <cstddef>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 struct nc_engine;
@@ -143,6 +144,13 @@ private:
     struct VoltageDetector { coord3 a; float radius; std::vector<uint32_t> near; };
     struct OutSyn { uint32_t to; float weight, length; uint8_t flag; };
 
+    void nearList(coord3 c, float radius, std::vector<uint32_t>& out);
+    static uint64_t packKey(long x, long y, long z);
+    uint64_t cellKey(float x, float y, float z) const;
+    std::unordered_map<uint64_t, std::vector<uint32_t>> gridCells_;  // unit-cell grid over `positions` for nearList
+    float gridLo_[3] = {0, 0, 0};
+    std::size_t gridN_ = 0;
+    bool gridOk_ = false;
     void scheduleInput(unsigned i, float deltaT, float frequency, std::vector<nc_event>& ev);
     void window(float t0, float t1, int flags, std::vector<nc_event>& ev);
     float stepInternal(bool sweep);

@@ -479,7 +479,12 @@ __device__ void lanes_replay(const View& v, const StepArgs& s, bool valid, uint6
 // shared-memory pool (cooperative, coalesced row scans), then every lane replays ONE of those neurons on its own
 // (lane-per-row: the per-neuron math — ordered accumulation, powf/exp, threshold, AP — is not replicated across lanes);
 // a row that alone exceeds the pool takes the warp-per-row path with the global spill area.
-__global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32, 6) k_neuron_pass(View v, StepArgs s) {
+// Two register budgets of the same code: MINB = 6 (80 registers; pool of 1024 staged slots per warp) for busy networks,
+// MINB = 8 (64 registers, a few spills in the replay; pool of 512) when rows hold few occupied slots and the pass is bound
+// by the latency of the row scan — a third more resident warps.  The host picks per window from the last window's counters;
+// the pool size only changes how rows are batched, never a result.
+template <int MINB>
+__global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32, MINB) k_neuron_pass(View v, StepArgs s) {
     extern __shared__ unsigned char smem[];
     math_tables_to_shared();
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
@@ -864,9 +869,11 @@ struct nc_engine {
     StepArgs pendingArgs;
     float lr = 1.0f, preF = 0.13f, postF = 0.30f, preD = 0.75f, postD = 0.65f;
     float minDelay = INFINITY;
-    uint32_t candCap = 1024, grid1 = 0, grid2 = 0, maskWordsSmem = 0;
+    uint32_t candCap = 1024, candCapSparse = 512, grid1 = 0, grid1s = 0, grid2 = 0, maskWordsSmem = 0;
+    int forceVariant = 0;                   // 0 auto, 1 dense, 2 sparse
+    double lastSlotsPerRun = 1e9;           // occupied slots visited per neuron run in the last window (picks the variant)
     bool maskInSmem = true;
-    size_t smem1 = 0, smem2 = 0;
+    size_t smem1 = 0, smem1s = 0, smem2 = 0;
     uint64_t launches = 0;
     // tape
     bool taping = false; std::vector<TapeStep> tape; nc_event* dTape = nullptr; uint64_t tapeCap = 0, tapeUsed = 0; uint32_t tapeMaxSteps = 0;
@@ -1042,10 +1049,14 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
     // launch geometry: persistent grids sized to the SM count x resident blocks per SM
     // the warp's shared-memory pool of staged slots: shared by the rows of a lane-per-row batch, so not tied to the row length
     e->candCap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(e->candCap, 32), 1024);
+    e->candCapSparse = std::min<uint32_t>(e->candCap, 512u);
     e->smem1 = (size_t)NC_WARPS_PER_BLOCK * 2 * e->candCap * 4;
-    CK(cudaFuncSetAttribute(k_neuron_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem1));
-    int occ1 = 1, occ2 = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_neuron_pass, NC_WARPS_PER_BLOCK * 32, e->smem1));
+    e->smem1s = (size_t)NC_WARPS_PER_BLOCK * 2 * e->candCapSparse * 4;
+    CK(cudaFuncSetAttribute(k_neuron_pass<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem1));
+    CK(cudaFuncSetAttribute(k_neuron_pass<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem1s));
+    int occ1 = 1, occ1s = 1, occ2 = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_neuron_pass<6>, NC_WARPS_PER_BLOCK * 32, e->smem1));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1s, k_neuron_pass<8>, NC_WARPS_PER_BLOCK * 32, e->smem1s));
     // synapse pass: the whole-network fire bitmask goes to shared memory when it fits (<= 160 KB, i.e. 1.3 M neurons),
     // otherwise the 32x smaller coarse mask does (2^30 neurons -> 128 KB).  NC_FORCE_COARSE_MASK=1 forces the latter (tests).
     uint64_t maskWords = (G1 + 31) / 32;
@@ -1062,11 +1073,18 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
     uint64_t needBlocks = ((nRows + 31) / 32 + NC_WARPS_PER_BLOCK - 1) / NC_WARPS_PER_BLOCK;  // one tile of 32 rows per warp at a time
     uint64_t needBlocks2 = (nRows + NC_P2_THREADS / 32 - 1) / (NC_P2_THREADS / 32);
     e->grid1 = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(needBlocks, (uint64_t)e->smCount * std::max(occ1, 1)));
+    e->grid1s = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(needBlocks, (uint64_t)e->smCount * std::max(occ1s, 1)));
+    {
+        const char* f = getenv("NC_NEURON_VARIANT");  // tuning/tests: "dense" or "sparse" pins the variant
+        e->forceVariant = f ? (f[0] == 's' ? 2 : 1) : 0;
+    }
     e->grid2 = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(needBlocks2, (uint64_t)e->smCount * std::max(occ2, 1)));
-    v.spillPerWarp = (uint32_t)(maxRow > e->candCap ? maxRow - e->candCap : 0);
-    uint64_t spillN = std::max<uint64_t>(1, (uint64_t)e->grid1 * NC_WARPS_PER_BLOCK * v.spillPerWarp);
+    // scratch sized for whichever variant needs more: spill beyond the smaller pool, one pool of slot indices per resident warp
+    v.spillPerWarp = (uint32_t)(maxRow > e->candCapSparse ? maxRow - e->candCapSparse : 0);
+    const uint64_t maxWarps = (uint64_t)std::max(e->grid1, e->grid1s) * NC_WARPS_PER_BLOCK;
+    uint64_t spillN = std::max<uint64_t>(1, maxWarps * v.spillPerWarp);
     CK(cudaMalloc(&v.spillA, spillN * 4)); CK(cudaMalloc(&v.spillD, spillN * 4)); CK(cudaMalloc(&v.spillJ, spillN * 4));
-    CK(cudaMalloc(&v.poolJ, (uint64_t)e->grid1 * NC_WARPS_PER_BLOCK * e->candCap * 4));
+    CK(cudaMalloc(&v.poolJ, maxWarps * e->candCap * 4));
     CK(cudaStreamSynchronize(e->stream));
     cudaFree(tmpLen); cudaFree(tmpInh);
     e->minDelay = minDelay;
@@ -1174,7 +1192,12 @@ static void fill_args(nc_engine* e, StepArgs& a, float t0, float t1, int sweep, 
     }
     a.t0 = t0; a.t1 = t1; a.sweep = sweep;
     a.lr = e->lr; a.preFactor = e->preF; a.postFactor = e->postF; a.preDecay = e->preD; a.postDecay = e->postD;
-    a.ev = dEv; a.nEv = nEv; a.candCap = e->candCap; a.world = (uint32_t)e->cfg.world;
+    a.ev = dEv; a.nEv = nEv; a.world = (uint32_t)e->cfg.world;
+    {   // sparse variant while a tile of 32 rows needs a small fraction of its 512-slot pool (measured: 14 % faster in the quiet
+        // regime with ~2 occupied slots per row, 4 % slower at 8.5 per row where the replay starts to matter)
+        const bool sparse = e->forceVariant ? e->forceVariant == 2 : e->lastSlotsPerRun * 32.0 * 4.0 < (double)e->candCapSparse;
+        a.candCap = sparse ? e->candCapSparse : e->candCap;
+    }
     {   // expected fired presynaptic IDs per 128-slot group, from the last window's network-wide fire count
         uint64_t fires = 0;
         for (int b = 0; b < e->cfg.world; b++) fires += e->lastCounts[b];
@@ -1187,10 +1210,16 @@ static void launch_synapse_pass(nc_engine* e, const StepArgs& a) {
     if (e->maskInSmem) k_synapse_pass<true><<<e->grid2, NC_P2_THREADS, e->smem2, e->stream>>>(e->v, a, e->maskWordsSmem);
     else k_synapse_pass<false><<<e->grid2, NC_P2_THREADS, e->smem2, e->stream>>>(e->v, a, e->maskWordsSmem);
 }
+static void launch_neuron_pass(nc_engine* e, const StepArgs& a) {
+    if (a.candCap == e->candCapSparse && e->candCapSparse != e->candCap)
+        k_neuron_pass<8><<<e->grid1s, NC_WARPS_PER_BLOCK * 32, e->smem1s, e->stream>>>(e->v, a);
+    else
+        k_neuron_pass<6><<<e->grid1, NC_WARPS_PER_BLOCK * 32, e->smem1, e->stream>>>(e->v, a);
+    e->launches++;
+}
 static int launch_pass1(nc_engine* e, const StepArgs& a) {
     if (a.nEv) { k_mark_events<<<(a.nEv + 255) / 256, 256, 0, e->stream>>>(e->v, a.ev, a.nEv, 1); e->launches++; }
-    k_neuron_pass<<<e->grid1, NC_WARPS_PER_BLOCK * 32, e->smem1, e->stream>>>(e->v, a);
-    e->launches++;
+    launch_neuron_pass(e, a);
     if (a.nEv) { k_mark_events<<<(a.nEv + 255) / 256, 256, 0, e->stream>>>(e->v, a.ev, a.nEv, 0); e->launches++; }
     CK(cudaGetLastError());
     return NC_OK;
@@ -1285,6 +1314,7 @@ static void sum_out(nc_engine* e, uint64_t* hidden, nc_step_stats* st) {
     unsigned long long t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int b = 0; b < e->cfg.world; b++)
         for (int i = 0; i < 8; i++) t[i] += e->hOut[b * 10 + i];
+    if (t[6]) e->lastSlotsPerRun = (double)t[7] / (double)t[6];
     if (hidden) *hidden = t[5];
     if (st) {
         st->fires = t[0]; st->deliveries = t[1]; st->loads_accepted = t[2]; st->loads_dropped = t[3];
@@ -1570,8 +1600,7 @@ extern "C" int nc_tape_replay(nc_engine* e, uint32_t first, uint32_t count, floa
         a.gStride = ts.units;
         if (a.nEv) { k_mark_events<<<(a.nEv + 255) / 256, 256, 0, e->stream>>>(e->v, a.ev, a.nEv, 1); e->launches++; }
         if (perKernel) CK(cudaEventRecord(evs[5 * k], e->stream));
-        k_neuron_pass<<<e->grid1, NC_WARPS_PER_BLOCK * 32, e->smem1, e->stream>>>(e->v, a);
-        e->launches++;
+        launch_neuron_pass(e, a);
         if (perKernel) CK(cudaEventRecord(evs[5 * k + 1], e->stream));
         if (e->cfg.world > 1) {
             int rc = exchange(e, e->v.localHdr, e->dGather, (size_t)ts.units * sizeof(FireRec));

@@ -6,14 +6,14 @@ S='import sys,json; d=json.loads(sys.stdin.read()); print("N", d["n_gpus"], d["c
 for n in 1 2 4 8; do
   if [ $n -le $N ]; then
     if [ $n -eq 1 ]; then
-      timeout 600 python bench.py --workload c2 --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/r1j_scale_c2_n$n.json 2> gpurun_out/scale_err_$n.log
+      timeout 600 python bench.py --workload c2 --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/scale_c2_n$n.json 2> gpurun_out/scale_err_$n.log
     else
-      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $n --workload c2 --steps 100 --warmup 10 > gpurun_out/r1j_scale_c2_n$n.json 2> gpurun_out/scale_err_$n.log
+      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $n --workload c2 --steps 100 --warmup 10 > gpurun_out/scale_c2_n$n.json 2> gpurun_out/scale_err_$n.log
     fi
-    tail -1 gpurun_out/r1j_scale_c2_n$n.json | python -c "$S" || tail -5 gpurun_out/scale_err_$n.log
+    tail -1 gpurun_out/scale_c2_n$n.json | python -c "$S" || tail -5 gpurun_out/scale_err_$n.log
   fi
 done
 if [ $N -ge 4 ]; then
-  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus $N --workload c3 --steps 20 --warmup 5 > gpurun_out/r1j_scale_c3_n$N.json 2> gpurun_out/scale_err_c3.log
-  tail -1 gpurun_out/r1j_scale_c3_n$N.json | python -c "$S" || tail -5 gpurun_out/scale_err_c3.log
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus $N --workload c3 --steps 20 --warmup 5 > gpurun_out/scale_c3_n$N.json 2> gpurun_out/scale_err_c3.log
+  tail -1 gpurun_out/scale_c3_n$N.json | python -c "$S" || tail -5 gpurun_out/scale_err_c3.log
 fi

@@ -293,7 +293,7 @@ def main():
     config = {"workload": wl_desc, "dt_ms": DT, "mode": "sweep (run() + full detector read), STDP on (learningRate 1), background firing on",
               "network": "stratified random stand-in (in-degree exactly K, lengths ~ r^2 in a ball, weights U(0.2,1)*%g, 20%% inhibitory), %d input firers with random phase" % (args.weight_scale, max(1, Nper * world // 250)) if K else "NeuCor(750)",
               "spinup_ms": spinup_ms,
-              "l2": ("inputs larger than L2: per-GPU state %.0f MB, of which %.0f MB (arrive + pre) are streamed every step, against a 126 MB L2; no flush between steps"
+              "l2": (("inputs larger than L2" if state_mb > 126 else "inputs SMALLER than L2") + ": per-GPU state %.0f MB, of which %.0f MB (arrive + pre) are streamed every step, against a 126 MB L2; no flush between steps"
                      % (state_mb, Nper * (K or 28) * 8 / 1e6))
                     + ("" if Nper * (K or 28) * 8 / 1e6 > 2 * 126 else " — the streamed arrays alone would fit L2, so HBM-roofline claims are made on c3, not here (this workload is bound by event processing, see roofline.frac)")}
 

@@ -311,6 +311,7 @@ def main():
         print(json.dumps(line))
         return
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the JSON line only
     import torch
     dev = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(dev)

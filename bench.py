@@ -311,7 +311,16 @@ def main():
         print(json.dumps(line))
         return
 
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the JSON line only
+    # stdout carries the JSON line only: whatever libraries print while the job runs (NCCL's version banner, ...) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     import torch
     dev = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(dev)
@@ -452,7 +461,7 @@ def main():
         r = cpu_reference_run(args.workload, 10_000, 2, spinup_ms, budget_s=24.0, weight_scale=args.weight_scale)
         line["cpu_baseline"] = {"value": r["events_per_s"], "unit": "delivered synaptic events/s", "cores": 1, "kind": r["kind"], "sample": r["sample"],
                                 "sim_ms_per_wall_s": r["sim_ms_per_wall_s"], "synapse_updates_per_s": r["synapse_updates_per_s"], "ms_per_step": r["ms_per_step"]}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -39,10 +39,11 @@ typedef struct nc_engine nc_engine;
 typedef struct nc_config {
     int32_t device;            /* CUDA device ordinal */
     int32_t rank, world;       /* neuron-range shard of this engine (world = 1: whole network) */
-    uint32_t fire_capacity;    /* max fire records per step (0 = default: 4*N_global + 1024) */
+    uint32_t fire_capacity;    /* max fire records of this shard per step (0 = default: 4*n_rows + 1024) */
     uint32_t cand_smem;        /* staged-slot pool per warp in shared memory, shared by the rows of a batch (0 = default 1024) */
     void* stream;              /* cudaStream_t to launch on (NULL = the engine creates its own) */
-    uint32_t reserved[2];
+    uint32_t flag_capacity;    /* max slots per step that deliver or are cleared (0 = default: S/8 + 65536, at least 2^20) */
+    uint32_t reserved;
 } nc_config;
 
 /* Host-generated event of one step (NeuCor::run's scheduling phase, NeuCor.cpp:599-607).
@@ -127,6 +128,11 @@ int nc_read_synapses(nc_engine* e, float* weight, float* arrive, float* depol, f
 int nc_read_fires(nc_engine* e, uint32_t capacity, uint32_t* neuron, float* time, uint32_t* count);
 /* Synapse::getPrePot / getPostPot at time `now` for every synapse of the shard (NeuCor.cpp:547-567). */
 int nc_read_synapse_pots(nc_engine* e, float now, float* prePot, float* postPot);
+/* Six position-weighted 64-bit checksums of the shard's state, computed on the device: potential, activity, lastFire,
+ * weight, arrive (+ depol of busy slots), lastSpikeArrival — sum of bits(x[i])*(i+1)*0x9E3779B97F4A7C15 mod 2^64 each.
+ * What the parity fixtures pin per step (the reference harness computes the same words from NeuCor's members), and a cheap
+ * way to validate a checkpoint. */
+int nc_state_signature(nc_engine* e, uint64_t* out6);
 /* NeuCor::resetActivities (NeuCor.cpp:233-235,460). */
 int nc_reset_activities(nc_engine* e, float now);
 /* VoltageDetector::getVoltage's averaging (NeuCor.cpp:360-365) over `near` (ascending IDs of this

@@ -90,6 +90,11 @@ def load_host_library(path=None):
     L.nch_export_network.argtypes = [vp, u64p, u32p, f32p, u8p, vp]
     L.nch_read_neurons.argtypes = [vp, f32p, f32p, f32p, f32p]
     L.nch_read_synapses.argtypes = [vp, f32p, f32p, f32p, f32p, f32p]
+    L.nch_state_signature.argtypes = [vp, u64p]
+    L.nch_record_fires.argtypes = [vp, C.c_int]
+    L.nch_last_fires_count.argtypes = [vp]
+    L.nch_last_fires_count.restype = C.c_uint64
+    L.nch_last_fires.argtypes = [vp, u32p, f32p]
     L.nch_input_count.argtypes = [vp]
     L.nch_input_count.restype = C.c_uint
     L.nch_input_near_count.argtypes = [vp, C.c_uint]
@@ -313,6 +318,24 @@ class NeuCor:
         a = [np.zeros(max(S, 1), np.float32) for _ in range(5)]
         self._ck(self.L.nch_read_synapses(self.h, *a))
         return dict(weight=a[0][:S], arrive=a[1][:S], depol=a[2][:S], lastArr=a[3][:S], lastStart=a[4][:S])
+
+    def state_signature(self):
+        """Six per-field checksums of this shard's state (== tests/helpers.state_signature of the read-back arrays),
+        computed on the device: one 48-byte read instead of the whole state."""
+        self.finalize()
+        out = np.zeros(6, np.uint64)
+        self._ck(self.L.nch_state_signature(self.h, out))
+        return out
+
+    def record_fires(self, on=True):
+        """Keep (neuron, time) of every fire of the last step — the raster source (Renderer.cpp:1856-1862)."""
+        self._ck(self.L.nch_record_fires(self.h, int(on)))
+
+    def last_fires(self):
+        n = int(self.L.nch_last_fires_count(self.h))
+        a, t = np.zeros(max(n, 1), np.uint32), np.zeros(max(n, 1), np.float32)
+        self._ck(self.L.nch_last_fires(self.h, a, t))
+        return a[:n], t[:n]
 
     def stats(self, total=True):
         out = np.zeros(8, np.uint64)

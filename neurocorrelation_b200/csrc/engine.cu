@@ -13,7 +13,7 @@
 //       place.  Never touches weights.  Rows whose occupied slots exceed the pool take a warp-per-row path with a spill area.
 //   exchange     — fire records of all shards are made visible to every shard (in-stream NCCL all-gather of
 //       the shards' record blocks; a no-op for world = 1), then k_index_build turns them into a per-neuron
-//       lookup (bitmask + coarse bitmask + linked records).
+//       lookup (bitmask + linked records).
 //   synapse pass (k_synapse_pass) — warps claim chunks of rows and stream `pre`: "did my presynaptic neuron fire" is a
 //       probe of the fire bitmask in shared memory (the pull gather); eventful slots — fired parent, fired row, flagged
 //       delivery/clear — are queued per warp and resolved 32 at a time: load (Synapse::fire, NeuCor.cpp:727-738), clear
@@ -41,9 +41,6 @@ using namespace ncm;
 using namespace ncs;
 
 #define NC_WARPS_PER_BLOCK 4
-#define NC_UNROLL_N 4         // neuron pass: independent 16-byte-per-lane row loads in flight per warp (8 was faster in the quiet regime, 30 % slower in the running one)
-#define NC_UNROLL4 4         // independent 16-byte-per-lane (512 B per warp) row loads kept in flight per warp
-#define NC_P2_THREADS 1024   // synapse pass: one persistent block per SM, fire bitmask staged in its shared memory
 
 // ------------------------------------------------------------------------------------------------
 // Neuron pass
@@ -132,82 +129,87 @@ __device__ __forceinline__ void warp_neuron_run(const View& v, NeuronState& n, C
 
 // ---- staging ------------------------------------------------------------------------------------------------
 // Occupied slots (arrive != 0 && arrive <= t1) of one row, compacted in row order (= ascending presynaptic ID).
-// Rows are walked in 128-slot groups aligned in the global slot index space: lane l owns slots 4l..4l+3 of a group, so every
-// lane issues one 16-byte load per group; slots outside [rs, re) are masked.  Per group the four ballots (one per sub-slot)
-// are also written to the candidate bitmap that lets the synapse pass skip its own read of `arrive`.
+// The row is not scanned: the busy-slot index (one bit per slot, kept in step with `arrive` by the synapse pass) says which
+// slots hold a spike at all, and only those are looked at.  Lane l takes the l-th 32-slot word of the row (one coalesced
+// 128-byte load covers 1024 slots), gathers `arrive` of its set bits, and the arrived ones (the rest are still in flight)
+// are ballot/prefix-compacted into the pool.
 //   SPILL = true : entries go to the CandView (shared memory first, per-warp global spill area after) — warp-per-row path
 //   SPILL = false: arrive times and slot indices (jbase + index in the row) go to pa/pj while they fit in `room`; the returned
 //                  count tells the caller whether they did; the caller gathers depol for the whole batch in one go
 // hasEv: some staged slot delivers (t0 < arrive) or re-queues its target (t0 < arrive + 2 <= t1) in this window.
 template <bool SPILL>
-__device__ __forceinline__ uint32_t stage_row(const View& v, const StepArgs& s, uint64_t row, uint64_t rs, uint64_t re, CandView& cv,
+__device__ __forceinline__ uint32_t stage_row(const View& v, const StepArgs& s, uint64_t rs, uint64_t re, CandView& cv,
                                               float* pa, uint32_t* pj, uint32_t jbase, uint32_t room, uint32_t lane, bool& hasEv) {
-    uint32_t cnt = 0, summ = 0;
+    const uint32_t FULL = 0xffffffffu;
+    uint32_t cnt = 0;
     bool ev = false;
-    const uint32_t len = (uint32_t)(re - rs);
     const uint32_t t1b = __float_as_uint(s.t1), t0b = __float_as_uint(s.t0);
-    const uint64_t g0 = rs >> 7;
-    const uint32_t ng = (uint32_t)(((re + 127) >> 7) - g0);
-    uint4* bm = reinterpret_cast<uint4*>(v.ownBits) + (g0 + row);
-    const float4* src = reinterpret_cast<const float4*>(v.arrive) + (g0 << 5) + lane;
-    const uint32_t relBase = 4u * lane - (uint32_t)(rs & 127u);  // row-relative index of this lane's first slot in group 0
-    for (uint32_t g = 0; g < ng; g += NC_UNROLL_N) {
-        float4 av[NC_UNROLL_N];
-        const float4* sp = src + ((uint64_t)g << 5);  // (one 64-bit address per batch; the unrolled loads use immediate offsets)
-#pragma unroll
-        for (int u = 0; u < NC_UNROLL_N; u++)
-            av[u] = (g + u < ng) ? __ldcs(sp + (u << 5)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int u = 0; u < NC_UNROLL_N; u++) {
-            if (g + u >= ng) break;
-            const uint32_t gi = g + u;
-            // slot index relative to the row start; one unsigned compare against the row length masks both ends
-            const uint32_t rel0 = relBase + (gi << 7);
-            const float a4[4] = {av[u].x, av[u].y, av[u].z, av[u].w};
-            bool is[4];
-            // arrive times are positive floats (0 = idle): as unsigned integers, (bits - 1) < bits(t1)  <=>  0 < arrive <= t1
-#pragma unroll
-            for (int k = 0; k < 4; k++) is[k] = (__float_as_uint(a4[k]) - 1u < t1b) && (rel0 + k < len);
-            if (!__any_sync(0xffffffffu, is[0] | is[1] | is[2] | is[3])) {
-                if (gi >= 31u && lane == 0) bm[gi] = make_uint4(0u, 0u, 0u, 0u);
-                continue;
-            }
-            // "own" bits for the synapse pass: the slot delivers in this window, or is old enough to be cleared by one of this
-            // window's runs (2 < T - arrive needs 2 < t1 - arrive); everything else about an occupied slot stays put
-            bool own[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) own[k] = is[k] && (__float_as_uint(a4[k]) > t0b || __float_as_uint(a4[k]) <= s.clrB);
-            if (__any_sync(0xffffffffu, own[0] | own[1] | own[2] | own[3])) {
-                uint32_t o[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) o[k] = __ballot_sync(0xffffffffu, own[k]);
-                if (lane == 0) bm[gi] = make_uint4(o[0], o[1], o[2], o[3]);
-                summ |= 1u << min(gi, 31u);
-            } else if (gi >= 31u && lane == 0) {
-                bm[gi] = make_uint4(0u, 0u, 0u, 0u);
-            }
-            uint32_t m[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) m[k] = __ballot_sync(0xffffffffu, is[k]);
-            const uint32_t lt = (1u << lane) - 1u;
-            uint32_t pos = cnt + __popc(m[0] & lt) + __popc(m[1] & lt) + __popc(m[2] & lt) + __popc(m[3] & lt);
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (is[k]) {
-                    const float a = a4[k];
-                    const uint32_t ab = __float_as_uint(a);
-                    ev |= (ab > t0b) || (ab > s.reqLoB && ab <= s.reqHiB);
-                    const uint32_t jr = rel0 + k;  // (32-bit wrap intended: rel0 is "negative" left of the row start)
-                    if (SPILL) { cv.A(pos) = a; cv.D(pos) = v.depol[rs + jr]; cv.J(pos) = jr; }
-                    else if (pos < room) { pa[pos] = a; pj[pos] = jbase + jr; }  // depol is gathered for the whole batch afterwards
-                    pos++;
-                }
-            cnt += __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+    const uint64_t w0 = rs >> 5, w1 = (re + 31) >> 5;  // the row's words of the busy index: [w0, w1)
+    for (uint64_t wb = w0; wb < w1; wb += 32) {
+        const uint64_t w = wb + lane;
+        uint32_t word = 0u;
+        if (w < w1) {
+            word = __ldcg(v.busy + w);
+            const uint32_t lo = (w == w0) ? (uint32_t)(rs & 31u) : 0u;                    // first bit that belongs to the row
+            const uint32_t hn = (w == w1 - 1) ? (uint32_t)(re - (w << 5)) : 32u;          // bits [0, hn) belong to the row
+            word &= (hn >= 32u ? FULL : ((1u << hn) - 1u)) & (FULL << lo);
         }
+        if (!__any_sync(FULL, word != 0u)) continue;
+        // which of this lane's busy slots have arrived: 0 < arrive <= t1 as ONE integer compare on the bit pattern
+        // (arrive times are positive floats: (bits - 1) < bits(t1)); the others are still travelling
+        const float* ap = v.arrive + (w << 5);
+        uint32_t im = 0u;
+        for (uint32_t m = word; m; m &= m - 1u) {
+            const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
+            const uint32_t ab = __float_as_uint(ap[b]);
+            if (ab - 1u < t1b) {
+                im |= 1u << b;
+                ev |= (ab > t0b) || (ab > s.reqLoB && ab <= s.reqHiB);
+            }
+        }
+        __syncwarp();
+        const uint32_t c = __popc(im);
+        uint32_t inc = c;  // inclusive prefix sum over lanes = row order (lane = word, bits ascend within the word)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(FULL, inc, o);
+            if (lane >= (uint32_t)o) inc += y;
+        }
+        uint32_t pos = cnt + inc - c;
+        cnt += __shfl_sync(FULL, inc, 31);
+        const uint32_t rel0 = (uint32_t)((w << 5) - rs);  // (32-bit wrap intended for the row's first, partial word)
+        for (uint32_t m = im; m; m &= m - 1u) {
+            const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
+            const float a = ap[b];  // (second touch: L1 hit)
+            const uint32_t jr = rel0 + b;
+            if (SPILL) { cv.A(pos) = a; cv.D(pos) = v.depol[rs + jr]; cv.J(pos) = jr; }
+            else if (pos < room) { pa[pos] = a; pj[pos] = jbase + jr; }  // depol is gathered for the whole batch afterwards
+            pos++;
+        }
+        __syncwarp();
     }
-    if (lane == 0) v.ownSumm[row] = summ;
-    hasEv = __any_sync(0xffffffffu, ev);
+    hasEv = __any_sync(FULL, ev);
     return cnt;
+}
+
+// Hand-over to the synapse pass: the staged slots that delivered in this window (t0 < arrive; staging guarantees <= t1) or
+// were cleared by one of its runs (arrive negated in the pool) go to the shard's flag list — one reservation per batch.
+__device__ __forceinline__ void flag_reserve(const View& v, uint32_t mine, uint32_t lane, uint32_t& at) {
+    const uint32_t FULL = 0xffffffffu;
+    uint32_t inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(FULL, inc, o);
+        if (lane >= (uint32_t)o) inc += y;
+    }
+    const uint32_t tot = __shfl_sync(FULL, inc, 31);
+    uint32_t base = 0u;
+    if (tot) {
+        if (lane == 0) base = atomicAdd(&v.flagCtl[0], tot);
+        base = __shfl_sync(FULL, base, 0);
+        if (base + tot > v.flagCap && lane == 0) v.flagCtl[1] = 1u;
+    }
+    at = base + inc - mine;
 }
 
 // host events of neuron q: [evLo, evHi) in the (neuron, time)-sorted list (bit set by k_mark_events for rows that have any)
@@ -232,7 +234,7 @@ __device__ void warp_row(const View& v, const StepArgs& s, uint64_t row, CandVie
     const uint32_t q = (uint32_t)(v.row0 + row);
     const uint64_t rs = v.rowptr[row], re = v.rowptr[row + 1];
     bool hasEv;
-    const uint32_t cnt = stage_row<true>(v, s, row, rs, re, cv, nullptr, nullptr, 0u, 0u, lane, hasEv);
+    const uint32_t cnt = stage_row<true>(v, s, rs, re, cv, nullptr, nullptr, 0u, 0u, lane, hasEv);
     __syncwarp();
     uint32_t evLo, evHi;
     host_event_range(v, s, row, q, evLo, evHi);
@@ -316,6 +318,16 @@ __device__ void warp_row(const View& v, const StepArgs& s, uint64_t row, CandVie
         v.lastRan[row] = n.lastRan; v.lastFire[row] = n.lastFire; v.firings[row] = n.firings;
     }
     __syncwarp();
+    // slots that delivered in this window or were cleared by it: over to the synapse pass
+    for (uint32_t base = 0; base < cnt; base += 32) {
+        const uint32_t c = base + lane;
+        bool f = false;
+        if (c < cnt) { const float a = cv.A(c); f = (a < 0.0f) || (a > s.t0); }
+        uint32_t at;
+        flag_reserve(v, f ? 1u : 0u, lane, at);
+        if (f && at < v.flagCap) { SlotRow sr; sr.slot = (uint32_t)(rs + cv.J(c)); sr.row = (uint32_t)row; v.flagList[at] = sr; }
+    }
+    __syncwarp();
 }
 
 // ---- lane-per-row path: one lane replays one neuron; its occupied slots sit in a slice of the warp's pool ------------------
@@ -382,11 +394,13 @@ __device__ void lanes_replay(const View& v, const StepArgs& s, bool valid, uint6
     // the neuron's next event is picked
     unsigned long long em = 0ull;
     bool evTail = false;
+    uint32_t nFlag = 0u;  // this lane's slots that deliver in the window or get cleared by it (handed to the synapse pass at the end)
     if (__any_sync(FULL, hasEv))
         for (uint32_t c = 0; c < maxCnt; c++)
             if (hasEv && c < cnt) {
                 const float a = A[c];
                 const float tR = add32(a, 2.0f);
+                nFlag += (a > s.t0) ? 1u : 0u;
                 if ((a > s.t0) || (tR > s.t0 && tR <= s.t1)) {
                     if (c < 64u) em |= 1ull << c; else evTail = true;
                 }
@@ -449,6 +463,7 @@ __device__ void lanes_replay(const View& v, const StepArgs& s, bool valid, uint6
                             np = (float)add64((double)np, chain_term(dT, D[c], E));
                             if (2.0f < off) {           // NeuCor.cpp:697 — the slot becomes idle; leave the when-and-why for the synapse pass
                                 A[c] = -araw;
+                                nFlag++;
                                 const uint64_t sidx = tb + __ldcg(J + c);
                                 v.arrive[sidx] = __uint_as_float(sentinel);
                                 v.depol[sidx] = T;
@@ -472,6 +487,19 @@ __device__ void lanes_replay(const View& v, const StepArgs& s, bool valid, uint6
         if (ran) n.act = neuron_activity(actF, actT, n.actStart);
         v.potAct[row] = make_float2(n.pot, n.act);
         v.lastRan[row] = n.lastRan; v.lastFire[row] = n.lastFire; v.firings[row] = n.firings;
+    }
+    // slots that delivered in this window (t0 < arrive) or were cleared by it (negated in the pool): over to the synapse pass
+    if (__any_sync(FULL, nFlag != 0u)) {
+        uint32_t at;
+        flag_reserve(v, nFlag, threadIdx.x & 31u, at);
+        if (nFlag)
+            for (uint32_t c = 0; c < cnt; c++) {
+                const float a = A[c];
+                if ((a < 0.0f) || (a > s.t0)) {
+                    if (at < v.flagCap) { SlotRow sr; sr.slot = (uint32_t)(tb + __ldcg(J + c)); sr.row = (uint32_t)row; v.flagList[at] = sr; }
+                    at++;
+                }
+            }
     }
 }
 
@@ -521,7 +549,7 @@ __global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32, MINB) k_neuron_pass(V
                 if (s.subset && !in_subset(s, (uint32_t)(v.row0 + row))) { r++; continue; }
                 const uint64_t rs = v.rowptr[row], re = v.rowptr[row + 1];
                 bool ev;
-                const uint32_t c = stage_row<false>(v, s, row, rs, re, cv, sA + used, sJ + used, (uint32_t)(rs - tb), cap - used, lane, ev);
+                const uint32_t c = stage_row<false>(v, s, rs, re, cv, sA + used, sJ + used, (uint32_t)(rs - tb), cap - used, lane, ev);
                 if (c > cap - used) { heavy = (nb == 0); break; }  // does not fit: close the batch (an over-long row goes alone)
                 if (lane == nb) { myRow = r; myOff = used; myCnt = c; myEv = ev; }
                 used += c; nb++; r++;
@@ -566,7 +594,6 @@ __global__ void k_index_build(View v, StepArgs s) {
         const uint32_t nrn = v.gRecs[idx].neuron;
         v.next[idx] = atomicExch(&v.head[nrn], (int32_t)idx);
         atomicOr(&v.mask[nrn >> 5], 1u << (nrn & 31u));
-        atomicOr(&v.coarse[nrn >> 10], 1u << ((nrn >> 5) & 31u));
     }
 }
 __global__ void k_index_reset(View v, StepArgs s) {
@@ -576,7 +603,6 @@ __global__ void k_index_reset(View v, StepArgs s) {
         const uint32_t nrn = v.gRecs[b * s.gStride + 1u + i].neuron;
         v.head[nrn] = -1;
         v.mask[nrn >> 5] = 0u;
-        v.coarse[nrn >> 10] = 0u;
     }
 }
 // End of a window: publish (or, for replay, accumulate) the shard's counters and its exchange header into `out`
@@ -589,167 +615,101 @@ __global__ void k_finish_step(View v, unsigned long long* out, int accumulate) {
         v.stats[i] = 0ull;
     } else if (i == 8) {
         out[8] = v.localHdr[0];
-        out[9] = accumulate ? (out[9] | v.localHdr[1]) : v.localHdr[1];
+        const unsigned long long ovf = (unsigned long long)v.localHdr[1] | ((unsigned long long)v.flagCtl[1] << 1);  // bit 0: fire records, bit 1: flag list
+        out[9] = accumulate ? (out[9] | ovf) : ovf;
     }
     __syncwarp();
-    if (i == 8) { v.localHdr[0] = 0u; v.localHdr[1] = 0u; v.tileCtr[0] = 0u; v.tileCtr[1] = 0u; }
+    if (i == 8) { v.localHdr[0] = 0u; v.localHdr[1] = 0u; v.tileCtr[0] = 0u; v.tileCtr[1] = 0u; v.flagCtl[0] = 0u; v.flagCtl[1] = 0u; }
 }
 
 // ------------------------------------------------------------------------------------------------
 // Synapse pass
 // ------------------------------------------------------------------------------------------------
-#define NC_P2_QUEUE 160  // per-warp queue of eventful slots (drained 32 at a time so that every lane resolves one)
-#define NC_P2_CHUNK 16   // rows claimed at a time by a warp
+// Only the synapses something happened to are touched.  Three sources name them, and every eventful
+// slot is owned by exactly one:
+//   k_syn_loads    for every neuron that fired (any shard): its out-synapses in this shard (CSC index) — Synapse::fire.
+//                  Skips slots whose row fired (k_syn_rows owns them) and slots on the flag list (k_syn_flagged owns them).
+//   k_syn_rows     for every neuron of this shard that fired: all its in-synapses (post-fire plasticity, plus whatever
+//                  else happened to them in the window).
+//   k_syn_flagged  the slots the neuron pass flagged (delivery in the window / cleared by one of its runs), unless their
+//                  row fired.
+// k_syn_loads runs first: it decides "flagged" from `arrive` as the neuron pass left it, which only it may have changed for
+// the slots it owns.  Each slot is resolved by resolve_slot() — all of the window's operations on it in canonical order.
+__device__ __forceinline__ bool fired_g(const View& v, uint32_t n) { return (__ldg(v.mask + (n >> 5)) >> (n & 31u)) & 1u; }
 
-// one queued slot per lane: fetch its row's context and apply all of the window's operations on it
-__device__ __forceinline__ void resolve_queued(const View& v, const StepArgs& s, const uint32_t* mask, uint32_t row, uint32_t rel, uint32_t pw, uint32_t* cnt) {
-    const uint32_t q = (uint32_t)(v.row0 + row);
-    const uint64_t rs = v.rowptr[row];
-    const bool qFired = (mask[q >> 5] >> (q & 31u)) & 1u;
-    const float lfS = v.lfStart[row];
-    const uint32_t p = pw & 0x7fffffffu;
-    const bool pFired = (mask[p >> 5] >> (p & 31u)) & 1u;
-    const uint32_t ab = __float_as_uint(v.arrive[rs + rel]);
-    resolve_slot(v, s, rs + rel, rs, q, p, (pw >> 31) != 0u, ab, pFired, qFired, lfS, cnt);
-}
-
-// MASK_SMEM: the whole-network fire bitmask (1 bit per neuron), probed once per synapse, is staged in shared memory
-// (a compile-time choice so that the probe is a plain 32-bit-addressed LDS).  Networks too large for that (> 1.3 M neurons,
-// i.e. multi-GPU runs) stage the 32x smaller COARSE bitmask instead (1 bit per word of the fire mask) and go to the fire
-// mask in L2 only where the coarse bit is set — with a few thousand fires among millions of neurons that is < 1 % of probes.
-template <bool MASK_SMEM>
-__global__ void __launch_bounds__(NC_P2_THREADS) k_synapse_pass(View v, StepArgs s, uint32_t maskWordsInSmem) {
-    extern __shared__ uint32_t smem2[];
-    math_tables_to_shared();
-    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    uint32_t* smask = smem2 + (size_t)wpb * 3 * NC_P2_QUEUE;
-    const uint32_t* __restrict__ gmask = v.mask;
-    {   // maskWordsInSmem words of the fire mask (MASK_SMEM) or of the coarse mask
-        const uint32_t* __restrict__ srcm = MASK_SMEM ? gmask : v.coarse;
-        for (uint32_t i = threadIdx.x; i < maskWordsInSmem; i += blockDim.x) smask[i] = srcm[i];
-        __syncthreads();
-    }
-    const uint32_t* mask = MASK_SMEM ? smask : gmask;  // for the (rare) per-entry probes of the resolve step
-    auto fired = [&](uint32_t n) -> bool {
-        if (MASK_SMEM) return (smask[n >> 5] >> (n & 31u)) & 1u;
-        if (!((smask[n >> 10] >> ((n >> 5) & 31u)) & 1u)) return false;
-        return (__ldg(gmask + (n >> 5)) >> (n & 31u)) & 1u;
-    };
-    auto fired_word = [&](uint32_t n) -> uint32_t {  // bit 0 = fired(n); the other bits are junk
-        if (MASK_SMEM) return __funnelshift_r(smask[n >> 5], 0u, n);
-        if (!((smask[n >> 10] >> ((n >> 5) & 31u)) & 1u)) return 0u;
-        return __funnelshift_r(__ldg(gmask + (n >> 5)), 0u, n);
-    };
-    // eventful slots are rare and scattered: queue them per warp — across rows — and resolve 32 at a time instead of
-    // diverging in place
-    uint32_t* qJ = smem2 + (size_t)wib * 3 * NC_P2_QUEUE;
-    uint32_t* qP = qJ + NC_P2_QUEUE;
-    uint32_t* qR = qP + NC_P2_QUEUE;
-    uint32_t cnt[5] = {0, 0, 0, 0, 0};  // loads accepted, dropped, plasticity calls, hidden rand, deliveries
-    uint32_t qn = 0;
-    const uint64_t nChunks = (v.nRows + NC_P2_CHUNK - 1) / NC_P2_CHUNK;
-    for (;;) {
-        uint32_t c32 = 0;
-        if (lane == 0) c32 = atomicAdd(&v.tileCtr[1], 1u);
-        const uint64_t chunk = __shfl_sync(0xffffffffu, c32, 0);
-        if (chunk >= nChunks) break;
-        const uint64_t rowEnd = min(v.nRows, (chunk + 1) * NC_P2_CHUNK);
-        for (uint64_t row = chunk * NC_P2_CHUNK; row < rowEnd; row++) {
-            const uint32_t q = (uint32_t)(v.row0 + row);
-            const uint64_t rs = v.rowptr[row], re = v.rowptr[row + 1];
-            const uint32_t len = (uint32_t)(re - rs);
-            const bool qFired = fired(q);
-            const uint32_t summ = v.ownSumm[row];  // groups in which the neuron pass saw slots that may deliver or have been cleared
-            const uint64_t g0 = rs >> 7;
-            const uint32_t ng = (uint32_t)(((re + 127) >> 7) - g0);
-            const uint4* bm = reinterpret_cast<const uint4*>(v.ownBits) + (g0 + row);
-            const uint4* src = reinterpret_cast<const uint4*>(v.pre) + (g0 << 5) + lane;
-            const uint32_t relBase = 4u * lane - (uint32_t)(rs & 127u);  // row-relative index of this lane's first slot in group 0
-            for (uint32_t g = 0; g < ng; g += NC_UNROLL4) {
-                uint4 pv[NC_UNROLL4];
-                const uint4* sp = src + ((uint64_t)g << 5);  // (one 64-bit address per batch; the unrolled loads use immediate offsets)
-#pragma unroll
-                for (int u = 0; u < NC_UNROLL4; u++)
-                    pv[u] = (g + u < ng) ? __ldcs(sp + (u << 5)) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-                for (int u = 0; u < NC_UNROLL4; u++) {
-                    if (g + u >= ng) break;
-                    const uint32_t gi = g + u;
-                    const uint32_t rel0 = relBase + (gi << 7);  // one unsigned compare against the row length masks both ends
-                    const uint32_t p4[4] = {pv[u].x, pv[u].y, pv[u].z, pv[u].w};
-                    // common case — nothing happened to any of the warp's 128 slots — decided with four raw probes per lane
-                    // (bit 0 of the shifted mask word; slots outside the row probe a neighbour's presynaptic ID, which can only
-                    // send the group down the exact path below for nothing)
-                    const bool flagged = (summ >> min(gi, 31u)) & 1u;  // (warp-uniform) the neuron pass flagged slots of this group
-                    if (s.sparseFires && !qFired && !flagged) {
-                        uint32_t anyb = 0u;
-#pragma unroll
-                        for (int k = 0; k < 4; k++) anyb |= fired_word(p4[k] & 0x7fffffffu);
-                        if (!__any_sync(0xffffffffu, anyb & 1u)) continue;
-                    }
-                    // exact per-slot evaluation: "did my presynaptic neuron (or my row's neuron) fire"
-                    bool ev[4];
-#pragma unroll
-                    for (int k = 0; k < 4; k++) ev[k] = (rel0 + k < len) && (qFired | fired(p4[k] & 0x7fffffffu));
-                    if (flagged) {
-                        const uint4 cb = __ldg(bm + gi);
-                        const uint32_t c4[4] = {cb.x, cb.y, cb.z, cb.w};
-#pragma unroll
-                        for (int k = 0; k < 4; k++)
-                            if ((rel0 + k < len) && ((c4[k] >> lane) & 1u)) {  // may deliver in this window / may have been cleared
-                                const uint32_t ab = __float_as_uint(v.arrive[rs + (uint32_t)(rel0 + k)]);
-                                const float a = __uint_as_float(ab);
-                                ev[k] = ev[k] || (ab & NC_SENT) || (a > s.t0 && a <= s.t1);
-                            }
-                    }
-                    if (!__any_sync(0xffffffffu, ev[0] | ev[1] | ev[2] | ev[3])) continue;
-                    uint32_t m[4];
-#pragma unroll
-                    for (int k = 0; k < 4; k++) m[k] = __ballot_sync(0xffffffffu, ev[k]);
-                    const uint32_t lt = (1u << lane) - 1u;
-                    uint32_t pos = qn + __popc(m[0] & lt) + __popc(m[1] & lt) + __popc(m[2] & lt) + __popc(m[3] & lt);
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        if (ev[k]) { qJ[pos] = rel0 + k; qP[pos] = p4[k]; qR[pos] = (uint32_t)row; pos++; }
-                    qn += __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
-                    while (qn >= 32) {  // drain the oldest 32 entries: one per lane
-                        __syncwarp();
-                        const uint32_t jj = qJ[lane], pw = qP[lane], rr = qR[lane];
-                        uint32_t keepJ[4], keepP[4], keepR[4];
-                        const uint32_t rest = qn - 32;
-#pragma unroll
-                        for (int t = 0; t < 4; t++) {
-                            const uint32_t idx = 32 + t * 32 + lane;
-                            const bool mv = t * 32 + lane < rest;
-                            keepJ[t] = mv ? qJ[idx] : 0u; keepP[t] = mv ? qP[idx] : 0u; keepR[t] = mv ? qR[idx] : 0u;
-                        }
-                        __syncwarp();
-#pragma unroll
-                        for (int t = 0; t < 4; t++)
-                            if (t * 32 + lane < rest) { qJ[t * 32 + lane] = keepJ[t]; qP[t * 32 + lane] = keepP[t]; qR[t * 32 + lane] = keepR[t]; }
-                        qn = rest;
-                        resolve_queued(v, s, mask, rr, jj, pw, cnt);
-                        __syncwarp();
-                    }
-                }
-            }
-        }
-    }
-    __syncwarp();
-    if (lane < qn) resolve_queued(v, s, mask, qR[lane], qJ[lane], qP[lane], cnt);
-    __syncwarp();
+__device__ __forceinline__ void flush_syn_counters(const View& v, uint32_t* cnt) {
 #pragma unroll
     for (int i = 0; i < 5; i++) {
         uint32_t x = cnt[i];
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
         cnt[i] = x;
     }
-    if (lane == 0) {
+    if ((threadIdx.x & 31u) == 0u) {
         if (cnt[0]) atomicAdd(&v.stats[2], (unsigned long long)cnt[0]);
         if (cnt[1]) atomicAdd(&v.stats[3], (unsigned long long)cnt[1]);
         if (cnt[2]) atomicAdd(&v.stats[4], (unsigned long long)cnt[2]);
         if (cnt[3]) atomicAdd(&v.stats[5], (unsigned long long)cnt[3]);
     }
+}
+
+#define NC_SYN_THREADS 128
+
+// One block per fire record; the record at the head of its neuron's list stands for the neuron (a neuron can fire more than
+// once in a window: input firers ignore the refractory period).
+__global__ void __launch_bounds__(NC_SYN_THREADS) k_syn_loads(View v, StepArgs s) {
+    const uint32_t b = blockIdx.y;
+    const uint32_t n = block_count(v, s, b);
+    uint32_t cnt[5] = {0, 0, 0, 0, 0};  // loads accepted, dropped, plasticity calls, hidden rand, deliveries
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint32_t idx = b * s.gStride + 1u + i;
+        const uint32_t p = v.gRecs[idx].neuron;
+        if (v.head[p] != (int32_t)idx) continue;
+        const uint64_t e0 = v.cscPtr[p], e1 = v.cscPtr[p + 1];
+        for (uint64_t e = e0 + threadIdx.x; e < e1; e += NC_SYN_THREADS) {
+            const SlotRow sr = v.cscEnt[e];
+            const uint32_t q = (uint32_t)(v.row0 + sr.row);
+            if (fired_g(v, q)) continue;  // k_syn_rows
+            const uint32_t ab = __float_as_uint(v.arrive[sr.slot]);
+            const float a = __uint_as_float(ab);
+            if ((ab & NC_SENT) || (ab != 0u && a > s.t0 && a <= s.t1)) continue;  // k_syn_flagged
+            // only loads can apply: neither the row context nor the plasticity tables are needed
+            resolve_slot(v, s, sr.slot, 0ull, q, p, (v.pre[sr.slot] >> 31) != 0u, ab, true, false, 0.0f, cnt);
+        }
+    }
+    flush_syn_counters(v, cnt);
+}
+__global__ void __launch_bounds__(NC_SYN_THREADS) k_syn_rows(View v, StepArgs s) {
+    math_tables_to_shared();
+    const uint32_t b = blockIdx.y;
+    const uint32_t n = block_count(v, s, b);
+    uint32_t cnt[5] = {0, 0, 0, 0, 0};
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint32_t idx = b * s.gStride + 1u + i;
+        const uint32_t q = v.gRecs[idx].neuron;
+        if (q < v.row0 || q >= v.row0 + v.nRows || v.head[q] != (int32_t)idx) continue;
+        const uint64_t row = q - v.row0;
+        const uint64_t rs = v.rowptr[row], re = v.rowptr[row + 1];
+        const float lfS = v.lfStart[row];
+        for (uint64_t j = rs + threadIdx.x; j < re; j += NC_SYN_THREADS) {
+            const uint32_t pw = v.pre[j], p = pw & 0x7fffffffu;
+            resolve_slot(v, s, j, rs, q, p, (pw >> 31) != 0u, __float_as_uint(v.arrive[j]), fired_g(v, p), true, lfS, cnt);
+        }
+    }
+    flush_syn_counters(v, cnt);
+}
+__global__ void __launch_bounds__(256) k_syn_flagged(View v, StepArgs s) {
+    math_tables_to_shared();
+    const uint32_t n = min(v.flagCtl[0], v.flagCap);
+    uint32_t cnt[5] = {0, 0, 0, 0, 0};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const SlotRow sr = v.flagList[i];
+        const uint32_t q = (uint32_t)(v.row0 + sr.row);
+        if (fired_g(v, q)) continue;  // k_syn_rows
+        const uint32_t pw = v.pre[sr.slot], p = pw & 0x7fffffffu;
+        resolve_slot(v, s, sr.slot, v.rowptr[sr.row], q, p, (pw >> 31) != 0u, __float_as_uint(v.arrive[sr.slot]), fired_g(v, p), false,
+                     v.lfStart[sr.row], cnt);
+    }
+    flush_syn_counters(v, cnt);
 }
 
 // Marks (set = 1) or unmarks the rows of this shard that have host events in this window.
@@ -787,6 +747,62 @@ __global__ void k_init_synapses(View v, const float* length, const unsigned char
 __global__ void k_fill_i32(int32_t* p, uint64_t n, int32_t val) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = val;
+}
+// Out-synapse index (CSC over global presynaptic IDs) of the shard's rows, built once at upload: count, (host) prefix sum, fill.
+// The order of a neuron's entries is arbitrary — every slot is resolved on its own.
+__global__ void k_csc_count(View v, uint32_t* cnt) {
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < v.S; j += (uint64_t)gridDim.x * blockDim.x)
+        atomicAdd(&cnt[v.pre[j] & 0x7fffffffu], 1u);
+}
+__global__ void k_csc_fill(View v, const uint64_t* ptr, uint32_t* cursor, SlotRow* ent) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nW = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t row = gw; row < v.nRows; row += nW) {
+        const uint64_t rs = v.rowptr[row], re = v.rowptr[row + 1];
+        for (uint64_t j = rs + lane; j < re; j += 32) {
+            const uint32_t p = v.pre[j] & 0x7fffffffu;
+            SlotRow sr; sr.slot = (uint32_t)j; sr.row = (uint32_t)row;
+            ent[ptr[p] + atomicAdd(&cursor[p], 1u)] = sr;
+        }
+    }
+}
+// Position-weighted 64-bit checksums of the shard's state (the six fields the parity fixtures pin, tests/helpers.py):
+// sum over i of bits(x[i]) * (i + 1) * 0x9E3779B97F4A7C15 mod 2^64 for pot, act, lastFire, weight, arrive (+ depol of the
+// busy slots), lastArr.  Integer sums commute, so the result does not depend on the thread layout.
+__global__ void k_state_signature(View v, unsigned long long* out) {
+    const unsigned long long C = 0x9E3779B97F4A7C15ull;
+    unsigned long long a[6] = {0, 0, 0, 0, 0, 0};
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nT = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = tid; i < v.nRows; i += nT) {
+        const float2 pa = v.potAct[i];
+        const unsigned long long k = (i + 1) * C;
+        a[0] += (unsigned long long)__float_as_uint(pa.x) * k;
+        a[1] += (unsigned long long)__float_as_uint(pa.y) * k;
+        a[2] += (unsigned long long)__float_as_uint(v.lastFire[i]) * k;
+    }
+    for (uint64_t j = tid; j < v.S; j += nT) {
+        const unsigned long long k = (j + 1) * C;
+        const uint32_t ab = __float_as_uint(v.arrive[j]);
+        a[3] += (unsigned long long)__float_as_uint(v.weight[j]) * k;
+        a[4] += (unsigned long long)ab * k;
+        if (v.arrive[j] != 0.0f) a[4] += (unsigned long long)__float_as_uint(v.depol[j]) * k;
+        a[5] += (unsigned long long)__float_as_uint(v.lastArr[j]) * k;
+    }
+#pragma unroll
+    for (int f = 0; f < 6; f++) {
+        unsigned long long x = a[f];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31u) == 0u && x) atomicAdd(&out[f], x);
+    }
+}
+// busy-slot index from `arrive` (after a restore, or for state loaded from a file)
+__global__ void k_rebuild_busy(View v, uint64_t words) {
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t m = 0u;
+        const uint64_t j0 = w << 5;
+        for (uint32_t b = 0; b < 32u && j0 + b < v.S; b++) m |= (v.arrive[j0 + b] != 0.0f ? 1u : 0u) << b;
+        v.busy[w] = m;
+    }
 }
 __global__ void k_reset_activities(View v, float now) {  // Neuron::resetActivity, NeuCor.cpp:460
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -831,7 +847,7 @@ __global__ void k_synapse_pots(View v, float now, float* prePot, float* postPot)
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 
-struct TapeStep { float t0, t1; int sweep; uint64_t evOff; uint32_t nEv; uint32_t units; };
+struct TapeStep { float t0, t1; int sweep; uint64_t evOff; uint32_t nEv; uint32_t units; uint32_t fires; };
 
 // NCCL is bound at run time (dlopen) so that single-GPU users need no NCCL at all; only the five entry points below are used.
 struct NcclApi {
@@ -855,6 +871,7 @@ struct nc_engine {
     nc_event* dEv = nullptr; uint32_t evCap = 0;
     nc_event* hEvPinned = nullptr; uint32_t hEvCap = 0;
     // per-window result block: 10 x u64 per shard (8 counters, fire count, overflow flag)
+    unsigned long long* dSig = nullptr; unsigned long long* hSig = nullptr;  // nc_state_signature
     unsigned long long* dOut = nullptr;     // this shard's block
     unsigned long long* dOutAll = nullptr;  // world blocks (world > 1)
     unsigned long long* hOut = nullptr;     // pinned, world blocks
@@ -869,16 +886,17 @@ struct nc_engine {
     StepArgs pendingArgs;
     float lr = 1.0f, preF = 0.13f, postF = 0.30f, preD = 0.75f, postD = 0.65f;
     float minDelay = INFINITY;
-    uint32_t candCap = 1024, candCapSparse = 512, grid1 = 0, grid1s = 0, grid2 = 0, maskWordsSmem = 0;
+    uint32_t candCap = 1024, candCapSparse = 512, grid1 = 0, grid1s = 0;
     int forceVariant = 0;                   // 0 auto, 1 dense, 2 sparse
     double lastSlotsPerRun = 1e9;           // occupied slots visited per neuron run in the last window (picks the variant)
-    bool maskInSmem = true;
-    size_t smem1 = 0, smem1s = 0, smem2 = 0;
+    size_t smem1 = 0, smem1s = 0;
+    uint64_t* dCscPtr = nullptr; SlotRow* dCscEnt = nullptr;  // out-synapse index (CSC over global presynaptic IDs)
     uint64_t launches = 0;
     // tape
     bool taping = false; std::vector<TapeStep> tape; nc_event* dTape = nullptr; uint64_t tapeCap = 0, tapeUsed = 0; uint32_t tapeMaxSteps = 0;
     // snapshot
-    struct Snap { float *arrive, *depol, *weight, *lastArr, *lastStart, *lastRan, *lastFire, *lfStart, *actStart; float2* potAct; uint32_t* firings; bool valid; } snap = {};
+    struct Snap { float *arrive, *depol, *weight, *lastArr, *lastStart, *lastRan, *lastFire, *lfStart, *actStart; float2* potAct; uint32_t *firings, *busy; bool valid; } snap = {};
+    uint64_t busyWords = 0;
     int smCount = 148;
 };
 
@@ -922,6 +940,8 @@ extern "C" int nc_create(const nc_config* cfg, nc_engine** out) {
     if (ce == cudaSuccess) ce = cudaMemcpyToSymbol(d_EXP_TAB, NC_EXP_TAB, sizeof(NC_EXP_TAB));
     if (ce == cudaSuccess) ce = cudaMallocHost(&e->hOut, (size_t)cfg->world * 10 * sizeof(unsigned long long));
     if (ce == cudaSuccess) ce = cudaMallocHost(&e->hHdrAll, (size_t)cfg->world * 4 * sizeof(uint32_t));
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->dSig, 6 * sizeof(unsigned long long));
+    if (ce == cudaSuccess) ce = cudaMallocHost(&e->hSig, 6 * sizeof(unsigned long long));
     if (ce == cudaSuccess) ce = cudaMalloc(&e->dOut, 10 * sizeof(unsigned long long));
     if (ce == cudaSuccess) ce = cudaMemset(e->dOut, 0, 10 * sizeof(unsigned long long));
     if (ce == cudaSuccess) ce = cudaMalloc(&e->dOutAll, (size_t)cfg->world * 10 * sizeof(unsigned long long));
@@ -942,13 +962,13 @@ static void free_all(nc_engine* e) {
     View& v = e->v;
     cudaFree((void*)v.rowptr); cudaFree(v.pre); cudaFree(v.arrive); cudaFree(v.depol); cudaFree(v.weight); cudaFree(v.lastArr);
     cudaFree(v.lastStart); cudaFree(e->dDelay); cudaFree(v.potAct); cudaFree(v.lastRan); cudaFree(v.lastFire); cudaFree(v.lfStart);
-    cudaFree(v.actStart); cudaFree(v.firings); cudaFree(v.localHdr); cudaFree(v.head); cudaFree(v.next); cudaFree(v.mask); cudaFree(v.coarse); cudaFree(v.evMask); cudaFree(v.ownBits); cudaFree(v.ownSumm);
+    cudaFree(v.actStart); cudaFree(v.firings); cudaFree(v.localHdr); cudaFree(v.head); cudaFree(v.next); cudaFree(v.mask); cudaFree(v.evMask); cudaFree(v.busy); cudaFree(v.flagList); cudaFree(v.flagCtl); cudaFree(e->dCscPtr); cudaFree(e->dCscEnt);
     cudaFree(v.spillA); cudaFree(v.spillD); cudaFree(v.spillJ); cudaFree(v.poolJ);
     cudaFree(e->dGather);
     cudaFree(e->dEv); cudaFree(e->dTape);
     auto& s = e->snap;
     cudaFree(s.arrive); cudaFree(s.depol); cudaFree(s.weight); cudaFree(s.lastArr); cudaFree(s.lastStart); cudaFree(s.lastRan);
-    cudaFree(s.lastFire); cudaFree(s.lfStart); cudaFree(s.actStart); cudaFree(s.potAct); cudaFree(s.firings);
+    cudaFree(s.lastFire); cudaFree(s.lfStart); cudaFree(s.actStart); cudaFree(s.potAct); cudaFree(s.firings); cudaFree(s.busy);
 }
 
 extern "C" void nc_destroy(nc_engine* e) {
@@ -957,7 +977,7 @@ extern "C" void nc_destroy(nc_engine* e) {
     cudaStreamSynchronize(e->stream);
     free_all(e);
     cudaFree(e->v.stats); cudaFree(e->v.tileCtr); cudaFree(e->dOut); cudaFree(e->dOutAll);
-    cudaFreeHost(e->hOut); cudaFreeHost(e->hHdrAll); cudaFreeHost(e->hEvPinned);
+    cudaFreeHost(e->hOut); cudaFreeHost(e->hHdrAll); cudaFreeHost(e->hEvPinned); cudaFree(e->dSig); cudaFreeHost(e->hSig);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     if (e->ownStream) cudaStreamDestroy(e->stream);
     delete e;
@@ -1006,16 +1026,22 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
     const uint64_t SP = ((S1 + 127) / 128 + 1) * 128;  // 16-byte row loads may touch the rest of the last 128-slot group
     CK(cudaMalloc(&v.pre, SP * 4)); CK(cudaMalloc(&v.arrive, SP * 4)); CK(cudaMalloc(&v.depol, S1 * 4));
     CK(cudaMemsetAsync(v.pre, 0, SP * 4, e->stream)); CK(cudaMemsetAsync(v.arrive, 0, SP * 4, e->stream));
-    CK(cudaMalloc(&v.ownBits, (SP / 128 + N1 + 1) * 16));
-    CK(cudaMemsetAsync(v.ownBits, 0, (SP / 128 + N1 + 1) * 16, e->stream));
-    CK(cudaMalloc(&v.ownSumm, N1 * 4));
-    CK(cudaMemsetAsync(v.ownSumm, 0, N1 * 4, e->stream));
+    // event index: busy-slot bitmap (1 bit per slot), flag list (neuron pass -> synapse pass), out-synapse index (CSC)
+    const uint64_t busyWords = SP / 32 + 64;
+    e->busyWords = busyWords;
+    CK(cudaMalloc(&v.busy, busyWords * 4));
+    CK(cudaMemsetAsync(v.busy, 0, busyWords * 4, e->stream));
+    v.flagCap = e->cfg.flag_capacity ? e->cfg.flag_capacity : (uint32_t)std::min<uint64_t>(std::max<uint64_t>(S1 / 8 + (1u << 16), 1u << 20), S1 + 1024);
+    CK(cudaMalloc(&v.flagList, (uint64_t)v.flagCap * sizeof(SlotRow)));
+    CK(cudaMalloc(&v.flagCtl, 2 * sizeof(uint32_t)));
+    CK(cudaMemsetAsync(v.flagCtl, 0, 2 * sizeof(uint32_t), e->stream));
     CK(cudaMalloc(&v.weight, S1 * 4)); CK(cudaMalloc(&v.lastArr, S1 * 4)); CK(cudaMalloc(&v.lastStart, S1 * 4));
     CK(cudaMalloc(&e->dDelay, S1 * 4)); v.delay = e->dDelay;
     CK(cudaMalloc(&v.potAct, N1 * 8)); CK(cudaMalloc(&v.lastRan, N1 * 4)); CK(cudaMalloc(&v.lastFire, N1 * 4));
     CK(cudaMalloc(&v.lfStart, N1 * 4)); CK(cudaMalloc(&v.actStart, N1 * 4)); CK(cudaMalloc(&v.firings, N1 * 4));
     v.fireCap = e->cfg.fire_capacity ? e->cfg.fire_capacity : (uint32_t)std::min<uint64_t>(4 * nRows + 1024, (1u << 28) / (uint32_t)e->cfg.world);
     const uint64_t blockUnits = (uint64_t)v.fireCap + 1;  // header unit + records
+    e->xchgUnits = (uint32_t)std::min<uint64_t>(e->xchgUnits, blockUnits);  // never gather past a shard's block
     CK(cudaMalloc(&v.localHdr, blockUnits * sizeof(FireRec)));
     v.localRecs = reinterpret_cast<FireRec*>(v.localHdr) + 1;
     CK(cudaMemsetAsync(v.localHdr, 0, 16, e->stream));
@@ -1024,8 +1050,6 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
     CK(cudaMalloc(&v.head, G1 * 4)); CK(cudaMalloc(&v.next, (uint64_t)e->cfg.world * blockUnits * 4));
     CK(cudaMalloc(&v.mask, ((G1 + 31) / 32) * 4));
     CK(cudaMemsetAsync(v.mask, 0, ((G1 + 31) / 32) * 4, e->stream));
-    CK(cudaMalloc(&v.coarse, ((G1 + 1023) / 1024) * 4));
-    CK(cudaMemsetAsync(v.coarse, 0, ((G1 + 1023) / 1024) * 4, e->stream));
     CK(cudaMalloc(&v.evMask, ((N1 + 31) / 32) * 4));
     CK(cudaMemsetAsync(v.evMask, 0, ((N1 + 31) / 32) * 4, e->stream));
     const float* dLen = length; const unsigned char* dInh = inh;
@@ -1046,6 +1070,28 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
     if (nRows) { k_init_neurons<<<(unsigned)((nRows + 255) / 256), 256, 0, e->stream>>>(v); e->launches++; }
     k_fill_i32<<<(unsigned)((G1 + 255) / 256), 256, 0, e->stream>>>(v.head, G1, -1); e->launches++;
     CK(cudaGetLastError());
+    {   // out-synapse index
+        if (S >= (1ull << 32)) return fail(e, NC_ERR_INVALID, "nc_upload_network: at most 2^32-1 synapses per shard");
+        uint32_t* dCnt = nullptr;
+        CK(cudaMalloc(&dCnt, G1 * 4));
+        CK(cudaMemsetAsync(dCnt, 0, G1 * 4, e->stream));
+        CK(cudaMalloc(&e->dCscPtr, (G1 + 1) * 8));
+        CK(cudaMalloc(&e->dCscEnt, S1 * sizeof(SlotRow)));
+        if (S) { k_csc_count<<<e->smCount * 16, 256, 0, e->stream>>>(v, dCnt); e->launches++; }
+        std::vector<uint32_t> hCnt(G1);
+        std::vector<uint64_t> hPtr(G1 + 1);
+        CK(cudaMemcpyAsync(hCnt.data(), dCnt, G1 * 4, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        hPtr[0] = 0;
+        for (uint64_t i = 0; i < G1; i++) hPtr[i + 1] = hPtr[i] + hCnt[i];
+        CK(cudaMemcpyAsync(e->dCscPtr, hPtr.data(), (G1 + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemsetAsync(dCnt, 0, G1 * 4, e->stream));
+        if (S) { k_csc_fill<<<e->smCount * 16, 256, 0, e->stream>>>(v, e->dCscPtr, dCnt, e->dCscEnt); e->launches++; }
+        CK(cudaStreamSynchronize(e->stream));
+        cudaFree(dCnt);
+        v.cscPtr = e->dCscPtr; v.cscEnt = e->dCscEnt;
+        CK(cudaGetLastError());
+    }
     // launch geometry: persistent grids sized to the SM count x resident blocks per SM
     // the warp's shared-memory pool of staged slots: shared by the rows of a lane-per-row batch, so not tied to the row length
     e->candCap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(e->candCap, 32), 1024);
@@ -1054,31 +1100,16 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
     e->smem1s = (size_t)NC_WARPS_PER_BLOCK * 2 * e->candCapSparse * 4;
     CK(cudaFuncSetAttribute(k_neuron_pass<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem1));
     CK(cudaFuncSetAttribute(k_neuron_pass<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem1s));
-    int occ1 = 1, occ1s = 1, occ2 = 1;
+    int occ1 = 1, occ1s = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_neuron_pass<6>, NC_WARPS_PER_BLOCK * 32, e->smem1));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1s, k_neuron_pass<8>, NC_WARPS_PER_BLOCK * 32, e->smem1s));
-    // synapse pass: the whole-network fire bitmask goes to shared memory when it fits (<= 160 KB, i.e. 1.3 M neurons),
-    // otherwise the 32x smaller coarse mask does (2^30 neurons -> 128 KB).  NC_FORCE_COARSE_MASK=1 forces the latter (tests).
-    uint64_t maskWords = (G1 + 31) / 32;
-    e->maskInSmem = maskWords * 4 <= 160 * 1024 && !getenv("NC_FORCE_COARSE_MASK");
-    e->maskWordsSmem = e->maskInSmem ? (uint32_t)maskWords : (uint32_t)((G1 + 1023) / 1024);
-    e->smem2 = (size_t)e->maskWordsSmem * 4 + (size_t)(NC_P2_THREADS / 32) * 3 * NC_P2_QUEUE * 4;
-    if (e->maskInSmem) {
-        CK(cudaFuncSetAttribute(k_synapse_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem2));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_synapse_pass<true>, NC_P2_THREADS, e->smem2));
-    } else {
-        CK(cudaFuncSetAttribute(k_synapse_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem2));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_synapse_pass<false>, NC_P2_THREADS, e->smem2));
-    }
     uint64_t needBlocks = ((nRows + 31) / 32 + NC_WARPS_PER_BLOCK - 1) / NC_WARPS_PER_BLOCK;  // one tile of 32 rows per warp at a time
-    uint64_t needBlocks2 = (nRows + NC_P2_THREADS / 32 - 1) / (NC_P2_THREADS / 32);
     e->grid1 = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(needBlocks, (uint64_t)e->smCount * std::max(occ1, 1)));
     e->grid1s = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(needBlocks, (uint64_t)e->smCount * std::max(occ1s, 1)));
     {
         const char* f = getenv("NC_NEURON_VARIANT");  // tuning/tests: "dense" or "sparse" pins the variant
         e->forceVariant = f ? (f[0] == 's' ? 2 : 1) : 0;
     }
-    e->grid2 = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(needBlocks2, (uint64_t)e->smCount * std::max(occ2, 1)));
     // scratch sized for whichever variant needs more: spill beyond the smaller pool, one pool of slot indices per resident warp
     v.spillPerWarp = (uint32_t)(maxRow > e->candCapSparse ? maxRow - e->candCapSparse : 0);
     const uint64_t maxWarps = (uint64_t)std::max(e->grid1, e->grid1s) * NC_WARPS_PER_BLOCK;
@@ -1198,17 +1229,16 @@ static void fill_args(nc_engine* e, StepArgs& a, float t0, float t1, int sweep, 
         const bool sparse = e->forceVariant ? e->forceVariant == 2 : e->lastSlotsPerRun * 32.0 * 4.0 < (double)e->candCapSparse;
         a.candCap = sparse ? e->candCapSparse : e->candCap;
     }
-    {   // expected fired presynaptic IDs per 128-slot group, from the last window's network-wide fire count
-        uint64_t fires = 0;
-        for (int b = 0; b < e->cfg.world; b++) fires += e->lastCounts[b];
-        a.sparseFires = (double)fires * 128.0 < 0.5 * (double)std::max<uint64_t>(e->v.nGlobal, 1);
-    }
     a.gStride = e->cfg.world == 1 ? e->v.fireCap + 1u : e->xchgUnits;
 }
 
-static void launch_synapse_pass(nc_engine* e, const StepArgs& a) {
-    if (e->maskInSmem) k_synapse_pass<true><<<e->grid2, NC_P2_THREADS, e->smem2, e->stream>>>(e->v, a, e->maskWordsSmem);
-    else k_synapse_pass<false><<<e->grid2, NC_P2_THREADS, e->smem2, e->stream>>>(e->v, a, e->maskWordsSmem);
+// one block per (expected) fire record, capped; the kernels stride over the records they find on the device
+static void launch_synapse_pass(nc_engine* e, const StepArgs& a, uint32_t expectFires) {
+    dim3 g(std::min<uint32_t>(std::max<uint32_t>(expectFires, 1u), (uint32_t)e->smCount * 16u), a.world);
+    k_syn_loads<<<g, NC_SYN_THREADS, 0, e->stream>>>(e->v, a);
+    k_syn_rows<<<g, NC_SYN_THREADS, 0, e->stream>>>(e->v, a);
+    k_syn_flagged<<<e->smCount * 8, 256, 0, e->stream>>>(e->v, a);
+    e->launches += 3;
 }
 static void launch_neuron_pass(nc_engine* e, const StepArgs& a) {
     if (a.candCap == e->candCapSparse && e->candCapSparse != e->candCap)
@@ -1230,10 +1260,10 @@ static int launch_pass2(nc_engine* e, const StepArgs& a, uint32_t expectMax, int
     const uint32_t gx = std::min<uint32_t>(std::max<uint32_t>((expectMax + 255u) / 256u, 1u), 1024u);
     dim3 g(gx, a.world);
     k_index_build<<<g, 256, 0, e->stream>>>(e->v, a);
-    launch_synapse_pass(e, a);
+    launch_synapse_pass(e, a, expectMax);
     k_index_reset<<<g, 256, 0, e->stream>>>(e->v, a);
     k_finish_step<<<1, 32, 0, e->stream>>>(e->v, e->dOut, accumulate);
-    e->launches += 4;
+    e->launches += 3;
     CK(cudaGetLastError());
     return NC_OK;
 }
@@ -1339,7 +1369,8 @@ static int wait_counters(nc_engine* e, uint64_t* hidden, nc_step_stats* st) {
     CK(cudaStreamSynchronize(e->stream));
     sum_out(e, hidden, st);
     for (int b = 0; b < W; b++)
-        if (e->hOut[b * 10 + 9]) return fail(e, NC_ERR_CAPACITY, "step: fire-record capacity exceeded (raise nc_config.fire_capacity)");
+        if (e->hOut[b * 10 + 9]) return fail(e, NC_ERR_CAPACITY, (e->hOut[b * 10 + 9] & 1ull) ? "step: fire-record capacity exceeded (raise nc_config.fire_capacity)"
+                                                                                              : "step: flag-list capacity exceeded (raise nc_config.flag_capacity)");
     return NC_OK;
 }
 static int finish_counters(nc_engine* e, uint64_t* hidden, nc_step_stats* st) {
@@ -1384,7 +1415,7 @@ static int step_second_half(nc_engine* e) {
         if (rc) return rc;
     }
     if (e->taping) {
-        e->tape.push_back({a.t0, a.t1, a.sweep, e->tapeUsed, a.nEv, a.gStride});
+        e->tape.push_back({a.t0, a.t1, a.sweep, e->tapeUsed, a.nEv, a.gStride, expect});
         e->tapeUsed += a.nEv;
     }
     int rc = launch_pass2(e, a, expect, 0);
@@ -1488,6 +1519,7 @@ extern "C" int nc_read_fires(nc_engine* e, uint32_t capacity, uint32_t* neuron, 
     for (uint32_t b = 0; b < (uint32_t)e->cfg.world; b++) {
         uint32_t c = e->lastCounts[b];
         if (!c) continue;
+        if (!capacity) { total += c; continue; }  // count only
         tmp.resize(c);
         CK(cudaMemcpy(tmp.data(), e->v.gRecs + (uint64_t)b * e->lastStride + 1, (uint64_t)c * sizeof(FireRec), cudaMemcpyDeviceToHost));
         for (uint32_t i = 0; i < c; i++, total++)
@@ -1508,6 +1540,19 @@ extern "C" int nc_read_synapse_pots(nc_engine* e, float now, float* prePot, floa
     if (prePot) CK(cudaMemcpy(prePot, dPre, S * 4, cudaMemcpyDeviceToHost));
     if (postPot) CK(cudaMemcpy(postPot, dPost, S * 4, cudaMemcpyDeviceToHost));
     cudaFree(dPre); cudaFree(dPost);
+    return NC_OK;
+}
+extern "C" int nc_state_signature(nc_engine* e, uint64_t* out6) {
+    if (!e->uploaded) return fail(e, NC_ERR_STATE, "signature: no network");
+    if (!out6) return fail(e, NC_ERR_INVALID, "signature: null output");
+    cudaSetDevice(e->cfg.device);
+    CK(cudaMemsetAsync(e->dSig, 0, 6 * sizeof(unsigned long long), e->stream));
+    const uint64_t work = std::max<uint64_t>(e->v.S, e->v.nRows);
+    const unsigned blocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>((work + 255) / 256, 1), (uint64_t)e->smCount * 16);
+    k_state_signature<<<blocks, 256, 0, e->stream>>>(e->v, e->dSig); e->launches++;
+    CK(cudaMemcpyAsync(e->hSig, e->dSig, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    for (int i = 0; i < 6; i++) out6[i] = e->hSig[i];
     return NC_OK;
 }
 extern "C" int nc_reset_activities(nc_engine* e, float now) {
@@ -1561,6 +1606,7 @@ static int snap_all(nc_engine* e, bool toSnap) {
     CK(snap_copy(s.lastFire, v.lastFire, v.nRows, e->stream, toSnap)); CK(snap_copy(s.lfStart, v.lfStart, v.nRows, e->stream, toSnap));
     CK(snap_copy(s.actStart, v.actStart, v.nRows, e->stream, toSnap)); CK(snap_copy(s.potAct, v.potAct, v.nRows, e->stream, toSnap));
     CK(snap_copy(s.firings, v.firings, v.nRows, e->stream, toSnap));
+    CK(snap_copy(s.busy, v.busy, e->busyWords, e->stream, toSnap));
     CK(cudaStreamSynchronize(e->stream));
     return NC_OK;
 }
@@ -1611,7 +1657,7 @@ extern "C" int nc_tape_replay(nc_engine* e, uint32_t first, uint32_t count, floa
         dim3 g(gx, a.world);
         k_index_build<<<g, 256, 0, e->stream>>>(e->v, a);
         if (perKernel) CK(cudaEventRecord(evs[5 * k + 3], e->stream));
-        launch_synapse_pass(e, a);
+        launch_synapse_pass(e, a, std::max<uint32_t>(ts.fires, 64u));
         if (perKernel) CK(cudaEventRecord(evs[5 * k + 4], e->stream));
         k_index_reset<<<g, 256, 0, e->stream>>>(e->v, a);
         k_finish_step<<<1, 32, 0, e->stream>>>(e->v, e->dOut, 1);

@@ -61,6 +61,10 @@ NC_HD bool pick_less(float t1, unsigned long long c1, float t2, unsigned long lo
     return t1 < t2 || (t1 == t2 && c1 < c2);
 }
 
+struct SlotRow {       // 8 B: a synapse slot of this shard and the row (target neuron - row0) it belongs to
+    uint32_t slot, row;
+};
+
 struct View {
     uint64_t nGlobal, row0, nRows, S;
     const uint64_t* rowptr;
@@ -80,10 +84,14 @@ struct View {
     int32_t* head;         // per global neuron: unit index of its first record or -1
     int32_t* next;         // per unit
     uint32_t* mask;        // one bit per global neuron: fired in this window
-    uint32_t* coarse;      // one bit per word of `mask`: the word is non-zero (first level of the probe when `mask` stays in L2)
     uint32_t* evMask;      // one bit per row of this shard: has host events in this window
-    uint32_t* ownBits;     // per row and 128-slot group: 4 ballot words marking the slots that may deliver / be cleared in this window
-    uint32_t* ownSumm;     // per row: bit min(g, 31) set when group g of the row has any such slot (groups >= 31 are always written)
+    // event index: which slots can matter to a window, so that neither pass visits idle synapses
+    uint32_t* busy;        // one bit per slot: arrive != 0 (a spike is in flight or being integrated); NULL in the CPU test double
+    SlotRow* flagList;     // written by the neuron pass: slots that delivered in this window or were cleared by one of its runs
+    uint32_t* flagCtl;     // [0] = entries in flagList, [1] = overflow flag
+    uint32_t flagCap;
+    const uint64_t* cscPtr;  // per GLOBAL presynaptic neuron: its out-synapses that land in this shard are cscEnt[cscPtr[p] .. cscPtr[p+1])
+    const SlotRow* cscEnt;
     // spill area for rows with more occupied slots than fit in shared memory
     float* spillA;
     float* spillD;
@@ -108,7 +116,6 @@ struct StepArgs {
     // float comparisons of the row scan as integer compares on the bit patterns of (positive) arrival times, fixed per window:
     //   t1 - a > 2  (old enough to be cleared)  <=>  bits(a) <= clrB;     t0 < a + 2 <= t1 (requeue)  <=>  reqLoB < bits(a) <= reqHiB
     uint32_t clrB, reqLoB, reqHiB;
-    uint32_t sparseFires;  // few enough neurons fired last window that most 128-slot groups see none: worth a cheap group-level pre-test
 };
 
 struct NeuronState {
@@ -332,7 +339,17 @@ NC_HD void resolve_slot(const View& v, const StepArgs& s, uint64_t j, uint64_t r
         }
         cur = best; have = true;
     }
-    if (cleared || loaded) v.arrive[j] = newArrive;
+    if (cleared || loaded) {
+        v.arrive[j] = newArrive;
+        if (v.busy && (newArrive != 0.0f) != (cleared || a != 0.0f)) {  // keep the busy-slot index in step (integer atomics only)
+            const uint32_t bit = 1u << (uint32_t)(j & 31u);
+#if defined(__CUDA_ARCH__)
+            if (newArrive != 0.0f) atomicOr(&v.busy[j >> 5], bit); else atomicAnd(&v.busy[j >> 5], ~bit);
+#else
+            if (newArrive != 0.0f) v.busy[j >> 5] |= bit; else v.busy[j >> 5] &= ~bit;
+#endif
+        }
+    }
     if (loaded) { v.depol[j] = newDepol; v.lastStart[j] = newStart; }
     if (wChanged) v.weight[j] = w;
     if (laChanged) v.lastArr[j] = lastArr;

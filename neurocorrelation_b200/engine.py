@@ -24,7 +24,7 @@ ABI_SYMBOLS = (
     "nc_global_error", "nc_device_count", "nc_create", "nc_destroy", "nc_last_error", "nc_upload_network",
     "nc_upload_network_device", "nc_min_delay",
     "nc_set_plasticity", "nc_step", "nc_step_launch", "nc_step_collect", "nc_run_neurons", "nc_read_neurons", "nc_read_synapses", "nc_read_fires",
-    "nc_read_synapse_pots", "nc_reset_activities", "nc_detector_mean", "nc_tape_begin", "nc_tape_end", "nc_snapshot",
+    "nc_read_synapse_pots", "nc_state_signature", "nc_reset_activities", "nc_detector_mean", "nc_tape_begin", "nc_tape_end", "nc_snapshot",
     "nc_restore", "nc_tape_replay", "nc_launch_count", "nc_comm_unique_id", "nc_comm_init", "nc_set_exchange",
     "nc_selftest_powf", "nc_selftest_exp",
 )
@@ -36,7 +36,7 @@ class EngineError(RuntimeError):
 
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32), ("fire_capacity", C.c_uint32),
-                ("cand_smem", C.c_uint32), ("stream", C.c_void_p), ("reserved", C.c_uint32 * 2)]
+                ("cand_smem", C.c_uint32), ("stream", C.c_void_p), ("flag_capacity", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class StepStats(C.Structure):
@@ -80,6 +80,7 @@ def load(path=None):
     L.nc_read_synapses.argtypes = [vp, vp, vp, vp, vp, vp]
     L.nc_read_fires.argtypes = [vp, C.c_uint32, vp, vp, C.POINTER(C.c_uint32)]
     L.nc_read_synapse_pots.argtypes = [vp, C.c_float, vp, vp]
+    L.nc_state_signature.argtypes = [vp, u64p]
     L.nc_reset_activities.argtypes = [vp, C.c_float]
     L.nc_detector_mean.argtypes = [vp, vp, C.c_uint32, C.POINTER(C.c_float)]
     L.nc_tape_begin.argtypes = [vp, C.c_uint32, C.c_uint64]
@@ -203,6 +204,12 @@ class Engine:
         a = [np.zeros(max(self.S, 1), np.float32) for _ in range(2)]
         self._ck(self.L.nc_read_synapse_pots(self.h, now, a[0].ctypes.data, a[1].ctypes.data))
         return a[0][:self.S], a[1][:self.S]
+
+    def state_signature(self):
+        """The six per-field checksums tests/helpers.state_signature computes from read-back arrays, computed on the device."""
+        out = np.zeros(6, np.uint64)
+        self._ck(self.L.nc_state_signature(self.h, out))
+        return out
 
     def reset_activities(self, now):
         self._ck(self.L.nc_reset_activities(self.h, now))

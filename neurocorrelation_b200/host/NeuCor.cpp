@@ -513,6 +513,10 @@ void NeuCor::finalize() {
         }
     }
     lastFireMirror_.assign(N, NAN);
+    // the trace decays are per-object copies taken when neurons / synapses are constructed (NeuCor.cpp:369,464;
+    // NeuCor.h:236,289): later writes to the NeuCor members do nothing in the reference, so they are latched here
+    preDecayLatched_ = presynapticTraceDecay;
+    postDecayLatched_ = postsynapticTraceDecay;
 }
 
 // ---- inputs and detectors ---------------------------------------------------------------------------------
@@ -620,6 +624,7 @@ float NeuCor::getDetectorVoltage(unsigned ID) {  // VoltageDetector::getVoltage,
     VoltageDetector& d = voltageDetectors.at(ID);
     finalize();
     if (world_ > 1) throw std::logic_error("NeuCor::getDetectorVoltage: not available on a sharded network (use runSwept)");
+    if (d.near.empty()) return 0.0f / (float)d.near.size();  // nothing within the radius: nothing is run, avgV/0 = NaN (NeuCor.cpp:360-365)
     uint64_t hidden = 0;
     nc_step_stats st;
     check(nc_run_neurons(engine_, currentTime, d.near.data(), (uint32_t)d.near.size(), &hidden, &st), "nc_run_neurons");
@@ -672,6 +677,14 @@ void NeuCor::window(float t0, float t1, int flags, std::vector<nc_event>& ev) {
         if (rs_ && rs_->attached) rs_->advance(hidden);
         else { RandWindow rw; rw.skip(hidden); }
     }
+    if (recordFires) {  // (neuron, time) of every Neuron::fire of this window, all shards — the GUI's raster source (Renderer.cpp:1856-1862)
+        uint32_t n = 0;
+        const std::size_t at = firesNeuron_.size();
+        check(nc_read_fires(engine_, 0, nullptr, nullptr, &n), "nc_read_fires");
+        firesNeuron_.resize(at + n); firesTime_.resize(at + n);
+        if (n) check(nc_read_fires(engine_, n, firesNeuron_.data() + at, firesTime_.data() + at, &n), "nc_read_fires");
+        d2hBytes_ += (uint64_t)n * 8;
+    }
     lastStats_.fires += st.fires; lastStats_.deliveries += st.deliveries; lastStats_.loadsAccepted += st.loads_accepted;
     lastStats_.loadsDropped += st.loads_dropped; lastStats_.plasticityCalls += st.plasticity_calls; lastStats_.hiddenRand += st.hidden_rand_calls;
     lastStats_.neuronRuns += st.neuron_runs; lastStats_.activeVisits += st.active_visits;
@@ -681,7 +694,7 @@ float NeuCor::stepInternal(bool sweep) {  // NeuCor::run, NeuCor.cpp:583-617
     assert(0 <= runSpeed);
     if (runSpeed <= 0.0f) return 0.0f;
     finalize();
-    check(nc_set_plasticity(engine_, learningRate, presynapticFactor, postsynapticFactor, presynapticTraceDecay, postsynapticTraceDecay), "nc_set_plasticity");
+    check(nc_set_plasticity(engine_, learningRate, presynapticFactor, postsynapticFactor, preDecayLatched_, postDecayLatched_), "nc_set_plasticity");
     lastStats_ = StepStats{};
     const std::size_t N = positions.size();
     // borrow libc's generator for the duration of this call (handed back, at the position consumed, on every exit path)
@@ -697,6 +710,7 @@ float NeuCor::stepInternal(bool sweep) {  // NeuCor::run, NeuCor.cpp:583-617
         ~Borrow() { if (r) r->detach(); }
     } borrow{(rs_->usable && static_cast<int>(600.0f / runSpeed) > 1 && rs_->attach()) ? rs_ : nullptr};
     events_.clear();
+    firesNeuron_.clear(); firesTime_.clear();
     for (unsigned i = 0; i < inputHandler.size(); i++) {
         const float inputFrequency = inputArray != nullptr && i < inputArraySize ? inputArray[i] : 0.0f;
         scheduleInput(i, runSpeed, inputFrequency, events_);
@@ -748,16 +762,25 @@ float NeuCor::stepInternal(bool sweep) {  // NeuCor::run, NeuCor.cpp:583-617
         window(t0, targetTime, startFlag | (sweep ? NC_SWEEP_END : 0), events_);
     } else {
         // The window must be shorter than the smallest synaptic delay: split it. Boundaries are invisible to the
-        // semantics (no neuron is run at them); only the last sub-window carries the end sweep.
+        // semantics (no neuron is run at them); only the last sub-window carries the end sweep, the first one that is
+        // executed carries the start sweep and the events at exactly t0.  Boundaries are forced to advance by at least
+        // one float ulp; when even one ulp is no shorter than the limit (simulated time beyond ~2^23 * minDelay ms) the
+        // float clock can no longer order a spike's departure and arrival and the engine refuses to go on.
         int pieces = (int)std::ceil((double)(targetTime - t0) / ((double)limit * 0.5)) + 1;
         float a = t0;
-        for (int k = 1; k <= pieces; k++) {
+        bool first = true;
+        for (int k = 1; k <= pieces && a < targetTime; k++) {
             float b = (k == pieces) ? targetTime : (float)((double)t0 + ((double)targetTime - (double)t0) * k / pieces);
-            if (!(b > a)) continue;
+            if (!(b > a)) b = std::nextafterf(a, INFINITY);
+            if (b > targetTime) b = targetTime;
+            if (!(b - a < limit))
+                throw std::runtime_error("NeuCor::run: simulated time too large — one float ulp of the clock is no shorter than the smallest synaptic delay");
+            const bool last = !(b < targetTime);
             winEvents_.clear();
             for (auto& e : events_)
-                if ((k == 1 ? e.time >= a : e.time > a) && e.time <= b) winEvents_.push_back(e);
-            window(a, b, (k == 1 ? startFlag : 0) | ((sweep && k == pieces) ? NC_SWEEP_END : 0), winEvents_);
+                if ((first ? e.time >= a : e.time > a) && e.time <= b) winEvents_.push_back(e);
+            window(a, b, (first ? startFlag : 0) | ((sweep && last) ? NC_SWEEP_END : 0), winEvents_);
+            first = false;
             a = b;
         }
     }
@@ -799,6 +822,10 @@ void NeuCor::readNeurons(float* pot, float* act, float* lastFire, float* lastRan
 void NeuCor::readSynapses(float* weight, float* arrive, float* depol, float* lastArrival, float* lastStart) {
     finalize();
     check(nc_read_synapses(engine_, weight, arrive, depol, lastArrival, lastStart), "nc_read_synapses");
+}
+void NeuCor::stateSignature(uint64_t out6[6]) {
+    finalize();
+    check(nc_state_signature(engine_, out6), "nc_state_signature");
 }
 void NeuCor::resetActivities() {  // NeuCor.cpp:233-235
     finalize();

@@ -126,6 +126,10 @@ public:
     const std::vector<uint8_t>& csrFlags() const { return flag_; }
     void readNeurons(float* pot, float* act, float* lastFire, float* lastRan);
     void readSynapses(float* weight, float* arrive, float* depol, float* lastArrival, float* lastStart);
+    void stateSignature(uint64_t out6[6]);  // six per-field checksums of this shard's state, computed on the device
+    bool recordFires = false;       // keep (neuron, time) of every fire of the last run() — the raster source (Renderer.cpp:1856-1862)
+    const std::vector<uint32_t>& lastFiresNeuron() const { return firesNeuron_; }
+    const std::vector<float>& lastFiresTime() const { return firesTime_; }
     std::vector<float> inputLastFire() const;
     std::vector<std::vector<uint32_t>> inputNear() const;
     struct StepStats { uint64_t fires, deliveries, loadsAccepted, loadsDropped, plasticityCalls, hiddenRand, neuronRuns, activeVisits; };
@@ -177,6 +181,9 @@ private:
     char commId_[128]; bool haveCommId_ = false;
     int (*xchgFn_)(void*, const void*, void*, uint64_t) = nullptr; void* xchgCtx_ = nullptr;
     float minDelay_ = 0.0f;
+    float preDecayLatched_ = 0.75f, postDecayLatched_ = 0.65f;
+    std::vector<uint32_t> firesNeuron_;
+    std::vector<float> firesTime_;
     std::vector<float> lastFireMirror_;
     std::vector<nc_event> events_, winEvents_;
     std::vector<float> schedScratch_;

@@ -113,6 +113,15 @@ int nch_read_neurons(void* hv, float* pot, float* act, float* lastFire, float* l
 int nch_read_synapses(void* hv, float* w, float* arrive, float* depol, float* lastArr, float* lastStart) {
     return guard([&] { B->readSynapses(w, arrive, depol, lastArr, lastStart); });
 }
+int nch_state_signature(void* hv, uint64_t* out6) { return guard([&] { B->stateSignature(out6); }); }
+int nch_record_fires(void* hv, int on) { return guard([&] { B->recordFires = on != 0; }); }
+uint64_t nch_last_fires_count(void* hv) { return B->lastFiresNeuron().size(); }
+int nch_last_fires(void* hv, uint32_t* neuron, float* time) {
+    return guard([&] {
+        auto& n = B->lastFiresNeuron(); auto& t = B->lastFiresTime();
+        if (n.size()) { memcpy(neuron, n.data(), n.size() * 4); memcpy(time, t.data(), t.size() * 4); }
+    });
+}
 unsigned nch_input_count(void* hv) { return (unsigned)B->inputNear().size(); }
 uint64_t nch_input_near_count(void* hv, unsigned i) { return B->inputNear().at(i).size(); }
 int nch_input_near(void* hv, unsigned i, uint32_t* out) {

@@ -8,7 +8,7 @@
  * engine (one global time-ordered queue, processed one event at a time, like the reference),
  * so agreement between the two is evidence and not a tautology.
  *
- * Parity pin: tests/test_oracle_vs_ref.py checks this file bit-for-bit (every neuron and synapse
+ * Parity pin: tests/test_oracle_pinned.py checks this file bit-for-bit (every neuron and synapse
  * field, every step) against oracle/_ref (the reference's own NeuCor.cpp compiled unmodified, and
  * its tie-canonicalised build) and against the committed golden fixtures in tests/golden/ that
  * were generated from oracle/_ref by tests/golden/make_golden.py.  The reference ships no tests
@@ -390,6 +390,26 @@ static uint64_t fnv(uint64_t h, const void *p, size_t n) {
     return h;
 }
 /* same definition as ref_state_hash in oracle/ref_harness.cpp */
+/* The six position-weighted checksums of tests/helpers.state_signature (and of the engine's nc_state_signature):
+   sum of bits(x[i]) * (i + 1) * 0x9E3779B97F4A7C15 mod 2^64 for pot, act, lastFire, weight, arrive (+ depol of busy slots), lastArr. */
+void orc_state_signature(Oracle *o, uint64_t *out) {
+    const uint64_t C = 0x9E3779B97F4A7C15ull;
+    uint32_t u;
+    for (int i = 0; i < 6; i++) out[i] = 0;
+    for (uint64_t q = 0; q < o->N; q++) {
+        const uint64_t k = (q + 1) * C;
+        memcpy(&u, &o->pot[q], 4); out[0] += (uint64_t)u * k;
+        memcpy(&u, &o->act[q], 4); out[1] += (uint64_t)u * k;
+        memcpy(&u, &o->lastFire[q], 4); out[2] += (uint64_t)u * k;
+    }
+    for (uint64_t s = 0; s < o->S; s++) {
+        const uint64_t k = (s + 1) * C;
+        memcpy(&u, &o->weight[s], 4); out[3] += (uint64_t)u * k;
+        memcpy(&u, &o->arrive[s], 4); out[4] += (uint64_t)u * k;
+        if (o->arrive[s] != 0) { memcpy(&u, &o->depol[s], 4); out[4] += (uint64_t)u * k; }
+        memcpy(&u, &o->lastArr[s], 4); out[5] += (uint64_t)u * k;
+    }
+}
 void orc_state_hash(Oracle *o, uint64_t *out) {
     uint64_t h0 = 1469598103934665603ull, h1 = h0, h2 = h0, h3 = h0, h4 = h0, h5 = h0;
     for (uint64_t q = 0; q < o->N; q++) {

@@ -61,6 +61,7 @@ def lib():
     L.orc_read_input_lastfire.argtypes = [vp, f32p]
     L.orc_stats.argtypes = [vp, u64p]
     L.orc_state_hash.argtypes = [vp, u64p]
+    L.orc_state_signature.argtypes = [vp, u64p]
     _L = L
     return L
 
@@ -147,6 +148,12 @@ class OracleBrain:
         out = np.zeros(8, np.uint64)
         self.L.orc_stats(self.h, out)
         return dict(zip(STAT_NAMES, (int(x) for x in out)))
+
+    def state_signature(self):
+        """== tests/helpers.state_signature(read_neurons(), read_synapses()), computed in C."""
+        out = np.zeros(6, np.uint64)
+        self.L.orc_state_signature(self.h, out)
+        return out
 
     def state_hash(self):
         out = np.zeros(6, np.uint64)

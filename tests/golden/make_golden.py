@@ -14,6 +14,15 @@
       the essay's only quantitative known answer — w(0->1) rises to 1, w(0->2) falls to 0 (essay §2.5.1).
   syn_<N>x<K>.npz     a C2-recipe synthetic network (neurocorrelation_b200.networks) built in the reference through
       createNeuron/createSynapse and stepped in sweep mode; same contents as the C1 files.
+  c1_long_seed<seed>_<flags>.npz   the C1 recipe at the STATED horizon (BASELINE.json configs[0]):
+      10 000 steps, seeds {1,2,4,8,9}, flags raw and normalised.  Signature-only: per step one folded 64-bit word
+      (helpers.fold_signature) + the detector voltage + the rates, the six field signatures every LONG_DETAIL steps,
+      the fire raster (neuron, step) and the final weights/potentials.
+  c1_control_h.npz    negative control for the horizon machinery: seed 7, dt = 2^-5, fixed
+      50/50/50 Hz inputs — the unmodified reference and its tie-canonicalised build part ways at step H = 1030 (an
+      equal-time tie that interacts; found by searching seeds 3..9 with this harness: 5 -> 1073, 7 -> 1030, the others
+      none within 3000 steps).  Holds the signatures of BOTH builds: an engine with the canonical tie order must match the
+      canonicalised build at every step and the unmodified one up to H only.
 Both the unmodified and the tie-canonicalised build are run; `horizon` is the first step at which they differ
 (-1: none within the run) and the stored signatures are the canonicalised build's.
 """
@@ -144,7 +153,73 @@ def make_few_neurons(steps=8000):
     print("few_neurons: final weights ref", out["ref"][-1], "canon", out["ref_canon"][-1])
 
 
+def run_c1_long(kind, seed, steps, flags, dt=DT_DEFAULT, fixed_rates=None):
+    from helpers import LONG_DETAIL, fold_signature
+    L = refbind._lib(kind)
+    L.ref_srand(seed)
+    b = RefBrain(750, kind)
+    if flags == "normalised":
+        b.normalise_flags()
+    drv = StandardDriver(b, b.rand, dt=dt)
+    if fixed_rates is not None:
+        drv.rates[:] = fixed_rates
+        for i, v in enumerate(drv.rates):
+            b.set_rate(i, float(v))
+    net, ins = b.export_network(), b.export_inputs()
+    b.srand(777)
+    folded, detail, volts, rates, raster = [], [], [], [], []
+    for k in range(steps):
+        t0 = b.time()
+        volts.append(drv.step() if fixed_rates is None else b.step())
+        rates.append(drv.rates.copy())
+        n, s = b.read_neurons(), b.read_synapses()
+        sig = state_signature(n, s)
+        folded.append(fold_signature(sig))
+        if k % LONG_DETAIL == 0 or k == steps - 1:
+            detail.append(sig)
+        raster.append(np.stack([np.nonzero(n["lastFire"] > t0)[0].astype(np.uint16), np.full(int((n["lastFire"] > t0).sum()), k, np.uint16)], 1))
+    return dict(net=net, ins=ins, folded=np.array(folded, np.uint64), detail=np.array(detail, np.uint64), volts=np.array(volts, np.float32),
+                rates=np.array(rates, np.float32), raster=np.concatenate(raster).astype(np.uint16), final_n=n, final_s=s,
+                time=np.float32(b.time()))
+
+
+def save_long(path, ref, can, extra):
+    net, ins = can["net"], can["ins"]
+    diff = np.nonzero(ref["folded"] != can["folded"])[0]
+    horizon = int(diff[0]) if len(diff) else -1
+    d = dict(N=net["N"], S=net["S"], rowptr=net["rowptr"], pre=net["pre"], weight=net["weight"], length=net["length"],
+             flag=net["flag"], positions=net["positions"], G=len(ins), folded=can["folded"], detail=can["detail"], volts=can["volts"],
+             rates=can["rates"], raster=can["raster"], horizon=horizon, final_pot=can["final_n"]["pot"], final_lastFire=can["final_n"]["lastFire"],
+             final_weight=can["final_s"]["weight"], final_time=can["time"], **extra)
+    if horizon >= 0:  # keep the unmodified build's view too: what an engine WITHOUT the canonical order would have to match
+        d["folded_ref"] = ref["folded"]
+        d["raster_ref"] = ref["raster"]
+    for i, inp in enumerate(ins):
+        d["near_%d" % i] = inp["near"]
+    np.savez_compressed(path, **d)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB, horizon", horizon, "fires", len(can["raster"]), flush=True)
+
+
+def make_c1_long(seed, flags, steps=10000):
+    ref = run_c1_long("ref", seed, steps, flags)
+    can = run_c1_long("ref_canon", seed, steps, flags)
+    save_long(os.path.join(HERE, "c1_long_seed%d_%s.npz" % (seed, flags)), ref, can, dict(seed=seed, dt=DT_DEFAULT, steps=steps, flags=flags))
+
+
+def make_control(seed=7, steps=1200, dt=0.03125):
+    fixed = np.array([50.0, 50.0, 50.0], np.float32)
+    ref = run_c1_long("ref", seed, steps, "normalised", dt=dt, fixed_rates=fixed)
+    can = run_c1_long("ref_canon", seed, steps, "normalised", dt=dt, fixed_rates=fixed)
+    save_long(os.path.join(HERE, "c1_control_h.npz"), ref, can, dict(seed=seed, dt=dt, steps=steps, flags="normalised"))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) >= 2 and sys.argv[1] == "long":
+        make_c1_long(int(sys.argv[2]), sys.argv[3])
+        sys.exit(0)
+    if len(sys.argv) >= 2 and sys.argv[1] == "control":
+        make_control(*[int(x) for x in sys.argv[2:3]])
+        sys.exit(0)
     what = sys.argv[1:] or ["c1", "syn", "few"]
     if "c1" in what:
         make_c1(1, 3000, "normalised")

@@ -40,6 +40,19 @@ def state_signature(neurons, synapses):
 SIG_NAMES = ("pot", "act", "lastFire", "weight", "arrive/depol", "lastArr")
 
 
+def fold_signature(sig):
+    """The six field signatures of one step folded into one 64-bit word (FNV-style xor-multiply) — what the 10 000-step
+    fixtures store per step; the six separate words are kept every LONG_DETAIL steps to name the field that differs."""
+    h = np.uint64(0xCBF29CE484222325)
+    with np.errstate(over="ignore"):
+        for x in sig:
+            h = (h ^ np.uint64(x)) * np.uint64(0x100000001B3)
+    return h
+
+
+LONG_DETAIL = 250
+
+
 def same_bits(a, b):
     return np.array_equal(np.ascontiguousarray(a).view(np.uint32), np.ascontiguousarray(b).view(np.uint32))
 
@@ -142,3 +155,42 @@ def lockstep(make_a, make_b, steps, srand_each):
         if bad:
             return k, bad, stats_a, b.stats()
     return -1, [], stats_a, b.stats()
+
+
+def run_c1_long_golden(brain, z, near, keyword_near, driver_draws=3, steps=None, sig_fn=None, fires_fn=None):
+    """Drives `brain` (already holding the fixture's network) through a 10 000-step C1 fixture (tests/golden/c1_long_*.npz,
+    c1_control_h.npz): recorded per-step rates, libc srand(777) for the core's own draws, `driver_draws` rand() per step
+    consumed where the reference's driver consumed them (main.cpp:100-105).  Per step: the folded state signature, the
+    detector voltage and — when fires_fn is given — the spike raster (neurons with a fire in the window, the GUI's rule
+    Renderer.cpp:1856-1862) against the fixture.  Returns (first bad step or -1, what differed)."""
+    rates = z["rates"]
+    steps = int(z["steps"]) if steps is None else steps
+    w = NearInputs(brain, near, keyword_near)
+    w.set_inputs(rates[0].copy())
+    brain.enable_sweep()
+    brain.set_params(float(z["dt"]), 1.0, False)
+    raster = z["raster"]
+    bounds = np.searchsorted(raster[:, 1], np.arange(steps + 1))
+    sig_fn = sig_fn or (lambda: state_signature(brain.read_neurons(), brain.read_synapses()))
+    libc.srand(777)
+    for k in range(steps):
+        for _ in range(driver_draws):
+            libc.rand()
+        for i, v in enumerate(rates[k]):
+            brain.set_rate(i, float(v))
+        volt = brain.step()
+        sig = sig_fn()
+        if fold_signature(sig) != z["folded"][k]:
+            what = ["state"]
+            if k % LONG_DETAIL == 0 or k == steps - 1:
+                d = z["detail"][min(k // LONG_DETAIL + (0 if k % LONG_DETAIL == 0 else 1), len(z["detail"]) - 1)]
+                what = [n for n, a, b in zip(SIG_NAMES, sig, d) if a != b]
+            return k, what
+        if np.float32(volt).view(np.uint32) != z["volts"][k].view(np.uint32):
+            return k, ["detector voltage"]
+        if fires_fn is not None:
+            got = np.unique(fires_fn())
+            want = raster[bounds[k]:bounds[k + 1], 0]
+            if not np.array_equal(got.astype(np.uint32), want.astype(np.uint32)):
+                return k, ["raster"]
+    return -1, []

@@ -339,6 +339,22 @@ int nc_read_synapse_pots(nc_engine* e, float, float* pre, float* post) {
     if (post) memset(post, 0, e->v.S * 4);
     return NC_OK;
 }
+int nc_state_signature(nc_engine* e, uint64_t* out) {
+    const unsigned long long C = 0x9E3779B97F4A7C15ull;
+    for (int i = 0; i < 6; i++) out[i] = 0;
+    for (uint64_t i = 0; i < e->v.nRows; i++) {
+        out[0] += (unsigned long long)as_u32(e->potAct[i].x) * ((i + 1) * C);
+        out[1] += (unsigned long long)as_u32(e->potAct[i].y) * ((i + 1) * C);
+        out[2] += (unsigned long long)as_u32(e->lastFire[i]) * ((i + 1) * C);
+    }
+    for (uint64_t j = 0; j < e->v.S; j++) {
+        out[3] += (unsigned long long)as_u32(e->weight[j]) * ((j + 1) * C);
+        out[4] += (unsigned long long)as_u32(e->arrive[j]) * ((j + 1) * C);
+        if (e->arrive[j] != 0.0f) out[4] += (unsigned long long)as_u32(e->depol[j]) * ((j + 1) * C);
+        out[5] += (unsigned long long)as_u32(e->lastArr[j]) * ((j + 1) * C);
+    }
+    return NC_OK;
+}
 int nc_reset_activities(nc_engine* e, float now) {
     for (uint64_t i = 0; i < e->v.nRows; i++) { e->firings[i] = 0; e->actStart[i] = now; e->potAct[i].y = 0.0f; }
     return NC_OK;

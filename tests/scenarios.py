@@ -6,8 +6,8 @@
 import numpy as np
 
 import neurocorrelation_b200 as nb
-from helpers import (NearInputs, compare_states, libc, load_golden, lockstep, run_c1_golden, same_bits, state_signature,
-                     synthetic_drive)
+from helpers import (NearInputs, compare_states, libc, load_golden, lockstep, run_c1_golden, run_c1_long_golden, same_bits,
+                     state_signature, synthetic_drive)
 from neurocorrelation_b200.networks import synthetic_network
 from oracle.orcbind import OracleBrain
 
@@ -26,6 +26,31 @@ def c1_golden(library, name, steps, check_every=1, cand_smem=0):
         raster = z["raster"]
         assert g.stats()["fires"] >= len(raster)
     g.close()
+
+
+def c1_long_golden(library, name, driver_draws=3, steps=None, device_signature=True):
+    """The C1 recipe at the stated horizon (10 000 steps) against a fixture recorded from the reference: state signature,
+    detector voltage and explicit spike raster (nc_read_fires) at EVERY step; final potentials / weights bit-exact and
+    the north-star's tolerance figures reported.  Returns the brain's counters."""
+    z, net, near = load_golden(name)
+    g = nb.NeuCor.from_network(net, library=library)
+    g.record_fires(True)
+    # the device-side signature must be the same six words as the host-side one computed from read-back arrays
+    sig_fn = g.state_signature if device_signature else None
+    bad, what = run_c1_long_golden(g, z, near, True, driver_draws=driver_draws, steps=steps, sig_fn=sig_fn, fires_fn=lambda: g.last_fires()[0])
+    assert bad == -1, "first divergence from the reference at step %d in %s" % (bad, what)
+    st = g.stats()
+    if steps is None or steps == int(z["steps"]):
+        n, s = g.read_neurons(), g.read_synapses()
+        assert np.array_equal(state_signature(n, s), g.state_signature())
+        assert np.float32(g.time()).view(np.uint32) == z["final_time"].view(np.uint32)
+        # north_star: spike trains and counts bit-exact; potentials / weights within 1e-5 relative after 10k steps — here: identical
+        assert same_bits(n["pot"], z["final_pot"]) and same_bits(n["lastFire"], z["final_lastFire"]) and same_bits(s["weight"], z["final_weight"])
+        rel = np.max(np.abs(s["weight"] - z["final_weight"]) / np.maximum(np.abs(z["final_weight"]), 1e-30))
+        assert rel <= 1e-5
+        assert st["fires"] >= len(z["raster"])
+    g.close()
+    return st, z
 
 
 def synthetic_vs_oracle(library, N, K, steps, seed=3, dt=0.0625, lr=1.0, cand_smem=0, run_all=False):
@@ -49,6 +74,41 @@ def synthetic_vs_oracle(library, N, K, steps, seed=3, dt=0.0625, lr=1.0, cand_sm
 
     bad, fields, so, sg = lockstep(make_o, make_g, steps, lambda: None)
     assert bad == -1, "first divergence from the oracle at step %d in %s" % (bad, fields)
+    assert so == sg, (so, sg)
+    return so
+
+
+def synthetic_vs_oracle_signatures(library, N, K, steps, seed=3):
+    """Oracle lock-step at sizes where moving the whole state to the host every step would dominate: per step the six
+    field signatures (computed in C by the oracle, on the device by the engine), the mean potential and the explicit
+    fire raster (the oracle's fire log against nc_read_fires: same neurons, same times)."""
+    net = synthetic_network(N, K, seed=seed)
+    o = OracleBrain(net)
+    synthetic_drive(o, net, False)
+    o.enable_fire_log(1 << 22)
+    want = []
+    for k in range(steps):
+        v = o.step()
+        fn, ft = o.fire_log()
+        order = np.lexsort((ft, fn))
+        want.append((np.float32(v), o.state_signature(), fn[order], ft[order]))
+    so = o.stats()
+    o.close()
+    g = nb.NeuCor.from_network(net, library=library)
+    synthetic_drive(g, net, True)
+    g.record_fires(True)
+    for k in range(steps):
+        v = g.step()
+        wv, wsig, wn, wt = want[k]
+        assert np.array_equal(g.state_signature(), wsig), "step %d: state differs" % k
+        assert np.float32(v).view(np.uint32) == wv.view(np.uint32), "step %d: mean potential" % k
+        fn, ft = g.last_fires()
+        order = np.lexsort((ft, fn))
+        assert np.array_equal(fn[order], wn) and same_bits(ft[order], wt), "step %d: fire raster differs" % k
+    sg = g.stats()
+    # the signatures are the same six words the host computes from read-back arrays
+    assert np.array_equal(state_signature(g.read_neurons(), g.read_synapses()), g.state_signature())
+    g.close()
     assert so == sg, (so, sg)
     return so
 
@@ -108,8 +168,12 @@ def detector_and_reset(library):
     for b, kw in ((o, False), (g, True)):
         synthetic_drive(b, net, kw)
         b.add_input_offset(0, 1.5)
+        if kw:  # a detector with nothing in range: getDetectorVoltage runs NO neuron and returns NaN (NeuCor.cpp:359-366)
+            b.add_detector(1e6, 1e6, 1e6, 0.5)
         out = []
         for k in range(300):
+            if kw and k % 7 == 3:
+                assert np.isnan(b.detector_voltage(0))
             if k == 100:
                 b.set_input_enabled(0, False)
             if k == 150:

@@ -15,6 +15,13 @@ def test_c1_golden_seed2_raw_flags(mock_host_lib):
     scenarios.c1_golden(mock_host_lib, "c1_seed2_raw.npz", 2000, check_every=1)
 
 
+def test_control_fixture_through_the_host_class(mock_host_lib):
+    """The horizon negative control (tie at step 1030) through the host class + the test double: canonical order, explicit
+    raster via nc_read_fires, the (model's) nc_state_signature."""
+    st, z = scenarios.c1_long_golden(mock_host_lib, "c1_control_h.npz", driver_draws=0)
+    assert int(z["horizon"]) == 1030
+
+
 def test_synthetic_dense_activity(mock_host_lib):
     st = scenarios.synthetic_vs_oracle(mock_host_lib, 800, 50, 500)
     assert st["deliveries"] > 50_000 and st["loads_dropped"] > 0 and st["hidden_rand"] > 0

@@ -5,7 +5,7 @@ Bit-exact on every field of every neuron and synapse at every step."""
 import numpy as np
 import pytest
 
-from helpers import GOLDEN, libc, load_golden, lockstep, run_c1_golden, NearInputs
+from helpers import GOLDEN, libc, load_golden, lockstep, run_c1_golden, run_c1_long_golden, NearInputs
 from oracle.orcbind import OracleBrain
 
 
@@ -35,6 +35,30 @@ def test_oracle_matches_reference_golden_synthetic():
         sig = state_signature(o.read_neurons(), o.read_synapses())
         assert np.array_equal(sig, z["sigs"][k]), "step %d" % k
         assert np.float32(v).view(np.uint32) == z["volts"][k].view(np.uint32)
+
+
+@pytest.mark.parametrize("name", ["c1_long_seed8_normalised.npz", "c1_long_seed9_raw.npz"])
+def test_oracle_matches_reference_at_stated_horizon(name):
+    """10 000 steps (BASELINE.json configs[0]): the oracle's state signature, detector voltage and spike raster at every
+    step against the fixture recorded from the reference itself."""
+    z, net, near = load_golden(name)
+    o = OracleBrain(net)
+    o.enable_fire_log(1 << 16)
+    bad, what = run_c1_long_golden(o, z, near, False, sig_fn=o.state_signature, fires_fn=lambda: o.fire_log()[0])
+    assert bad == -1, "first divergence at step %d in %s" % (bad, what)
+    assert int(z["horizon"]) == -1
+
+
+def test_oracle_follows_canonical_order_past_the_horizon():
+    """Negative control: the unmodified reference leaves the tie-canonicalised build at step H = 1030; the oracle stays with
+    the canonicalised build to the end."""
+    z, net, near = load_golden("c1_control_h.npz")
+    o = OracleBrain(net)
+    o.enable_fire_log(1 << 16)
+    bad, what = run_c1_long_golden(o, z, near, False, driver_draws=0, sig_fn=o.state_signature, fires_fn=lambda: o.fire_log()[0])
+    assert bad == -1, (bad, what)
+    H = int(z["horizon"])
+    assert H == 1030 and np.array_equal(z["folded"][:H], z["folded_ref"][:H]) and z["folded"][H] != z["folded_ref"][H]
 
 
 def test_golden_horizons_recorded():

@@ -151,6 +151,12 @@ int nc_restore(nc_engine* e);
  * fire exchange (may be NULL; asking for them adds event records between the launches). */
 int nc_tape_replay(nc_engine* e, uint32_t first, uint32_t count, float* ms_total, float* ms_pass1, float* ms_pass2,
                    float* ms_exchange, uint64_t* hidden_rand_calls, nc_step_stats* stats_or_null);
+/* Per-kernel sums [ms] of the last nc_tape_replay that asked for per-kernel times:
+ * out4 = { k_stage, k_neuron_pass, fire exchange, synapse kernels (loads + rows + flagged) }. */
+int nc_replay_breakdown(const nc_engine* e, float* out4);
+/* Work done through the event index since the last call: out2 = { busy slots the staging kernel looked at,
+ * flag-list entries (slots that delivered or were cleared) }.  For the traffic model of bench.py. */
+int nc_index_stats(nc_engine* e, uint64_t* out2);
 /* Number of kernel launches issued by this engine since creation. */
 uint64_t nc_launch_count(const nc_engine* e);
 

@@ -78,8 +78,7 @@ __device__ __forceinline__ void warp_neuron_run(const View& v, NeuronState& n, C
                         if (2.0f < off) {       // NeuCor.cpp:697 — the slot becomes idle; leave the when-and-why for the synapse pass
                             cv.A(c) = -a;
                             uint64_t sidx = rs + cv.J(c);
-                            v.arrive[sidx] = __uint_as_float(sentinel);
-                            v.depol[sidx] = T;
+                            v.ad[sidx] = make_float2(__uint_as_float(sentinel), T);
                         }
                     }
                 }
@@ -157,11 +156,11 @@ __device__ __forceinline__ uint32_t stage_row(const View& v, const StepArgs& s, 
         if (!__any_sync(FULL, word != 0u)) continue;
         // which of this lane's busy slots have arrived: 0 < arrive <= t1 as ONE integer compare on the bit pattern
         // (arrive times are positive floats: (bits - 1) < bits(t1)); the others are still travelling
-        const float* ap = v.arrive + (w << 5);
+        const float2* ap = v.ad + (w << 5);
         uint32_t im = 0u;
         for (uint32_t m = word; m; m &= m - 1u) {
             const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
-            const uint32_t ab = __float_as_uint(ap[b]);
+            const uint32_t ab = __float_as_uint(ap[b].x);
             if (ab - 1u < t1b) {
                 im |= 1u << b;
                 ev |= (ab > t0b) || (ab > s.reqLoB && ab <= s.reqHiB);
@@ -180,9 +179,9 @@ __device__ __forceinline__ uint32_t stage_row(const View& v, const StepArgs& s, 
         const uint32_t rel0 = (uint32_t)((w << 5) - rs);  // (32-bit wrap intended for the row's first, partial word)
         for (uint32_t m = im; m; m &= m - 1u) {
             const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
-            const float a = ap[b];  // (second touch: L1 hit)
+            const float a = ap[b].x;  // (second touch: L1 hit)
             const uint32_t jr = rel0 + b;
-            if (SPILL) { cv.A(pos) = a; cv.D(pos) = v.depol[rs + jr]; cv.J(pos) = jr; }
+            if (SPILL) { cv.A(pos) = a; cv.D(pos) = v.ad[rs + jr].y; cv.J(pos) = jr; }
             else if (pos < room) { pa[pos] = a; pj[pos] = jbase + jr; }  // depol is gathered for the whole batch afterwards
             pos++;
         }
@@ -212,6 +211,113 @@ __device__ __forceinline__ void flag_reserve(const View& v, uint32_t mine, uint3
     at = base + inc - mine;
 }
 
+// ---- staging kernel ------------------------------------------------------------------------------------------
+// The occupied slots of every row, found through the busy-slot index and written — per tile of 32 rows, in row order — to
+// the tile's staging region for k_neuron_pass.  Separate from the replay so that it can run at full occupancy (it is all
+// memory latency: index word -> gather of the (arrive, depol) records of the set bits): a warp streams the tile's index
+// words 32 at a time (1024 slots), lists the set bits in shared memory so that the gathers are spread evenly over the
+// lanes whatever the bit pattern, keeps the slots that have arrived (0 < arrive <= t1, one integer compare; the others are
+// still travelling) and counts them per row with a ballot walk over the tile's row ends.
+#define NC_STG_WARPS 8
+__global__ void __launch_bounds__(NC_STG_WARPS * 32, 8) k_stage(View v, StepArgs s) {
+    __shared__ uint16_t slist[NC_STG_WARPS][1024];
+    const uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint16_t* list = slist[threadIdx.x >> 5];
+    const uint32_t t1b = __float_as_uint(s.t1);
+    const uint64_t nTiles = (v.nRows + 31) >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    unsigned long long busySeen = 0ull;  // set bits of the index this warp looked at (reported by nc_index_stats)
+    for (;;) {
+        uint32_t t32 = 0;
+        if (lane == 0) t32 = atomicAdd(&v.tileCtr[1], 1u);
+        const uint64_t tile = __shfl_sync(FULL, t32, 0);
+        if (tile >= nTiles) break;
+        const uint64_t rowBase = tile << 5;
+        const uint32_t nr = (uint32_t)min((uint64_t)32, v.nRows - rowBase);
+        const uint64_t myRe = v.rowptr[rowBase + min(lane, nr - 1u) + 1u];  // end of this lane's row (lanes >= nr repeat the last row)
+        const uint64_t tb = v.rowptr[rowBase];
+        const uint64_t te = __shfl_sync(FULL, myRe, 31);
+        const uint64_t reg = tile * v.stCap;
+        const uint64_t wBeg = tb >> 5, wEnd = (te + 31) >> 5;
+        uint32_t used = 0, myCnt = 0, rcur = 0;
+        bool overflow = false;
+        uint3 next = make_uint3(0u, 0u, 0x7f800000u);
+        if (wBeg + lane < wEnd) next = make_uint3(__ldcs(v.busy + wBeg + lane), __ldcs(v.arrived + wBeg + lane), __ldcs(v.wordNext + wBeg + lane));
+        for (uint64_t wb = wBeg; wb < wEnd && !overflow; wb += 32) {
+            const uint64_t w = wb + lane;
+            uint32_t word = next.x, arr = next.y;
+            const uint32_t nx = next.z;
+            next = make_uint3(0u, 0u, 0x7f800000u);  // the next 1024 slots' words are on their way while these are gathered
+            if (w + 32 < wEnd) next = make_uint3(__ldcs(v.busy + w + 32), __ldcs(v.arrived + w + 32), __ldcs(v.wordNext + w + 32));
+            bool whole = true;  // the word lies inside the tile (a word that straddles two tiles is masked by each of them)
+            if (w == wBeg && (tb & 31u)) { word &= FULL << (uint32_t)(tb & 31u); whole = false; }
+            if (w == wEnd - 1 && (te & 31u)) { word &= (1u << (uint32_t)(te & 31u)) - 1u; whole = false; }
+            arr &= word;
+            // Slots still in flight are not looked at until the word's earliest arrival bound says one of them may have landed
+            // (0.8 % of the words per step at C3): then this lane checks its in-flight slots, marks the arrived ones and renews the bound.
+            const uint32_t infl = word & ~arr;
+            if (infl && nx <= t1b) {
+                uint32_t im = 0u, nmin = 0x7f800000u;
+                for (uint32_t m = infl; m; m &= m - 1u) {
+                    const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
+                    const uint32_t ab = __float_as_uint(v.ad[(w << 5) + b].x);
+                    if (ab <= t1b) im |= 1u << b; else nmin = min(nmin, ab);
+                }
+                busySeen += (unsigned long long)__popc(infl);  // (per-lane count, summed over the warp at the end)
+                if (im) atomicOr(&v.arrived[w], im);
+                if (whole) v.wordNext[w] = nmin;  // (a straddling word keeps its old, lower bound: it is simply looked at every window)
+                arr |= im;
+            }
+            __syncwarp();
+            word = arr;  // the slots whose spike has arrived: these are staged
+            const uint32_t c = __popc(word);
+            uint32_t inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(FULL, inc, o);
+                if (lane >= (uint32_t)o) inc += y;
+            }
+            const uint32_t tot = __shfl_sync(FULL, inc, 31);
+            if (!tot) continue;
+            busySeen += c;
+            uint32_t p = inc - c;
+            for (uint32_t m = word; m; m &= m - 1u) list[p++] = (uint16_t)((lane << 5) | ((uint32_t)__ffs((int)m) - 1u));
+            __syncwarp();
+            for (uint32_t base = 0; base < tot; base += 32) {
+                const uint32_t i = base + lane;
+                const bool have = i < tot;
+                const uint64_t slot = (wb << 5) + (have ? (uint32_t)list[i] : 0u);
+                float2 ad = make_float2(0.0f, 0.0f);
+                if (have) ad = v.ad[slot];
+                const bool is = have && (__float_as_uint(ad.x) - 1u < t1b);
+                const uint32_t m = __ballot_sync(FULL, is);
+                if (!m) continue;
+                const uint32_t n = (uint32_t)__popc(m);
+                if (used + n > v.stCap) { overflow = true; break; }
+                if (is) {
+                    const uint64_t at = reg + used + (uint32_t)__popc(m & lt);
+                    v.stAD[at] = ad;
+                    v.stJ[at] = (uint32_t)(slot - tb);
+                }
+                used += n;
+                uint32_t rem = m;  // per-row counts: the entries ascend in slot order, so do the rows
+                while (rem) {
+                    const uint64_t re_r = __shfl_sync(FULL, myRe, rcur);
+                    const uint32_t inrow = __ballot_sync(FULL, is && slot < re_r) & rem;
+                    if (lane == rcur) myCnt += (uint32_t)__popc(inrow);
+                    rem &= ~inrow;
+                    if (rem) rcur++;
+                }
+            }
+            __syncwarp();
+        }
+        if (lane < nr) v.stCnt[rowBase + lane] = overflow ? 0xffffffffu : myCnt;
+    }
+    for (int o = 16; o > 0; o >>= 1) busySeen += __shfl_xor_sync(FULL, busySeen, o);
+    if (lane == 0 && busySeen) atomicAdd(&v.stats[8], busySeen);
+}
+
 // host events of neuron q: [evLo, evHi) in the (neuron, time)-sorted list (bit set by k_mark_events for rows that have any)
 __device__ __forceinline__ void host_event_range(const View& v, const StepArgs& s, uint64_t row, uint32_t q, uint32_t& evLo, uint32_t& evHi) {
     evLo = 0; evHi = 0;
@@ -239,6 +345,7 @@ __device__ void warp_row(const View& v, const StepArgs& s, uint64_t row, CandVie
     uint32_t evLo, evHi;
     host_event_range(v, s, row, q, evLo, evHi);
     NeuronState n;
+    float lfS0;
     {
         float2 pa = v.potAct[row];
         n.pot = pa.x; n.act = pa.y;
@@ -247,6 +354,7 @@ __device__ void warp_row(const View& v, const StepArgs& s, uint64_t row, CandVie
         n.sched = __uint_as_float(0x7fc00000u);
         for (uint32_t e = evLo; e < evHi; e++)
             if (s.ev[e].kind == 2u && (s.ev[e].index_or_flags & 1u)) n.sched = s.ev[e].time;
+        lfS0 = n.lastFire;
         if (lane == 0) v.lfStart[row] = n.lastFire;
     }
     // ---- replay in-window events in canonical order ----
@@ -260,8 +368,7 @@ __device__ void warp_row(const View& v, const StepArgs& s, uint64_t row, CandVie
             for (uint32_t c = lane; c < cnt; c += 32) {
                 float a = fabsf(cv.A(c));
                 if (a > s.t0) {  // delivery in this window (a <= t1 by staging)
-                    uint32_t p = v.pre[rs + cv.J(c)] & 0x7fffffffu;
-                    unsigned long long code = (1ull << 32) | p;
+                    unsigned long long code = (1ull << 32) | cv.J(c);  // in-row index: ascends with the presynaptic ID
                     if ((first || pick_less(curT, curC, a, code)) && pick_less(a, code, best.t, best.code)) {
                         best.t = a; best.code = code; best.src = c;
                     }
@@ -325,7 +432,7 @@ __device__ void warp_row(const View& v, const StepArgs& s, uint64_t row, CandVie
         if (c < cnt) { const float a = cv.A(c); f = (a < 0.0f) || (a > s.t0); }
         uint32_t at;
         flag_reserve(v, f ? 1u : 0u, lane, at);
-        if (f && at < v.flagCap) { SlotRow sr; sr.slot = (uint32_t)(rs + cv.J(c)); sr.row = (uint32_t)row; v.flagList[at] = sr; }
+        if (f && at < v.flagCap) { FlagEnt fe; fe.slot = (uint32_t)(rs + cv.J(c)); fe.row = (uint32_t)row; fe.lfStart = lfS0; fe.inRow = cv.J(c); v.flagList[at] = fe; }
     }
     __syncwarp();
 }
@@ -339,11 +446,11 @@ __device__ void warp_row(const View& v, const StepArgs& s, uint64_t row, CandVie
 // per addition (NeuCor.cpp:688-700); the neuron's next event is then picked among the few slots that carry one.
 struct LanePick { float t; unsigned long long code; uint32_t src; };
 
-__device__ __forceinline__ void pick_from_slot(const View& v, const StepArgs& s, uint64_t tb, const uint32_t* J, uint32_t c, float a,
+__device__ __forceinline__ void pick_from_slot(const View& v, const StepArgs& s, uint32_t rowOff, const uint32_t* J, uint32_t c, float a,
                                                bool first, float curT, unsigned long long curC, LanePick& nx) {
     if (a > s.t0) {  // delivery in this window (a <= t1 by staging)
-        const uint32_t p = v.pre[tb + __ldcg(J + c)] & 0x7fffffffu;
-        const unsigned long long code = (1ull << 32) | p;
+        // equal-time deliveries to one neuron are ordered by presynaptic ID = by the slot's index within the row (rows ascend in it)
+        const unsigned long long code = (1ull << 32) | (J[c] - rowOff);
         if ((first || pick_less(curT, curC, a, code)) && pick_less(a, code, nx.t, nx.code)) { nx.t = a; nx.code = code; nx.src = c; }
     }
     const float tR = add32(a, 2.0f);  // Neuron::transfer's requeue (NeuCor.cpp:665)
@@ -375,6 +482,7 @@ __device__ void lanes_replay(const View& v, const StepArgs& s, bool valid, uint6
     uint32_t evLo = 0, evHi = 0;
     NeuronState n;
     n.pot = 0.f; n.act = 0.f; n.lastRan = 0.f; n.lastFire = 0.f; n.actStart = 0.f; n.firings = 0u; n.sched = __uint_as_float(0x7fc00000u);
+    float lfS0 = 0.0f;
     if (valid) {
         host_event_range(v, s, row, q, evLo, evHi);
         float2 pa = v.potAct[row];
@@ -383,6 +491,7 @@ __device__ void lanes_replay(const View& v, const StepArgs& s, bool valid, uint6
         n.firings = v.firings[row];
         for (uint32_t e = evLo; e < evHi; e++)
             if (s.ev[e].kind == 2u && (s.ev[e].index_or_flags & 1u)) n.sched = s.ev[e].time;
+        lfS0 = n.lastFire;
         v.lfStart[row] = n.lastFire;
     }
     const uint32_t maxCnt = __reduce_max_sync(FULL, cnt);
@@ -410,10 +519,10 @@ __device__ void lanes_replay(const View& v, const StepArgs& s, bool valid, uint6
         while (m) {
             const uint32_t c = (uint32_t)__ffsll((long long)m) - 1u;
             m &= m - 1ull;
-            pick_from_slot(v, s, tb, J, c, fabsf(A[c]), first, curT, curC, out);
+            pick_from_slot(v, s, rowOff, J, c, fabsf(A[c]), first, curT, curC, out);
         }
         if (evTail)
-            for (uint32_t c = 64u; c < cnt; c++) pick_from_slot(v, s, tb, J, c, fabsf(A[c]), first, curT, curC, out);
+            for (uint32_t c = 64u; c < cnt; c++) pick_from_slot(v, s, rowOff, J, c, fabsf(A[c]), first, curT, curC, out);
     };
     LanePick nx;
     nx.t = INFINITY; nx.code = NONE; nx.src = 0xffffffffu;
@@ -440,7 +549,7 @@ __device__ void lanes_replay(const View& v, const StepArgs& s, bool valid, uint6
             } else {
                 if (rank == 1u) {  // Synapse::run → Neuron::transfer (NeuCor.cpp:718-726,663-666)
                     ctr.deliveries++;
-                    rk1 = (1u << 30) | q; k2 = k; sentinel = NC_SENT | (1u << 29) | (__ldcg(J + cur.src) - rowOff);
+                    rk1 = (1u << 30) | q; k2 = k; sentinel = NC_SENT | (1u << 29) | (J[cur.src] - rowOff);
                 } else {           // rank 2: queued Neuron::run; rank 3: end-of-window sweep
                     rk1 = (rank << 30) | q; k2 = 0u; sentinel = NC_SENT | (rank << 29);
                 }
@@ -464,9 +573,8 @@ __device__ void lanes_replay(const View& v, const StepArgs& s, bool valid, uint6
                             if (2.0f < off) {           // NeuCor.cpp:697 — the slot becomes idle; leave the when-and-why for the synapse pass
                                 A[c] = -araw;
                                 nFlag++;
-                                const uint64_t sidx = tb + __ldcg(J + c);
-                                v.arrive[sidx] = __uint_as_float(sentinel);
-                                v.depol[sidx] = T;
+                                const uint64_t sidx = tb + J[c];
+                                v.ad[sidx] = make_float2(__uint_as_float(sentinel), T);
                             }
                         }
                     }
@@ -496,7 +604,7 @@ __device__ void lanes_replay(const View& v, const StepArgs& s, bool valid, uint6
             for (uint32_t c = 0; c < cnt; c++) {
                 const float a = A[c];
                 if ((a < 0.0f) || (a > s.t0)) {
-                    if (at < v.flagCap) { SlotRow sr; sr.slot = (uint32_t)(tb + __ldcg(J + c)); sr.row = (uint32_t)row; v.flagList[at] = sr; }
+                    if (at < v.flagCap) { FlagEnt fe; fe.slot = (uint32_t)(tb + J[c]); fe.row = (uint32_t)row; fe.lfStart = lfS0; fe.inRow = J[c] - rowOff; v.flagList[at] = fe; }
                     at++;
                 }
             }
@@ -520,10 +628,10 @@ __global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32, MINB) k_neuron_pass(V
     // pool of staged slots: arrival time and depolarisation factor (touched on every visit) in shared memory, the slot index
     // (needed only where a slot delivers or is cleared) in an L2-resident per-warp scratch — 8 instead of 12 bytes of shared
     // memory per staged slot buys two more resident blocks per SM
-    float* sA = reinterpret_cast<float*>(smem) + (size_t)wib * 2 * cap;
+    float* sA = reinterpret_cast<float*>(smem) + (size_t)wib * 3 * cap;
     float* sD = sA + cap;
+    uint32_t* sJ = reinterpret_cast<uint32_t*>(sD + cap);
     const uint64_t gw = (uint64_t)blockIdx.x * NC_WARPS_PER_BLOCK + wib;
-    uint32_t* sJ = v.poolJ + gw * cap;
     CandView cv;
     cv.a = sA; cv.d = sD; cv.j = sJ; cv.cap = cap;
     cv.sa = v.spillA + gw * v.spillPerWarp; cv.sd = v.spillD + gw * v.spillPerWarp; cv.sj = v.spillJ + gw * v.spillPerWarp;
@@ -531,16 +639,51 @@ __global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32, MINB) k_neuron_pass(V
     P1Counters ctrL = {0, 0, 0, 0};  // this lane's counts of the lane-per-row path
     const uint64_t nTiles = (v.nRows + 31) >> 5;
 
-    for (;;) {  // tiles are claimed dynamically: their cost varies with the activity of their neurons
-        uint32_t t32 = 0;
-        if (lane == 0) t32 = atomicAdd(&v.tileCtr[0], 1u);
+    uint32_t t32 = 0;  // tiles are claimed dynamically (their cost varies with the activity of their neurons), one tile ahead:
+    if (lane == 0) t32 = atomicAdd(&v.tileCtr[0], 1u);  // the counter's round trip overlaps with the work on the current tile
+    for (;;) {
         const uint64_t tile = __shfl_sync(0xffffffffu, t32, 0);
         if (tile >= nTiles) break;
+        if (lane == 0) t32 = atomicAdd(&v.tileCtr[0], 1u);
         const uint64_t rowBase = tile << 5;
         const uint32_t nr = (uint32_t)min((uint64_t)32, v.nRows - rowBase);
         const uint64_t tb = v.rowptr[rowBase];  // staged slot indices are relative to the tile's first slot (rows < 2^27 slots)
         uint32_t r = 0;
-        while (r < nr) {
+        const uint32_t stc = (lane < nr) ? v.stCnt[rowBase + lane] : 0u;
+        if (__shfl_sync(0xffffffffu, stc, 0) != 0xffffffffu) {
+            // ---- the tile was staged by k_stage: copy batches of rows from its region into the pool and replay, lane = row ----
+            const bool inSub = lane < nr && (!s.subset || in_subset(s, (uint32_t)(v.row0 + rowBase + lane)));
+            uint32_t inc = stc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= (uint32_t)o) inc += y;
+            }
+            const uint32_t offL = inc - stc;  // this row's first entry within the region
+            const uint64_t reg = tile * v.stCap;
+            while (r < nr) {
+                const uint32_t base = __shfl_sync(0xffffffffu, offL, r);
+                const bool fits = lane >= r && lane < nr && (inc - base <= cap);
+                const uint32_t fm = __ballot_sync(0xffffffffu, fits) >> r;
+                const uint32_t nb = min(fm == 0xffffffffu ? 32u : (uint32_t)__ffs((int)~fm) - 1u, nr - r);  // rows r .. r+nb-1 fit the pool together
+                if (nb == 0u) {  // a row whose occupied slots alone exceed the pool
+                    if (__shfl_sync(0xffffffffu, inSub ? 1u : 0u, r)) warp_row(v, s, rowBase + r, cv, lane, ctrW);
+                    r++;
+                    continue;
+                }
+                const uint32_t used = __shfl_sync(0xffffffffu, inc, r + nb - 1u) - base;
+                const float2* src = v.stAD + reg + base;
+                const uint32_t* srcJ = v.stJ + reg + base;
+                for (uint32_t i = lane; i < used; i += 32) { const float2 x = __ldcs(src + i); sA[i] = x.x; sD[i] = x.y; sJ[i] = __ldcs(srcJ + i); }
+                __syncwarp();
+                const bool mine = inSub && lane >= r && lane < r + nb;
+                const uint32_t o = mine ? offL - base : 0u;
+                lanes_replay(v, s, mine, rowBase + lane, tb, sA + o, sD + o, sJ + o, mine ? stc : 0u, mine && stc != 0u, ctrL);
+                __syncwarp();
+                r += nb;
+            }
+        }
+        while (r < nr) {  // (tiles that did not fit their staging region are staged here, through the busy-slot index, row by row)
             // ---- batch: stage rows r, r+1, ... while their occupied slots fit the pool; the i-th staged row goes to lane i ----
             uint32_t used = 0, nb = 0, myRow = 0, myOff = 0, myCnt = 0;
             bool myEv = false, heavy = false;
@@ -558,7 +701,7 @@ __global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32, MINB) k_neuron_pass(V
             if (heavy) { warp_row(v, s, rowBase + r, cv, lane, ctrW); r++; continue; }
             // depolarisation factors of all staged slots of the batch: one round of independent gathers instead of a dependent
             // load per 128-slot group during staging
-            for (uint32_t i = lane; i < used; i += 32) sD[i] = v.depol[tb + __ldcg(sJ + i)];
+            for (uint32_t i = lane; i < used; i += 32) sD[i] = v.ad[tb + sJ[i]].y;
             __syncwarp();
             lanes_replay(v, s, lane < nb, rowBase + myRow, tb, sA + myOff, sD + myOff, sJ + myOff, myCnt, myEv, ctrL);
             __syncwarp();
@@ -613,6 +756,9 @@ __global__ void k_finish_step(View v, unsigned long long* out, int accumulate) {
         unsigned long long x = v.stats[i];
         out[i] = accumulate ? out[i] + x : x;
         v.stats[i] = 0ull;
+    } else if (i == 9) {  // running totals for nc_index_stats: busy slots visited, flag-list entries
+        v.stats[10] += v.stats[8]; v.stats[8] = 0ull;
+        v.stats[11] += min(v.flagCtl[0], v.flagCap);
     } else if (i == 8) {
         out[8] = v.localHdr[0];
         const unsigned long long ovf = (unsigned long long)v.localHdr[1] | ((unsigned long long)v.flagCtl[1] << 1);  // bit 0: fire records, bit 1: flag list
@@ -654,26 +800,29 @@ __device__ __forceinline__ void flush_syn_counters(const View& v, uint32_t* cnt)
 
 #define NC_SYN_THREADS 128
 
-// One block per fire record; the record at the head of its neuron's list stands for the neuron (a neuron can fire more than
+// Work item = (fire record, 128-entry chunk of its list): one thread per synapse, so that a window with a few hundred fires
+// still fills the machine.  The record at the head of its neuron's list stands for the neuron (a neuron can fire more than
 // once in a window: input firers ignore the refractory period).
 __global__ void __launch_bounds__(NC_SYN_THREADS) k_syn_loads(View v, StepArgs s) {
     const uint32_t b = blockIdx.y;
-    const uint32_t n = block_count(v, s, b);
+    const uint64_t items = (uint64_t)block_count(v, s, b) * v.cprLoads;
     uint32_t cnt[5] = {0, 0, 0, 0, 0};  // loads accepted, dropped, plasticity calls, hidden rand, deliveries
-    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
-        const uint32_t idx = b * s.gStride + 1u + i;
+    for (uint64_t item = blockIdx.x; item < items; item += gridDim.x) {
+        const uint32_t idx = b * s.gStride + 1u + (uint32_t)(item / v.cprLoads);
         const uint32_t p = v.gRecs[idx].neuron;
         if (v.head[p] != (int32_t)idx) continue;
-        const uint64_t e0 = v.cscPtr[p], e1 = v.cscPtr[p + 1];
-        for (uint64_t e = e0 + threadIdx.x; e < e1; e += NC_SYN_THREADS) {
+        const uint64_t e1 = v.cscPtr[p + 1];
+        {
+            const uint64_t e = v.cscPtr[p] + (item % v.cprLoads) * NC_SYN_THREADS + threadIdx.x;
+            if (e >= e1) continue;
             const SlotRow sr = v.cscEnt[e];
             const uint32_t q = (uint32_t)(v.row0 + sr.row);
             if (fired_g(v, q)) continue;  // k_syn_rows
-            const uint32_t ab = __float_as_uint(v.arrive[sr.slot]);
+            const uint32_t ab = __float_as_uint(v.ad[sr.slot].x);
             const float a = __uint_as_float(ab);
             if ((ab & NC_SENT) || (ab != 0u && a > s.t0 && a <= s.t1)) continue;  // k_syn_flagged
             // only loads can apply: neither the row context nor the plasticity tables are needed
-            resolve_slot(v, s, sr.slot, 0ull, q, p, (v.pre[sr.slot] >> 31) != 0u, ab, true, false, 0.0f, cnt);
+            resolve_slot(v, s, sr.slot, 0u, q, v.rec[sr.slot], ab, true, false, 0.0f, cnt);
         }
     }
     flush_syn_counters(v, cnt);
@@ -681,18 +830,20 @@ __global__ void __launch_bounds__(NC_SYN_THREADS) k_syn_loads(View v, StepArgs s
 __global__ void __launch_bounds__(NC_SYN_THREADS) k_syn_rows(View v, StepArgs s) {
     math_tables_to_shared();
     const uint32_t b = blockIdx.y;
-    const uint32_t n = block_count(v, s, b);
+    const uint64_t items = (uint64_t)block_count(v, s, b) * v.cprRows;
     uint32_t cnt[5] = {0, 0, 0, 0, 0};
-    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
-        const uint32_t idx = b * s.gStride + 1u + i;
+    for (uint64_t item = blockIdx.x; item < items; item += gridDim.x) {
+        const uint32_t idx = b * s.gStride + 1u + (uint32_t)(item / v.cprRows);
         const uint32_t q = v.gRecs[idx].neuron;
         if (q < v.row0 || q >= v.row0 + v.nRows || v.head[q] != (int32_t)idx) continue;
         const uint64_t row = q - v.row0;
         const uint64_t rs = v.rowptr[row], re = v.rowptr[row + 1];
         const float lfS = v.lfStart[row];
-        for (uint64_t j = rs + threadIdx.x; j < re; j += NC_SYN_THREADS) {
-            const uint32_t pw = v.pre[j], p = pw & 0x7fffffffu;
-            resolve_slot(v, s, j, rs, q, p, (pw >> 31) != 0u, __float_as_uint(v.arrive[j]), fired_g(v, p), true, lfS, cnt);
+        {
+            const uint64_t j = rs + (item % v.cprRows) * NC_SYN_THREADS + threadIdx.x;
+            if (j >= re) continue;
+            const SynRec r0 = v.rec[j];
+            resolve_slot(v, s, j, (uint32_t)(j - rs), q, r0, __float_as_uint(v.ad[j].x), fired_g(v, r0.pre & 0x7fffffffu), true, lfS, cnt);
         }
     }
     flush_syn_counters(v, cnt);
@@ -702,12 +853,11 @@ __global__ void __launch_bounds__(256) k_syn_flagged(View v, StepArgs s) {
     const uint32_t n = min(v.flagCtl[0], v.flagCap);
     uint32_t cnt[5] = {0, 0, 0, 0, 0};
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const SlotRow sr = v.flagList[i];
-        const uint32_t q = (uint32_t)(v.row0 + sr.row);
+        const FlagEnt fe = v.flagList[i];
+        const uint32_t q = (uint32_t)(v.row0 + fe.row);
         if (fired_g(v, q)) continue;  // k_syn_rows
-        const uint32_t pw = v.pre[sr.slot], p = pw & 0x7fffffffu;
-        resolve_slot(v, s, sr.slot, v.rowptr[sr.row], q, p, (pw >> 31) != 0u, __float_as_uint(v.arrive[sr.slot]), fired_g(v, p), false,
-                     v.lfStart[sr.row], cnt);
+        const SynRec r0 = v.rec[fe.slot];
+        resolve_slot(v, s, fe.slot, fe.inRow, q, r0, __float_as_uint(v.ad[fe.slot].x), fired_g(v, r0.pre & 0x7fffffffu), false, fe.lfStart, cnt);
     }
     flush_syn_counters(v, cnt);
 }
@@ -736,13 +886,16 @@ __global__ void k_init_neurons(View v) {
     v.actStart[i] = 0.0f;
     v.firings[i] = 0u;
 }
-__global__ void k_init_synapses(View v, const float* length, const unsigned char* inh, float* delay) {
+__global__ void k_init_synapses(View v, const uint32_t* pre, const float* weight, const float* length, const unsigned char* inh) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= v.S) return;
-    v.arrive[i] = 0.0f; v.depol[i] = 0.0f; v.lastStart[i] = 0.0f;
-    v.lastArr[i] = __uint_as_float(0xff800000u);  // -INFINITY, NeuCor.cpp:469
-    delay[i] = mul32(length[i], 2.0f);             // length * AP_speed, NeuCor.cpp:485,733
-    if (inh[i]) v.pre[i] |= 0x80000000u;
+    v.ad[i] = make_float2(0.0f, 0.0f); v.lastStart[i] = 0.0f;
+    SynRec r;
+    r.pre = pre[i] | (inh[i] ? 0x80000000u : 0u);
+    r.weight = weight[i];
+    r.lastArr = __uint_as_float(0xff800000u);  // -INFINITY, NeuCor.cpp:469
+    r.delay = mul32(length[i], 2.0f);           // length * AP_speed, NeuCor.cpp:485,733
+    v.rec[i] = r;
 }
 __global__ void k_fill_i32(int32_t* p, uint64_t n, int32_t val) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -752,7 +905,7 @@ __global__ void k_fill_i32(int32_t* p, uint64_t n, int32_t val) {
 // The order of a neuron's entries is arbitrary — every slot is resolved on its own.
 __global__ void k_csc_count(View v, uint32_t* cnt) {
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < v.S; j += (uint64_t)gridDim.x * blockDim.x)
-        atomicAdd(&cnt[v.pre[j] & 0x7fffffffu], 1u);
+        atomicAdd(&cnt[v.rec[j].pre & 0x7fffffffu], 1u);
 }
 __global__ void k_csc_fill(View v, const uint64_t* ptr, uint32_t* cursor, SlotRow* ent) {
     const uint32_t lane = threadIdx.x & 31u;
@@ -760,7 +913,7 @@ __global__ void k_csc_fill(View v, const uint64_t* ptr, uint32_t* cursor, SlotRo
     for (uint64_t row = gw; row < v.nRows; row += nW) {
         const uint64_t rs = v.rowptr[row], re = v.rowptr[row + 1];
         for (uint64_t j = rs + lane; j < re; j += 32) {
-            const uint32_t p = v.pre[j] & 0x7fffffffu;
+            const uint32_t p = v.rec[j].pre & 0x7fffffffu;
             SlotRow sr; sr.slot = (uint32_t)j; sr.row = (uint32_t)row;
             ent[ptr[p] + atomicAdd(&cursor[p], 1u)] = sr;
         }
@@ -782,11 +935,11 @@ __global__ void k_state_signature(View v, unsigned long long* out) {
     }
     for (uint64_t j = tid; j < v.S; j += nT) {
         const unsigned long long k = (j + 1) * C;
-        const uint32_t ab = __float_as_uint(v.arrive[j]);
-        a[3] += (unsigned long long)__float_as_uint(v.weight[j]) * k;
+        const uint32_t ab = __float_as_uint(v.ad[j].x);
+        a[3] += (unsigned long long)__float_as_uint(v.rec[j].weight) * k;
         a[4] += (unsigned long long)ab * k;
-        if (v.arrive[j] != 0.0f) a[4] += (unsigned long long)__float_as_uint(v.depol[j]) * k;
-        a[5] += (unsigned long long)__float_as_uint(v.lastArr[j]) * k;
+        if (v.ad[j].x != 0.0f) a[4] += (unsigned long long)__float_as_uint(v.ad[j].y) * k;
+        a[5] += (unsigned long long)__float_as_uint(v.rec[j].lastArr) * k;
     }
 #pragma unroll
     for (int f = 0; f < 6; f++) {
@@ -795,13 +948,19 @@ __global__ void k_state_signature(View v, unsigned long long* out) {
         if ((threadIdx.x & 31u) == 0u && x) atomicAdd(&out[f], x);
     }
 }
+__global__ void k_extract_ad(View v, int which, float* out) {  // which: 0 arrive, 1 depol, 2 weight, 3 lastArr
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < v.S; j += (uint64_t)gridDim.x * blockDim.x)
+        out[j] = which == 0 ? v.ad[j].x : which == 1 ? v.ad[j].y : which == 2 ? v.rec[j].weight : v.rec[j].lastArr;
+}
 // busy-slot index from `arrive` (after a restore, or for state loaded from a file)
 __global__ void k_rebuild_busy(View v, uint64_t words) {
     for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t m = 0u;
         const uint64_t j0 = w << 5;
-        for (uint32_t b = 0; b < 32u && j0 + b < v.S; b++) m |= (v.arrive[j0 + b] != 0.0f ? 1u : 0u) << b;
+        for (uint32_t b = 0; b < 32u && j0 + b < v.S; b++) m |= (v.ad[j0 + b].x != 0.0f ? 1u : 0u) << b;
         v.busy[w] = m;
+        v.arrived[w] = 0u;   // unknown: the staging kernel looks at every busy slot of the word once (bound 0) and sorts them out
+        v.wordNext[w] = 0u;
     }
 }
 __global__ void k_reset_activities(View v, float now) {  // Neuron::resetActivity, NeuCor.cpp:460
@@ -832,7 +991,7 @@ __global__ void k_synapse_pots(View v, float now, float* prePot, float* postPot)
     math_tables_to_shared();
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= v.S) return;
-    float a = v.arrive[i], w = v.weight[i], dl = v.delay[i];
+    float a = v.ad[i].x, w = v.rec[i].weight, dl = v.rec[i].delay;
     float pre = 0.0f, post = 0.0f;
     if (a != 0.0f) {
         pre = mul32(render_behaviour(div32(sub32(now, v.lastStart[i]), dl)), w);
@@ -867,7 +1026,6 @@ struct nc_engine {
     bool ownStream = false;
     bool uploaded = false;
     View v;
-    float* dDelay = nullptr;
     nc_event* dEv = nullptr; uint32_t evCap = 0;
     nc_event* hEvPinned = nullptr; uint32_t hEvCap = 0;
     // per-window result block: 10 x u64 per shard (8 counters, fire count, overflow flag)
@@ -886,16 +1044,18 @@ struct nc_engine {
     StepArgs pendingArgs;
     float lr = 1.0f, preF = 0.13f, postF = 0.30f, preD = 0.75f, postD = 0.65f;
     float minDelay = INFINITY;
-    uint32_t candCap = 1024, candCapSparse = 512, grid1 = 0, grid1s = 0;
+    uint32_t candCap = 704, candCapSparse = 512, grid1 = 0, grid1s = 0, gridStage = 0;
     int forceVariant = 0;                   // 0 auto, 1 dense, 2 sparse
     double lastSlotsPerRun = 1e9;           // occupied slots visited per neuron run in the last window (picks the variant)
     size_t smem1 = 0, smem1s = 0;
     uint64_t* dCscPtr = nullptr; SlotRow* dCscEnt = nullptr;  // out-synapse index (CSC over global presynaptic IDs)
     uint64_t launches = 0;
+    cudaEvent_t* tick = nullptr;            // per-kernel timing of a replay: recorded between the staging kernel and the neuron pass
+    float breakdown[4] = {0, 0, 0, 0};      // last per-kernel replay: k_stage, k_neuron_pass, fire exchange, synapse kernels [ms, summed]
     // tape
     bool taping = false; std::vector<TapeStep> tape; nc_event* dTape = nullptr; uint64_t tapeCap = 0, tapeUsed = 0; uint32_t tapeMaxSteps = 0;
     // snapshot
-    struct Snap { float *arrive, *depol, *weight, *lastArr, *lastStart, *lastRan, *lastFire, *lfStart, *actStart; float2* potAct; uint32_t *firings, *busy; bool valid; } snap = {};
+    struct Snap { float2* ad; SynRec* rec; float *lastStart, *lastRan, *lastFire, *lfStart, *actStart; float2* potAct; uint32_t *firings, *busy, *arrived, *wordNext; bool valid; } snap = {};
     uint64_t busyWords = 0;
     int smCount = 148;
 };
@@ -931,6 +1091,12 @@ extern "C" int nc_create(const nc_config* cfg, nc_engine** out) {
     e->cfg = *cfg;
     memset(&e->v, 0, sizeof(View));
     cudaError_t ce = cudaSetDevice(cfg->device);
+    if (ce == cudaSuccess && !getenv("NC_KEEP_L2_FETCH")) {
+        // both passes gather single 8-/16-byte records scattered over tens of GB: ask L2 to fetch 32-byte sectors, not
+        // 64/128-byte groups, from HBM (a hint; measured effect in profiles/README.md)
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+        cudaGetLastError();
+    }
     if (ce == cudaSuccess) {
         if (cfg->stream) { e->stream = (cudaStream_t)cfg->stream; }
         else { ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking); e->ownStream = true; }
@@ -945,8 +1111,8 @@ extern "C" int nc_create(const nc_config* cfg, nc_engine** out) {
     if (ce == cudaSuccess) ce = cudaMalloc(&e->dOut, 10 * sizeof(unsigned long long));
     if (ce == cudaSuccess) ce = cudaMemset(e->dOut, 0, 10 * sizeof(unsigned long long));
     if (ce == cudaSuccess) ce = cudaMalloc(&e->dOutAll, (size_t)cfg->world * 10 * sizeof(unsigned long long));
-    if (ce == cudaSuccess) ce = cudaMalloc(&e->v.stats, 8 * sizeof(unsigned long long));
-    if (ce == cudaSuccess) ce = cudaMemset(e->v.stats, 0, 8 * sizeof(unsigned long long));
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->v.stats, 12 * sizeof(unsigned long long));
+    if (ce == cudaSuccess) ce = cudaMemset(e->v.stats, 0, 12 * sizeof(unsigned long long));
     if (ce == cudaSuccess) ce = cudaMalloc(&e->v.tileCtr, 2 * sizeof(uint32_t));
     if (ce == cudaSuccess) ce = cudaMemset(e->v.tileCtr, 0, 2 * sizeof(uint32_t));
     cudaDeviceProp prop;
@@ -960,15 +1126,15 @@ extern "C" int nc_create(const nc_config* cfg, nc_engine** out) {
 
 static void free_all(nc_engine* e) {
     View& v = e->v;
-    cudaFree((void*)v.rowptr); cudaFree(v.pre); cudaFree(v.arrive); cudaFree(v.depol); cudaFree(v.weight); cudaFree(v.lastArr);
-    cudaFree(v.lastStart); cudaFree(e->dDelay); cudaFree(v.potAct); cudaFree(v.lastRan); cudaFree(v.lastFire); cudaFree(v.lfStart);
-    cudaFree(v.actStart); cudaFree(v.firings); cudaFree(v.localHdr); cudaFree(v.head); cudaFree(v.next); cudaFree(v.mask); cudaFree(v.evMask); cudaFree(v.busy); cudaFree(v.flagList); cudaFree(v.flagCtl); cudaFree(e->dCscPtr); cudaFree(e->dCscEnt);
-    cudaFree(v.spillA); cudaFree(v.spillD); cudaFree(v.spillJ); cudaFree(v.poolJ);
+    cudaFree((void*)v.rowptr); cudaFree(v.rec); cudaFree(v.ad);
+    cudaFree(v.lastStart); cudaFree(v.potAct); cudaFree(v.lastRan); cudaFree(v.lastFire); cudaFree(v.lfStart);
+    cudaFree(v.actStart); cudaFree(v.firings); cudaFree(v.localHdr); cudaFree(v.head); cudaFree(v.next); cudaFree(v.mask); cudaFree(v.evMask); cudaFree(v.busy); cudaFree(v.arrived); cudaFree(v.wordNext); cudaFree(v.stCnt); cudaFree(v.stAD); cudaFree(v.stJ); cudaFree(v.flagList); cudaFree(v.flagCtl); cudaFree(e->dCscPtr); cudaFree(e->dCscEnt);
+    cudaFree(v.spillA); cudaFree(v.spillD); cudaFree(v.spillJ);
     cudaFree(e->dGather);
     cudaFree(e->dEv); cudaFree(e->dTape);
     auto& s = e->snap;
-    cudaFree(s.arrive); cudaFree(s.depol); cudaFree(s.weight); cudaFree(s.lastArr); cudaFree(s.lastStart); cudaFree(s.lastRan);
-    cudaFree(s.lastFire); cudaFree(s.lfStart); cudaFree(s.actStart); cudaFree(s.potAct); cudaFree(s.firings); cudaFree(s.busy);
+    cudaFree(s.ad); cudaFree(s.rec); cudaFree(s.lastStart); cudaFree(s.lastRan);
+    cudaFree(s.lastFire); cudaFree(s.lfStart); cudaFree(s.actStart); cudaFree(s.potAct); cudaFree(s.firings); cudaFree(s.busy); cudaFree(s.arrived); cudaFree(s.wordNext);
 }
 
 extern "C" void nc_destroy(nc_engine* e) {
@@ -1024,19 +1190,22 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
     const uint64_t S1 = std::max<uint64_t>(S, 1), N1 = std::max<uint64_t>(nRows, 1), G1 = std::max<uint64_t>(nGlobal, 1);
     CK(cudaMalloc((void**)&v.rowptr, (nRows + 1) * 8));
     const uint64_t SP = ((S1 + 127) / 128 + 1) * 128;  // 16-byte row loads may touch the rest of the last 128-slot group
-    CK(cudaMalloc(&v.pre, SP * 4)); CK(cudaMalloc(&v.arrive, SP * 4)); CK(cudaMalloc(&v.depol, S1 * 4));
-    CK(cudaMemsetAsync(v.pre, 0, SP * 4, e->stream)); CK(cudaMemsetAsync(v.arrive, 0, SP * 4, e->stream));
+    CK(cudaMalloc(&v.rec, S1 * sizeof(SynRec))); CK(cudaMalloc(&v.ad, SP * 8));
+    CK(cudaMemsetAsync(v.ad, 0, SP * 8, e->stream));
     // event index: busy-slot bitmap (1 bit per slot), flag list (neuron pass -> synapse pass), out-synapse index (CSC)
     const uint64_t busyWords = SP / 32 + 64;
     e->busyWords = busyWords;
     CK(cudaMalloc(&v.busy, busyWords * 4));
     CK(cudaMemsetAsync(v.busy, 0, busyWords * 4, e->stream));
+    CK(cudaMalloc(&v.arrived, busyWords * 4));
+    CK(cudaMemsetAsync(v.arrived, 0, busyWords * 4, e->stream));
+    CK(cudaMalloc(&v.wordNext, busyWords * 4));
+    k_fill_i32<<<(unsigned)((busyWords + 255) / 256), 256, 0, e->stream>>>(reinterpret_cast<int32_t*>(v.wordNext), busyWords, 0x7f800000); e->launches++;  // +inf: nothing in flight
     v.flagCap = e->cfg.flag_capacity ? e->cfg.flag_capacity : (uint32_t)std::min<uint64_t>(std::max<uint64_t>(S1 / 8 + (1u << 16), 1u << 20), S1 + 1024);
-    CK(cudaMalloc(&v.flagList, (uint64_t)v.flagCap * sizeof(SlotRow)));
+    CK(cudaMalloc(&v.flagList, (uint64_t)v.flagCap * sizeof(FlagEnt)));
     CK(cudaMalloc(&v.flagCtl, 2 * sizeof(uint32_t)));
     CK(cudaMemsetAsync(v.flagCtl, 0, 2 * sizeof(uint32_t), e->stream));
-    CK(cudaMalloc(&v.weight, S1 * 4)); CK(cudaMalloc(&v.lastArr, S1 * 4)); CK(cudaMalloc(&v.lastStart, S1 * 4));
-    CK(cudaMalloc(&e->dDelay, S1 * 4)); v.delay = e->dDelay;
+    CK(cudaMalloc(&v.lastStart, S1 * 4));
     CK(cudaMalloc(&v.potAct, N1 * 8)); CK(cudaMalloc(&v.lastRan, N1 * 4)); CK(cudaMalloc(&v.lastFire, N1 * 4));
     CK(cudaMalloc(&v.lfStart, N1 * 4)); CK(cudaMalloc(&v.actStart, N1 * 4)); CK(cudaMalloc(&v.firings, N1 * 4));
     v.fireCap = e->cfg.fire_capacity ? e->cfg.fire_capacity : (uint32_t)std::min<uint64_t>(4 * nRows + 1024, (1u << 28) / (uint32_t)e->cfg.world);
@@ -1052,19 +1221,19 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
     CK(cudaMemsetAsync(v.mask, 0, ((G1 + 31) / 32) * 4, e->stream));
     CK(cudaMalloc(&v.evMask, ((N1 + 31) / 32) * 4));
     CK(cudaMemsetAsync(v.evMask, 0, ((N1 + 31) / 32) * 4, e->stream));
-    const float* dLen = length; const unsigned char* dInh = inh;
-    float* tmpLen = nullptr; unsigned char* tmpInh = nullptr;
+    const uint32_t* dPre = pre; const float* dW = weight; const float* dLen = length; const unsigned char* dInh = inh;
+    uint32_t* tmpPre = nullptr; float *tmpW = nullptr, *tmpLen = nullptr; unsigned char* tmpInh = nullptr;
     CK(cudaMemcpyAsync((void*)v.rowptr, rowptr, (nRows + 1) * 8, kind, e->stream));
     if (S) {
-        CK(cudaMemcpyAsync(v.pre, pre, S * 4, kind, e->stream));
-        CK(cudaMemcpyAsync(v.weight, weight, S * 4, kind, e->stream));
-        if (kind == cudaMemcpyHostToDevice) {
-            CK(cudaMalloc(&tmpLen, S1 * 4)); CK(cudaMalloc(&tmpInh, S1));
+        if (kind == cudaMemcpyHostToDevice) {  // (device-resident arrays are read where they lie)
+            CK(cudaMalloc(&tmpPre, S1 * 4)); CK(cudaMalloc(&tmpW, S1 * 4)); CK(cudaMalloc(&tmpLen, S1 * 4)); CK(cudaMalloc(&tmpInh, S1));
+            CK(cudaMemcpyAsync(tmpPre, pre, S * 4, kind, e->stream));
+            CK(cudaMemcpyAsync(tmpW, weight, S * 4, kind, e->stream));
             CK(cudaMemcpyAsync(tmpLen, length, S * 4, kind, e->stream));
             CK(cudaMemcpyAsync(tmpInh, inh, S, kind, e->stream));
-            dLen = tmpLen; dInh = tmpInh;
+            dPre = tmpPre; dW = tmpW; dLen = tmpLen; dInh = tmpInh;
         }
-        k_init_synapses<<<(unsigned)((S + 255) / 256), 256, 0, e->stream>>>(v, dLen, dInh, e->dDelay);
+        k_init_synapses<<<(unsigned)((S + 255) / 256), 256, 0, e->stream>>>(v, dPre, dW, dLen, dInh);
         e->launches++;
     }
     if (nRows) { k_init_neurons<<<(unsigned)((nRows + 255) / 256), 256, 0, e->stream>>>(v); e->launches++; }
@@ -1083,7 +1252,10 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
         CK(cudaMemcpyAsync(hCnt.data(), dCnt, G1 * 4, cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
         hPtr[0] = 0;
-        for (uint64_t i = 0; i < G1; i++) hPtr[i + 1] = hPtr[i] + hCnt[i];
+        uint32_t maxOut = 0;
+        for (uint64_t i = 0; i < G1; i++) { hPtr[i + 1] = hPtr[i] + hCnt[i]; maxOut = std::max(maxOut, hCnt[i]); }
+        v.cprLoads = std::max<uint32_t>(1u, (maxOut + NC_SYN_THREADS - 1) / NC_SYN_THREADS);
+        v.cprRows = std::max<uint32_t>(1u, (uint32_t)((maxRow + NC_SYN_THREADS - 1) / NC_SYN_THREADS));
         CK(cudaMemcpyAsync(e->dCscPtr, hPtr.data(), (G1 + 1) * 8, cudaMemcpyHostToDevice, e->stream));
         CK(cudaMemsetAsync(dCnt, 0, G1 * 4, e->stream));
         if (S) { k_csc_fill<<<e->smCount * 16, 256, 0, e->stream>>>(v, e->dCscPtr, dCnt, e->dCscEnt); e->launches++; }
@@ -1094,10 +1266,10 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
     }
     // launch geometry: persistent grids sized to the SM count x resident blocks per SM
     // the warp's shared-memory pool of staged slots: shared by the rows of a lane-per-row batch, so not tied to the row length
-    e->candCap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(e->candCap, 32), 1024);
+    e->candCap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(e->candCap, 32), 704);
     e->candCapSparse = std::min<uint32_t>(e->candCap, 512u);
-    e->smem1 = (size_t)NC_WARPS_PER_BLOCK * 2 * e->candCap * 4;
-    e->smem1s = (size_t)NC_WARPS_PER_BLOCK * 2 * e->candCapSparse * 4;
+    e->smem1 = (size_t)NC_WARPS_PER_BLOCK * 3 * e->candCap * 4;
+    e->smem1s = (size_t)NC_WARPS_PER_BLOCK * 3 * e->candCapSparse * 4;
     CK(cudaFuncSetAttribute(k_neuron_pass<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem1));
     CK(cudaFuncSetAttribute(k_neuron_pass<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem1s));
     int occ1 = 1, occ1s = 1;
@@ -1110,14 +1282,24 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
         const char* f = getenv("NC_NEURON_VARIANT");  // tuning/tests: "dense" or "sparse" pins the variant
         e->forceVariant = f ? (f[0] == 's' ? 2 : 1) : 0;
     }
+    {   // staging regions: one per tile of 32 rows, large enough for every slot of the largest tile up to 8192 entries
+        // (beyond that a tile that is this busy takes the in-kernel staging path); NC_STAGE_CAP overrides (tests)
+        uint64_t cap = std::min<uint64_t>(std::max<uint64_t>((32 * maxRow + 31) / 32 * 32, 64), 8192);
+        if (const char* f = getenv("NC_STAGE_CAP")) cap = std::max<uint64_t>(strtoull(f, nullptr, 10), 1);
+        v.stCap = (uint32_t)cap;
+        const uint64_t nTiles = (N1 + 31) / 32;
+        CK(cudaMalloc(&v.stCnt, nTiles * 32 * 4));
+        CK(cudaMalloc(&v.stAD, nTiles * cap * 8));
+        CK(cudaMalloc(&v.stJ, nTiles * cap * 4));
+        e->gridStage = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((nTiles + NC_STG_WARPS - 1) / NC_STG_WARPS, (uint64_t)e->smCount * 8));
+    }
     // scratch sized for whichever variant needs more: spill beyond the smaller pool, one pool of slot indices per resident warp
     v.spillPerWarp = (uint32_t)(maxRow > e->candCapSparse ? maxRow - e->candCapSparse : 0);
     const uint64_t maxWarps = (uint64_t)std::max(e->grid1, e->grid1s) * NC_WARPS_PER_BLOCK;
     uint64_t spillN = std::max<uint64_t>(1, maxWarps * v.spillPerWarp);
     CK(cudaMalloc(&v.spillA, spillN * 4)); CK(cudaMalloc(&v.spillD, spillN * 4)); CK(cudaMalloc(&v.spillJ, spillN * 4));
-    CK(cudaMalloc(&v.poolJ, maxWarps * e->candCap * 4));
     CK(cudaStreamSynchronize(e->stream));
-    cudaFree(tmpLen); cudaFree(tmpInh);
+    cudaFree(tmpPre); cudaFree(tmpW); cudaFree(tmpLen); cudaFree(tmpInh);
     e->minDelay = minDelay;
     e->uploaded = true;
     return NC_OK;
@@ -1234,13 +1416,17 @@ static void fill_args(nc_engine* e, StepArgs& a, float t0, float t1, int sweep, 
 
 // one block per (expected) fire record, capped; the kernels stride over the records they find on the device
 static void launch_synapse_pass(nc_engine* e, const StepArgs& a, uint32_t expectFires) {
-    dim3 g(std::min<uint32_t>(std::max<uint32_t>(expectFires, 1u), (uint32_t)e->smCount * 16u), a.world);
-    k_syn_loads<<<g, NC_SYN_THREADS, 0, e->stream>>>(e->v, a);
-    k_syn_rows<<<g, NC_SYN_THREADS, 0, e->stream>>>(e->v, a);
+    const uint64_t cap = (uint64_t)e->smCount * 32u, f = std::max<uint32_t>(expectFires, 1u);
+    dim3 gl((uint32_t)std::min<uint64_t>(f * e->v.cprLoads, cap), a.world), gr((uint32_t)std::min<uint64_t>(f * e->v.cprRows, cap), a.world);
+    k_syn_loads<<<gl, NC_SYN_THREADS, 0, e->stream>>>(e->v, a);
+    k_syn_rows<<<gr, NC_SYN_THREADS, 0, e->stream>>>(e->v, a);
     k_syn_flagged<<<e->smCount * 8, 256, 0, e->stream>>>(e->v, a);
     e->launches += 3;
 }
 static void launch_neuron_pass(nc_engine* e, const StepArgs& a) {
+    k_stage<<<e->gridStage, NC_STG_WARPS * 32, 0, e->stream>>>(e->v, a);
+    e->launches++;
+    if (e->tick) cudaEventRecord(*e->tick, e->stream);
     if (a.candCap == e->candCapSparse && e->candCapSparse != e->candCap)
         k_neuron_pass<8><<<e->grid1s, NC_WARPS_PER_BLOCK * 32, e->smem1s, e->stream>>>(e->v, a);
     else
@@ -1503,10 +1689,20 @@ extern "C" int nc_read_synapses(nc_engine* e, float* weight, float* arrive, floa
     cudaSetDevice(e->cfg.device);
     CK(cudaStreamSynchronize(e->stream));
     uint64_t b = e->v.S * 4;
-    if (weight) CK(cudaMemcpy(weight, e->v.weight, b, cudaMemcpyDeviceToHost));
-    if (arrive) CK(cudaMemcpy(arrive, e->v.arrive, b, cudaMemcpyDeviceToHost));
-    if (depol) CK(cudaMemcpy(depol, e->v.depol, b, cudaMemcpyDeviceToHost));
-    if (lastArr) CK(cudaMemcpy(lastArr, e->v.lastArr, b, cudaMemcpyDeviceToHost));
+    if ((arrive || depol || weight || lastArr) && e->v.S) {  // these live in interleaved records on the device: de-interleave through a temporary
+        float* tmp = nullptr;
+        CK(cudaMalloc(&tmp, b));
+        float* dsts[4] = {arrive, depol, weight, lastArr};
+        for (int which = 0; which < 4; which++) {
+            float* dst = dsts[which];
+            if (!dst) continue;
+            k_extract_ad<<<(unsigned)std::min<uint64_t>((e->v.S + 255) / 256, 1u << 20), 256, 0, e->stream>>>(e->v, which, tmp); e->launches++;
+            cudaError_t ce = cudaMemcpyAsync(dst, tmp, b, cudaMemcpyDeviceToHost, e->stream);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+            if (ce != cudaSuccess) { cudaFree(tmp); e->err = std::string("nc_read_synapses: ") + cudaGetErrorString(ce); return NC_ERR_CUDA; }
+        }
+        cudaFree(tmp);
+    }
     if (lastStart) CK(cudaMemcpy(lastStart, e->v.lastStart, b, cudaMemcpyDeviceToHost));
     return NC_OK;
 }
@@ -1600,13 +1796,15 @@ static cudaError_t snap_copy(T*& dst, const T* src, uint64_t n, cudaStream_t st,
 }
 static int snap_all(nc_engine* e, bool toSnap) {
     View& v = e->v; auto& s = e->snap;
-    CK(snap_copy(s.arrive, v.arrive, v.S, e->stream, toSnap)); CK(snap_copy(s.depol, v.depol, v.S, e->stream, toSnap));
-    CK(snap_copy(s.weight, v.weight, v.S, e->stream, toSnap)); CK(snap_copy(s.lastArr, v.lastArr, v.S, e->stream, toSnap));
+    CK(snap_copy(s.ad, v.ad, v.S, e->stream, toSnap));
+    CK(snap_copy(s.rec, v.rec, v.S, e->stream, toSnap));
     CK(snap_copy(s.lastStart, v.lastStart, v.S, e->stream, toSnap)); CK(snap_copy(s.lastRan, v.lastRan, v.nRows, e->stream, toSnap));
     CK(snap_copy(s.lastFire, v.lastFire, v.nRows, e->stream, toSnap)); CK(snap_copy(s.lfStart, v.lfStart, v.nRows, e->stream, toSnap));
     CK(snap_copy(s.actStart, v.actStart, v.nRows, e->stream, toSnap)); CK(snap_copy(s.potAct, v.potAct, v.nRows, e->stream, toSnap));
     CK(snap_copy(s.firings, v.firings, v.nRows, e->stream, toSnap));
     CK(snap_copy(s.busy, v.busy, e->busyWords, e->stream, toSnap));
+    CK(snap_copy(s.arrived, v.arrived, e->busyWords, e->stream, toSnap));
+    CK(snap_copy(s.wordNext, v.wordNext, e->busyWords, e->stream, toSnap));
     CK(cudaStreamSynchronize(e->stream));
     return NC_OK;
 }
@@ -1635,7 +1833,8 @@ extern "C" int nc_tape_replay(nc_engine* e, uint32_t first, uint32_t count, floa
     CK(cudaMemsetAsync(e->dOut, 0, 10 * sizeof(unsigned long long), e->stream));
     const bool perKernel = msP1 || msP2 || msXchg;
     std::vector<cudaEvent_t> evs;
-    if (perKernel) { evs.resize((size_t)count * 5); for (auto& x : evs) CK(cudaEventCreate(&x)); }
+    std::vector<cudaEvent_t> evStage;
+    if (perKernel) { evs.resize((size_t)count * 5); for (auto& x : evs) CK(cudaEventCreate(&x)); evStage.resize(count); for (auto& x : evStage) CK(cudaEventCreate(&x)); }
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     const uint32_t gx = (uint32_t)std::min<uint64_t>(std::max<uint64_t>((e->v.nRows / 64 + 255) / 256, 1), 1024);
     CK(cudaEventRecord(e0, e->stream));
@@ -1645,8 +1844,9 @@ extern "C" int nc_tape_replay(nc_engine* e, uint32_t first, uint32_t count, floa
         fill_args(e, a, ts.t0, ts.t1, ts.sweep, e->dTape + ts.evOff, ts.nEv);
         a.gStride = ts.units;
         if (a.nEv) { k_mark_events<<<(a.nEv + 255) / 256, 256, 0, e->stream>>>(e->v, a.ev, a.nEv, 1); e->launches++; }
-        if (perKernel) CK(cudaEventRecord(evs[5 * k], e->stream));
+        if (perKernel) { CK(cudaEventRecord(evs[5 * k], e->stream)); e->tick = &evStage[k]; }
         launch_neuron_pass(e, a);
+        e->tick = nullptr;
         if (perKernel) CK(cudaEventRecord(evs[5 * k + 1], e->stream));
         if (e->cfg.world > 1) {
             int rc = exchange(e, e->v.localHdr, e->dGather, (size_t)ts.units * sizeof(FireRec));
@@ -1669,8 +1869,9 @@ extern "C" int nc_tape_replay(nc_engine* e, uint32_t first, uint32_t count, floa
     CK(cudaMemsetAsync(e->dOut, 0, 10 * sizeof(unsigned long long), e->stream));
     if (msTotal) CK(cudaEventElapsedTime(msTotal, e0, e1));
     if (perKernel) {
-        float s1 = 0, s2 = 0, sx = 0, x;
+        float s1 = 0, s2 = 0, sx = 0, sS = 0, x;
         for (uint32_t k = 0; k < count; k++) {
+            CK(cudaEventElapsedTime(&x, evs[5 * k], evStage[k])); sS += x;
             CK(cudaEventElapsedTime(&x, evs[5 * k], evs[5 * k + 1])); s1 += x;
             CK(cudaEventElapsedTime(&x, evs[5 * k + 1], evs[5 * k + 2])); sx += x;
             CK(cudaEventElapsedTime(&x, evs[5 * k + 3], evs[5 * k + 4])); s2 += x;
@@ -1678,10 +1879,28 @@ extern "C" int nc_tape_replay(nc_engine* e, uint32_t first, uint32_t count, floa
         if (msP1) *msP1 = s1;
         if (msP2) *msP2 = s2;
         if (msXchg) *msXchg = sx;
+        e->breakdown[0] = sS; e->breakdown[1] = s1 - sS; e->breakdown[2] = sx; e->breakdown[3] = s2;
         for (auto& x2 : evs) cudaEventDestroy(x2);
+        for (auto& x2 : evStage) cudaEventDestroy(x2);
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return rc;
+}
+
+extern "C" int nc_index_stats(nc_engine* e, uint64_t* out2) {
+    if (!out2) return fail(e, NC_ERR_INVALID, "nc_index_stats: null output");
+    cudaSetDevice(e->cfg.device);
+    CK(cudaStreamSynchronize(e->stream));
+    unsigned long long h[2];
+    CK(cudaMemcpy(h, e->v.stats + 10, 16, cudaMemcpyDeviceToHost));
+    CK(cudaMemset(e->v.stats + 10, 0, 16));
+    out2[0] = h[0]; out2[1] = h[1];
+    return NC_OK;
+}
+extern "C" int nc_replay_breakdown(const nc_engine* e, float* out4) {
+    if (!out4) return NC_ERR_INVALID;
+    for (int i = 0; i < 4; i++) out4[i] = e->breakdown[i];
+    return NC_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

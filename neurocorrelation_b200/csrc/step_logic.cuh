@@ -32,7 +32,7 @@ struct FireRec {       // 16 B; canonical key of the event that caused the fire
 };
 // Canonical event order: (time, rank, k1, k2)
 //   rank 0 input firer  (k1 = firer index, k2 = neuron)      InputFirer::run
-//   rank 1 delivery     (k1 = target,      k2 = parent)      Synapse::run
+//   rank 1 delivery     (k1 = target,      k2 = the synapse's index within the target's row: ascends with the parent ID)   Synapse::run
 //   rank 2 neuron event (k1 = neuron,      k2 = 0)           Neuron::run queued by transfer/scheduleFire
 //   rank 3 sweep        (k1 = neuron,      k2 = 0)           end-of-window run of every neuron, ascending ID
 // Within one event the operations on a synapse are ordered load/clear (0) < post-fire plasticity (1) < delivery (2).
@@ -65,12 +65,24 @@ struct SlotRow {       // 8 B: a synapse slot of this shard and the row (target 
     uint32_t slot, row;
 };
 
+struct SynRec {        // 16 B: what resolving a synapse needs besides its (arrive, depol) record — one sector per visit
+    uint32_t pre;      // presynaptic neuron (global ID); bit 31 = Synapse::inhibitory
+    float weight;      // Synapse::weight
+    float lastArr;     // Synapse::lastSpikeArrival (-inf initially)
+    float delay;       // length * AP_speed, computed once in fp32 exactly as NeuCor.cpp:733
+};
+struct FlagEnt {       // 16 B: a slot the neuron pass hands to the synapse pass (delivered in the window / cleared by one of its runs)
+    uint32_t slot, row;
+    float lfStart;     // the row neuron's lastFire at the start of the window
+    uint32_t inRow;    // the slot's index within its row
+};
+
 struct View {
     uint64_t nGlobal, row0, nRows, S;
     const uint64_t* rowptr;
-    uint32_t* pre;  // bit 31 = inhibitory flag
-    float *arrive, *depol, *weight, *lastArr, *lastStart;
-    const float* delay;
+    SynRec* rec;
+    float2* ad;  // per slot (arrive, depol): Synapse::AP_fireTime (0 = idle) and AP_depolFac of the spike in flight — one 8-byte record, one sector per visit
+    float* lastStart;  // Synapse::lastSpikeStart (renderer only)
     float2* potAct;
     float *lastRan, *lastFire, *lfStart, *actStart;
     uint32_t* firings;
@@ -87,9 +99,18 @@ struct View {
     uint32_t* evMask;      // one bit per row of this shard: has host events in this window
     // event index: which slots can matter to a window, so that neither pass visits idle synapses
     uint32_t* busy;        // one bit per slot: arrive != 0 (a spike is in flight or being integrated); NULL in the CPU test double
-    SlotRow* flagList;     // written by the neuron pass: slots that delivered in this window or were cleared by one of its runs
+    uint32_t* arrived;     // one bit per slot, subset of busy: the spike has arrived (it was staged by an earlier window)
+    uint32_t* wordNext;    // per 32-slot word: bit pattern of a lower bound on the earliest arrival among its slots still in flight (+inf: none)
+    FlagEnt* flagList;     // written by the neuron pass: slots that delivered in this window or were cleared by one of its runs
     uint32_t* flagCtl;     // [0] = entries in flagList, [1] = overflow flag
     uint32_t flagCap;
+    // staged rows (k_stage -> k_neuron_pass): per tile of 32 rows a region of stCap entries holding the tile's occupied slots
+    // (arrive <= t1) in row order — (arrive, depol) and the slot index relative to the tile's first slot — and per row its count
+    uint32_t* stCnt;       // per row; 0xffffffff on every row of a tile whose occupied slots did not fit its region
+    float2* stAD;
+    uint32_t* stJ;
+    uint32_t stCap;
+    uint32_t cprLoads, cprRows;  // 128-entry chunks that cover the longest out-list / the longest row (work split of the synapse kernels)
     const uint64_t* cscPtr;  // per GLOBAL presynaptic neuron: its out-synapses that land in this shard are cscEnt[cscPtr[p] .. cscPtr[p+1])
     const SlotRow* cscEnt;
     // spill area for rows with more occupied slots than fit in shared memory
@@ -97,7 +118,6 @@ struct View {
     float* spillD;
     uint32_t* spillJ;
     uint32_t spillPerWarp;
-    uint32_t* poolJ;            // per warp of the neuron pass: slot indices of the staged slots (L2-resident scratch; rarely read)
     unsigned long long* stats;  // 8 counters (nc_step_stats order)
     uint32_t* tileCtr;          // [0] neuron pass, [1] synapse pass: next unclaimed tile of the window (dynamic scheduling)
 };
@@ -262,8 +282,10 @@ NC_HD float plasticity(const StepArgs& s, float w, bool inh, float T, float last
 //   P  one per fire of q   synapticPlasticity from Neuron::fire
 //   D  delivery when t0 < arrive <= t1: lastSpikeArrival = now; synapticPlasticity
 // cnt: [0] loads accepted, [1] loads dropped, [2] plasticity calls, [3] hidden rand, [4] deliveries
-NC_HD void resolve_slot(const View& v, const StepArgs& s, uint64_t j, uint64_t rs, uint32_t q, uint32_t p, bool inh,
+NC_HD void resolve_slot(const View& v, const StepArgs& s, uint64_t j, uint32_t inRow, uint32_t q, const SynRec r0,
                         uint32_t abits, bool pFired, bool qFired, float lfStart, uint32_t* cnt) {
+    const uint32_t p = r0.pre & 0x7fffffffu;
+    const bool inh = (r0.pre >> 31) != 0u;
     float a = as_f32(abits);
     const bool cleared = (abits & NC_SENT) != 0u;
     Key kc;
@@ -272,14 +294,14 @@ NC_HD void resolve_slot(const View& v, const StepArgs& s, uint64_t j, uint64_t r
         uint32_t rank = (abits >> 29) & 3u;
         kc.rk1 = (rank << 30) | q;
         if (rank == 3u) { kc.t = s.t1; kc.k2 = 0u; }
-        else if (rank == 2u) { kc.t = v.depol[j]; kc.k2 = 0u; }
-        else { kc.t = v.depol[j]; kc.k2 = v.pre[rs + (abits & 0x1fffffffu)] & 0x7fffffffu; }
+        else if (rank == 2u) { kc.t = v.ad[j].y; kc.k2 = 0u; }
+        else { kc.t = v.ad[j].y; kc.k2 = abits & 0x1fffffffu; }  // the delivering slot's index within the row
     }
     const bool hasD = !cleared && a != 0.0f && a > s.t0 && a <= s.t1;
     Key kd;
-    kd.t = a; kd.rk1 = (1u << 30) | q; kd.k2 = p; kd.local = 2;
+    kd.t = a; kd.rk1 = (1u << 30) | q; kd.k2 = inRow; kd.local = 2;
     bool busy = cleared || a != 0.0f;
-    float w = v.weight[j], lastArr = v.lastArr[j];
+    float w = r0.weight, lastArr = r0.lastArr;
     float newArrive = cleared ? 0.0f : a, newDepol = 0.0f, newStart = 0.0f;
     bool loaded = false, wChanged = false, laChanged = false;
     Key cur;
@@ -310,7 +332,7 @@ NC_HD void resolve_slot(const View& v, const StepArgs& s, uint64_t j, uint64_t r
             else {
                 float d = (float)mul64((double)0.2f, 52.0);  // AP_depolFac *= 52.0 (float *= double)
                 newDepol = mul32(d, w);                      // AP_depolFac *= weight
-                newArrive = add32(v.delay[j], bestT);        // length*AP_speed + now
+                newArrive = add32(r0.delay, bestT);          // length*AP_speed + now
                 newStart = bestT;
                 busy = true; loaded = true;
                 cnt[0]++;
@@ -340,19 +362,21 @@ NC_HD void resolve_slot(const View& v, const StepArgs& s, uint64_t j, uint64_t r
         cur = best; have = true;
     }
     if (cleared || loaded) {
-        v.arrive[j] = newArrive;
-        if (v.busy && (newArrive != 0.0f) != (cleared || a != 0.0f)) {  // keep the busy-slot index in step (integer atomics only)
+        v.ad[j].x = newArrive;
+        if (v.busy) {  // keep the event index in step (integer atomics only)
             const uint32_t bit = 1u << (uint32_t)(j & 31u);
 #if defined(__CUDA_ARCH__)
-            if (newArrive != 0.0f) atomicOr(&v.busy[j >> 5], bit); else atomicAnd(&v.busy[j >> 5], ~bit);
+            if ((newArrive != 0.0f) != (cleared || a != 0.0f)) { if (newArrive != 0.0f) atomicOr(&v.busy[j >> 5], bit); else atomicAnd(&v.busy[j >> 5], ~bit); }
+            if (cleared) atomicAnd(&v.arrived[j >> 5], ~bit);                      // an idle or re-loaded slot has not arrived
+            if (loaded) atomicMin(&v.wordNext[j >> 5], as_u32(newArrive));         // positive floats order as unsigned integers
 #else
-            if (newArrive != 0.0f) v.busy[j >> 5] |= bit; else v.busy[j >> 5] &= ~bit;
+            if ((newArrive != 0.0f) != (cleared || a != 0.0f)) { if (newArrive != 0.0f) v.busy[j >> 5] |= bit; else v.busy[j >> 5] &= ~bit; }
 #endif
         }
     }
-    if (loaded) { v.depol[j] = newDepol; v.lastStart[j] = newStart; }
-    if (wChanged) v.weight[j] = w;
-    if (laChanged) v.lastArr[j] = lastArr;
+    if (loaded) { v.ad[j].y = newDepol; v.lastStart[j] = newStart; }
+    if (wChanged) v.rec[j].weight = w;
+    if (laChanged) v.rec[j].lastArr = lastArr;
 }
 
 }  // namespace ncs

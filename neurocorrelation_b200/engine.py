@@ -25,7 +25,7 @@ ABI_SYMBOLS = (
     "nc_upload_network_device", "nc_min_delay",
     "nc_set_plasticity", "nc_step", "nc_step_launch", "nc_step_collect", "nc_run_neurons", "nc_read_neurons", "nc_read_synapses", "nc_read_fires",
     "nc_read_synapse_pots", "nc_state_signature", "nc_reset_activities", "nc_detector_mean", "nc_tape_begin", "nc_tape_end", "nc_snapshot",
-    "nc_restore", "nc_tape_replay", "nc_launch_count", "nc_comm_unique_id", "nc_comm_init", "nc_set_exchange",
+    "nc_restore", "nc_tape_replay", "nc_replay_breakdown", "nc_index_stats", "nc_launch_count", "nc_comm_unique_id", "nc_comm_init", "nc_set_exchange",
     "nc_selftest_powf", "nc_selftest_exp",
 )
 
@@ -89,6 +89,8 @@ def load(path=None):
     L.nc_restore.argtypes = [vp]
     L.nc_tape_replay.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                  C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.POINTER(StepStats)]
+    L.nc_replay_breakdown.argtypes = [vp, f32p]
+    L.nc_index_stats.argtypes = [vp, u64p]
     L.nc_launch_count.argtypes = [vp]
     L.nc_launch_count.restype = C.c_uint64
     L.nc_comm_unique_id.argtypes = [vp]
@@ -240,8 +242,19 @@ class Engine:
         self._ck(self.L.nc_tape_replay(self.h, first, count, C.byref(ms), C.byref(m1) if per_kernel else None,
                                        C.byref(m2) if per_kernel else None, C.byref(mx) if per_kernel else None,
                                        C.byref(hidden), C.byref(st)))
-        return dict(ms_total=ms.value, ms_pass1=m1.value, ms_pass2=m2.value, ms_exchange=mx.value, hidden=hidden.value,
-                    stats=st.as_dict())
+        out = dict(ms_total=ms.value, ms_pass1=m1.value, ms_pass2=m2.value, ms_exchange=mx.value, hidden=hidden.value,
+                   stats=st.as_dict())
+        if per_kernel:
+            b = np.zeros(4, np.float32)
+            self._ck(self.L.nc_replay_breakdown(self.h, b))
+            out.update(ms_stage=float(b[0]), ms_neuron=float(b[1]), ms_synapse=float(b[3]))
+        return out
+
+    def index_stats(self):
+        """(busy slots visited by the staging kernel, flag-list entries) since the last call."""
+        out = np.zeros(2, np.uint64)
+        self._ck(self.L.nc_index_stats(self.h, out))
+        return int(out[0]), int(out[1])
 
     def launch_count(self):
         return int(self.L.nc_launch_count(self.h))

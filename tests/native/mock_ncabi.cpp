@@ -23,8 +23,10 @@ struct nc_engine {
     std::string err;
     View v;
     std::vector<uint64_t> rowptr;
-    std::vector<uint32_t> pre, firings, hdr, mask, spillJ;
-    std::vector<float> arrive, depol, weight, lastArr, lastStart, delay, lastRan, lastFire, lfStart, actStart, spillA, spillD;
+    std::vector<SynRec> rec;
+    std::vector<uint32_t> firings, hdr, mask, spillJ;
+    std::vector<float2> ad;
+    std::vector<float> lastStart, lastRan, lastFire, lfStart, actStart, spillA, spillD;
     std::vector<float2> potAct;
     std::vector<FireRec> units, gather;  // exchange block (header unit + records) and the gathered blocks of all shards
     std::vector<int32_t> head, next;
@@ -45,6 +47,8 @@ const char* nc_global_error(void) { return g_err.c_str(); }
 const char* nc_last_error(const nc_engine* e) { return e ? e->err.c_str() : g_err.c_str(); }
 int nc_device_count(void) { return 1; }
 uint64_t nc_launch_count(const nc_engine*) { return 0; }
+int nc_index_stats(nc_engine*, uint64_t* out2) { out2[0] = out2[1] = 0; return NC_OK; }
+int nc_replay_breakdown(const nc_engine*, float* out4) { for (int i = 0; i < 4; i++) out4[i] = 0.0f; return NC_OK; }
 int nc_create(const nc_config* cfg, nc_engine** out) {
     nc_engine* e = new nc_engine();
     memset(&e->v, 0, sizeof(View));
@@ -62,9 +66,12 @@ int nc_upload_network(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t nR
                       const float* weight, const float* length, const uint8_t* inh) {
     uint64_t S = rowptr[nRows], maxRow = 0;
     e->rowptr.assign(rowptr, rowptr + nRows + 1);
-    e->pre.assign(pre, pre + S); e->weight.assign(weight, weight + S);
-    e->arrive.assign(S, 0.0f); e->depol.assign(S, 0.0f); e->lastStart.assign(S, 0.0f); e->lastArr.assign(S, -INFINITY); e->delay.resize(S);
-    for (uint64_t i = 0; i < S; i++) { e->delay[i] = length[i] * 2.0f; e->minDelay = std::min(e->minDelay, e->delay[i]); if (inh[i]) e->pre[i] |= 0x80000000u; }
+    e->rec.resize(S);
+    e->ad.assign(S, make_float2(0.0f, 0.0f)); e->lastStart.assign(S, 0.0f);
+    for (uint64_t i = 0; i < S; i++) {
+        SynRec r; r.pre = pre[i] | (inh[i] ? 0x80000000u : 0u); r.weight = weight[i]; r.lastArr = -INFINITY; r.delay = length[i] * 2.0f;
+        e->rec[i] = r; e->minDelay = std::min(e->minDelay, r.delay);
+    }
     for (uint64_t r = 0; r < nRows; r++) maxRow = std::max(maxRow, rowptr[r + 1] - rowptr[r]);
     e->potAct.assign(nRows, make_float2(-70.0f, 0.0f)); e->lastRan.assign(nRows, 0.0f); e->lastFire.assign(nRows, NAN);
     e->lfStart.assign(nRows, NAN); e->actStart.assign(nRows, 0.0f); e->firings.assign(nRows, 0u);
@@ -73,9 +80,9 @@ int nc_upload_network(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t nR
     e->head.assign(nGlobal, -1); e->next.assign((size_t)e->world * (cap + 1), -1); e->mask.assign((nGlobal + 31) / 32 + 1, 0u);
     e->spillA.resize(maxRow + 1); e->spillD.resize(maxRow + 1); e->spillJ.resize(maxRow + 1);
     View& v = e->v;
-    v.nGlobal = nGlobal; v.row0 = row0; v.nRows = nRows; v.S = S; v.rowptr = e->rowptr.data(); v.pre = e->pre.data();
-    v.arrive = e->arrive.data(); v.depol = e->depol.data(); v.weight = e->weight.data(); v.lastArr = e->lastArr.data(); v.lastStart = e->lastStart.data();
-    v.delay = e->delay.data(); v.potAct = e->potAct.data(); v.lastRan = e->lastRan.data(); v.lastFire = e->lastFire.data(); v.lfStart = e->lfStart.data();
+    v.nGlobal = nGlobal; v.row0 = row0; v.nRows = nRows; v.S = S; v.rowptr = e->rowptr.data(); v.rec = e->rec.data();
+    v.ad = e->ad.data(); v.lastStart = e->lastStart.data();
+    v.potAct = e->potAct.data(); v.lastRan = e->lastRan.data(); v.lastFire = e->lastFire.data(); v.lfStart = e->lfStart.data();
     v.actStart = e->actStart.data(); v.firings = e->firings.data(); v.localHdr = reinterpret_cast<uint32_t*>(e->units.data()); v.localRecs = e->units.data() + 1; v.fireCap = cap;
     v.gRecs = e->world > 1 ? e->gather.data() : e->units.data(); v.head = e->head.data(); v.next = e->next.data(); v.mask = e->mask.data();
     v.spillA = e->spillA.data(); v.spillD = e->spillD.data(); v.spillJ = e->spillJ.data(); v.spillPerWarp = (uint32_t)maxRow; v.stats = e->stats;
@@ -108,7 +115,7 @@ static void model_neuron_run(const View& v, NeuronState& n, CandView& cv, uint32
                 if (!(off > 0.0f)) continue;
                 todo |= 1u << lane;
                 t[lane] = chain_term(dT, cv.D(c), E);
-                if (2.0f < off) { cv.A(c) = -a; uint64_t sidx = rs + cv.J(c); v.arrive[sidx] = as_f32(sentinel); v.depol[sidx] = T; }
+                if (2.0f < off) { cv.A(c) = -a; uint64_t sidx = rs + cv.J(c); v.ad[sidx] = make_float2(as_f32(sentinel), T); }
             }
             nVisits += __builtin_popcount(todo);
             while (todo) {
@@ -154,8 +161,8 @@ static void model_pass1(nc_engine* e, const StepArgs& s) {
         const uint64_t rs = v.rowptr[row], re = v.rowptr[row + 1];
         uint32_t cnt = 0;
         for (uint64_t j = rs; j < re; j++) {
-            float a = v.arrive[j];
-            if (a != 0.0f && a <= s.t1) { cv.A(cnt) = a; cv.D(cnt) = v.depol[j]; cv.J(cnt) = (uint32_t)(j - rs); cnt++; }
+            float a = v.ad[j].x;
+            if (a != 0.0f && a <= s.t1) { cv.A(cnt) = a; cv.D(cnt) = v.ad[j].y; cv.J(cnt) = (uint32_t)(j - rs); cnt++; }
         }
         uint32_t evLo = (uint32_t)(std::lower_bound(s.ev, s.ev + s.nEv, q, [](const nc_event& x, uint32_t k) { return x.neuron < k; }) - s.ev);
         uint32_t evHi = (uint32_t)(std::upper_bound(s.ev, s.ev + s.nEv, q, [](uint32_t k, const nc_event& x) { return k < x.neuron; }) - s.ev);
@@ -171,8 +178,7 @@ static void model_pass1(nc_engine* e, const StepArgs& s) {
                 for (uint32_t c = 0; c < cnt; c++) {
                     float a = fabsf(cv.A(c));
                     if (a > s.t0) {
-                        uint32_t p = v.pre[rs + cv.J(c)] & 0x7fffffffu;
-                        unsigned long long code = (1ull << 32) | p;
+                        unsigned long long code = (1ull << 32) | cv.J(c);
                         if ((first || pick_less(curT, curC, a, code)) && pick_less(a, code, bt, bc)) { bt = a; bc = code; bsrc = c; }
                     }
                     float tR = add32(a, 2.0f);
@@ -225,11 +231,12 @@ static void model_pass2(nc_engine* e, const StepArgs& s) {
         const bool qFired = (v.mask[q >> 5] >> (q & 31u)) & 1u;
         const float lfS = v.lfStart[row];
         for (uint64_t j = rs; j < re; j++) {
-            uint32_t pw = v.pre[j], p = pw & 0x7fffffffu, ab = as_u32(v.arrive[j]);
+            const SynRec r0 = v.rec[j];
+            uint32_t p = r0.pre & 0x7fffffffu, ab = as_u32(v.ad[j].x);
             bool pFired = (v.mask[p >> 5] >> (p & 31u)) & 1u;
             float a = as_f32(ab);
             bool eventful = qFired || pFired || (ab & NC_SENT) || (ab != 0u && a > s.t0 && a <= s.t1);
-            if (eventful) resolve_slot(v, s, j, rs, q, p, (pw >> 31) != 0u, ab, pFired, qFired, lfS, cnt);
+            if (eventful) resolve_slot(v, s, j, (uint32_t)(j - rs), q, r0, ab, pFired, qFired, lfS, cnt);
         }
     }
     v.stats[2] += cnt[0]; v.stats[3] += cnt[1]; v.stats[4] += cnt[2]; v.stats[5] += cnt[3];
@@ -319,10 +326,8 @@ int nc_read_neurons(nc_engine* e, float* potAct, float* lastFire, float* lastRan
 }
 int nc_read_synapses(nc_engine* e, float* w, float* a, float* d, float* la, float* ls) {
     uint64_t b = e->v.S * 4;
-    if (w) memcpy(w, e->weight.data(), b);
-    if (a) memcpy(a, e->arrive.data(), b);
-    if (d) memcpy(d, e->depol.data(), b);
-    if (la) memcpy(la, e->lastArr.data(), b);
+    for (uint64_t j = 0; j < e->v.S; j++) { if (w) w[j] = e->rec[j].weight; if (la) la[j] = e->rec[j].lastArr; }
+    for (uint64_t j = 0; j < e->v.S; j++) { if (a) a[j] = e->ad[j].x; if (d) d[j] = e->ad[j].y; }
     if (ls) memcpy(ls, e->lastStart.data(), b);
     return NC_OK;
 }
@@ -348,10 +353,10 @@ int nc_state_signature(nc_engine* e, uint64_t* out) {
         out[2] += (unsigned long long)as_u32(e->lastFire[i]) * ((i + 1) * C);
     }
     for (uint64_t j = 0; j < e->v.S; j++) {
-        out[3] += (unsigned long long)as_u32(e->weight[j]) * ((j + 1) * C);
-        out[4] += (unsigned long long)as_u32(e->arrive[j]) * ((j + 1) * C);
-        if (e->arrive[j] != 0.0f) out[4] += (unsigned long long)as_u32(e->depol[j]) * ((j + 1) * C);
-        out[5] += (unsigned long long)as_u32(e->lastArr[j]) * ((j + 1) * C);
+        out[3] += (unsigned long long)as_u32(e->rec[j].weight) * ((j + 1) * C);
+        out[4] += (unsigned long long)as_u32(e->ad[j].x) * ((j + 1) * C);
+        if (e->ad[j].x != 0.0f) out[4] += (unsigned long long)as_u32(e->ad[j].y) * ((j + 1) * C);
+        out[5] += (unsigned long long)as_u32(e->rec[j].lastArr) * ((j + 1) * C);
     }
     return NC_OK;
 }

@@ -3,10 +3,13 @@ vectors generated from the reference itself and against the CPU oracle on the sa
 import numpy as np
 import pytest
 
+import os
+
 import scenarios
 from helpers import libc, same_bits, state_signature, synthetic_drive
 
 pytestmark = pytest.mark.gpu
+FAST = os.environ.get("NC_FAST_TESTS") == "1"  # development iterations: two of the ten 10k-step fixtures, no 1000-step oracle run
 
 
 def test_c1_golden_seed1_full(native_libs):
@@ -26,6 +29,8 @@ LONG = [("c1_long_seed%d_%s.npz" % (seed, flags)) for seed in (1, 2, 4, 8, 9) fo
 
 @pytest.mark.parametrize("name", LONG)
 def test_c1_stated_horizon_10k_steps(native_libs, name):
+    if FAST and name not in (LONG[1], LONG[6]):
+        pytest.skip("NC_FAST_TESTS")
     """BASELINE.json configs[0] at the stated horizon: 10 000 steps, seeds {1,2,4,8,9}, raw and normalised flags —
     state signature, detector voltage and the explicit spike raster (nc_read_fires) at every step against the
     reference's own run; final potentials, weights and lastFire bit-identical."""
@@ -89,8 +94,18 @@ def test_synthetic_c2_recipe_10k(native_libs):
 def test_synthetic_c2_recipe_10k_1000_steps(native_libs):
     """Same network for 1000 steps (SURVEY.md §8d asks for ~1000): per step the six state signatures, the mean potential
     and the explicit fire raster (neuron, time) against the oracle.  The oracle needs ~70 ms per step in the running regime."""
+    if FAST:
+        pytest.skip("NC_FAST_TESTS")
     st = scenarios.synthetic_vs_oracle_signatures(None, 10_000, 100, 1000)
     assert st["deliveries"] > 5_000_000 and st["loads_dropped"] > 1_000_000 and st["hidden_rand"] > 100_000
+
+
+def test_staging_region_overflow_takes_the_in_kernel_path(native_libs, monkeypatch):
+    """Tiles whose occupied slots exceed their staging region (here: 8 entries per tile of 32 rows) are flagged by k_stage and
+    staged inside k_neuron_pass row by row through the busy-slot index: same results."""
+    monkeypatch.setenv("NC_STAGE_CAP", "8")
+    st = scenarios.synthetic_vs_oracle(None, 1500, 60, 400)
+    assert st["deliveries"] > 50_000 and st["loads_dropped"] > 0
 
 
 def test_long_rows_take_the_warp_per_row_path(native_libs):

@@ -124,10 +124,28 @@ int nc_run_neurons(nc_engine* e, float now, const uint32_t* ids, uint32_t n_ids,
  * Any pointer may be NULL. potAct is the interleaved (potential, activity) array of this shard. */
 int nc_read_neurons(nc_engine* e, float* potAct, float* lastFire, float* lastRan);
 int nc_read_synapses(nc_engine* e, float* weight, float* arrive, float* depol, float* lastArrival, float* lastStart);
+/* Neuron::activityStartTime / firings (NeuCor.h:239-240) — with nc_read_neurons and nc_read_synapses the complete dynamic state. */
+int nc_read_neuron_counters(nc_engine* e, float* actStart, uint32_t* firings);
+/* The shard's network as uploaded (rows of the CSR), read back from the device records. Any pointer may be NULL. */
+int nc_read_network(nc_engine* e, uint64_t* rowptr, uint32_t* pre, float* length, uint8_t* inhibitory);
+/* Checkpoint resume (the reference has no serialisation at all): the inverse of the readers above.
+ * NULL keeps what is there.  After nc_write_synapses the event index is rebuilt from `arrive`. */
+int nc_write_neurons(nc_engine* e, const float* potAct, const float* lastFire, const float* lastRan, const float* actStart, const uint32_t* firings);
+int nc_write_synapses(nc_engine* e, const float* weight, const float* arrive, const float* depol, const float* lastArrival, const float* lastStart);
 /* Fire events of the last step, all shards: (neuron, time); returns the total count in *count. */
 int nc_read_fires(nc_engine* e, uint32_t capacity, uint32_t* neuron, float* time, uint32_t* count);
 /* Synapse::getPrePot / getPostPot at time `now` for every synapse of the shard (NeuCor.cpp:547-567). */
 int nc_read_synapse_pots(nc_engine* e, float now, float* prePot, float* postPot);
+/* The same potentials written into caller-provided DEVICE (or host-mapped / graphics-interop) buffers of S floats each,
+ * in-stream, no staging copy — the renderer's per-frame gather (Renderer.cpp:655-699). Either pointer may be NULL. */
+int nc_synapse_pots_device(nc_engine* e, float now, float* d_prePot, float* d_postPot);
+/* NeuCor_Renderer's "Statistics" panel reduced on the device (Renderer.cpp:1733-1876): the neuron-activity and the
+ * synapse-weight distribution (span index = floor(spans * (x - range_min) / (range_max - range_min)), values outside the
+ * range counted in *below / *above; an empty range leaves all bins 0 as the reference does), and one frame of the raster
+ * plot by the GUI's own rule `now - lastFire < runSpeed` (ascending neuron IDs; *count may exceed capacity). */
+int nc_render_activity_histogram(nc_engine* e, uint32_t spans, float range_min, float range_max, uint32_t* bins, uint32_t* below, uint32_t* above);
+int nc_render_weight_histogram(nc_engine* e, uint32_t spans, float range_min, float range_max, uint32_t* bins, uint32_t* below, uint32_t* above);
+int nc_render_raster(nc_engine* e, float now, float run_speed, uint32_t capacity, uint32_t* ids, uint32_t* count);
 /* Six position-weighted 64-bit checksums of the shard's state, computed on the device: potential, activity, lastFire,
  * weight, arrive (+ depol of busy slots), lastSpikeArrival — sum of bits(x[i])*(i+1)*0x9E3779B97F4A7C15 mod 2^64 each.
  * What the parity fixtures pin per step (the reference harness computes the same words from NeuCor's members), and a cheap
@@ -154,6 +172,22 @@ int nc_tape_replay(nc_engine* e, uint32_t first, uint32_t count, float* ms_total
 /* Per-kernel sums [ms] of the last nc_tape_replay that asked for per-kernel times:
  * out4 = { k_stage, k_neuron_pass, fire exchange, synapse kernels (loads + rows + flagged) }. */
 int nc_replay_breakdown(const nc_engine* e, float* out4);
+/* Device-resident replica of libc's rand() stream.  glibc's default generator is
+ * x[n] = x[n-31] + x[n-3] (mod 2^32), rand() = x[n] >> 1; `x31` are its 31 most recent raw values, oldest first.  Once a
+ * state is set the engine keeps the stream's position itself: nc_background_draw consumes the draws of NeuCor::run's
+ * background-firing loop (NeuCor.cpp:604-607), every window moves the stream on by its hidden rand() calls
+ * (NeuCor.cpp:752, summed over the shards), and nc_rand_get_state returns where the stream stands so that the host can
+ * put libc's generator there (the application's own rand() calls go on where the reference's would). */
+int nc_rand_set_state(nc_engine* e, const uint32_t* x31);
+int nc_rand_get_state(nc_engine* e, uint32_t* x31);
+/* The background-firing draws of one NeuCor::run() starting at t0 (NeuCor.cpp:604-607), on the device: one test draw per
+ * neuron of the WHOLE network (`period` = max(1, int(600 / runSpeed))), two more per hit; the resulting events (kind 2,
+ * the last one of a neuron flagged as its scheduledFireTime) of this shard's neurons are merged into the event lists of
+ * the nc_step windows that follow, until the next draw or nc_background_clear.  Every shard makes the same call. */
+int nc_background_draw(nc_engine* e, float t0, float run_speed, uint32_t period, uint64_t n_neurons);
+int nc_background_clear(nc_engine* e);
+/* The events of the active background draw that belong to this shard (sorted by neuron) and the number of hits of the whole network. */
+int nc_background_read(nc_engine* e, uint32_t capacity, nc_event* out, uint32_t* count, uint32_t* hits);
 /* Work done through the event index since the last call: out2 = { busy slots the staging kernel looked at,
  * flag-list entries (slots that delivered or were cleared) }.  For the traffic model of bench.py. */
 int nc_index_stats(nc_engine* e, uint64_t* out2);

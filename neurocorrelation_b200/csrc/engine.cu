@@ -36,6 +36,8 @@
 
 #include "../../include/neucor_b200.h"
 #include "step_logic.cuh"
+#include "rand_stream.cuh"
+#include "peer_exchange.cuh"
 
 using namespace ncm;
 using namespace ncs;
@@ -321,10 +323,11 @@ __global__ void __launch_bounds__(NC_STG_WARPS * 32, 8) k_stage(View v, StepArgs
 // host events of neuron q: [evLo, evHi) in the (neuron, time)-sorted list (bit set by k_mark_events for rows that have any)
 __device__ __forceinline__ void host_event_range(const View& v, const StepArgs& s, uint64_t row, uint32_t q, uint32_t& evLo, uint32_t& evHi) {
     evLo = 0; evHi = 0;
-    if (s.nEv && ((v.evMask[row >> 5] >> (row & 31u)) & 1u)) {
-        uint32_t lo = 0, hi = s.nEv;
+    if ((s.nEv || s.nEvDev) && ((v.evMask[row >> 5] >> (row & 31u)) & 1u)) {
+        const uint32_t nEv = s.nEvDev ? *s.nEvDev : s.nEv;
+        uint32_t lo = 0, hi = nEv;
         while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (s.ev[mid].neuron < q) lo = mid + 1; else hi = mid; }
-        evLo = lo; hi = s.nEv;
+        evLo = lo; hi = nEv;
         while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (s.ev[mid].neuron <= q) lo = mid + 1; else hi = mid; }
         evHi = lo;
     }
@@ -750,11 +753,12 @@ __global__ void k_index_reset(View v, StepArgs s) {
 }
 // End of a window: publish (or, for replay, accumulate) the shard's counters and its exchange header into `out`
 // (10 x u64: the 8 nc_step_stats counters, fire count, overflow flag), then clear both for the next window.
-__global__ void k_finish_step(View v, unsigned long long* out, int accumulate) {
+__global__ void k_finish_step(View v, unsigned long long* out, int accumulate, unsigned long long* win) {
     const uint32_t i = threadIdx.x;
     if (i < 8) {
         unsigned long long x = v.stats[i];
         out[i] = accumulate ? out[i] + x : x;
+        win[i] = x;  // this window's own counters (the rand() stream moves on by win[5], summed over the shards)
         v.stats[i] = 0ull;
     } else if (i == 9) {  // running totals for nc_index_stats: busy slots visited, flag-list entries
         v.stats[10] += v.stats[8]; v.stats[8] = 0ull;
@@ -863,14 +867,47 @@ __global__ void __launch_bounds__(256) k_syn_flagged(View v, StepArgs s) {
 }
 
 // Marks (set = 1) or unmarks the rows of this shard that have host events in this window.
-__global__ void k_mark_events(View v, const nc_event* ev, uint32_t nEv, int set) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nEv) return;
-    uint64_t n = ev[i].neuron;
-    if (n < v.row0 || n >= v.row0 + v.nRows) return;
-    uint64_t row = n - v.row0;
-    if (set) atomicOr(&v.evMask[row >> 5], 1u << (row & 31u));
-    else v.evMask[row >> 5] = 0u;
+__global__ void k_mark_events(View v, const nc_event* ev, uint32_t nEv, const uint32_t* nEvDev, int set) {
+    if (nEvDev) nEv = *nEvDev;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nEv; i += gridDim.x * blockDim.x) {
+        uint64_t n = ev[i].neuron;
+        if (n < v.row0 || n >= v.row0 + v.nRows) continue;
+        uint64_t row = n - v.row0;
+        if (set) atomicOr(&v.evMask[row >> 5], 1u << (row & 31u));
+        else v.evMask[row >> 5] = 0u;
+    }
+}
+// The window's event list when the background events live on the device: the host's (input-firer) events, sorted by neuron,
+// merged with the background events of the run that fall into the window — sorted by neuron, input events before background
+// events of the same neuron, each group in its own order (what the host's stable sort of [inputs..., background...] gives).
+// One block; both lists are short.  bgCtl[0] = number of background events of the run; outCount <- merged length.
+__global__ void __launch_bounds__(1024) k_merge_events(const nc_event* host, uint32_t nHost, const nc_event* bg, const uint32_t* bgCtl, float t0, float t1,
+                                                      int strict, nc_event* out, uint32_t outCap, uint32_t* outCount) {
+    __shared__ uint32_t sIn;
+    const uint32_t nBg = bgCtl[0];
+    if (threadIdx.x == 0) sIn = 0u;
+    __syncthreads();
+    auto inWin = [&](const nc_event& e) { return (strict ? e.time > t0 : e.time >= t0) && e.time <= t1; };
+    // background event j -> position = (in-window background events before it) + (host events with neuron <= its neuron)
+    for (uint32_t j = threadIdx.x; j < nBg; j += blockDim.x) {
+        const nc_event e = bg[j];
+        if (!inWin(e)) continue;
+        uint32_t before = 0;
+        for (uint32_t k = 0; k < j; k++) before += inWin(bg[k]) ? 1u : 0u;
+        uint32_t lo = 0, hi = nHost;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (host[mid].neuron <= e.neuron) lo = mid + 1; else hi = mid; }
+        if (before + lo < outCap) out[before + lo] = e;
+        atomicAdd(&sIn, 1u);
+    }
+    // host event i -> position = i + (in-window background events with a smaller neuron)
+    for (uint32_t i = threadIdx.x; i < nHost; i += blockDim.x) {
+        const nc_event e = host[i];
+        uint32_t below = 0;
+        for (uint32_t k = 0; k < nBg; k++) below += (bg[k].neuron < e.neuron && inWin(bg[k])) ? 1u : 0u;
+        if (i + below < outCap) out[i + below] = e;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *outCount = min(nHost + sIn, outCap);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -952,6 +989,20 @@ __global__ void k_extract_ad(View v, int which, float* out) {  // which: 0 arriv
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < v.S; j += (uint64_t)gridDim.x * blockDim.x)
         out[j] = which == 0 ? v.ad[j].x : which == 1 ? v.ad[j].y : which == 2 ? v.rec[j].weight : v.rec[j].lastArr;
 }
+// state injection (checkpoint resume): which 0 arrive, 1 depol, 2 weight, 3 lastArr
+__global__ void k_inject_syn(View v, int which, const float* in) {
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < v.S; j += (uint64_t)gridDim.x * blockDim.x) {
+        const float x = in[j];
+        if (which == 0) v.ad[j].x = x; else if (which == 1) v.ad[j].y = x; else if (which == 2) v.rec[j].weight = x; else v.rec[j].lastArr = x;
+    }
+}
+// the network as uploaded, back from the device records: which 0 pre, 1 length (delay / 2, exact), 2 inhibitory flag
+__global__ void k_extract_net(View v, int which, uint32_t* out) {
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < v.S; j += (uint64_t)gridDim.x * blockDim.x) {
+        const SynRec r = v.rec[j];
+        out[j] = which == 0 ? (r.pre & 0x7fffffffu) : which == 1 ? __float_as_uint(mul32(r.delay, 0.5f)) : (r.pre >> 31);
+    }
+}
 // busy-slot index from `arrive` (after a restore, or for state loaded from a file)
 __global__ void k_rebuild_busy(View v, uint64_t words) {
     for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (uint64_t)gridDim.x * blockDim.x) {
@@ -975,6 +1026,31 @@ __global__ void k_detector_mean(View v, const uint32_t* near, uint32_t n, float*
     float avg = 0.0f;
     for (uint32_t i = 0; i < n; i++) avg = add32(avg, v.potAct[near[i] - v.row0].x);
     *out = div32(avg, (float)n);
+}
+// ---- NeuCor_Renderer's "Statistics" panel on the device (/root/reference/src/NeuCor_Renderer.cpp:1733-1876) -----------------------
+// span index = floor(spans * (x - range_min) / range) with the reference's float typing (int * float, float / float, floor);
+// values outside [0, spans) are counted as below / above.  which: 0 = Neuron::activity() of every neuron (:1749-1761),
+// 1 = Synapse::getWeight() of every synapse (:1801-1815).  out[0..spans) bins, out[spans] below, out[spans+1] above.
+__global__ void k_render_histogram(View v, int which, uint32_t spans, float rmin, float range, unsigned int* out) {
+    const uint64_t n = which ? v.S : v.nRows;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float x = which ? v.rec[i].weight : v.potAct[i].y;
+        const float f = floorf(div32(mul32((float)(int)spans, sub32(x, rmin)), range));
+        uint32_t slot;
+        if (!(f >= 0.0f)) slot = spans;                  // negative, or NaN (the reference's (int)NaN is INT_MIN)
+        else if (f >= (float)spans) slot = spans + 1u;
+        else slot = (uint32_t)f;
+        atomicAdd(&out[slot], 1u);
+    }
+}
+// Raster frame by the GUI's rule: neurons with now - lastFire < runSpeed (Renderer.cpp:1856-1862); IDs in no particular order.
+__global__ void k_render_raster(View v, float now, float runSpeed, uint32_t cap, uint32_t* ids, unsigned int* count) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < v.nRows; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (sub32(now, v.lastFire[i]) < runSpeed) {
+            const uint32_t at = atomicAdd(count, 1u);
+            if (at < cap) ids[at] = (uint32_t)(v.row0 + i);
+        }
+    }
 }
 // Synapse::getPrePot / getPostPot (NeuCor.cpp:547-567)
 __device__ __forceinline__ float render_behaviour(float valf) {  // AP_RENDER_BEHAVIOUR, NeuCor.cpp:547-550
@@ -1006,7 +1082,7 @@ __global__ void k_synapse_pots(View v, float now, float* prePot, float* postPot)
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 
-struct TapeStep { float t0, t1; int sweep; uint64_t evOff; uint32_t nEv; uint32_t units; uint32_t fires; };
+struct TapeStep { float t0, t1; int sweep; uint64_t evOff; uint32_t nEv; uint32_t units; uint32_t fires; bool bgDraw, bgActive, bgStrict; ncr::BgArgs bg; };
 
 // NCCL is bound at run time (dlopen) so that single-GPU users need no NCCL at all; only the five entry points below are used.
 struct NcclApi {
@@ -1030,6 +1106,21 @@ struct nc_engine {
     nc_event* hEvPinned = nullptr; uint32_t hEvCap = 0;
     // per-window result block: 10 x u64 per shard (8 counters, fire count, overflow flag)
     unsigned long long* dSig = nullptr; unsigned long long* hSig = nullptr;  // nc_state_signature
+    // device-resident rand() stream and background firing (rand_stream.cuh)
+    ncr::RandTables rtab = {nullptr, nullptr};
+    uint32_t *dRandState = nullptr, *dRandNext = nullptr;  // 31-word stream state (oldest value first) and the buffer the next one is written to
+    uint32_t* hRand = nullptr;               // pinned: [0..31) state after the last window, [32..36) background control block
+    bool randOn = false, hRandFresh = false;
+    uint32_t* dDraws = nullptr; uint64_t drawsCap = 0; uint32_t* dHitMask = nullptr;
+    nc_event *dBgTmp = nullptr, *dBgEv = nullptr; uint32_t bgCap = 0;
+    uint32_t *dCand = nullptr, *dCandRaw = nullptr; uint32_t candListCap = 0;
+    uint32_t* dBgCtl = nullptr;              // [0] events of this shard, [1] hits (network), [2] overflow, [3] draws consumed
+    bool bgActive = false, bgFirstWindow = false;
+    nc_event* dEvMerged = nullptr; uint32_t mergedCap = 0; uint32_t* dMergedCount = nullptr;
+    bool bgPendingTape = false; ncr::BgArgs bgPendingArgs = {};
+    bool pendingBgActive = false, pendingBgStrict = false;  // of the window in flight (for the tape)
+    unsigned long long* dWin = nullptr; unsigned long long* dWinAll = nullptr;  // the last window's own counters (replay accumulates dOut)
+    uint32_t* snapRand = nullptr; bool snapRandOn = false;
     unsigned long long* dOut = nullptr;     // this shard's block
     unsigned long long* dOutAll = nullptr;  // world blocks (world > 1)
     unsigned long long* hOut = nullptr;     // pinned, world blocks
@@ -1039,17 +1130,23 @@ struct nc_engine {
     void* comm = nullptr;
     nc_allgather_fn xchgFn = nullptr; void* xchgCtx = nullptr;
     uint32_t xchgUnits = 1u + 1024u;        // units per shard moved by the fire exchange; grows on demand
+    // peer exchange over NVLink (peer_exchange.cuh): this shard's arena and every shard's arena as mapped here
+    bool p2p = false;
+    char* arena = nullptr; char* peerBase[NC_MAX_WORLD] = {nullptr};
+    size_t offCnt = 0, offG[2] = {0, 0};
+    uint32_t xseq = 0; uint32_t* dPushCtr = nullptr;
     uint32_t lastCounts[NC_MAX_WORLD] = {0}; uint32_t lastStride = 0;
     bool pending = false;                   // nc_step_launch issued, nc_step_collect outstanding
     StepArgs pendingArgs;
     float lr = 1.0f, preF = 0.13f, postF = 0.30f, preD = 0.75f, postD = 0.65f;
     float minDelay = INFINITY;
-    uint32_t candCap = 704, candCapSparse = 512, grid1 = 0, grid1s = 0, gridStage = 0;
-    int forceVariant = 0;                   // 0 auto, 1 dense, 2 sparse
+    uint32_t candCap = 704, candCapSparse = 512, candCapBig = 1024, grid1 = 0, grid1s = 0, grid1b = 0, gridStage = 0;
+    int forceVariant = 0;                   // 0 auto, 1 big, 2 dense, 3 sparse
     double lastSlotsPerRun = 1e9;           // occupied slots visited per neuron run in the last window (picks the variant)
-    size_t smem1 = 0, smem1s = 0;
+    size_t smem1 = 0, smem1s = 0, smem1b = 0;
     uint64_t* dCscPtr = nullptr; SlotRow* dCscEnt = nullptr;  // out-synapse index (CSC over global presynaptic IDs)
     uint64_t launches = 0;
+    void* dScratch = nullptr; size_t scratchBytes = 0;  // read-back / render entry points
     cudaEvent_t* tick = nullptr;            // per-kernel timing of a replay: recorded between the staging kernel and the neuron pass
     float breakdown[4] = {0, 0, 0, 0};      // last per-kernel replay: k_stage, k_neuron_pass, fire exchange, synapse kernels [ms, summed]
     // tape
@@ -1108,6 +1205,26 @@ extern "C" int nc_create(const nc_config* cfg, nc_engine** out) {
     if (ce == cudaSuccess) ce = cudaMallocHost(&e->hHdrAll, (size_t)cfg->world * 4 * sizeof(uint32_t));
     if (ce == cudaSuccess) ce = cudaMalloc(&e->dSig, 6 * sizeof(unsigned long long));
     if (ce == cudaSuccess) ce = cudaMallocHost(&e->hSig, 6 * sizeof(unsigned long long));
+    if (ce == cudaSuccess) {
+        std::vector<uint32_t> T, J;
+        ncr::build_rand_tables(T, J);
+        uint32_t *dT = nullptr, *dJ = nullptr;
+        ce = cudaMalloc(&dT, T.size() * 4);
+        if (ce == cudaSuccess) ce = cudaMalloc(&dJ, J.size() * 4);
+        if (ce == cudaSuccess) ce = cudaMemcpy(dT, T.data(), T.size() * 4, cudaMemcpyHostToDevice);
+        if (ce == cudaSuccess) ce = cudaMemcpy(dJ, J.data(), J.size() * 4, cudaMemcpyHostToDevice);
+        e->rtab.T = dT; e->rtab.J = dJ;
+    }
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->dRandState, 32 * 4);
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->dRandNext, 32 * 4);
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->snapRand, 32 * 4);
+    if (ce == cudaSuccess) ce = cudaMallocHost(&e->hRand, 40 * 4);
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->dBgCtl, 8 * 4);  // [0..4) control block of the walk, [4] candidate counter of the generator
+    if (ce == cudaSuccess) ce = cudaMemset(e->dBgCtl, 0, 8 * 4);
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->dMergedCount, 4);
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->dWin, 10 * sizeof(unsigned long long));
+    if (ce == cudaSuccess) ce = cudaMemset(e->dWin, 0, 10 * sizeof(unsigned long long));
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->dWinAll, (size_t)cfg->world * 10 * sizeof(unsigned long long));
     if (ce == cudaSuccess) ce = cudaMalloc(&e->dOut, 10 * sizeof(unsigned long long));
     if (ce == cudaSuccess) ce = cudaMemset(e->dOut, 0, 10 * sizeof(unsigned long long));
     if (ce == cudaSuccess) ce = cudaMalloc(&e->dOutAll, (size_t)cfg->world * 10 * sizeof(unsigned long long));
@@ -1144,6 +1261,11 @@ extern "C" void nc_destroy(nc_engine* e) {
     free_all(e);
     cudaFree(e->v.stats); cudaFree(e->v.tileCtr); cudaFree(e->dOut); cudaFree(e->dOutAll);
     cudaFreeHost(e->hOut); cudaFreeHost(e->hHdrAll); cudaFreeHost(e->hEvPinned); cudaFree(e->dSig); cudaFreeHost(e->hSig);
+    cudaFree((void*)e->rtab.T); cudaFree((void*)e->rtab.J); cudaFree(e->dRandState); cudaFree(e->dRandNext); cudaFree(e->snapRand); cudaFreeHost(e->hRand);
+    cudaFree(e->dDraws); cudaFree(e->dHitMask); cudaFree(e->dBgTmp); cudaFree(e->dBgEv); cudaFree(e->dCand); cudaFree(e->dCandRaw); cudaFree(e->dBgCtl); cudaFree(e->dEvMerged); cudaFree(e->dMergedCount);
+    cudaFree(e->dWin); cudaFree(e->dWinAll);
+    for (int r = 0; r < e->cfg.world; r++) if (e->p2p && r != e->cfg.rank && e->peerBase[r]) cudaIpcCloseMemHandle(e->peerBase[r]);
+    cudaFree(e->arena); cudaFree(e->dPushCtr); cudaFree(e->dScratch);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     if (e->ownStream) cudaStreamDestroy(e->stream);
     delete e;
@@ -1214,8 +1336,7 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
     CK(cudaMalloc(&v.localHdr, blockUnits * sizeof(FireRec)));
     v.localRecs = reinterpret_cast<FireRec*>(v.localHdr) + 1;
     CK(cudaMemsetAsync(v.localHdr, 0, 16, e->stream));
-    if (e->cfg.world > 1) { CK(cudaMalloc(&e->dGather, (uint64_t)e->cfg.world * blockUnits * sizeof(FireRec))); v.gRecs = e->dGather; }
-    else v.gRecs = reinterpret_cast<FireRec*>(v.localHdr);
+    v.gRecs = reinterpret_cast<FireRec*>(v.localHdr);  // (world > 1: the gathered blocks — peer-exchange arena, or ensure_gather's buffer)
     CK(cudaMalloc(&v.head, G1 * 4)); CK(cudaMalloc(&v.next, (uint64_t)e->cfg.world * blockUnits * 4));
     CK(cudaMalloc(&v.mask, ((G1 + 31) / 32) * 4));
     CK(cudaMemsetAsync(v.mask, 0, ((G1 + 31) / 32) * 4, e->stream));
@@ -1266,21 +1387,28 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
     }
     // launch geometry: persistent grids sized to the SM count x resident blocks per SM
     // the warp's shared-memory pool of staged slots: shared by the rows of a lane-per-row batch, so not tied to the row length
-    e->candCap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(e->candCap, 32), 704);
-    e->candCapSparse = std::min<uint32_t>(e->candCap, 512u);
+    // Three builds of the same neuron pass, picked per window from the last window's occupancy (fill_args): a 1024-slot pool at
+    // 4 blocks per SM for busy networks (a tile of 32 rows then mostly fits ONE batch), 704 slots at 6 blocks, 512 at 8 blocks.
+    // nc_config.cand_smem pins all three to one size (tests).
+    if (e->cfg.cand_smem) { e->candCap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(e->candCap, 32), 1024); e->candCapBig = e->candCapSparse = e->candCap; }
+    else { e->candCap = 704; e->candCapSparse = 512; e->candCapBig = 1024; }
     e->smem1 = (size_t)NC_WARPS_PER_BLOCK * 3 * e->candCap * 4;
     e->smem1s = (size_t)NC_WARPS_PER_BLOCK * 3 * e->candCapSparse * 4;
+    e->smem1b = (size_t)NC_WARPS_PER_BLOCK * 3 * e->candCapBig * 4;
+    CK(cudaFuncSetAttribute(k_neuron_pass<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem1b));
     CK(cudaFuncSetAttribute(k_neuron_pass<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem1));
     CK(cudaFuncSetAttribute(k_neuron_pass<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem1s));
-    int occ1 = 1, occ1s = 1;
+    int occ1 = 1, occ1s = 1, occ1b = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1b, k_neuron_pass<4>, NC_WARPS_PER_BLOCK * 32, e->smem1b));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_neuron_pass<6>, NC_WARPS_PER_BLOCK * 32, e->smem1));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1s, k_neuron_pass<8>, NC_WARPS_PER_BLOCK * 32, e->smem1s));
     uint64_t needBlocks = ((nRows + 31) / 32 + NC_WARPS_PER_BLOCK - 1) / NC_WARPS_PER_BLOCK;  // one tile of 32 rows per warp at a time
+    e->grid1b = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(needBlocks, (uint64_t)e->smCount * std::max(occ1b, 1)));
     e->grid1 = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(needBlocks, (uint64_t)e->smCount * std::max(occ1, 1)));
     e->grid1s = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(needBlocks, (uint64_t)e->smCount * std::max(occ1s, 1)));
     {
-        const char* f = getenv("NC_NEURON_VARIANT");  // tuning/tests: "dense" or "sparse" pins the variant
-        e->forceVariant = f ? (f[0] == 's' ? 2 : 1) : 0;
+        const char* f = getenv("NC_NEURON_VARIANT");  // tuning/tests: "big", "dense" or "sparse" pins the variant
+        e->forceVariant = f ? (f[0] == 's' ? 3 : f[0] == 'b' ? 1 : 2) : 0;
     }
     {   // staging regions: one per tile of 32 rows, large enough for every slot of the largest tile up to 8192 entries
         // (beyond that a tile that is this busy takes the in-kernel staging path); NC_STAGE_CAP overrides (tests)
@@ -1295,7 +1423,7 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
     }
     // scratch sized for whichever variant needs more: spill beyond the smaller pool, one pool of slot indices per resident warp
     v.spillPerWarp = (uint32_t)(maxRow > e->candCapSparse ? maxRow - e->candCapSparse : 0);
-    const uint64_t maxWarps = (uint64_t)std::max(e->grid1, e->grid1s) * NC_WARPS_PER_BLOCK;
+    const uint64_t maxWarps = (uint64_t)std::max(std::max(e->grid1, e->grid1s), e->grid1b) * NC_WARPS_PER_BLOCK;
     uint64_t spillN = std::max<uint64_t>(1, maxWarps * v.spillPerWarp);
     CK(cudaMalloc(&v.spillA, spillN * 4)); CK(cudaMalloc(&v.spillD, spillN * 4)); CK(cudaMalloc(&v.spillJ, spillN * 4));
     CK(cudaStreamSynchronize(e->stream));
@@ -1408,8 +1536,9 @@ static void fill_args(nc_engine* e, StepArgs& a, float t0, float t1, int sweep, 
     a.ev = dEv; a.nEv = nEv; a.world = (uint32_t)e->cfg.world;
     {   // sparse variant while a tile of 32 rows needs a small fraction of its 512-slot pool (measured: 14 % faster in the quiet
         // regime with ~2 occupied slots per row, 4 % slower at 8.5 per row where the replay starts to matter)
-        const bool sparse = e->forceVariant ? e->forceVariant == 2 : e->lastSlotsPerRun * 32.0 * 4.0 < (double)e->candCapSparse;
-        a.candCap = sparse ? e->candCapSparse : e->candCap;
+        const double perTile = e->lastSlotsPerRun * 32.0;  // occupied slots of a tile of 32 rows, from the last window
+        a.variant = e->forceVariant ? (uint32_t)e->forceVariant - 1u : perTile * 4.0 < (double)e->candCapSparse ? 2u : perTile > 0.85 * (double)e->candCap ? 0u : 1u;
+        a.candCap = a.variant == 0u ? e->candCapBig : a.variant == 1u ? e->candCap : e->candCapSparse;
     }
     a.gStride = e->cfg.world == 1 ? e->v.fireCap + 1u : e->xchgUnits;
 }
@@ -1427,19 +1556,56 @@ static void launch_neuron_pass(nc_engine* e, const StepArgs& a) {
     k_stage<<<e->gridStage, NC_STG_WARPS * 32, 0, e->stream>>>(e->v, a);
     e->launches++;
     if (e->tick) cudaEventRecord(*e->tick, e->stream);
-    if (a.candCap == e->candCapSparse && e->candCapSparse != e->candCap)
-        k_neuron_pass<8><<<e->grid1s, NC_WARPS_PER_BLOCK * 32, e->smem1s, e->stream>>>(e->v, a);
-    else
-        k_neuron_pass<6><<<e->grid1, NC_WARPS_PER_BLOCK * 32, e->smem1, e->stream>>>(e->v, a);
+    if (a.variant == 2u) k_neuron_pass<8><<<e->grid1s, NC_WARPS_PER_BLOCK * 32, e->smem1s, e->stream>>>(e->v, a);
+    else if (a.variant == 0u) k_neuron_pass<4><<<e->grid1b, NC_WARPS_PER_BLOCK * 32, e->smem1b, e->stream>>>(e->v, a);
+    else k_neuron_pass<6><<<e->grid1, NC_WARPS_PER_BLOCK * 32, e->smem1, e->stream>>>(e->v, a);
+    e->launches++;
+}
+static void mark_events(nc_engine* e, const StepArgs& a, int set) {
+    if (!a.nEv && !a.nEvDev) return;
+    const unsigned blocks = a.nEvDev ? 32u : (a.nEv + 255u) / 256u;
+    k_mark_events<<<blocks, 256, 0, e->stream>>>(e->v, a.ev, a.nEv, a.nEvDev, set);
     e->launches++;
 }
 static int launch_pass1(nc_engine* e, const StepArgs& a) {
-    if (a.nEv) { k_mark_events<<<(a.nEv + 255) / 256, 256, 0, e->stream>>>(e->v, a.ev, a.nEv, 1); e->launches++; }
+    mark_events(e, a, 1);
     launch_neuron_pass(e, a);
-    if (a.nEv) { k_mark_events<<<(a.nEv + 255) / 256, 256, 0, e->stream>>>(e->v, a.ev, a.nEv, 0); e->launches++; }
+    mark_events(e, a, 0);
     CK(cudaGetLastError());
     return NC_OK;
 }
+// the background events of the current run() live on the device: merge those of this window into the host's event list
+static int merge_background(nc_engine* e, StepArgs& a, bool strict) {
+    const uint32_t need = a.nEv + e->bgCap;
+    if (need > e->mergedCap) { cudaFree(e->dEvMerged); e->mergedCap = need * 2 + 1024; CK(cudaMalloc(&e->dEvMerged, (size_t)e->mergedCap * sizeof(nc_event))); }
+    k_merge_events<<<1, 1024, 0, e->stream>>>(a.ev, a.nEv, e->dBgEv, e->dBgCtl, a.t0, a.t1, strict ? 1 : 0, e->dEvMerged, e->mergedCap, e->dMergedCount);
+    e->launches++;
+    a.ev = e->dEvMerged; a.nEvDev = e->dMergedCount;
+    return NC_OK;
+}
+static int launch_background(nc_engine* e, const ncr::BgArgs& a) {
+    const unsigned blocks = (unsigned)((a.nDraws + NC_RS_CHUNK - 1) / NC_RS_CHUNK);
+    ncr::k_bg_generate<<<blocks, NC_RS_ROWS, 0, e->stream>>>(e->rtab, e->dRandState, a, e->dDraws, e->dCandRaw, e->candListCap, e->dBgCtl + 4);
+    ncr::k_bg_walk<<<1, 1024, 0, e->stream>>>(e->dRandState, a, e->dDraws, e->dCandRaw, e->dBgCtl + 4, e->dCand, e->candListCap, e->dBgTmp, e->dBgEv, e->bgCap, e->dBgCtl, e->dRandNext);
+    e->launches += 2;
+    std::swap(e->dRandState, e->dRandNext);
+    CK(cudaGetLastError());
+    return NC_OK;
+}
+// after a window's counters are final: the hidden rand() calls of its plasticity move the stream ahead (NeuCor.cpp:752)
+static int rand_after_window(nc_engine* e, const unsigned long long* counters, bool toHost) {
+    if (!e->randOn) return NC_OK;
+    ncr::k_rand_advance<<<1, 32, 0, e->stream>>>(e->rtab, e->dRandState, counters, (uint32_t)e->cfg.world);
+    e->launches++;
+    if (toHost) {
+        CK(cudaMemcpyAsync(e->hRand, e->dRandState, 31 * 4, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(e->hRand + 32, e->dBgCtl, 4 * 4, cudaMemcpyDeviceToHost, e->stream));
+        e->hRandFresh = true;
+    }
+    CK(cudaGetLastError());
+    return NC_OK;
+}
+static int rand_after_window(nc_engine* e);  // replay form: gathers the window's counters over the shards first
 // Index build over the gathered blocks (counts are read from the block headers on the device), synapse pass, index reset,
 // and the end-of-window kernel that publishes the counters + exchange header into dOut and clears them.
 static int launch_pass2(nc_engine* e, const StepArgs& a, uint32_t expectMax, int accumulate) {
@@ -1448,7 +1614,7 @@ static int launch_pass2(nc_engine* e, const StepArgs& a, uint32_t expectMax, int
     k_index_build<<<g, 256, 0, e->stream>>>(e->v, a);
     launch_synapse_pass(e, a, expectMax);
     k_index_reset<<<g, 256, 0, e->stream>>>(e->v, a);
-    k_finish_step<<<1, 32, 0, e->stream>>>(e->v, e->dOut, accumulate);
+    k_finish_step<<<1, 32, 0, e->stream>>>(e->v, e->dOut, accumulate, e->dWin);
     e->launches += 3;
     CK(cudaGetLastError());
     return NC_OK;
@@ -1491,6 +1657,96 @@ static bool nccl_load(std::string& err) {
     g_nccl = a;
     return true;
 }
+// Peer exchange set-up (collective over the job's ranks, uses the fresh NCCL communicator as its out-of-band channel):
+// allocate this shard's arena, all-gather the CUDA IPC handles, map every peer's arena.  Any rank that cannot do it makes
+// all ranks keep the NCCL all-gather path (the decision is itself all-gathered).  NC_NO_P2P=1 skips it.
+static int nccl_gather_bytes(nc_engine* e, const void* hostSrc, void* hostDst, size_t bytes) {
+    const int W = e->cfg.world;
+    char* d = nullptr;
+    CK(cudaMalloc(&d, (size_t)(W + 1) * bytes));
+    CK(cudaMemcpy(d + (size_t)W * bytes, hostSrc, bytes, cudaMemcpyHostToDevice));
+    int rc = g_nccl.AllGather(d + (size_t)W * bytes, d, bytes, /*ncclChar*/ 0, e->comm, e->stream);
+    if (rc) { cudaFree(d); return fail(e, NC_ERR_CUDA, std::string("ncclAllGather: ") + g_nccl.GetErrorString(rc)); }
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(hostDst, d, (size_t)W * bytes, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return NC_OK;
+}
+static int p2p_setup(nc_engine* e) {
+    const int W = e->cfg.world;
+    if (W < 2 || !e->uploaded) return NC_OK;
+    const uint64_t blockUnits = (uint64_t)e->v.fireCap + 1;
+    const size_t gBytes = (((size_t)W * blockUnits * sizeof(FireRec)) + 4095) / 4096 * 4096;
+    e->offCnt = NC_X_FLAGS_BYTES; e->offG[0] = NC_X_FLAGS_BYTES + NC_X_CNT_BYTES; e->offG[1] = e->offG[0] + gBytes;
+    int ok = getenv("NC_NO_P2P") ? 0 : 1;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (ok && cudaMalloc(&e->arena, e->offG[1] + gBytes) != cudaSuccess) { cudaGetLastError(); e->arena = nullptr; ok = 0; }
+    if (ok && cudaMemset(e->arena, 0, e->offG[1] + gBytes) != cudaSuccess) ok = 0;
+    if (ok && cudaIpcGetMemHandle(&mine, e->arena) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    std::vector<cudaIpcMemHandle_t> all(W);
+    int rc = nccl_gather_bytes(e, &mine, all.data(), sizeof(mine));
+    if (rc) return rc;
+    std::vector<int> oks(W);
+    rc = nccl_gather_bytes(e, &ok, oks.data(), sizeof(int));
+    if (rc) return rc;
+    for (int r = 0; r < W; r++) ok = ok && oks[r];
+    if (ok) {
+        for (int r = 0; r < W && ok; r++) {
+            if (r == e->cfg.rank) { e->peerBase[r] = e->arena; continue; }
+            void* p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+            e->peerBase[r] = (char*)p;
+        }
+    }
+    rc = nccl_gather_bytes(e, &ok, oks.data(), sizeof(int));  // everybody mapped everybody (also: nobody pushes before all are ready)
+    if (rc) return rc;
+    for (int r = 0; r < W; r++) ok = ok && oks[r];
+    if (!ok) {
+        for (int r = 0; r < W; r++) if (r != e->cfg.rank && e->peerBase[r]) cudaIpcCloseMemHandle(e->peerBase[r]);
+        cudaFree(e->arena); e->arena = nullptr;
+        return NC_OK;  // the NCCL all-gather path stays
+    }
+    CK(cudaMalloc(&e->dPushCtr, 4));
+    CK(cudaMemset(e->dPushCtr, 0, 4));
+    e->p2p = true;
+    return NC_OK;
+}
+static ncx::PeerTab peer_tab(const nc_engine* e, uint32_t parity) {
+    ncx::PeerTab t;
+    memset(&t, 0, sizeof(t));
+    for (int r = 0; r < e->cfg.world; r++) {
+        t.gather[r] = reinterpret_cast<FireRec*>(e->peerBase[r] + e->offG[parity]);
+        t.counters[r] = reinterpret_cast<unsigned long long*>(e->peerBase[r] + e->offCnt);
+        t.flags[r] = reinterpret_cast<uint32_t*>(e->peerBase[r]);
+    }
+    return t;
+}
+// fire blocks of this window -> every shard, wait for everybody's; the gathered blocks are then in this shard's arena
+static int p2p_exchange_fires(nc_engine* e, StepArgs& a, uint32_t expectOwn) {
+    const uint32_t seq = ++e->xseq, parity = seq & 1u;
+    const ncx::PeerTab pt = peer_tab(e, parity);
+    const uint32_t blockUnits = e->v.fireCap + 1u;
+    dim3 g(std::min<uint32_t>(std::max<uint32_t>((expectOwn + 256u) / 256u, 1u), 16u), (uint32_t)e->cfg.world);
+    ncx::k_push_fires<<<g, 256, 0, e->stream>>>(e->v, pt, (uint32_t)e->cfg.world, (uint32_t)e->cfg.rank, blockUnits, seq, e->dPushCtr);
+    ncx::k_wait_flags<<<1, 32, 0, e->stream>>>(reinterpret_cast<const uint32_t*>(e->arena), 0u, (uint32_t)e->cfg.world, seq, e->v.flagCtl + 1);
+    e->launches += 2;
+    e->v.gRecs = reinterpret_cast<const FireRec*>(e->arena + e->offG[parity]);
+    a.gStride = blockUnits;
+    e->lastStride = blockUnits;
+    CK(cudaGetLastError());
+    return NC_OK;
+}
+// the window's counters -> every shard, wait for everybody's: `world` blocks of 10 x u64 in this shard's arena
+static int p2p_exchange_counters(nc_engine* e, const unsigned long long* win) {
+    const uint32_t seq = e->xseq;
+    const ncx::PeerTab pt = peer_tab(e, seq & 1u);
+    ncx::k_push_counters<<<1, 32, 0, e->stream>>>(win, pt, (uint32_t)e->cfg.world, (uint32_t)e->cfg.rank, seq);
+    ncx::k_wait_flags<<<1, 32, 0, e->stream>>>(reinterpret_cast<const uint32_t*>(e->arena), 1u, (uint32_t)e->cfg.world, seq, e->v.flagCtl + 1);
+    e->launches += 2;
+    CK(cudaGetLastError());
+    return NC_OK;
+}
 extern "C" int nc_comm_unique_id(nc_comm_id* out) {
     if (!out) { g_err = "nc_comm_unique_id: null argument"; return NC_ERR_INVALID; }
     if (!nccl_load(g_err)) return NC_ERR_NO_DEVICE;
@@ -1505,7 +1761,7 @@ extern "C" int nc_comm_init(nc_engine* e, const nc_comm_id* id) {
     cudaSetDevice(e->cfg.device);
     int rc = g_nccl.CommInitRank(&e->comm, e->cfg.world, *id, e->cfg.rank);
     if (rc) { e->comm = nullptr; return fail(e, NC_ERR_CUDA, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc)); }
-    return NC_OK;
+    return p2p_setup(e);
 }
 extern "C" int nc_set_exchange(nc_engine* e, nc_allgather_fn fn, void* ctx) {
     e->xchgFn = fn; e->xchgCtx = ctx;
@@ -1542,6 +1798,10 @@ static int enqueue_counters(nc_engine* e) {
     const int W = e->cfg.world;
     if (W == 1) {
         CK(cudaMemcpyAsync(e->hOut, e->dOut, 10 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    } else if (e->p2p) {
+        int rc = p2p_exchange_counters(e, e->dOut);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(e->hOut, e->arena + e->offCnt, (size_t)W * 10 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
     } else {
         int rc = exchange(e, e->dOut, e->dOutAll, 10 * sizeof(unsigned long long));
         if (rc) return rc;
@@ -1553,10 +1813,14 @@ static int enqueue_counters(nc_engine* e) {
 static int wait_counters(nc_engine* e, uint64_t* hidden, nc_step_stats* st) {
     const int W = e->cfg.world;
     CK(cudaStreamSynchronize(e->stream));
+    if (e->randOn && e->bgActive && e->hRandFresh && e->hRand[32 + 2])
+        return fail(e, NC_ERR_CAPACITY, "background firing: more hits than the device generator made room for");
     sum_out(e, hidden, st);
-    for (int b = 0; b < W; b++)
+    for (int b = 0; b < W; b++) {
+        if (e->hOut[b * 10 + 9] & 8ull) return fail(e, NC_ERR_CUDA, "step: the peer exchange timed out (a shard of the job stopped stepping)");
         if (e->hOut[b * 10 + 9]) return fail(e, NC_ERR_CAPACITY, (e->hOut[b * 10 + 9] & 1ull) ? "step: fire-record capacity exceeded (raise nc_config.fire_capacity)"
                                                                                               : "step: flag-list capacity exceeded (raise nc_config.flag_capacity)");
+    }
     return NC_OK;
 }
 static int finish_counters(nc_engine* e, uint64_t* hidden, nc_step_stats* st) {
@@ -1567,8 +1831,15 @@ static int finish_counters(nc_engine* e, uint64_t* hidden, nc_step_stats* st) {
 
 // The fire exchange of a live window (world > 1): all-gather of the first xchgUnits units of every shard's block, then a
 // look at the gathered headers; when a shard fired more than that the size is raised and the all-gather repeated.
+static int ensure_gather(nc_engine* e) {  // gather buffer of the all-gather path (NCCL without peer mapping, caller-provided transport)
+    if (e->dGather) return NC_OK;
+    CK(cudaMalloc(&e->dGather, (uint64_t)e->cfg.world * ((uint64_t)e->v.fireCap + 1) * sizeof(FireRec)));
+    e->v.gRecs = e->dGather;
+    return NC_OK;
+}
 static int exchange_fires(nc_engine* e, StepArgs& a, uint32_t* maxCount) {
     const int W = e->cfg.world;
+    { int rc0 = ensure_gather(e); if (rc0) return rc0; }
     for (;;) {
         int rc = exchange(e, e->v.localHdr, e->dGather, (size_t)e->xchgUnits * sizeof(FireRec));
         if (rc) return rc;
@@ -1597,16 +1868,31 @@ static int step_second_half(nc_engine* e) {
     StepArgs& a = e->pendingArgs;
     uint32_t expect = std::max<uint32_t>(e->lastCounts[0], 256u);
     if (e->cfg.world > 1) {
-        int rc = exchange_fires(e, a, &expect);
+        int rc = e->p2p ? p2p_exchange_fires(e, a, expect) : exchange_fires(e, a, &expect);
         if (rc) return rc;
+        if (e->p2p) expect = (uint32_t)std::min<uint64_t>((uint64_t)expect * e->cfg.world, 1u << 24);  // (own count of the last window x shards: a launch-size hint)
     }
     if (e->taping) {
-        e->tape.push_back({a.t0, a.t1, a.sweep, e->tapeUsed, a.nEv, a.gStride, expect});
+        TapeStep ts = {a.t0, a.t1, a.sweep, e->tapeUsed, a.nEv, a.gStride, expect, e->bgPendingTape, e->pendingBgActive, e->pendingBgStrict, e->bgPendingArgs};
+        e->tape.push_back(ts);
         e->tapeUsed += a.nEv;
+        e->bgPendingTape = false;
     }
     int rc = launch_pass2(e, a, expect, 0);
     if (rc) return rc;
-    return enqueue_counters(e);
+    rc = enqueue_counters(e);
+    if (rc) return rc;
+    const unsigned long long* all = e->cfg.world == 1 ? e->dOut : e->p2p ? reinterpret_cast<const unsigned long long*>(e->arena + e->offCnt) : e->dOutAll;
+    return rand_after_window(e, all, true);
+}
+static int rand_after_window(nc_engine* e) {
+    if (!e->randOn) return NC_OK;
+    if (e->cfg.world > 1) {
+        int rc = e->p2p ? p2p_exchange_counters(e, e->dWin) : exchange(e, e->dWin, e->dWinAll, 10 * sizeof(unsigned long long));
+        if (rc) return rc;
+    }
+    const unsigned long long* all = e->cfg.world == 1 ? e->dWin : e->p2p ? reinterpret_cast<const unsigned long long*>(e->arena + e->offCnt) : e->dWinAll;
+    return rand_after_window(e, all, false);
 }
 extern "C" int nc_step_launch(nc_engine* e, float t0, float t1, int sweep, const nc_event* events, uint32_t nEv) {
     if (e->pending) return fail(e, NC_ERR_STATE, "nc_step_launch: the previous window has not been collected");
@@ -1619,6 +1905,12 @@ extern "C" int nc_step_launch(nc_engine* e, float t0, float t1, int sweep, const
     if (e->taping && e->tape.size() >= e->tapeMaxSteps) return fail(e, NC_ERR_CAPACITY, "tape: step capacity exceeded");
     StepArgs a;
     fill_args(e, a, t0, t1, sweep, dEv, nEv);
+    e->pendingBgActive = e->bgActive; e->pendingBgStrict = !e->bgFirstWindow;
+    if (e->bgActive) {
+        rc = merge_background(e, a, !e->bgFirstWindow);
+        if (rc) return rc;
+        e->bgFirstWindow = false;
+    }
     rc = launch_pass1(e, a);
     if (rc) return rc;
     e->pendingArgs = a;
@@ -1641,6 +1933,7 @@ extern "C" int nc_step_collect(nc_engine* e, uint64_t* hidden, nc_step_stats* st
     }
     int rc = wait_counters(e, hidden, st);
     if (e->cfg.world == 1) { e->lastCounts[0] = (uint32_t)std::min<unsigned long long>(e->hOut[8], e->v.fireCap); e->lastStride = e->v.fireCap + 1u; }
+    else if (e->p2p) for (int b = 0; b < e->cfg.world; b++) e->lastCounts[b] = (uint32_t)std::min<unsigned long long>(e->hOut[b * 10 + 8], e->v.fireCap);
     return rc;
 }
 extern "C" int nc_step(nc_engine* e, float t0, float t1, int sweep, const nc_event* events, uint32_t nEv, uint64_t* hidden,
@@ -1706,6 +1999,78 @@ extern "C" int nc_read_synapses(nc_engine* e, float* weight, float* arrive, floa
     if (lastStart) CK(cudaMemcpy(lastStart, e->v.lastStart, b, cudaMemcpyDeviceToHost));
     return NC_OK;
 }
+static int scratch(nc_engine* e, size_t bytes, void** out);
+extern "C" int nc_read_neuron_counters(nc_engine* e, float* actStart, uint32_t* firings) {
+    if (!e->uploaded) return fail(e, NC_ERR_STATE, "read: no network");
+    cudaSetDevice(e->cfg.device);
+    CK(cudaStreamSynchronize(e->stream));
+    if (actStart) CK(cudaMemcpy(actStart, e->v.actStart, e->v.nRows * 4, cudaMemcpyDeviceToHost));
+    if (firings) CK(cudaMemcpy(firings, e->v.firings, e->v.nRows * 4, cudaMemcpyDeviceToHost));
+    return NC_OK;
+}
+extern "C" int nc_read_network(nc_engine* e, uint64_t* rowptr, uint32_t* pre, float* length, uint8_t* inhibitory) {
+    if (!e->uploaded) return fail(e, NC_ERR_STATE, "read: no network");
+    cudaSetDevice(e->cfg.device);
+    CK(cudaStreamSynchronize(e->stream));
+    if (rowptr) CK(cudaMemcpy(rowptr, e->v.rowptr, (e->v.nRows + 1) * 8, cudaMemcpyDeviceToHost));
+    const uint64_t S = e->v.S;
+    if (!S) return NC_OK;
+    void* d = nullptr;
+    int rc = scratch(e, S * 4, &d);
+    if (rc) return rc;
+    const unsigned blocks = (unsigned)std::min<uint64_t>((S + 255) / 256, 1u << 20);
+    std::vector<uint32_t> tmp;
+    for (int which = 0; which < 3; which++) {
+        void* dst = which == 0 ? (void*)pre : which == 1 ? (void*)length : (void*)inhibitory;
+        if (!dst) continue;
+        k_extract_net<<<blocks, 256, 0, e->stream>>>(e->v, which, (uint32_t*)d); e->launches++;
+        if (which < 2) { CK(cudaMemcpyAsync(dst, d, S * 4, cudaMemcpyDeviceToHost, e->stream)); CK(cudaStreamSynchronize(e->stream)); }
+        else {
+            tmp.resize(S);
+            CK(cudaMemcpyAsync(tmp.data(), d, S * 4, cudaMemcpyDeviceToHost, e->stream)); CK(cudaStreamSynchronize(e->stream));
+            for (uint64_t j = 0; j < S; j++) inhibitory[j] = (uint8_t)tmp[j];
+        }
+    }
+    return NC_OK;
+}
+// Checkpoint resume: the inverse of nc_read_neurons / nc_read_neuron_counters / nc_read_synapses (NULL = keep what is there).
+extern "C" int nc_write_neurons(nc_engine* e, const float* potAct, const float* lastFire, const float* lastRan, const float* actStart, const uint32_t* firings) {
+    if (!e->uploaded) return fail(e, NC_ERR_STATE, "write: no network");
+    if (e->pending) return fail(e, NC_ERR_STATE, "write: a window is in flight");
+    cudaSetDevice(e->cfg.device);
+    CK(cudaStreamSynchronize(e->stream));
+    const uint64_t n = e->v.nRows;
+    if (potAct) CK(cudaMemcpy(e->v.potAct, potAct, n * 8, cudaMemcpyHostToDevice));
+    if (lastFire) CK(cudaMemcpy(e->v.lastFire, lastFire, n * 4, cudaMemcpyHostToDevice));
+    if (lastRan) CK(cudaMemcpy(e->v.lastRan, lastRan, n * 4, cudaMemcpyHostToDevice));
+    if (actStart) CK(cudaMemcpy(e->v.actStart, actStart, n * 4, cudaMemcpyHostToDevice));
+    if (firings) CK(cudaMemcpy(e->v.firings, firings, n * 4, cudaMemcpyHostToDevice));
+    return NC_OK;
+}
+extern "C" int nc_write_synapses(nc_engine* e, const float* weight, const float* arrive, const float* depol, const float* lastArr, const float* lastStart) {
+    if (!e->uploaded) return fail(e, NC_ERR_STATE, "write: no network");
+    if (e->pending) return fail(e, NC_ERR_STATE, "write: a window is in flight");
+    cudaSetDevice(e->cfg.device);
+    const uint64_t S = e->v.S;
+    if (!S) return NC_OK;
+    void* d = nullptr;
+    int rc = scratch(e, S * 4, &d);
+    if (rc) return rc;
+    const unsigned blocks = (unsigned)std::min<uint64_t>((S + 255) / 256, 1u << 20);
+    const float* srcs[4] = {arrive, depol, weight, lastArr};
+    for (int which = 0; which < 4; which++) {
+        if (!srcs[which]) continue;
+        CK(cudaMemcpyAsync(d, srcs[which], S * 4, cudaMemcpyHostToDevice, e->stream));
+        k_inject_syn<<<blocks, 256, 0, e->stream>>>(e->v, which, (const float*)d); e->launches++;
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    if (lastStart) CK(cudaMemcpy(e->v.lastStart, lastStart, S * 4, cudaMemcpyHostToDevice));
+    if (arrive) {  // the event index follows `arrive`: every busy slot is looked at once by the next staging pass, which sorts out the arrived ones
+        k_rebuild_busy<<<(unsigned)std::min<uint64_t>((e->busyWords + 255) / 256, 1u << 20), 256, 0, e->stream>>>(e->v, e->busyWords); e->launches++;
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    return NC_OK;
+}
 extern "C" int nc_read_fires(nc_engine* e, uint32_t capacity, uint32_t* neuron, float* time, uint32_t* count) {
     if (!e->uploaded) return fail(e, NC_ERR_STATE, "read: no network");
     cudaSetDevice(e->cfg.device);
@@ -1724,18 +2089,93 @@ extern "C" int nc_read_fires(nc_engine* e, uint32_t capacity, uint32_t* neuron, 
     *count = total;
     return NC_OK;
 }
+// persistent device scratch of the read-back entry points (grown on demand, freed with the engine)
+static int scratch(nc_engine* e, size_t bytes, void** out) {
+    if (bytes > e->scratchBytes) {
+        cudaFree(e->dScratch); e->dScratch = nullptr; e->scratchBytes = 0;
+        CK(cudaMalloc(&e->dScratch, bytes + bytes / 4 + 256));
+        e->scratchBytes = bytes + bytes / 4 + 256;
+    }
+    *out = e->dScratch;
+    return NC_OK;
+}
+// Per-frame synapse potentials written straight into caller-provided DEVICE (or host-mapped / graphics-interop) buffers:
+// what NeuCor_Renderer::updateView gathers per synapse every frame (Renderer.cpp:655-699), without a staging copy.
+extern "C" int nc_synapse_pots_device(nc_engine* e, float now, float* dPrePot, float* dPostPot) {
+    if (!e->uploaded) return fail(e, NC_ERR_STATE, "read: no network");
+    cudaSetDevice(e->cfg.device);
+    if (!e->v.S) return NC_OK;
+    k_synapse_pots<<<(unsigned)((e->v.S + 255) / 256), 256, 0, e->stream>>>(e->v, now, dPrePot, dPostPot); e->launches++;
+    CK(cudaGetLastError());
+    return NC_OK;
+}
 extern "C" int nc_read_synapse_pots(nc_engine* e, float now, float* prePot, float* postPot) {
     if (!e->uploaded) return fail(e, NC_ERR_STATE, "read: no network");
     cudaSetDevice(e->cfg.device);
-    uint64_t S = e->v.S;
+    const uint64_t S = e->v.S;
     if (!S) return NC_OK;
-    float *dPre, *dPost;
-    CK(cudaMalloc(&dPre, S * 4)); CK(cudaMalloc(&dPost, S * 4));
-    k_synapse_pots<<<(unsigned)((S + 255) / 256), 256, 0, e->stream>>>(e->v, now, dPre, dPost); e->launches++;
+    void* d = nullptr;
+    int rc = scratch(e, S * 8, &d);
+    if (rc) return rc;
+    float *dPre = (float*)d, *dPost = dPre + S;
+    rc = nc_synapse_pots_device(e, now, dPre, dPost);
+    if (rc) return rc;
+    if (prePot) CK(cudaMemcpyAsync(prePot, dPre, S * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (postPot) CK(cudaMemcpyAsync(postPot, dPost, S * 4, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
-    if (prePot) CK(cudaMemcpy(prePot, dPre, S * 4, cudaMemcpyDeviceToHost));
-    if (postPot) CK(cudaMemcpy(postPot, dPost, S * 4, cudaMemcpyDeviceToHost));
-    cudaFree(dPre); cudaFree(dPost);
+    return NC_OK;
+}
+static int render_histogram(nc_engine* e, int which, uint32_t spans, float rmin, float rmax, uint32_t* bins, uint32_t* below, uint32_t* above) {
+    if (!e->uploaded) return fail(e, NC_ERR_STATE, "render: no network");
+    if (spans == 0 || spans > (1u << 20) || !bins) return fail(e, NC_ERR_INVALID, "render: bad histogram arguments");
+    cudaSetDevice(e->cfg.device);
+    for (uint32_t i = 0; i < spans; i++) bins[i] = 0;
+    if (below) *below = 0;
+    if (above) *above = 0;
+    const float range = rmax - rmin;
+    if (!(0.0f < range)) return NC_OK;  // the reference leaves the distribution empty (Renderer.cpp:1748,1799)
+    void* d = nullptr;
+    int rc = scratch(e, (size_t)(spans + 2) * 4, &d);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(d, 0, (size_t)(spans + 2) * 4, e->stream));
+    const uint64_t n = which ? e->v.S : e->v.nRows;
+    const unsigned blocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>((n + 255) / 256, 1), (uint64_t)e->smCount * 16);
+    k_render_histogram<<<blocks, 256, 0, e->stream>>>(e->v, which, spans, rmin, range, (unsigned int*)d); e->launches++;
+    std::vector<uint32_t> h(spans + 2);
+    CK(cudaMemcpyAsync(h.data(), d, (size_t)(spans + 2) * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    for (uint32_t i = 0; i < spans; i++) bins[i] = h[i];
+    if (below) *below = h[spans];
+    if (above) *above = h[spans + 1];
+    return NC_OK;
+}
+extern "C" int nc_render_activity_histogram(nc_engine* e, uint32_t spans, float rmin, float rmax, uint32_t* bins, uint32_t* below, uint32_t* above) {
+    return render_histogram(e, 0, spans, rmin, rmax, bins, below, above);
+}
+extern "C" int nc_render_weight_histogram(nc_engine* e, uint32_t spans, float rmin, float rmax, uint32_t* bins, uint32_t* below, uint32_t* above) {
+    return render_histogram(e, 1, spans, rmin, rmax, bins, below, above);
+}
+extern "C" int nc_render_raster(nc_engine* e, float now, float runSpeed, uint32_t capacity, uint32_t* ids, uint32_t* count) {
+    if (!e->uploaded) return fail(e, NC_ERR_STATE, "render: no network");
+    if (!count) return fail(e, NC_ERR_INVALID, "render: null count");
+    cudaSetDevice(e->cfg.device);
+    void* d = nullptr;
+    int rc = scratch(e, (size_t)capacity * 4 + 16, &d);
+    if (rc) return rc;
+    unsigned int* dCount = (unsigned int*)d;
+    uint32_t* dIds = (uint32_t*)d + 4;
+    CK(cudaMemsetAsync(dCount, 0, 4, e->stream));
+    const unsigned blocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>((e->v.nRows + 255) / 256, 1), (uint64_t)e->smCount * 16);
+    k_render_raster<<<blocks, 256, 0, e->stream>>>(e->v, now, runSpeed, capacity, dIds, dCount); e->launches++;
+    uint32_t c = 0;
+    CK(cudaMemcpyAsync(&c, dCount, 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    *count = c;
+    const uint32_t k = std::min(c, capacity);
+    if (ids && k) {
+        CK(cudaMemcpy(ids, dIds, (size_t)k * 4, cudaMemcpyDeviceToHost));
+        std::sort(ids, ids + k);  // ascending ID, the order the GUI's loop over brain->neurons produces
+    }
     return NC_OK;
 }
 extern "C" int nc_state_signature(nc_engine* e, uint64_t* out6) {
@@ -1764,13 +2204,14 @@ extern "C" int nc_detector_mean(nc_engine* e, const uint32_t* near, uint32_t n, 
     if (!n) { *out = NAN; return NC_OK; }  // 0/0 as in the reference
     for (uint32_t i = 0; i < n; i++)
         if (near[i] < e->v.row0 || near[i] >= e->v.row0 + e->v.nRows) return fail(e, NC_ERR_INVALID, "detector: neuron outside this shard");
-    uint32_t* dNear; float* dOut;
-    CK(cudaMalloc(&dNear, (size_t)n * 4)); CK(cudaMalloc(&dOut, 4));
+    void* d = nullptr;
+    int rc = scratch(e, (size_t)n * 4 + 16, &d);
+    if (rc) return rc;
+    float* dOut = (float*)d; uint32_t* dNear = (uint32_t*)d + 4;
     CK(cudaMemcpyAsync(dNear, near, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
     k_detector_mean<<<1, 32, 0, e->stream>>>(e->v, dNear, n, dOut); e->launches++;
     CK(cudaMemcpyAsync(out, dOut, 4, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
-    cudaFree(dNear); cudaFree(dOut);
     return NC_OK;
 }
 
@@ -1802,6 +2243,8 @@ static int snap_all(nc_engine* e, bool toSnap) {
     CK(snap_copy(s.lastFire, v.lastFire, v.nRows, e->stream, toSnap)); CK(snap_copy(s.lfStart, v.lfStart, v.nRows, e->stream, toSnap));
     CK(snap_copy(s.actStart, v.actStart, v.nRows, e->stream, toSnap)); CK(snap_copy(s.potAct, v.potAct, v.nRows, e->stream, toSnap));
     CK(snap_copy(s.firings, v.firings, v.nRows, e->stream, toSnap));
+    if (toSnap) { CK(cudaMemcpyAsync(e->snapRand, e->dRandState, 31 * 4, cudaMemcpyDeviceToDevice, e->stream)); e->snapRandOn = e->randOn; }
+    else { CK(cudaMemcpyAsync(e->dRandState, e->snapRand, 31 * 4, cudaMemcpyDeviceToDevice, e->stream)); e->randOn = e->snapRandOn; e->hRandFresh = false; }
     CK(snap_copy(s.busy, v.busy, e->busyWords, e->stream, toSnap));
     CK(snap_copy(s.arrived, v.arrived, e->busyWords, e->stream, toSnap));
     CK(snap_copy(s.wordNext, v.wordNext, e->busyWords, e->stream, toSnap));
@@ -1843,24 +2286,28 @@ extern "C" int nc_tape_replay(nc_engine* e, uint32_t first, uint32_t count, floa
         StepArgs a;
         fill_args(e, a, ts.t0, ts.t1, ts.sweep, e->dTape + ts.evOff, ts.nEv);
         a.gStride = ts.units;
-        if (a.nEv) { k_mark_events<<<(a.nEv + 255) / 256, 256, 0, e->stream>>>(e->v, a.ev, a.nEv, 1); e->launches++; }
+        if (ts.bgDraw) { int rc = launch_background(e, ts.bg); if (rc) return rc; }
+        if (ts.bgActive) { int rc = merge_background(e, a, ts.bgStrict); if (rc) return rc; }
+        mark_events(e, a, 1);
         if (perKernel) { CK(cudaEventRecord(evs[5 * k], e->stream)); e->tick = &evStage[k]; }
         launch_neuron_pass(e, a);
         e->tick = nullptr;
         if (perKernel) CK(cudaEventRecord(evs[5 * k + 1], e->stream));
         if (e->cfg.world > 1) {
-            int rc = exchange(e, e->v.localHdr, e->dGather, (size_t)ts.units * sizeof(FireRec));
+            int rc = e->p2p ? p2p_exchange_fires(e, a, ts.fires) : ensure_gather(e);
+            if (!rc && !e->p2p) rc = exchange(e, e->v.localHdr, e->dGather, (size_t)ts.units * sizeof(FireRec));
             if (rc) return rc;
         }
         if (perKernel) CK(cudaEventRecord(evs[5 * k + 2], e->stream));
-        if (a.nEv) { k_mark_events<<<(a.nEv + 255) / 256, 256, 0, e->stream>>>(e->v, a.ev, a.nEv, 0); e->launches++; }
+        mark_events(e, a, 0);
         dim3 g(gx, a.world);
         k_index_build<<<g, 256, 0, e->stream>>>(e->v, a);
         if (perKernel) CK(cudaEventRecord(evs[5 * k + 3], e->stream));
         launch_synapse_pass(e, a, std::max<uint32_t>(ts.fires, 64u));
         if (perKernel) CK(cudaEventRecord(evs[5 * k + 4], e->stream));
         k_index_reset<<<g, 256, 0, e->stream>>>(e->v, a);
-        k_finish_step<<<1, 32, 0, e->stream>>>(e->v, e->dOut, 1);
+        k_finish_step<<<1, 32, 0, e->stream>>>(e->v, e->dOut, 1, e->dWin);
+        { int rc = rand_after_window(e); if (rc) return rc; }
         e->launches += 4;
     }
     CK(cudaEventRecord(e1, e->stream));
@@ -1887,6 +2334,71 @@ extern "C" int nc_tape_replay(nc_engine* e, uint32_t first, uint32_t count, floa
     return rc;
 }
 
+extern "C" int nc_rand_set_state(nc_engine* e, const uint32_t* x31) {
+    if (!x31) return fail(e, NC_ERR_INVALID, "nc_rand_set_state: null state");
+    cudaSetDevice(e->cfg.device);
+    memcpy(e->hRand, x31, 31 * 4);
+    CK(cudaMemcpyAsync(e->dRandState, e->hRand, 31 * 4, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));  // (hRand is reused by the read-back of the next window)
+    e->randOn = true; e->hRandFresh = true;
+    return NC_OK;
+}
+extern "C" int nc_rand_get_state(nc_engine* e, uint32_t* x31) {
+    if (!x31) return fail(e, NC_ERR_INVALID, "nc_rand_get_state: null output");
+    if (!e->randOn) return fail(e, NC_ERR_STATE, "nc_rand_get_state: no stream state has been set");
+    cudaSetDevice(e->cfg.device);
+    if (!e->hRandFresh) CK(cudaMemcpyAsync(e->hRand, e->dRandState, 31 * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->hRandFresh = true;
+    memcpy(x31, e->hRand, 31 * 4);
+    return NC_OK;
+}
+extern "C" int nc_background_draw(nc_engine* e, float t0, float runSpeed, uint32_t period, uint64_t nNeurons) {
+    if (!e->uploaded) return fail(e, NC_ERR_STATE, "nc_background_draw: no network uploaded");
+    if (!e->randOn) return fail(e, NC_ERR_STATE, "nc_background_draw: set the stream state first (nc_rand_set_state)");
+    if (e->pending) return fail(e, NC_ERR_STATE, "nc_background_draw: a window is in flight");
+    if (period == 0 || nNeurons == 0 || nNeurons >= (1ull << 31)) return fail(e, NC_ERR_INVALID, "nc_background_draw: bad period / neuron count");
+    cudaSetDevice(e->cfg.device);
+    // one test draw per neuron + two more per hit; room for four times the expected number of hits (never more than one per neuron)
+    const uint64_t room = std::min<uint64_t>(nNeurons, 4 * (nNeurons / period) + 256);
+    ncr::BgArgs a = {};
+    a.t0 = t0; a.runSpeed = runSpeed; a.period = period; a.nNeurons = nNeurons; a.nDraws = nNeurons + 2 * room + 64;
+    a.row0 = e->v.row0; a.nRows = e->v.nRows;
+    if (a.nDraws > e->drawsCap) {
+        cudaFree(e->dDraws);
+        e->drawsCap = a.nDraws + a.nDraws / 8;
+        CK(cudaMalloc(&e->dDraws, e->drawsCap * 4));
+    }
+    if (a.nDraws >= (1ull << 32)) return fail(e, NC_ERR_INVALID, "nc_background_draw: too many neurons for 32-bit draw positions");
+    const uint32_t wantCap = (uint32_t)std::min<uint64_t>(room + 64, 1u << 26);
+    if (wantCap > e->bgCap) {
+        cudaFree(e->dBgTmp); cudaFree(e->dBgEv); cudaFree(e->dCand); cudaFree(e->dCandRaw);
+        e->bgCap = wantCap;
+        e->candListCap = (uint32_t)std::min<uint64_t>(2ull * wantCap + 1024, 1u << 27);
+        CK(cudaMalloc(&e->dCand, (size_t)e->candListCap * 4));
+        CK(cudaMalloc(&e->dCandRaw, (size_t)e->candListCap * 4));
+        CK(cudaMalloc(&e->dBgTmp, (size_t)e->bgCap * sizeof(nc_event)));
+        CK(cudaMalloc(&e->dBgEv, (size_t)e->bgCap * sizeof(nc_event)));
+    }
+    int rc = launch_background(e, a);
+    if (rc) return rc;
+    e->bgActive = true; e->bgFirstWindow = true; e->hRandFresh = false;
+    if (e->taping) { e->bgPendingTape = true; e->bgPendingArgs = a; }
+    return NC_OK;
+}
+extern "C" int nc_background_clear(nc_engine* e) { e->bgActive = false; return NC_OK; }
+extern "C" int nc_background_read(nc_engine* e, uint32_t capacity, nc_event* out, uint32_t* count, uint32_t* hits) {
+    if (!e->bgActive) return fail(e, NC_ERR_STATE, "nc_background_read: no background draw is active");
+    cudaSetDevice(e->cfg.device);
+    uint32_t ctl[4];
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(ctl, e->dBgCtl, 16, cudaMemcpyDeviceToHost));
+    if (ctl[2]) return fail(e, NC_ERR_CAPACITY, "background firing: more hits than the device generator made room for");
+    if (count) *count = ctl[0];
+    if (hits) *hits = ctl[1];
+    if (out && capacity) CK(cudaMemcpy(out, e->dBgEv, (size_t)std::min(capacity, ctl[0]) * sizeof(nc_event), cudaMemcpyDeviceToHost));
+    return NC_OK;
+}
 extern "C" int nc_index_stats(nc_engine* e, uint64_t* out2) {
     if (!out2) return fail(e, NC_ERR_INVALID, "nc_index_stats: null output");
     cudaSetDevice(e->cfg.device);

@@ -1,0 +1,79 @@
+// Fire exchange over NVLink peer memory: the one collective of the path, fused into the step.
+//
+// Every shard owns an exchange ARENA in its device memory — two gather buffers (window parity) with one block per shard
+// (header unit {count, overflow} + fire records), one counter block per shard, and flag words — and maps every other
+// shard's arena through CUDA IPC (all shards are processes of one node; NVSwitch gives every pair full bandwidth).
+// After the neuron pass a shard STORES its block straight into slot `rank` of every peer's gather buffer, fences, and
+// raises its flag in every peer (the window's sequence number); the consumer side waits on its own flag words and goes
+// on to build the fire index.  The per-window counters (incl. the hidden rand() count that moves the stream on) travel the
+// same way.  There is no host round trip and no library call in the step; the payload is exactly count + 1 units.
+//
+// Why two gather buffers are enough: a peer can push window w+1 only after it has finished window w, which needed this
+// shard's block of window w and its counters — so it can be at most one window ahead, and never two.
+#pragma once
+#include <stdint.h>
+
+#include "step_logic.cuh"
+
+namespace ncx {
+using namespace ncs;
+
+#define NC_X_FLAGS_BYTES 4096      // flag words: [kind 0 fires / 1 counters][world]
+#define NC_X_CNT_BYTES 4096        // counter blocks: world x 10 x u64
+#define NC_X_TIMEOUT_CYCLES 6000000000ll  // ~3 s: a peer that died must not hang the GPU
+
+struct PeerTab {  // this window's view of every shard's arena (device pointers valid on THIS device)
+    FireRec* gather[NC_MAX_WORLD];            // the window's gather buffer of shard r
+    unsigned long long* counters[NC_MAX_WORLD];
+    uint32_t* flags[NC_MAX_WORLD];
+};
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ void st_flag(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_flag(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// This shard's block (header + count records) -> slot `rank` of every shard's gather buffer; the last block to finish raises the flags.
+__global__ void __launch_bounds__(256) k_push_fires(View v, PeerTab pt, uint32_t world, uint32_t rank, uint32_t blockUnits, uint32_t seq, uint32_t* doneCtr) {
+    const uint32_t units = min(v.localHdr[0], v.fireCap) + 1u;
+    const uint4* src = reinterpret_cast<const uint4*>(v.localHdr);
+    for (uint32_t r = blockIdx.y; r < world; r += gridDim.y) {
+        uint4* dst = reinterpret_cast<uint4*>(pt.gather[r] + (uint64_t)rank * blockUnits);
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < units; i += gridDim.x * blockDim.x) dst[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(doneCtr, 1u) == gridDim.x * gridDim.y - 1u) {
+        *doneCtr = 0u;
+        __threadfence_system();
+        for (uint32_t r = 0; r < world; r++) st_flag(pt.flags[r] + rank, seq);
+    }
+}
+// The window's counter block (10 x u64) -> slot `rank` of every shard's counter area, then the flag.  One warp.
+__global__ void k_push_counters(const unsigned long long* win, PeerTab pt, uint32_t world, uint32_t rank, uint32_t seq) {
+    const uint32_t lane = threadIdx.x;
+    for (uint32_t r = 0; r < world; r++)
+        if (lane < 10u) pt.counters[r][rank * 10u + lane] = win[lane];
+    __threadfence_system();
+    __syncwarp();
+    if (lane < world) st_flag(pt.flags[lane] + NC_MAX_WORLD + rank, seq);
+}
+// Wait until every shard's flag of `kind` has reached this window's sequence number (signed distance: the counter wraps).
+// A peer that never arrives sets the shard's exchange-error word instead of hanging the GPU.
+__global__ void k_wait_flags(const uint32_t* flags, uint32_t kind, uint32_t world, uint32_t seq, uint32_t* errWord) {
+    const uint32_t lane = threadIdx.x;
+    if (lane < world) {
+        const long long t0 = clock64();
+        while ((int32_t)(ld_flag(flags + kind * NC_MAX_WORLD + lane) - seq) < 0) {
+            __nanosleep(64);
+            if (clock64() - t0 > NC_X_TIMEOUT_CYCLES) { atomicOr(errWord, 4u); break; }
+        }
+    }
+    __threadfence_system();
+}
+#endif
+
+}  // namespace ncx

@@ -128,9 +128,11 @@ struct StepArgs {
     float lr, preFactor, postFactor, preDecay, postDecay;
     const nc_event* ev;
     uint32_t nEv;
+    const uint32_t* nEvDev;  // when set: the number of events is read from the device (host events merged with the device-generated background events)
     const uint32_t* subset;  // nc_run_neurons: ascending IDs that take part in the sweep (NULL = all)
     uint32_t nSubset;
     uint32_t candCap;
+    uint32_t variant;  // which build of the neuron pass runs this window (0: 1024-slot pool, 1: 704, 2: 512)
     uint32_t gStride;  // units per gathered block (header included)
     uint32_t world;
     // float comparisons of the row scan as integer compares on the bit patterns of (positive) arrival times, fixed per window:

@@ -23,9 +23,9 @@ NC_SWEEP_START = 2
 ABI_SYMBOLS = (
     "nc_global_error", "nc_device_count", "nc_create", "nc_destroy", "nc_last_error", "nc_upload_network",
     "nc_upload_network_device", "nc_min_delay",
-    "nc_set_plasticity", "nc_step", "nc_step_launch", "nc_step_collect", "nc_run_neurons", "nc_read_neurons", "nc_read_synapses", "nc_read_fires",
-    "nc_read_synapse_pots", "nc_state_signature", "nc_reset_activities", "nc_detector_mean", "nc_tape_begin", "nc_tape_end", "nc_snapshot",
-    "nc_restore", "nc_tape_replay", "nc_replay_breakdown", "nc_index_stats", "nc_launch_count", "nc_comm_unique_id", "nc_comm_init", "nc_set_exchange",
+    "nc_set_plasticity", "nc_step", "nc_step_launch", "nc_step_collect", "nc_run_neurons", "nc_read_neurons", "nc_read_synapses", "nc_read_neuron_counters", "nc_read_network", "nc_write_neurons", "nc_write_synapses", "nc_read_fires",
+    "nc_read_synapse_pots", "nc_synapse_pots_device", "nc_render_activity_histogram", "nc_render_weight_histogram", "nc_render_raster", "nc_state_signature", "nc_reset_activities", "nc_detector_mean", "nc_tape_begin", "nc_tape_end", "nc_snapshot",
+    "nc_restore", "nc_tape_replay", "nc_replay_breakdown", "nc_rand_set_state", "nc_rand_get_state", "nc_background_draw", "nc_background_clear", "nc_background_read", "nc_index_stats", "nc_launch_count", "nc_comm_unique_id", "nc_comm_init", "nc_set_exchange",
     "nc_selftest_powf", "nc_selftest_exp",
 )
 
@@ -78,9 +78,17 @@ def load(path=None):
     L.nc_run_neurons.argtypes = [vp, C.c_float, vp, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(StepStats)]
     L.nc_read_neurons.argtypes = [vp, vp, vp, vp]
     L.nc_read_synapses.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.nc_read_neuron_counters.argtypes = [vp, vp, vp]
+    L.nc_read_network.argtypes = [vp, vp, vp, vp, vp]
+    L.nc_write_neurons.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.nc_write_synapses.argtypes = [vp, vp, vp, vp, vp, vp]
     L.nc_read_fires.argtypes = [vp, C.c_uint32, vp, vp, C.POINTER(C.c_uint32)]
     L.nc_read_synapse_pots.argtypes = [vp, C.c_float, vp, vp]
     L.nc_state_signature.argtypes = [vp, u64p]
+    L.nc_synapse_pots_device.argtypes = [vp, C.c_float, vp, vp]
+    L.nc_render_activity_histogram.argtypes = [vp, C.c_uint32, C.c_float, C.c_float, u32p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.nc_render_weight_histogram.argtypes = [vp, C.c_uint32, C.c_float, C.c_float, u32p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.nc_render_raster.argtypes = [vp, C.c_float, C.c_float, C.c_uint32, u32p, C.POINTER(C.c_uint32)]
     L.nc_reset_activities.argtypes = [vp, C.c_float]
     L.nc_detector_mean.argtypes = [vp, vp, C.c_uint32, C.POINTER(C.c_float)]
     L.nc_tape_begin.argtypes = [vp, C.c_uint32, C.c_uint64]
@@ -91,6 +99,11 @@ def load(path=None):
                                  C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.POINTER(StepStats)]
     L.nc_replay_breakdown.argtypes = [vp, f32p]
     L.nc_index_stats.argtypes = [vp, u64p]
+    L.nc_rand_set_state.argtypes = [vp, u32p]
+    L.nc_rand_get_state.argtypes = [vp, u32p]
+    L.nc_background_draw.argtypes = [vp, C.c_float, C.c_float, C.c_uint32, C.c_uint64]
+    L.nc_background_clear.argtypes = [vp]
+    L.nc_background_read.argtypes = [vp, C.c_uint32, vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.nc_launch_count.argtypes = [vp]
     L.nc_launch_count.restype = C.c_uint64
     L.nc_comm_unique_id.argtypes = [vp]
@@ -207,6 +220,20 @@ class Engine:
         self._ck(self.L.nc_read_synapse_pots(self.h, now, a[0].ctypes.data, a[1].ctypes.data))
         return a[0][:self.S], a[1][:self.S]
 
+    def render_histogram(self, which, spans, rmin, rmax):
+        """which = 'activity' | 'weight' -> (bins, below, above), Renderer.cpp:1733-1822 reduced on the device."""
+        bins = np.zeros(spans, np.uint32)
+        lo, hi = C.c_uint32(), C.c_uint32()
+        fn = self.L.nc_render_activity_histogram if which == "activity" else self.L.nc_render_weight_histogram
+        self._ck(fn(self.h, spans, rmin, rmax, bins, C.byref(lo), C.byref(hi)))
+        return bins, lo.value, hi.value
+
+    def render_raster(self, now, run_speed, capacity=1 << 20):
+        ids = np.zeros(capacity, np.uint32)
+        c = C.c_uint32()
+        self._ck(self.L.nc_render_raster(self.h, now, run_speed, capacity, ids, C.byref(c)))
+        return ids[:min(c.value, capacity)].copy(), c.value
+
     def state_signature(self):
         """The six per-field checksums tests/helpers.state_signature computes from read-back arrays, computed on the device."""
         out = np.zeros(6, np.uint64)
@@ -255,6 +282,23 @@ class Engine:
         out = np.zeros(2, np.uint64)
         self._ck(self.L.nc_index_stats(self.h, out))
         return int(out[0]), int(out[1])
+
+    def rand_set_state(self, x31):
+        self._ck(self.L.nc_rand_set_state(self.h, np.ascontiguousarray(x31, np.uint32)))
+
+    def rand_get_state(self):
+        out = np.zeros(31, np.uint32)
+        self._ck(self.L.nc_rand_get_state(self.h, out))
+        return out
+
+    def background_draw(self, t0, run_speed, period, n_neurons):
+        self._ck(self.L.nc_background_draw(self.h, t0, run_speed, period, n_neurons))
+
+    def background_read(self, capacity=1 << 20):
+        ev = np.zeros(capacity, EVENT_DTYPE)
+        c, h = C.c_uint32(), C.c_uint32()
+        self._ck(self.L.nc_background_read(self.h, capacity, ev.ctypes.data, C.byref(c), C.byref(h)))
+        return ev[:min(c.value, capacity)].copy(), h.value
 
     def launch_count(self):
         return int(self.L.nc_launch_count(self.h))

@@ -110,6 +110,35 @@ private:
 };
 bool RandWindow::checked_ = false;
 bool RandWindow::usable_ = false;
+
+// libc's generator state as the device-resident stream wants it: the 31 most recent raw values, oldest first.
+// (glibc TYPE_3 only; the state array is reached through the public setstate() API, as above.)
+int32_t g_parking3[34];
+bool libcPeek(uint32_t h[31]) {
+    g_parking3[0] = 3;
+    for (int i = 1; i < 34; i++) g_parking3[i] = (int32_t)((uint32_t)i * 2654435761u + 7u);
+    char* cur = setstate(reinterpret_cast<char*>(g_parking3));
+    if (!cur) return false;
+    int32_t* w = reinterpret_cast<int32_t*>(cur);
+    const bool ok = (w[0] % 5 == 3);
+    if (ok) {
+        const int r = w[0] / 5, f = (r + 3) % 31;
+        for (int i = 0; i < 31; i++) h[i] = (uint32_t)w[1 + (f + i) % 31];
+    }
+    setstate(cur);
+    return ok;
+}
+bool libcPoke(const uint32_t h[31]) {
+    g_parking3[0] = 3;
+    char* cur = setstate(reinterpret_cast<char*>(g_parking3));
+    if (!cur) return false;
+    int32_t* w = reinterpret_cast<int32_t*>(cur);
+    if (w[0] % 5 != 3) { setstate(cur); return false; }
+    for (int i = 0; i < 31; i++) w[1 + (3 + i) % 31] = (int32_t)h[i];  // oldest value at ring position 3, rear index 0
+    w[0] = 3;
+    setstate(cur);
+    return true;
+}
 }  // namespace
 
 // ---- RandStream: look-ahead view of libc's rand() stream -------------------------------------------------------
@@ -656,6 +685,7 @@ void NeuCor::scheduleInput(unsigned i, float deltaT, float frequency, std::vecto
 }
 
 void NeuCor::window(float t0, float t1, int flags, std::vector<nc_event>& ev) {
+    const bool devRand = devRandThisRun_;
     uint64_t hidden = 0;
     nc_step_stats st;
     if (world_ > 1) {  // every process schedules the whole network's events (same rand() stream); a shard takes those of its rows
@@ -673,7 +703,8 @@ void NeuCor::window(float t0, float t1, int flags, std::vector<nc_event>& ev) {
     d2hBytes_ += 16 + 8 * sizeof(uint64_t);
     // the rand() calls hidden in synapticPlasticity's short-circuit (NeuCor.cpp:752): only their number matters
     lastHidden_ = hidden;
-    if (hidden) {
+    if (devRand) d2hBytes_ += 31 * 4 + 16;  // the stream state and the background control block come back with the counters
+    if (hidden && !devRand) {  // (the device-resident stream has moved on by itself)
         if (rs_ && rs_->attached) rs_->advance(hidden);
         else { RandWindow rw; rw.skip(hidden); }
     }
@@ -705,10 +736,29 @@ float NeuCor::stepInternal(bool sweep) {  // NeuCor::run, NeuCor.cpp:583-617
         const char* env = getenv("NC_RAND_THREAD");
         randThread_ = env ? atoi(env) != 0 : false;
     }
+    // Device-resident rand() stream: the per-neuron background draws and the hidden calls of the
+    // plasticity never touch the host; libc's state is handed to the device when the application has drawn from it since
+    // the last run() and put back afterwards.  NC_HOST_RAND=1 keeps the draws on the host (the look-ahead stream below).
+    const int bgPeriod = std::max(1, static_cast<int>(600.0f / runSpeed));
+    devRandThisRun_ = false;
+    if (deviceRand_ < 0) { const char* env = getenv("NC_HOST_RAND"); deviceRand_ = (env && atoi(env) != 0) ? 0 : 1; }
+    if (deviceRand_ == 1 && bgPeriod >= 2 && N > 0) {
+        { RandWindow probe; if (!probe.bulk()) deviceRand_ = 0; }  // self-test of the recurrence against rand()
+        uint32_t h[31];
+        if (deviceRand_ == 1 && libcPeek(h)) {
+            if (!randMirrorValid_ || memcmp(h, randMirror_, sizeof(h)) != 0) {
+                check(nc_rand_set_state(engine_, h), "nc_rand_set_state");
+                h2dBytes_ += sizeof(h);
+            }
+            check(nc_background_draw(engine_, currentTime, runSpeed, (uint32_t)bgPeriod, (uint64_t)N), "nc_background_draw");
+            devRandThisRun_ = true;
+        }
+    }
+    if (!devRandThisRun_) { check(nc_background_clear(engine_), "nc_background_clear"); randMirrorValid_ = false; }
     struct Borrow {
         RandStream* r;
         ~Borrow() { if (r) r->detach(); }
-    } borrow{(rs_->usable && static_cast<int>(600.0f / runSpeed) > 1 && rs_->attach()) ? rs_ : nullptr};
+    } borrow{(!devRandThisRun_ && rs_->usable && bgPeriod > 1 && rs_->attach()) ? rs_ : nullptr};
     events_.clear();
     firesNeuron_.clear(); firesTime_.clear();
     for (unsigned i = 0; i < inputHandler.size(); i++) {
@@ -717,7 +767,7 @@ float NeuCor::stepInternal(bool sweep) {  // NeuCor::run, NeuCor.cpp:583-617
     }
     // background firing, NeuCor.cpp:604-607
     const std::size_t bgBegin = events_.size();
-    {
+    if (!devRandThisRun_) {
         const int backgroundFirePeriod = std::max(1, static_cast<int>(600.0f / runSpeed));
         if (rs_ && rs_->attached && backgroundFirePeriod > 1) {
             // neuron i tests draw number p + i + 2 * (hits before it); a hit consumes the next two draws (NeuCor.cpp:606)
@@ -783,6 +833,13 @@ float NeuCor::stepInternal(bool sweep) {  // NeuCor::run, NeuCor.cpp:583-617
             first = false;
             a = b;
         }
+    }
+    if (devRandThisRun_) {  // libc's generator continues where the reference's would
+        uint32_t h[31];
+        check(nc_rand_get_state(engine_, h), "nc_rand_get_state");
+        libcPoke(h);
+        memcpy(randMirror_, h, sizeof(h));
+        randMirrorValid_ = true;
     }
     currentTime = targetTime;
     totalStats_.fires += lastStats_.fires; totalStats_.deliveries += lastStats_.deliveries; totalStats_.loadsAccepted += lastStats_.loadsAccepted;

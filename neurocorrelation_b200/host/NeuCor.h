@@ -191,6 +191,10 @@ private:
     RandStream* rs_ = nullptr;
     uint64_t lastHidden_ = 0;
     bool randThread_ = false;
+    int deviceRand_ = -1;           // -1 undecided, 1 rand() stream on the device, 0 on the host (NC_HOST_RAND=1 or not glibc's TYPE_3 generator)
+    bool devRandThisRun_ = false;
+    uint32_t randMirror_[31];       // libc's state as this class last left it (detects draws by the application in between)
+    bool randMirrorValid_ = false;
     StepStats lastStats_ = {}, totalStats_ = {};
     uint64_t h2dBytes_ = 0, d2hBytes_ = 0;
 };

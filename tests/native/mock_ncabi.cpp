@@ -38,6 +38,10 @@ struct nc_engine {
     float lr = 1.0f, preF = 0.13f, postF = 0.30f, preD = 0.75f, postD = 0.65f, minDelay = INFINITY;
     uint32_t candCap = 8;  // deliberately tiny so that the spill path is exercised
     bool uploaded = false;
+    // serial model of the device-resident rand() stream (csrc/rand_stream.cuh): x[n] = x[n-31] + x[n-3], rand() = x[n] >> 1
+    uint32_t rstate[31]; bool randOn = false;
+    std::vector<nc_event> bg; bool bgActive = false, bgFirst = false;
+    uint32_t rs_next() { uint32_t x = rstate[0] + rstate[28]; memmove(rstate, rstate + 1, 30 * 4); rstate[30] = x; return x; }
 };
 static std::string g_err;
 static int fail(nc_engine* e, int code, const char* m) { e->err = m; return code; }
@@ -284,16 +288,55 @@ static int exchange_fires(nc_engine* e, StepArgs& a) {
 int nc_set_exchange(nc_engine* e, nc_allgather_fn fn, void* ctx) { e->xchgFn = fn; e->xchgCtx = ctx; return NC_OK; }
 int nc_comm_unique_id(nc_comm_id*) { g_err = "the CPU test double has no NCCL"; return NC_ERR_NO_DEVICE; }
 int nc_comm_init(nc_engine* e, const nc_comm_id*) { return fail(e, NC_ERR_NO_DEVICE, "the CPU test double has no NCCL"); }
+int nc_rand_set_state(nc_engine* e, const uint32_t* x31) { memcpy(e->rstate, x31, 31 * 4); e->randOn = true; return NC_OK; }
+int nc_rand_get_state(nc_engine* e, uint32_t* x31) { if (!e->randOn) return fail(e, NC_ERR_STATE, "no stream state"); memcpy(x31, e->rstate, 31 * 4); return NC_OK; }
+// NeuCor::run's background-firing loop (NeuCor.cpp:604-607), serially, on the model's copy of the stream
+int nc_background_draw(nc_engine* e, float t0, float runSpeed, uint32_t period, uint64_t nNeurons) {
+    if (!e->randOn) return fail(e, NC_ERR_STATE, "nc_background_draw: set the stream state first");
+    e->bg.clear();
+    for (uint64_t i = 0; i < nNeurons; i++) {
+        if ((e->rs_next() >> 1) % period != 0u) continue;
+        uint32_t n = (uint32_t)((uint64_t)(e->rs_next() >> 1) % nNeurons);
+        float u = (float)(int)(e->rs_next() >> 1) / 2147483648.0f;
+        float time = t0 + u * runSpeed;
+        if (n >= e->v.row0 && n < e->v.row0 + e->v.nRows) e->bg.push_back(nc_event{n, time, 2u, 0u});
+    }
+    std::stable_sort(e->bg.begin(), e->bg.end(), [](const nc_event& a, const nc_event& b) { return a.neuron < b.neuron; });
+    for (size_t i = 0; i < e->bg.size(); i++)
+        if (i + 1 == e->bg.size() || e->bg[i + 1].neuron != e->bg[i].neuron) e->bg[i].index_or_flags = 1u;
+    e->bgActive = true; e->bgFirst = true;
+    return NC_OK;
+}
+int nc_background_clear(nc_engine* e) { e->bgActive = false; return NC_OK; }
+int nc_background_read(nc_engine* e, uint32_t capacity, nc_event* out, uint32_t* count, uint32_t* hits) {
+    if (count) *count = (uint32_t)e->bg.size();
+    if (hits) *hits = 0;
+    for (uint32_t i = 0; out && i < capacity && i < e->bg.size(); i++) out[i] = e->bg[i];
+    return NC_OK;
+}
 int nc_step(nc_engine* e, float t0, float t1, int sweep, const nc_event* ev, uint32_t nEv, uint64_t* hidden, nc_step_stats* st) {
     if (!e->uploaded) return fail(e, NC_ERR_STATE, "step: no network uploaded");
     if (!(t1 > t0)) return fail(e, NC_ERR_INVALID, "step: window must have t1 > t0");
     if (!(t1 - t0 < e->minDelay) || !(t1 - t0 < 2.0f)) return fail(e, NC_ERR_INVALID, "step: window too long");
+    std::vector<nc_event> merged;
+    if (e->bgActive) {  // the window's share of the run's background events, after the host's events of the same neuron
+        merged.assign(ev, ev + nEv);
+        for (auto& b : e->bg)
+            if ((e->bgFirst ? b.time >= t0 : b.time > t0) && b.time <= t1) merged.push_back(b);
+        std::stable_sort(merged.begin(), merged.end(), [](const nc_event& a, const nc_event& b) { return a.neuron < b.neuron; });
+        e->bgFirst = false;
+        ev = merged.data(); nEv = (uint32_t)merged.size();
+    }
     StepArgs a; fill(e, a, t0, t1, sweep, ev, nEv);
     model_pass1(e, a);
     if (e->v.localHdr[1]) return fail(e, NC_ERR_CAPACITY, "fire capacity");
     if (e->world > 1) { int rc = exchange_fires(e, a); if (rc) return rc; }
     model_pass2(e, a);
-    return finish(e, hidden, st);
+    uint64_t h = 0;
+    int rc = finish(e, &h, st);
+    if (hidden) *hidden = h;
+    if (rc == NC_OK && e->randOn) for (uint64_t k = 0; k < h; k++) (void)e->rs_next();  // the hidden rand() calls of the window (NeuCor.cpp:752)
+    return rc;
 }
 // the two-halves form of nc_step: the test double does the work in the first half and hands the result over in the second
 static uint64_t g_pendingHidden; static nc_step_stats g_pendingStats; static int g_pendingRc = NC_ERR_STATE;
@@ -331,6 +374,39 @@ int nc_read_synapses(nc_engine* e, float* w, float* a, float* d, float* la, floa
     if (ls) memcpy(ls, e->lastStart.data(), b);
     return NC_OK;
 }
+int nc_read_neuron_counters(nc_engine* e, float* actStart, uint32_t* firings) {
+    if (actStart) memcpy(actStart, e->actStart.data(), e->v.nRows * 4);
+    if (firings) memcpy(firings, e->firings.data(), e->v.nRows * 4);
+    return NC_OK;
+}
+int nc_read_network(nc_engine* e, uint64_t* rowptr, uint32_t* pre, float* length, uint8_t* inh) {
+    if (rowptr) memcpy(rowptr, e->rowptr.data(), (e->v.nRows + 1) * 8);
+    for (uint64_t j = 0; j < e->v.S; j++) {
+        if (pre) pre[j] = e->rec[j].pre & 0x7fffffffu;
+        if (length) length[j] = e->rec[j].delay * 0.5f;
+        if (inh) inh[j] = (uint8_t)(e->rec[j].pre >> 31);
+    }
+    return NC_OK;
+}
+int nc_write_neurons(nc_engine* e, const float* potAct, const float* lastFire, const float* lastRan, const float* actStart, const uint32_t* firings) {
+    uint64_t n = e->v.nRows;
+    if (potAct) memcpy(e->potAct.data(), potAct, n * 8);
+    if (lastFire) memcpy(e->lastFire.data(), lastFire, n * 4);
+    if (lastRan) memcpy(e->lastRan.data(), lastRan, n * 4);
+    if (actStart) memcpy(e->actStart.data(), actStart, n * 4);
+    if (firings) memcpy(e->firings.data(), firings, n * 4);
+    return NC_OK;
+}
+int nc_write_synapses(nc_engine* e, const float* w, const float* a, const float* d, const float* la, const float* ls) {
+    for (uint64_t j = 0; j < e->v.S; j++) {
+        if (w) e->rec[j].weight = w[j];
+        if (a) e->ad[j].x = a[j];
+        if (d) e->ad[j].y = d[j];
+        if (la) e->rec[j].lastArr = la[j];
+        if (ls) e->lastStart[j] = ls[j];
+    }
+    return NC_OK;
+}
 int nc_read_fires(nc_engine* e, uint32_t cap, uint32_t* neuron, float* time, uint32_t* count) {
     uint32_t total = 0;
     for (int b = 0; b < e->world; b++)
@@ -342,6 +418,30 @@ int nc_read_fires(nc_engine* e, uint32_t cap, uint32_t* neuron, float* time, uin
 int nc_read_synapse_pots(nc_engine* e, float, float* pre, float* post) {
     if (pre) memset(pre, 0, e->v.S * 4);
     if (post) memset(post, 0, e->v.S * 4);
+    return NC_OK;
+}
+int nc_synapse_pots_device(nc_engine*, float, float*, float*) { return NC_OK; }
+static int model_histogram(nc_engine* e, int which, uint32_t spans, float rmin, float rmax, uint32_t* bins, uint32_t* below, uint32_t* above) {
+    for (uint32_t i = 0; i < spans; i++) bins[i] = 0;
+    uint32_t lo = 0, hi = 0;
+    const float range = rmax - rmin;
+    const uint64_t n = which ? e->v.S : e->v.nRows;
+    for (uint64_t i = 0; 0.0f < range && i < n; i++) {
+        const float x = which ? e->rec[i].weight : e->potAct[i].y;
+        const float f = floorf(((float)(int)spans * (x - rmin)) / range);
+        if (!(f >= 0.0f)) lo++; else if (f >= (float)spans) hi++; else bins[(uint32_t)f]++;
+    }
+    if (below) *below = lo;
+    if (above) *above = hi;
+    return NC_OK;
+}
+int nc_render_activity_histogram(nc_engine* e, uint32_t spans, float a, float b, uint32_t* bins, uint32_t* lo, uint32_t* hi) { return model_histogram(e, 0, spans, a, b, bins, lo, hi); }
+int nc_render_weight_histogram(nc_engine* e, uint32_t spans, float a, float b, uint32_t* bins, uint32_t* lo, uint32_t* hi) { return model_histogram(e, 1, spans, a, b, bins, lo, hi); }
+int nc_render_raster(nc_engine* e, float now, float runSpeed, uint32_t cap, uint32_t* ids, uint32_t* count) {
+    uint32_t c = 0;
+    for (uint64_t i = 0; i < e->v.nRows; i++)
+        if (now - e->lastFire[i] < runSpeed) { if (c < cap && ids) ids[c] = (uint32_t)(e->v.row0 + i); c++; }
+    *count = c;
     return NC_OK;
 }
 int nc_state_signature(nc_engine* e, uint64_t* out) {

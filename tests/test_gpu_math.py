@@ -80,3 +80,62 @@ def test_device_exp_hot_path_arguments(E):
     dev = E.selftest_exp(x)
     ref = np.array([libm.exp(float(v)) for v in x], np.float64)
     assert np.array_equal(dev.view(np.uint64), ref.view(np.uint64))
+
+
+def glibc_state_after_srand(seed):
+    """glibc's TYPE_3 generator right after srand(seed): the 31 most recent raw values, oldest first (stdlib/random_r.c:
+    r[i] = 16807 * r[i-1] mod (2^31 - 1), 310 outputs discarded)."""
+    r = [seed if seed else 1]
+    for i in range(1, 31):
+        v = (16807 * r[i - 1]) % 2147483647
+        r.append(v)
+    for i in range(31, 34):
+        r.append(r[i - 31])
+    for i in range(34, 344):
+        r.append((r[i - 31] + r[i - 3]) & 0xFFFFFFFF)
+    return np.array(r[313:344], np.uint32)
+
+
+@pytest.mark.parametrize("seed,N,period", [(1, 5000, 97), (777, 200_000, 9600), (123456789, 1_000_003, 150), (5, 40, 2)])
+def test_device_rand_stream_and_background_draw(native_libs, seed, N, period):
+    """The device-resident replica of libc's rand() stream (csrc/rand_stream.cuh) against libc itself: the background-firing
+    loop of NeuCor::run (NeuCor.cpp:604-607) run with rand() on the host and with nc_background_draw on the device gives
+    the same events, consumes the same number of draws and leaves the generator in the same state."""
+    from helpers import libc
+    from neurocorrelation_b200 import engine
+    F = np.float32
+    net = dict(N=N, S=0, rowptr=np.zeros(N + 1, np.uint64), pre=np.zeros(1, np.uint32), weight=np.zeros(1, np.float32),
+               length=np.zeros(1, np.float32), flag=np.zeros(1, np.uint8))
+    E = engine.Engine()
+    E.upload(net)
+    t0, dt = F(12.5), F(0.0625)
+    # host: the reference's loop on libc's own generator
+    libc.srand(seed)
+    want = []
+    for i in range(N):
+        if libc.rand() % period == 0:
+            n = libc.rand() % N
+            u = F(libc.rand()) / F(2147483647)
+            want.append((n, F(t0 + F(u * dt))))
+    tail = [libc.rand() for _ in range(64)]
+    # device: same stream, from the state srand() leaves
+    E.rand_set_state(glibc_state_after_srand(seed))
+    E.background_draw(float(t0), float(dt), period, N)
+    ev, hits = E.background_read()
+    assert hits == len(want) and len(ev) == len(want)
+    order = sorted(range(len(want)), key=lambda k: (want[k][0], k))  # sorted by neuron, stable in draw order
+    assert [int(x) for x in ev["neuron"]] == [want[k][0] for k in order]
+    assert np.array_equal(ev["time"].view(np.uint32), np.array([want[k][1] for k in order], np.float32).view(np.uint32))
+    last = {}
+    for k, (n, _) in enumerate(want):
+        last[n] = k
+    assert [int(f) for f in ev["index_or_flags"]] == [1 if last[want[k][0]] == k else 0 for k in order]
+    # the stream afterwards: the next 64 values of the recurrence from the returned state are libc's next 64 outputs
+    st = [int(x) for x in E.rand_get_state()]
+    out = []
+    for _ in range(64):
+        x = (st[0] + st[28]) & 0xFFFFFFFF
+        st = st[1:] + [x]
+        out.append(x >> 1)
+    assert out == tail
+    E.close()

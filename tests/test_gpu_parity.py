@@ -76,6 +76,53 @@ def test_renderer_readback_golden(native_libs):
     g.close()
 
 
+def test_renderer_statistics_on_device(native_libs):
+    """NeuCor_Renderer's Statistics panel reduced on the device (Renderer.cpp:1733-1876): activity and weight distributions and
+    the raster frame by the GUI's rule `now - lastFire < runSpeed`, against the same float expressions evaluated with numpy
+    on the state read back from the device; the per-frame potentials written into a caller's device buffer."""
+    import neurocorrelation_b200 as nb
+    from helpers import load_golden, run_c1_golden
+    from neurocorrelation_b200 import engine
+    import torch
+    z, net, near = load_golden("c1_seed1_normalised.npz")
+    g = nb.NeuCor.from_network(net)
+    bad, fields = run_c1_golden(g, z, near, 700, keyword_near=True, check_every=100)
+    assert bad == -1
+    E = engine.Engine(borrowed=g.engine_handle())
+    E.N, E.S, E.row0, E.n_rows = net["N"], net["S"], 0, net["N"]
+    n, s = g.read_neurons(), g.read_synapses()
+    F = np.float32
+
+    def hist(x, spans, lo, hi):
+        f = np.floor((F(spans) * (x.astype(F) - F(lo))).astype(F) / F(hi - lo)).astype(F)
+        below = int(np.sum(~(f >= 0)))
+        above = int(np.sum(f >= spans))
+        ok = (f >= 0) & (f < spans)
+        return np.bincount(f[ok].astype(np.int64), minlength=spans).astype(np.uint32), below, above
+
+    for which, x, spans, lo, hi in (("activity", n["act"], 25, 0.0, 6.0), ("activity", n["act"], 7, 0.5, 3.0),
+                                    ("weight", s["weight"], 20, -1.0, 1.0), ("weight", s["weight"], 9, -0.3, 0.45)):
+        bins, below, above = E.render_histogram(which, spans, lo, hi)
+        wb, wl, wh = hist(x, spans, lo, hi)
+        assert np.array_equal(bins, wb) and (below, above) == (wl, wh), which
+        assert int(bins.sum()) + below + above == len(x)
+    assert int(E.render_histogram("weight", 10, 1.0, 1.0)[0].sum()) == 0  # an empty range leaves the distribution empty
+    now, dt = F(g.time()), F(0.0625)
+    ids, count = E.render_raster(float(now), float(dt))
+    with np.errstate(invalid="ignore"):
+        want = np.nonzero((now - n["lastFire"]).astype(F) < dt)[0]
+    assert count == len(want) and np.array_equal(ids, want.astype(np.uint32))
+    # the synapse potentials straight into the caller's device memory
+    pre_h, post_h = E.read_synapse_pots(float(now))
+    d = torch.zeros(2 * net["S"], dtype=torch.float32, device="cuda")
+    E._ck(E.L.nc_synapse_pots_device(E.h, float(now), d.data_ptr(), d.data_ptr() + 4 * net["S"]))
+    torch.cuda.synchronize()
+    g.read_neurons()  # (drains the engine's stream)
+    got = d.cpu().numpy()
+    assert same_bits(got[:net["S"]], pre_h) and same_bits(got[net["S"]:], post_h)
+    g.close()
+
+
 def test_c1_golden_tiny_shared_memory_spill(native_libs):
     """Rows with more occupied slots than staged in shared memory take the spill path: same results."""
     scenarios.c1_golden(None, "c1_seed1_normalised.npz", 800, check_every=1, cand_smem=32)

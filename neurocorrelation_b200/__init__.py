@@ -91,6 +91,8 @@ def load_host_library(path=None):
     L.nch_read_neurons.argtypes = [vp, f32p, f32p, f32p, f32p]
     L.nch_read_synapses.argtypes = [vp, f32p, f32p, f32p, f32p, f32p]
     L.nch_state_signature.argtypes = [vp, u64p]
+    L.nch_save_checkpoint.argtypes = [vp, C.c_char_p]
+    L.nch_load_checkpoint.argtypes = [vp, C.c_char_p]
     L.nch_record_fires.argtypes = [vp, C.c_int]
     L.nch_last_fires_count.argtypes = [vp]
     L.nch_last_fires_count.restype = C.c_uint64
@@ -154,6 +156,16 @@ class NeuCor:
         b.set_shard(rank, world)
         b._ck(b.L.nch_import_shard_device(b.h, int(N), int(S_local), d_rowptr, d_pre, d_weight, d_length, d_flag, float(global_min_delay)))
         return b
+
+    @classmethod
+    def from_checkpoint(cls, path, device=0, library=None):
+        """Network + complete state (+ libc's rand() position) from a file written by save_checkpoint: the run continues bit for bit."""
+        b = cls(0, device, library)
+        b._ck(b.L.nch_load_checkpoint(b.h, os.fsencode(path)))
+        return b
+
+    def save_checkpoint(self, path):
+        self._ck(self.L.nch_save_checkpoint(self.h, os.fsencode(path)))
 
     # ---- multi-GPU: one process per shard; call before the first step ----
     def set_shard(self, rank, world):

@@ -37,7 +37,7 @@ def _run(cmd):
 
 
 def build_engine(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in ("engine.cu", "step_logic.cuh", "glibc_math.cuh", "glibc_tables.h")]
+    srcs = [os.path.join(CSRC, f) for f in ("engine.cu", "step_logic.cuh", "glibc_math.cuh", "glibc_tables.h", "rand_stream.cuh", "peer_exchange.cuh")]
     srcs.append(os.path.join(ROOT, "..", "include", "neucor_b200.h"))
     if force or _newer(ENGINE_SO, srcs):
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -49,9 +49,9 @@ def build_engine(force=False, verbose=False):
 
 
 def build_host(force=False):
-    srcs = [os.path.join(HOST, f) for f in ("NeuCor.cpp", "capi.cpp", "NeuCor.h")]
+    srcs = [os.path.join(HOST, f) for f in ("NeuCor.cpp", "capi.cpp", "checkpoint.cpp", "NeuCor.h")]
     if force or _newer(HOST_SO, srcs + [ENGINE_SO]):
-        _run(["g++"] + HOST_FLAGS + srcs[:2] + ["-o", HOST_SO, "-L" + CSRC, "-lneucor_b200", "-Wl,-rpath,$ORIGIN/../csrc"])
+        _run(["g++"] + HOST_FLAGS + srcs[:3] + ["-o", HOST_SO, "-L" + CSRC, "-lneucor_b200", "-Wl,-rpath,$ORIGIN/../csrc"])
     return HOST_SO
 
 

@@ -330,6 +330,7 @@ __device__ __forceinline__ void host_event_range(const View& v, const StepArgs& 
         evLo = lo; hi = nEv;
         while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (s.ev[mid].neuron <= q) lo = mid + 1; else hi = mid; }
         evHi = lo;
+        atomicAnd(&v.evMask[row >> 5], ~(1u << (row & 31u)));  // every row is visited once per window: it takes its mark down itself
     }
 }
 __device__ __forceinline__ bool in_subset(const StepArgs& s, uint32_t q) {  // nc_run_neurons: only the listed neurons are run
@@ -623,7 +624,7 @@ __device__ void lanes_replay(const View& v, const StepArgs& s, bool valid, uint6
 // by the latency of the row scan — a third more resident warps.  The host picks per window from the last window's counters;
 // the pool size only changes how rows are batched, never a result.
 template <int MINB>
-__global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32, MINB) k_neuron_pass(View v, StepArgs s) {
+__global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32, MINB) k_neuron_pass(View v, StepArgs s, ncx::XchgArgs xa) {
     extern __shared__ unsigned char smem[];
     math_tables_to_shared();
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
@@ -721,6 +722,7 @@ __global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32, MINB) k_neuron_pass(V
         if (c4[2]) atomicAdd(&v.stats[6], c4[2]);
         if (c4[3]) atomicAdd(&v.stats[7], c4[3]);
     }
+    if (xa.world > 1u) ncx::push_fires_tail(v, xa);  // the fire exchange: this shard's records straight into every peer's memory
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -732,7 +734,8 @@ __device__ __forceinline__ uint32_t block_count(const View& v, const StepArgs& s
     const uint32_t* hdr = reinterpret_cast<const uint32_t*>(v.gRecs + (uint64_t)b * s.gStride);
     return min(hdr[0], s.gStride - 1u);
 }
-__global__ void k_index_build(View v, StepArgs s) {
+__global__ void k_index_build(View v, StepArgs s, ncx::XchgArgs xa) {
+    if (xa.world > 1u) ncx::wait_flags_head(xa, 0u);  // every shard's records of this window have landed in this shard's gather buffer
     const uint32_t b = blockIdx.y;
     const uint32_t n = block_count(v, s, b);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -753,7 +756,8 @@ __global__ void k_index_reset(View v, StepArgs s) {
 }
 // End of a window: publish (or, for replay, accumulate) the shard's counters and its exchange header into `out`
 // (10 x u64: the 8 nc_step_stats counters, fire count, overflow flag), then clear both for the next window.
-__global__ void k_finish_step(View v, unsigned long long* out, int accumulate, unsigned long long* win) {
+__global__ void k_finish_step(View v, unsigned long long* out, int accumulate, unsigned long long* win, ncx::XchgArgs xa, ncr::RandTables rtab,
+                              uint32_t* randState) {
     const uint32_t i = threadIdx.x;
     if (i < 8) {
         unsigned long long x = v.stats[i];
@@ -770,6 +774,17 @@ __global__ void k_finish_step(View v, unsigned long long* out, int accumulate, u
     }
     __syncwarp();
     if (i == 8) { v.localHdr[0] = 0u; v.localHdr[1] = 0u; v.tileCtr[0] = 0u; v.tileCtr[1] = 0u; v.flagCtl[0] = 0u; v.flagCtl[1] = 0u; }
+    if (xa.world > 1u) {  // the window's counters to every shard (the hidden rand() count moves every shard's stream on)
+        if (i == 8) { win[8] = out[8]; win[9] = out[9]; }
+        ncx::push_counters_tail(win, xa);
+    } else if (randState) {  // single shard: the hidden rand() calls of this window move the device-resident stream on right here
+        __shared__ uint32_t st[32];
+        __syncwarp();
+        if (i < NC_RS_K) st[i] = randState[i];
+        __syncwarp();
+        ncr::rs_jump(rtab, st, win[5], i);
+        if (i < NC_RS_K) randState[i] = st[i];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -881,7 +896,7 @@ __global__ void k_mark_events(View v, const nc_event* ev, uint32_t nEv, const ui
 // merged with the background events of the run that fall into the window — sorted by neuron, input events before background
 // events of the same neuron, each group in its own order (what the host's stable sort of [inputs..., background...] gives).
 // One block; both lists are short.  bgCtl[0] = number of background events of the run; outCount <- merged length.
-__global__ void __launch_bounds__(1024) k_merge_events(const nc_event* host, uint32_t nHost, const nc_event* bg, const uint32_t* bgCtl, float t0, float t1,
+__global__ void __launch_bounds__(1024) k_merge_events(View v, const nc_event* host, uint32_t nHost, const nc_event* bg, const uint32_t* bgCtl, float t0, float t1,
                                                       int strict, nc_event* out, uint32_t outCap, uint32_t* outCount) {
     __shared__ uint32_t sIn;
     const uint32_t nBg = bgCtl[0];
@@ -907,7 +922,12 @@ __global__ void __launch_bounds__(1024) k_merge_events(const nc_event* host, uin
         if (i + below < outCap) out[i + below] = e;
     }
     __syncthreads();
-    if (threadIdx.x == 0) *outCount = min(nHost + sIn, outCap);
+    const uint32_t n = min(nHost + sIn, outCap);
+    if (threadIdx.x == 0) *outCount = n;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {  // mark the rows of this shard that have events in the window
+        const uint64_t q = out[i].neuron;
+        if (q >= v.row0 && q < v.row0 + v.nRows) atomicOr(&v.evMask[(q - v.row0) >> 5], 1u << ((q - v.row0) & 31u));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1135,6 +1155,7 @@ struct nc_engine {
     char* arena = nullptr; char* peerBase[NC_MAX_WORLD] = {nullptr};
     size_t offCnt = 0, offG[2] = {0, 0};
     uint32_t xseq = 0; uint32_t* dPushCtr = nullptr;
+    ncx::XchgArgs xa = {};                  // the exchange arguments of the window in flight (world = 0: none)
     uint32_t lastCounts[NC_MAX_WORLD] = {0}; uint32_t lastStride = 0;
     bool pending = false;                   // nc_step_launch issued, nc_step_collect outstanding
     StepArgs pendingArgs;
@@ -1522,6 +1543,10 @@ static uint32_t last_true_bits(uint32_t hi, P pred) {
     }
     return lo;
 }
+struct WaitCounters {  // head of k_rand_advance on a sharded engine: every shard's counter block of the window has arrived
+    ncx::XchgArgs xa;
+    __device__ void operator()() const { if (xa.world > 1u) ncx::wait_flags_head(xa, 1u); }
+};
 static void fill_args(nc_engine* e, StepArgs& a, float t0, float t1, int sweep, const nc_event* dEv, uint32_t nEv) {
     memset(&a, 0, sizeof(a));
     {
@@ -1556,9 +1581,9 @@ static void launch_neuron_pass(nc_engine* e, const StepArgs& a) {
     k_stage<<<e->gridStage, NC_STG_WARPS * 32, 0, e->stream>>>(e->v, a);
     e->launches++;
     if (e->tick) cudaEventRecord(*e->tick, e->stream);
-    if (a.variant == 2u) k_neuron_pass<8><<<e->grid1s, NC_WARPS_PER_BLOCK * 32, e->smem1s, e->stream>>>(e->v, a);
-    else if (a.variant == 0u) k_neuron_pass<4><<<e->grid1b, NC_WARPS_PER_BLOCK * 32, e->smem1b, e->stream>>>(e->v, a);
-    else k_neuron_pass<6><<<e->grid1, NC_WARPS_PER_BLOCK * 32, e->smem1, e->stream>>>(e->v, a);
+    if (a.variant == 2u) k_neuron_pass<8><<<e->grid1s, NC_WARPS_PER_BLOCK * 32, e->smem1s, e->stream>>>(e->v, a, e->xa);
+    else if (a.variant == 0u) k_neuron_pass<4><<<e->grid1b, NC_WARPS_PER_BLOCK * 32, e->smem1b, e->stream>>>(e->v, a, e->xa);
+    else k_neuron_pass<6><<<e->grid1, NC_WARPS_PER_BLOCK * 32, e->smem1, e->stream>>>(e->v, a, e->xa);
     e->launches++;
 }
 static void mark_events(nc_engine* e, const StepArgs& a, int set) {
@@ -1568,9 +1593,9 @@ static void mark_events(nc_engine* e, const StepArgs& a, int set) {
     e->launches++;
 }
 static int launch_pass1(nc_engine* e, const StepArgs& a) {
-    mark_events(e, a, 1);
+    if (!a.nEvDev) mark_events(e, a, 1);  // (merged lists are marked by k_merge_events; rows un-mark themselves in the neuron pass)
     launch_neuron_pass(e, a);
-    mark_events(e, a, 0);
+    if (a.subset) mark_events(e, a, 0);   // (nc_run_neurons skips rows: none of them may keep a mark)
     CK(cudaGetLastError());
     return NC_OK;
 }
@@ -1578,7 +1603,7 @@ static int launch_pass1(nc_engine* e, const StepArgs& a) {
 static int merge_background(nc_engine* e, StepArgs& a, bool strict) {
     const uint32_t need = a.nEv + e->bgCap;
     if (need > e->mergedCap) { cudaFree(e->dEvMerged); e->mergedCap = need * 2 + 1024; CK(cudaMalloc(&e->dEvMerged, (size_t)e->mergedCap * sizeof(nc_event))); }
-    k_merge_events<<<1, 1024, 0, e->stream>>>(a.ev, a.nEv, e->dBgEv, e->dBgCtl, a.t0, a.t1, strict ? 1 : 0, e->dEvMerged, e->mergedCap, e->dMergedCount);
+    k_merge_events<<<1, 1024, 0, e->stream>>>(e->v, a.ev, a.nEv, e->dBgEv, e->dBgCtl, a.t0, a.t1, strict ? 1 : 0, e->dEvMerged, e->mergedCap, e->dMergedCount);
     e->launches++;
     a.ev = e->dEvMerged; a.nEvDev = e->dMergedCount;
     return NC_OK;
@@ -1595,8 +1620,11 @@ static int launch_background(nc_engine* e, const ncr::BgArgs& a) {
 // after a window's counters are final: the hidden rand() calls of its plasticity move the stream ahead (NeuCor.cpp:752)
 static int rand_after_window(nc_engine* e, const unsigned long long* counters, bool toHost) {
     if (!e->randOn) return NC_OK;
-    ncr::k_rand_advance<<<1, 32, 0, e->stream>>>(e->rtab, e->dRandState, counters, (uint32_t)e->cfg.world);
-    e->launches++;
+    if (e->cfg.world > 1) {  // (a single shard's stream was moved on by k_finish_step)
+        WaitCounters wc; wc.xa = e->xa;
+        ncr::k_rand_advance<<<1, 32, 0, e->stream>>>(e->rtab, e->dRandState, counters, (uint32_t)e->cfg.world, wc);
+        e->launches++;
+    }
     if (toHost) {
         CK(cudaMemcpyAsync(e->hRand, e->dRandState, 31 * 4, cudaMemcpyDeviceToHost, e->stream));
         CK(cudaMemcpyAsync(e->hRand + 32, e->dBgCtl, 4 * 4, cudaMemcpyDeviceToHost, e->stream));
@@ -1611,10 +1639,10 @@ static int rand_after_window(nc_engine* e);  // replay form: gathers the window'
 static int launch_pass2(nc_engine* e, const StepArgs& a, uint32_t expectMax, int accumulate) {
     const uint32_t gx = std::min<uint32_t>(std::max<uint32_t>((expectMax + 255u) / 256u, 1u), 1024u);
     dim3 g(gx, a.world);
-    k_index_build<<<g, 256, 0, e->stream>>>(e->v, a);
+    k_index_build<<<g, 256, 0, e->stream>>>(e->v, a, e->xa);
     launch_synapse_pass(e, a, expectMax);
     k_index_reset<<<g, 256, 0, e->stream>>>(e->v, a);
-    k_finish_step<<<1, 32, 0, e->stream>>>(e->v, e->dOut, accumulate, e->dWin);
+    k_finish_step<<<1, 32, 0, e->stream>>>(e->v, e->dOut, accumulate, e->dWin, e->xa, e->rtab, (e->randOn && e->cfg.world == 1) ? e->dRandState : nullptr);
     e->launches += 3;
     CK(cudaGetLastError());
     return NC_OK;
@@ -1722,27 +1750,25 @@ static ncx::PeerTab peer_tab(const nc_engine* e, uint32_t parity) {
     }
     return t;
 }
-// fire blocks of this window -> every shard, wait for everybody's; the gathered blocks are then in this shard's arena
-static int p2p_exchange_fires(nc_engine* e, StepArgs& a, uint32_t expectOwn) {
+// A sharded window begins: its sequence number, gather buffer (window parity) and the arguments the step's own kernels need
+// to push / await the fire records and the counters (peer_exchange.cuh).  Without the peer mapping: no-op (all-gather path).
+static void begin_exchange(nc_engine* e, StepArgs& a) {
+    memset(&e->xa, 0, sizeof(e->xa));
+    if (!e->p2p) return;
     const uint32_t seq = ++e->xseq, parity = seq & 1u;
-    const ncx::PeerTab pt = peer_tab(e, parity);
-    const uint32_t blockUnits = e->v.fireCap + 1u;
-    dim3 g(std::min<uint32_t>(std::max<uint32_t>((expectOwn + 256u) / 256u, 1u), 16u), (uint32_t)e->cfg.world);
-    ncx::k_push_fires<<<g, 256, 0, e->stream>>>(e->v, pt, (uint32_t)e->cfg.world, (uint32_t)e->cfg.rank, blockUnits, seq, e->dPushCtr);
-    ncx::k_wait_flags<<<1, 32, 0, e->stream>>>(reinterpret_cast<const uint32_t*>(e->arena), 0u, (uint32_t)e->cfg.world, seq, e->v.flagCtl + 1);
-    e->launches += 2;
+    e->xa.pt = peer_tab(e, parity);
+    e->xa.world = (uint32_t)e->cfg.world; e->xa.rank = (uint32_t)e->cfg.rank; e->xa.blockUnits = e->v.fireCap + 1u; e->xa.seq = seq;
+    e->xa.doneCtr = e->dPushCtr; e->xa.errWord = e->v.flagCtl + 1;
     e->v.gRecs = reinterpret_cast<const FireRec*>(e->arena + e->offG[parity]);
-    a.gStride = blockUnits;
-    e->lastStride = blockUnits;
-    CK(cudaGetLastError());
-    return NC_OK;
+    a.gStride = e->xa.blockUnits;
+    e->lastStride = e->xa.blockUnits;
 }
-// the window's counters -> every shard, wait for everybody's: `world` blocks of 10 x u64 in this shard's arena
-static int p2p_exchange_counters(nc_engine* e, const unsigned long long* win) {
-    const uint32_t seq = e->xseq;
+// a replay's accumulated counters -> every shard (their own area and flag kind), wait for everybody's
+static int p2p_exchange_totals(nc_engine* e, const unsigned long long* totals) {
+    const uint32_t seq = ++e->xseq;
     const ncx::PeerTab pt = peer_tab(e, seq & 1u);
-    ncx::k_push_counters<<<1, 32, 0, e->stream>>>(win, pt, (uint32_t)e->cfg.world, (uint32_t)e->cfg.rank, seq);
-    ncx::k_wait_flags<<<1, 32, 0, e->stream>>>(reinterpret_cast<const uint32_t*>(e->arena), 1u, (uint32_t)e->cfg.world, seq, e->v.flagCtl + 1);
+    ncx::k_push_counters<<<1, 32, 0, e->stream>>>(totals, pt, (uint32_t)e->cfg.world, (uint32_t)e->cfg.rank, seq, 2u);
+    ncx::k_wait_flags<<<1, 32, 0, e->stream>>>(reinterpret_cast<const uint32_t*>(e->arena), 2u, (uint32_t)e->cfg.world, seq, e->v.flagCtl + 1);
     e->launches += 2;
     CK(cudaGetLastError());
     return NC_OK;
@@ -1794,13 +1820,19 @@ static void sum_out(nc_engine* e, uint64_t* hidden, nc_step_stats* st) {
     }
 }
 // Per-window result blocks (own, or all shards' after an all-gather): enqueue the read-back ...
-static int enqueue_counters(nc_engine* e) {
+static int enqueue_counters(nc_engine* e, bool totals = false) {
     const int W = e->cfg.world;
     if (W == 1) {
         CK(cudaMemcpyAsync(e->hOut, e->dOut, 10 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
-    } else if (e->p2p) {
-        int rc = p2p_exchange_counters(e, e->dOut);
+    } else if (e->p2p && totals) {  // end of a replay: the accumulated counters of every shard
+        int rc = p2p_exchange_totals(e, e->dOut);
         if (rc) return rc;
+        CK(cudaMemcpyAsync(e->hOut, e->arena + e->offCnt + NC_X_CNT_AREA, (size_t)W * 10 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    } else if (e->p2p) {  // a live window: k_finish_step pushed the counters; they are awaited by k_rand_advance or here
+        if (!e->randOn) {
+            ncx::k_wait_flags<<<1, 32, 0, e->stream>>>(reinterpret_cast<const uint32_t*>(e->arena), 1u, (uint32_t)W, e->xa.seq, e->v.flagCtl + 1);
+            e->launches++;
+        }
         CK(cudaMemcpyAsync(e->hOut, e->arena + e->offCnt, (size_t)W * 10 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
     } else {
         int rc = exchange(e, e->dOut, e->dOutAll, 10 * sizeof(unsigned long long));
@@ -1824,7 +1856,7 @@ static int wait_counters(nc_engine* e, uint64_t* hidden, nc_step_stats* st) {
     return NC_OK;
 }
 static int finish_counters(nc_engine* e, uint64_t* hidden, nc_step_stats* st) {
-    int rc = enqueue_counters(e);
+    int rc = enqueue_counters(e, true);
     if (rc) return rc;
     return wait_counters(e, hidden, st);
 }
@@ -1868,9 +1900,8 @@ static int step_second_half(nc_engine* e) {
     StepArgs& a = e->pendingArgs;
     uint32_t expect = std::max<uint32_t>(e->lastCounts[0], 256u);
     if (e->cfg.world > 1) {
-        int rc = e->p2p ? p2p_exchange_fires(e, a, expect) : exchange_fires(e, a, &expect);
-        if (rc) return rc;
         if (e->p2p) expect = (uint32_t)std::min<uint64_t>((uint64_t)expect * e->cfg.world, 1u << 24);  // (own count of the last window x shards: a launch-size hint)
+        else { int rc = exchange_fires(e, a, &expect); if (rc) return rc; }
     }
     if (e->taping) {
         TapeStep ts = {a.t0, a.t1, a.sweep, e->tapeUsed, a.nEv, a.gStride, expect, e->bgPendingTape, e->pendingBgActive, e->pendingBgStrict, e->bgPendingArgs};
@@ -1880,15 +1911,19 @@ static int step_second_half(nc_engine* e) {
     }
     int rc = launch_pass2(e, a, expect, 0);
     if (rc) return rc;
+    if (e->p2p) {  // (the stream advance awaits the shards' counters; the read-back follows it)
+        rc = rand_after_window(e, reinterpret_cast<const unsigned long long*>(e->arena + e->offCnt), true);
+        if (rc) return rc;
+        return enqueue_counters(e);
+    }
     rc = enqueue_counters(e);
     if (rc) return rc;
-    const unsigned long long* all = e->cfg.world == 1 ? e->dOut : e->p2p ? reinterpret_cast<const unsigned long long*>(e->arena + e->offCnt) : e->dOutAll;
-    return rand_after_window(e, all, true);
+    return rand_after_window(e, e->cfg.world == 1 ? e->dOut : e->dOutAll, true);
 }
 static int rand_after_window(nc_engine* e) {
     if (!e->randOn) return NC_OK;
-    if (e->cfg.world > 1) {
-        int rc = e->p2p ? p2p_exchange_counters(e, e->dWin) : exchange(e, e->dWin, e->dWinAll, 10 * sizeof(unsigned long long));
+    if (e->cfg.world > 1 && !e->p2p) {
+        int rc = exchange(e, e->dWin, e->dWinAll, 10 * sizeof(unsigned long long));
         if (rc) return rc;
     }
     const unsigned long long* all = e->cfg.world == 1 ? e->dWin : e->p2p ? reinterpret_cast<const unsigned long long*>(e->arena + e->offCnt) : e->dWinAll;
@@ -1905,6 +1940,7 @@ extern "C" int nc_step_launch(nc_engine* e, float t0, float t1, int sweep, const
     if (e->taping && e->tape.size() >= e->tapeMaxSteps) return fail(e, NC_ERR_CAPACITY, "tape: step capacity exceeded");
     StepArgs a;
     fill_args(e, a, t0, t1, sweep, dEv, nEv);
+    if (e->cfg.world > 1) begin_exchange(e, a);
     e->pendingBgActive = e->bgActive; e->pendingBgStrict = !e->bgFirstWindow;
     if (e->bgActive) {
         rc = merge_background(e, a, !e->bgFirstWindow);
@@ -2286,27 +2322,27 @@ extern "C" int nc_tape_replay(nc_engine* e, uint32_t first, uint32_t count, floa
         StepArgs a;
         fill_args(e, a, ts.t0, ts.t1, ts.sweep, e->dTape + ts.evOff, ts.nEv);
         a.gStride = ts.units;
+        if (e->cfg.world > 1) begin_exchange(e, a);
         if (ts.bgDraw) { int rc = launch_background(e, ts.bg); if (rc) return rc; }
         if (ts.bgActive) { int rc = merge_background(e, a, ts.bgStrict); if (rc) return rc; }
-        mark_events(e, a, 1);
+        if (!a.nEvDev) mark_events(e, a, 1);
         if (perKernel) { CK(cudaEventRecord(evs[5 * k], e->stream)); e->tick = &evStage[k]; }
         launch_neuron_pass(e, a);
         e->tick = nullptr;
         if (perKernel) CK(cudaEventRecord(evs[5 * k + 1], e->stream));
-        if (e->cfg.world > 1) {
-            int rc = e->p2p ? p2p_exchange_fires(e, a, ts.fires) : ensure_gather(e);
-            if (!rc && !e->p2p) rc = exchange(e, e->v.localHdr, e->dGather, (size_t)ts.units * sizeof(FireRec));
+        if (e->cfg.world > 1 && !e->p2p) {
+            int rc = ensure_gather(e);
+            if (!rc) rc = exchange(e, e->v.localHdr, e->dGather, (size_t)ts.units * sizeof(FireRec));
             if (rc) return rc;
         }
         if (perKernel) CK(cudaEventRecord(evs[5 * k + 2], e->stream));
-        mark_events(e, a, 0);
         dim3 g(gx, a.world);
-        k_index_build<<<g, 256, 0, e->stream>>>(e->v, a);
+        k_index_build<<<g, 256, 0, e->stream>>>(e->v, a, e->xa);
         if (perKernel) CK(cudaEventRecord(evs[5 * k + 3], e->stream));
         launch_synapse_pass(e, a, std::max<uint32_t>(ts.fires, 64u));
         if (perKernel) CK(cudaEventRecord(evs[5 * k + 4], e->stream));
         k_index_reset<<<g, 256, 0, e->stream>>>(e->v, a);
-        k_finish_step<<<1, 32, 0, e->stream>>>(e->v, e->dOut, 1, e->dWin);
+        k_finish_step<<<1, 32, 0, e->stream>>>(e->v, e->dOut, 1, e->dWin, e->xa, e->rtab, (e->randOn && e->cfg.world == 1) ? e->dRandState : nullptr);
         { int rc = rand_after_window(e); if (rc) return rc; }
         e->launches += 4;
     }
@@ -2320,7 +2356,7 @@ extern "C" int nc_tape_replay(nc_engine* e, uint32_t first, uint32_t count, floa
         for (uint32_t k = 0; k < count; k++) {
             CK(cudaEventElapsedTime(&x, evs[5 * k], evStage[k])); sS += x;
             CK(cudaEventElapsedTime(&x, evs[5 * k], evs[5 * k + 1])); s1 += x;
-            CK(cudaEventElapsedTime(&x, evs[5 * k + 1], evs[5 * k + 2])); sx += x;
+            CK(cudaEventElapsedTime(&x, evs[5 * k + 1], evs[5 * k + 3])); sx += x;  // end of the neuron pass -> fire index of all shards built
             CK(cudaEventElapsedTime(&x, evs[5 * k + 3], evs[5 * k + 4])); s2 += x;
         }
         if (msP1) *msP1 = s1;

@@ -880,6 +880,11 @@ void NeuCor::readSynapses(float* weight, float* arrive, float* depol, float* las
     finalize();
     check(nc_read_synapses(engine_, weight, arrive, depol, lastArrival, lastStart), "nc_read_synapses");
 }
+bool NeuCor::checkpointPeekRand(uint32_t x31[31]) {
+    { RandWindow probe; if (!probe.bulk()) return false; }  // (the probe borrows libc's state while it lives)
+    return libcPeek(x31);
+}
+bool NeuCor::checkpointPokeRand(const uint32_t x31[31]) { return libcPoke(x31); }
 void NeuCor::stateSignature(uint64_t out6[6]) {
     finalize();
     check(nc_state_signature(engine_, out6), "nc_state_signature");

@@ -86,6 +86,13 @@ public:
     void setInputEnabled(unsigned inputID, bool enabled);  // InputFirer::enabled (Renderer.cpp:2036)
 
     // ---- extensions ----
+    // On-disk network + state file (host/checkpoint.cpp): the post-sorted CSR incl. the flag bytes, positions, the complete
+    // dynamic state, input firers / detectors with their `near` lists and libc's rand() position.  loadCheckpoint works on an
+    // empty NeuCor(0) before its first run(); the caller owns the rate array as with setInputRateArray (NeuCor.cpp:46-48):
+    // the saved rates are handed back and attachInputRates() points the brain at the caller's array.
+    void saveCheckpoint(const char* path);
+    void loadCheckpoint(const char* path, std::vector<float>* inputRates = nullptr);
+    void attachInputRates(float inputs[], unsigned inputCount);
     struct Synapse {                // one row entry of the exported network
         uint32_t from, to;
         float weight, length;
@@ -142,6 +149,9 @@ public:
     unsigned candidateSmem = 0;     // nc_config.cand_smem override (0 = default)
 
 private:
+    friend class NeuCor_Renderer;   // as in the reference (NeuCor.h:98): the renderer reads inputHandler, voltageDetectors, ... directly
+    static bool checkpointPeekRand(uint32_t x31[31]);
+    static bool checkpointPokeRand(const uint32_t x31[31]);
     struct InputFirer {
         coord3 a; float radius; bool enabled; float lastFire; std::vector<uint32_t> near;
     };

@@ -113,6 +113,14 @@ int nch_read_neurons(void* hv, float* pot, float* act, float* lastFire, float* l
 int nch_read_synapses(void* hv, float* w, float* arrive, float* depol, float* lastArr, float* lastStart) {
     return guard([&] { B->readSynapses(w, arrive, depol, lastArr, lastStart); });
 }
+int nch_save_checkpoint(void* hv, const char* path) { return guard([&] { B->saveCheckpoint(path); }); }
+int nch_load_checkpoint(void* hv, const char* path) {
+    return guard([&] {
+        Handle* h = (Handle*)hv;
+        h->brain->loadCheckpoint(path, &h->rates);
+        h->brain->attachInputRates(h->rates.data(), (unsigned)h->rates.size());
+    });
+}
 int nch_state_signature(void* hv, uint64_t* out6) { return guard([&] { B->stateSignature(out6); }); }
 int nch_record_fires(void* hv, int on) { return guard([&] { B->recordFires = on != 0; }); }
 uint64_t nch_last_fires_count(void* hv) { return B->lastFiresNeuron().size(); }

@@ -47,7 +47,8 @@ def mock_host_lib():
     out = os.path.join(out_dir, "libneucor_host_mock.so")
     srcs = [os.path.join(ROOT, "tests", "native", "mock_ncabi.cpp"),
             os.path.join(ROOT, "neurocorrelation_b200", "host", "NeuCor.cpp"),
-            os.path.join(ROOT, "neurocorrelation_b200", "host", "capi.cpp")]
+            os.path.join(ROOT, "neurocorrelation_b200", "host", "capi.cpp"),
+            os.path.join(ROOT, "neurocorrelation_b200", "host", "checkpoint.cpp")]
     deps = srcs + [os.path.join(ROOT, "neurocorrelation_b200", "csrc", f) for f in ("step_logic.cuh", "glibc_math.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-mfma", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I" + ROOT] + srcs + ["-o", out])

@@ -204,3 +204,35 @@ def host_constructor_matches_reference(library, have_ref):
     N, S = g.counts()
     assert (N, S) == (rnet["N"], rnet["S"])
     return g, rnet
+
+
+def checkpoint_resume(library, tmp_path):
+    """Save after 150 steps, resume in a fresh object from the file, and continue: every later step is bit-identical to the
+    uninterrupted run (state, background firing through the restored rand() position, input firer phases), and the file
+    round-trips the network exactly as the reference harness exports it."""
+    net = synthetic_network(700, 40, seed=9)
+    path = str(tmp_path / "brain.ncb")
+    a = nb.NeuCor.from_network(net, library=library)
+    synthetic_drive(a, net, True)
+    a.add_input_offset(1, 0.7)
+    for _ in range(150):
+        a.step()
+    a.save_checkpoint(path)
+    want = []
+    for _ in range(200):
+        v = a.step()
+        want.append((np.float32(v), a.state_signature()))
+    stats_a = a.stats()
+    a.close()
+    libc.srand(99)  # whatever happened to libc's generator in between: the file carries its position
+    b = nb.NeuCor.from_checkpoint(path, library=library)
+    b.enable_sweep()
+    exp = b.export_network()
+    assert np.array_equal(exp["rowptr"], net["rowptr"]) and np.array_equal(exp["pre"], net["pre"]) and same_bits(exp["length"], net["length"])
+    assert np.array_equal(exp["flag"], net["flag"]) and same_bits(exp["positions"], net["positions"])
+    for k in range(200):
+        v = b.step()
+        assert np.float32(v).view(np.uint32) == want[k][0].view(np.uint32), "step %d after resume: mean potential" % k
+        assert np.array_equal(b.state_signature(), want[k][1]), "step %d after resume: state" % k
+    b.close()
+    assert stats_a["fires"] > 0

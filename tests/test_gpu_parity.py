@@ -237,3 +237,7 @@ def test_replay_is_bit_identical_and_deterministic(native_libs):
         r = E.tape_replay(0, 40)
         assert np.array_equal(state_signature(E.read_neurons(), E.read_synapses()), live)
     assert r["stats"]["fires"] > 0
+
+
+def test_checkpoint_resume(native_libs, tmp_path):
+    scenarios.checkpoint_resume(None, tmp_path)

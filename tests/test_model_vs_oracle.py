@@ -51,3 +51,7 @@ def test_host_constructor_matches_reference(mock_host_lib, have_ref):
     assert np.array_equal(net["rowptr"], rnet["rowptr"]) and np.array_equal(net["pre"], rnet["pre"])
     assert same_bits(net["weight"], rnet["weight"]) and same_bits(net["length"], rnet["length"])
     assert same_bits(net["positions"], rnet["positions"]) and np.array_equal(net["flag"], rnet["flag"])
+
+
+def test_checkpoint_resume(mock_host_lib, tmp_path):
+    scenarios.checkpoint_resume(mock_host_lib, tmp_path)

@@ -214,107 +214,270 @@ __device__ __forceinline__ void flag_reserve(const View& v, uint32_t mine, uint3
 }
 
 // ---- staging kernel ------------------------------------------------------------------------------------------
-// The occupied slots of every row, found through the busy-slot index and written — per tile of 32 rows, in row order — to
-// the tile's staging region for k_neuron_pass.  Separate from the replay so that it can run at full occupancy (it is all
-// memory latency: index word -> gather of the (arrive, depol) records of the set bits): a warp streams the tile's index
-// words 32 at a time (1024 slots), lists the set bits in shared memory so that the gathers are spread evenly over the
-// lanes whatever the bit pattern, keeps the slots that have arrived (0 < arrive <= t1, one integer compare; the others are
-// still travelling) and counts them per row with a ballot walk over the tile's row ends.
+// Keeps, per tile of 32 rows, the list of the tile's occupied slots (spike arrived, not yet cleared) in row order —
+// (arrive, depol) and the slot index relative to the tile's first slot, plus a count per row — for k_neuron_pass.
+// Separate from the replay so that it can run at full occupancy (it is all memory latency).
+//   * A list PERSISTS: while a slot is in it its (arrive, depol) cannot change, so a window only has to (1) find the slots
+//     that ARRIVED in it — the per-word arrival bounds (wordNext) name the ~1 % of index words worth looking at — and
+//     (2) drop the entries the previous neuron pass cleared (it negates their arrive in the list and sets the tile's dirty
+//     bit).  The merged list goes to the tile's other region (ping-pong).  Nothing else of the synapse state is touched:
+//     one 4-byte bound per 32 slots + the lists themselves.
+//   * A tile without a valid list (first window, after a restore / state upload, after an overflow, after too many
+//     arrivals at once) is REBUILT from the index: the warp streams the tile's busy / arrived words 32 at a time, lists the
+//     set bits in shared memory so that the gathers of the (arrive, depol) records are spread evenly over the lanes, and
+//     counts the entries per row with a ballot walk over the tile's row ends.
 #define NC_STG_WARPS 8
+#define NC_STG_NEW 128  // arrivals of one tile in one window that the incremental path takes (more: the tile is rebuilt)
+
+struct StageTile {
+    uint64_t tile, rowBase, myRe, tb, te, wBeg, wEnd;
+    uint32_t nr;
+};
+
+// in-flight slots of index word w whose bound says one may have landed: marks the arrived ones, renews the bound; returns their bits
+__device__ __forceinline__ uint32_t stage_check_word(const View& v, uint64_t w, uint32_t infl, bool whole, uint32_t t1b, unsigned long long& busySeen) {
+    uint32_t im = 0u, nmin = 0x7f800000u;
+    for (uint32_t m = infl; m; m &= m - 1u) {
+        const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
+        const uint32_t ab = __float_as_uint(v.ad[(w << 5) + b].x);
+        if (ab <= t1b) im |= 1u << b; else nmin = min(nmin, ab);
+    }
+    busySeen += (unsigned long long)__popc(infl);  // (per-lane count, summed over the warp at the end)
+    if (im) atomicOr(&v.arrived[w], im);
+    if (whole) v.wordNext[w] = nmin;  // (a word that straddles two tiles keeps its old, lower bound: it is simply looked at every window)
+    return im;
+}
+__device__ __forceinline__ uint32_t stage_tile_mask(const StageTile& t, uint64_t w, bool& whole) {
+    uint32_t m = 0xffffffffu;
+    whole = true;
+    if (w == t.wBeg && (t.tb & 31u)) { m &= 0xffffffffu << (uint32_t)(t.tb & 31u); whole = false; }
+    if (w == t.wEnd - 1 && (t.te & 31u)) { m &= (1u << (uint32_t)(t.te & 31u)) - 1u; whole = false; }
+    return m;
+}
+
+// REBUILD: the tile's list from the index, into region 0.  Returns false when the entries do not fit the region.
+__device__ bool stage_rebuild(const View& v, const StageTile& t, uint32_t t1b, uint16_t* list, uint32_t lane, uint32_t& myCnt, unsigned long long& busySeen) {
+    const uint32_t FULL = 0xffffffffu, lt = (1u << lane) - 1u;
+    const uint64_t reg = (t.tile * 2) * v.stCap;
+    uint32_t used = 0, rcur = 0;
+    myCnt = 0;
+    uint3 next = make_uint3(0u, 0u, 0x7f800000u);
+    if (t.wBeg + lane < t.wEnd) next = make_uint3(__ldcs(v.busy + t.wBeg + lane), __ldcs(v.arrived + t.wBeg + lane), __ldcs(v.wordNext + t.wBeg + lane));
+    for (uint64_t wb = t.wBeg; wb < t.wEnd; wb += 32) {
+        const uint64_t w = wb + lane;
+        uint32_t word = next.x, arr = next.y;
+        const uint32_t nx = next.z;
+        next = make_uint3(0u, 0u, 0x7f800000u);  // the next 1024 slots' words are on their way while these are gathered
+        if (w + 32 < t.wEnd) next = make_uint3(__ldcs(v.busy + w + 32), __ldcs(v.arrived + w + 32), __ldcs(v.wordNext + w + 32));
+        bool whole;
+        word &= stage_tile_mask(t, w, whole);
+        arr &= word;
+        const uint32_t infl = word & ~arr;
+        if (infl && nx <= t1b) arr |= stage_check_word(v, w, infl, whole, t1b, busySeen);
+        __syncwarp();
+        word = arr;  // the slots whose spike has arrived: these are staged
+        const uint32_t c = __popc(word);
+        uint32_t inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(FULL, inc, o);
+            if (lane >= (uint32_t)o) inc += y;
+        }
+        const uint32_t tot = __shfl_sync(FULL, inc, 31);
+        if (!tot) continue;
+        busySeen += c;
+        uint32_t p = inc - c;
+        for (uint32_t m = word; m; m &= m - 1u) list[p++] = (uint16_t)((lane << 5) | ((uint32_t)__ffs((int)m) - 1u));
+        __syncwarp();
+        for (uint32_t base = 0; base < tot; base += 32) {
+            const uint32_t i = base + lane;
+            const bool have = i < tot;
+            const uint64_t slot = (wb << 5) + (have ? (uint32_t)list[i] : 0u);
+            float2 ad = make_float2(0.0f, 0.0f);
+            if (have) ad = v.ad[slot];
+            const bool is = have && (__float_as_uint(ad.x) - 1u < t1b);
+            const uint32_t m = __ballot_sync(FULL, is);
+            if (!m) continue;
+            const uint32_t n = (uint32_t)__popc(m);
+            if (used + n > v.stCap) return false;
+            if (is) {
+                const uint64_t at = reg + used + (uint32_t)__popc(m & lt);
+                v.stAD[at] = ad;
+                v.stJ[at] = (uint32_t)(slot - t.tb);
+            }
+            used += n;
+            uint32_t rem = m;  // per-row counts: the entries ascend in slot order, so do the rows
+            while (rem) {
+                const uint64_t re_r = __shfl_sync(FULL, t.myRe, rcur);
+                const uint32_t inrow = __ballot_sync(FULL, is && slot < re_r) & rem;
+                if (lane == rcur) myCnt += (uint32_t)__popc(inrow);
+                rem &= ~inrow;
+                if (rem) rcur++;
+            }
+        }
+        __syncwarp();
+    }
+    return true;
+}
+
+// INCREMENTAL: returns 0 = done (list current), 1 = rebuild the tile instead (too many arrivals at once), 2 = the merged list does not fit.
+// scratch: 2 KB per warp — newJ[128] u32, newAD[128] float2, hist[129..] u32 (arrivals-below histogram of the old entries).
+__device__ int stage_incremental(const View& v, const StageTile& t, uint32_t state, uint32_t t1b, uint32_t* scratch, uint32_t lane, uint32_t& myCnt,
+                                 unsigned long long& busySeen) {
+    const uint32_t FULL = 0xffffffffu, lt = (1u << lane) - 1u;
+    uint32_t* newJ = scratch;
+    float2* newAD = reinterpret_cast<float2*>(scratch + NC_STG_NEW);
+    uint32_t* hist = scratch + 3 * NC_STG_NEW;  // hist[b] = alive old entries with exactly b arrivals below them (b <= m < 128)
+    uint32_t m = 0;  // arrivals of this window (warp-uniform)
+    // (1) the slots that arrived in this window: only the index words whose arrival bound has been reached are looked at.
+    //     Every lane takes four consecutive bounds per round (one 16-byte load: 4096 slots per warp and round trip).
+    const uint64_t gBeg = t.wBeg & ~3ull;
+    const uint4 none = make_uint4(0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u);
+    const uint4* nxp = reinterpret_cast<const uint4*>(v.wordNext);
+    uint4 next = (gBeg + 4 * lane < t.wEnd) ? __ldcs(nxp + (gBeg >> 2) + lane) : none;
+    for (uint64_t wb = gBeg; wb < t.wEnd; wb += 128) {
+        const uint64_t w0 = wb + 4 * lane;
+        const uint4 nx4 = next;
+        next = (w0 + 128 < t.wEnd) ? __ldcs(nxp + ((wb + 128) >> 2) + lane) : none;
+        const uint32_t nxs[4] = {nx4.x, nx4.y, nx4.z, nx4.w};
+        uint32_t im[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint64_t w = w0 + q;
+            if (nxs[q] <= t1b && w >= t.wBeg && w < t.wEnd) {
+                bool whole;
+                const uint32_t msk = stage_tile_mask(t, w, whole);
+                const uint32_t infl = v.busy[w] & ~v.arrived[w] & msk;
+                if (infl) im[q] = stage_check_word(v, w, infl, whole, t1b, busySeen);
+                else if (whole) v.wordNext[w] = 0x7f800000u;  // nothing in flight any more: the bound was stale
+            }
+        }
+        if (!__any_sync(FULL, (im[0] | im[1] | im[2] | im[3]) != 0u)) continue;
+        const uint32_t c = __popc(im[0]) + __popc(im[1]) + __popc(im[2]) + __popc(im[3]);
+        uint32_t inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(FULL, inc, o);
+            if (lane >= (uint32_t)o) inc += y;
+        }
+        const uint32_t tot = __shfl_sync(FULL, inc, 31);
+        if (m + tot > NC_STG_NEW - 1) return 1;  // (the arrived bits are set: the rebuild finds these slots through them)
+        uint32_t p = m + inc - c;
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            for (uint32_t mm = im[q]; mm; mm &= mm - 1u) {
+                const uint64_t slot = ((w0 + q) << 5) + (uint32_t)__ffs((int)mm) - 1u;
+                newJ[p] = (uint32_t)(slot - t.tb);
+                newAD[p] = v.ad[slot];  // (second touch: L1)
+                p++;
+            }
+        m += tot;
+        __syncwarp();
+    }
+    const uint32_t oldCnt = lane < t.nr ? (v.stCnt[t.rowBase + lane] & 0x3fffffffu) : 0u;
+    if (m == 0u && !(state & 4u)) { myCnt = oldCnt; return 0; }  // nothing arrived, nothing was cleared: the list stands
+    uint32_t n = oldCnt;
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(FULL, n, o);
+    // (2) merge: old entries that are still alive keep their order, the arrivals slot in by slot index; counts per row
+    const uint32_t par = (state >> 1) & 1u;
+    const uint64_t src = (t.tile * 2 + par) * v.stCap, dst = (t.tile * 2 + (par ^ 1u)) * v.stCap;
+    for (uint32_t k = lane; k <= m; k += 32) hist[k] = 0u;
+    uint32_t myNew = 0u, myAlive = 0u;
+    __syncwarp();
+    for (uint32_t k = 0; k < m; k++) {  // row of arrival k = number of rows that end at or before its slot
+        const uint32_t r = (uint32_t)__popc(__ballot_sync(FULL, t.myRe <= t.tb + newJ[k]) & ((t.nr >= 32u) ? FULL : ((1u << t.nr) - 1u)));
+        if (lane == r) myNew++;
+    }
+    uint32_t aliveBefore = 0u, rcur = 0u;
+    for (uint32_t base = 0; base < n; base += 32) {
+        const uint32_t i = base + lane;
+        const bool have = i < n;
+        float2 ad = make_float2(0.0f, 0.0f);
+        uint32_t j = 0xffffffffu;
+        if (have) { ad = __ldcs(v.stAD + src + i); j = __ldcs(v.stJ + src + i); }
+        const bool alive = have && ad.x > 0.0f;  // (a cleared entry carries its arrive negated)
+        const uint32_t am = __ballot_sync(FULL, alive);
+        uint32_t lo = 0u, hi = m;  // arrivals below this entry: lower bound in the (sorted) arrival list
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (newJ[mid] < j) lo = mid + 1u; else hi = mid; }
+        if (alive) {
+            const uint32_t out = aliveBefore + (uint32_t)__popc(am & lt) + lo;
+            if (out < v.stCap) { v.stAD[dst + out] = ad; v.stJ[dst + out] = j; }
+            atomicAdd(&hist[lo], 1u);
+        }
+        uint32_t rem = am;
+        while (rem) {
+            const uint64_t re_r = __shfl_sync(FULL, t.myRe, rcur);
+            const uint32_t inrow = __ballot_sync(FULL, alive && t.tb + j < re_r) & rem;
+            if (lane == rcur) myAlive += (uint32_t)__popc(inrow);
+            rem &= ~inrow;
+            if (rem) rcur++;
+        }
+        aliveBefore += (uint32_t)__popc(am);
+    }
+    if (aliveBefore + m > v.stCap) return 2;
+    __syncwarp();
+    // arrival k goes after the alive old entries that have at most k arrivals below them: prefix sum of the histogram
+    uint32_t carry = 0u;
+    for (uint32_t k0 = 0; k0 < m; k0 += 32) {
+        const uint32_t k = k0 + lane;
+        const uint32_t h = k < m ? hist[k] : 0u;
+        uint32_t inc = h;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(FULL, inc, o);
+            if (lane >= (uint32_t)o) inc += y;
+        }
+        if (k < m) {
+            const uint32_t out = carry + inc + k;
+            v.stAD[dst + out] = newAD[k];
+            v.stJ[dst + out] = newJ[k];
+        }
+        carry += __shfl_sync(FULL, inc, 31);
+    }
+    myCnt = myAlive + myNew;
+    if (lane == 0) v.tileState[t.tile] = 1u | ((par ^ 1u) << 1);
+    return 0;
+}
+
 __global__ void __launch_bounds__(NC_STG_WARPS * 32, 8) k_stage(View v, StepArgs s) {
-    __shared__ uint16_t slist[NC_STG_WARPS][1024];
+    __shared__ uint32_t sscr[NC_STG_WARPS][512];  // 2 KB per warp: the rebuild's slot list (u16[1024]) / the merge's arrivals
     const uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u;
-    uint16_t* list = slist[threadIdx.x >> 5];
+    uint32_t* scratch = sscr[threadIdx.x >> 5];
     const uint32_t t1b = __float_as_uint(s.t1);
     const uint64_t nTiles = (v.nRows + 31) >> 5;
-    const uint32_t lt = (1u << lane) - 1u;
-    unsigned long long busySeen = 0ull;  // set bits of the index this warp looked at (reported by nc_index_stats)
+    unsigned long long busySeen = 0ull;  // slots of the synapse arrays this warp looked at (reported by nc_index_stats)
     for (;;) {
         uint32_t t32 = 0;
         if (lane == 0) t32 = atomicAdd(&v.tileCtr[1], 1u);
-        const uint64_t tile = __shfl_sync(FULL, t32, 0);
-        if (tile >= nTiles) break;
-        const uint64_t rowBase = tile << 5;
-        const uint32_t nr = (uint32_t)min((uint64_t)32, v.nRows - rowBase);
-        const uint64_t myRe = v.rowptr[rowBase + min(lane, nr - 1u) + 1u];  // end of this lane's row (lanes >= nr repeat the last row)
-        const uint64_t tb = v.rowptr[rowBase];
-        const uint64_t te = __shfl_sync(FULL, myRe, 31);
-        const uint64_t reg = tile * v.stCap;
-        const uint64_t wBeg = tb >> 5, wEnd = (te + 31) >> 5;
-        uint32_t used = 0, myCnt = 0, rcur = 0;
-        bool overflow = false;
-        uint3 next = make_uint3(0u, 0u, 0x7f800000u);
-        if (wBeg + lane < wEnd) next = make_uint3(__ldcs(v.busy + wBeg + lane), __ldcs(v.arrived + wBeg + lane), __ldcs(v.wordNext + wBeg + lane));
-        for (uint64_t wb = wBeg; wb < wEnd && !overflow; wb += 32) {
-            const uint64_t w = wb + lane;
-            uint32_t word = next.x, arr = next.y;
-            const uint32_t nx = next.z;
-            next = make_uint3(0u, 0u, 0x7f800000u);  // the next 1024 slots' words are on their way while these are gathered
-            if (w + 32 < wEnd) next = make_uint3(__ldcs(v.busy + w + 32), __ldcs(v.arrived + w + 32), __ldcs(v.wordNext + w + 32));
-            bool whole = true;  // the word lies inside the tile (a word that straddles two tiles is masked by each of them)
-            if (w == wBeg && (tb & 31u)) { word &= FULL << (uint32_t)(tb & 31u); whole = false; }
-            if (w == wEnd - 1 && (te & 31u)) { word &= (1u << (uint32_t)(te & 31u)) - 1u; whole = false; }
-            arr &= word;
-            // Slots still in flight are not looked at until the word's earliest arrival bound says one of them may have landed
-            // (0.8 % of the words per step at C3): then this lane checks its in-flight slots, marks the arrived ones and renews the bound.
-            const uint32_t infl = word & ~arr;
-            if (infl && nx <= t1b) {
-                uint32_t im = 0u, nmin = 0x7f800000u;
-                for (uint32_t m = infl; m; m &= m - 1u) {
-                    const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
-                    const uint32_t ab = __float_as_uint(v.ad[(w << 5) + b].x);
-                    if (ab <= t1b) im |= 1u << b; else nmin = min(nmin, ab);
-                }
-                busySeen += (unsigned long long)__popc(infl);  // (per-lane count, summed over the warp at the end)
-                if (im) atomicOr(&v.arrived[w], im);
-                if (whole) v.wordNext[w] = nmin;  // (a straddling word keeps its old, lower bound: it is simply looked at every window)
-                arr |= im;
-            }
-            __syncwarp();
-            word = arr;  // the slots whose spike has arrived: these are staged
-            const uint32_t c = __popc(word);
-            uint32_t inc = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(FULL, inc, o);
-                if (lane >= (uint32_t)o) inc += y;
-            }
-            const uint32_t tot = __shfl_sync(FULL, inc, 31);
-            if (!tot) continue;
-            busySeen += c;
-            uint32_t p = inc - c;
-            for (uint32_t m = word; m; m &= m - 1u) list[p++] = (uint16_t)((lane << 5) | ((uint32_t)__ffs((int)m) - 1u));
-            __syncwarp();
-            for (uint32_t base = 0; base < tot; base += 32) {
-                const uint32_t i = base + lane;
-                const bool have = i < tot;
-                const uint64_t slot = (wb << 5) + (have ? (uint32_t)list[i] : 0u);
-                float2 ad = make_float2(0.0f, 0.0f);
-                if (have) ad = v.ad[slot];
-                const bool is = have && (__float_as_uint(ad.x) - 1u < t1b);
-                const uint32_t m = __ballot_sync(FULL, is);
-                if (!m) continue;
-                const uint32_t n = (uint32_t)__popc(m);
-                if (used + n > v.stCap) { overflow = true; break; }
-                if (is) {
-                    const uint64_t at = reg + used + (uint32_t)__popc(m & lt);
-                    v.stAD[at] = ad;
-                    v.stJ[at] = (uint32_t)(slot - tb);
-                }
-                used += n;
-                uint32_t rem = m;  // per-row counts: the entries ascend in slot order, so do the rows
-                while (rem) {
-                    const uint64_t re_r = __shfl_sync(FULL, myRe, rcur);
-                    const uint32_t inrow = __ballot_sync(FULL, is && slot < re_r) & rem;
-                    if (lane == rcur) myCnt += (uint32_t)__popc(inrow);
-                    rem &= ~inrow;
-                    if (rem) rcur++;
-                }
-            }
-            __syncwarp();
+        StageTile t;
+        t.tile = __shfl_sync(FULL, t32, 0);
+        if (t.tile >= nTiles) break;
+        t.rowBase = t.tile << 5;
+        t.nr = (uint32_t)min((uint64_t)32, v.nRows - t.rowBase);
+        t.myRe = v.rowptr[t.rowBase + min(lane, t.nr - 1u) + 1u];  // end of this lane's row (lanes >= nr repeat the last row)
+        t.tb = v.rowptr[t.rowBase];
+        t.te = __shfl_sync(FULL, t.myRe, 31);
+        t.wBeg = t.tb >> 5; t.wEnd = (t.te + 31) >> 5;
+        const uint32_t state = v.tileState[t.tile];
+        uint32_t myCnt = 0u;
+        int how = ((state & 1u) && !v.stageRebuild) ? stage_incremental(v, t, state, t1b, scratch, lane, myCnt, busySeen) : 1;
+        __syncwarp();
+        if (how == 1) {
+            const bool ok = stage_rebuild(v, t, t1b, reinterpret_cast<uint16_t*>(scratch), lane, myCnt, busySeen);
+            how = ok ? 0 : 2;
+            if (ok && lane == 0) v.tileState[t.tile] = 1u;
         }
-        if (lane < nr) v.stCnt[rowBase + lane] = overflow ? 0xffffffffu : myCnt;
+        if (how == 2) {  // does not fit the region: k_neuron_pass stages this tile itself, through the index
+            myCnt = 0xffffffffu;
+            if (lane == 0) v.tileState[t.tile] = 0u;
+        } else {
+            // bit 30 of every count: which of the tile's two regions holds the list (k_neuron_pass needs nothing but the counts)
+            const uint32_t st2 = __shfl_sync(FULL, lane == 0 ? *(volatile uint32_t*)(v.tileState + t.tile) : 0u, 0);
+            myCnt |= ((st2 >> 1) & 1u) << 30;
+        }
+        if (lane < t.nr) v.stCnt[t.rowBase + lane] = myCnt;
+        __syncwarp();
     }
     for (int o = 16; o > 0; o >>= 1) busySeen += __shfl_xor_sync(FULL, busySeen, o);
     if (lane == 0 && busySeen) atomicAdd(&v.stats[8], busySeen);
@@ -653,8 +816,9 @@ __global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32, MINB) k_neuron_pass(V
         const uint32_t nr = (uint32_t)min((uint64_t)32, v.nRows - rowBase);
         const uint64_t tb = v.rowptr[rowBase];  // staged slot indices are relative to the tile's first slot (rows < 2^27 slots)
         uint32_t r = 0;
-        const uint32_t stc = (lane < nr) ? v.stCnt[rowBase + lane] : 0u;
-        if (__shfl_sync(0xffffffffu, stc, 0) != 0xffffffffu) {
+        const uint32_t stcRaw = (lane < nr) ? v.stCnt[rowBase + lane] : 0u;
+        const uint32_t stc = stcRaw & 0x3fffffffu;
+        if (__shfl_sync(0xffffffffu, stcRaw, 0) != 0xffffffffu) {
             // ---- the tile was staged by k_stage: copy batches of rows from its region into the pool and replay, lane = row ----
             const bool inSub = lane < nr && (!s.subset || in_subset(s, (uint32_t)(v.row0 + rowBase + lane)));
             uint32_t inc = stc;
@@ -664,14 +828,16 @@ __global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32, MINB) k_neuron_pass(V
                 if (lane >= (uint32_t)o) inc += y;
             }
             const uint32_t offL = inc - stc;  // this row's first entry within the region
-            const uint64_t reg = tile * v.stCap;
+            const uint64_t reg = (tile * 2 + ((__shfl_sync(0xffffffffu, stcRaw, 0) >> 30) & 1u)) * v.stCap;  // the region that holds the tile's current list
+            bool anyDead = false;
             while (r < nr) {
                 const uint32_t base = __shfl_sync(0xffffffffu, offL, r);
                 const bool fits = lane >= r && lane < nr && (inc - base <= cap);
                 const uint32_t fm = __ballot_sync(0xffffffffu, fits) >> r;
                 const uint32_t nb = min(fm == 0xffffffffu ? 32u : (uint32_t)__ffs((int)~fm) - 1u, nr - r);  // rows r .. r+nb-1 fit the pool together
-                if (nb == 0u) {  // a row whose occupied slots alone exceed the pool
-                    if (__shfl_sync(0xffffffffu, inSub ? 1u : 0u, r)) warp_row(v, s, rowBase + r, cv, lane, ctrW);
+                if (nb == 0u) {  // a row whose occupied slots alone exceed the pool: staged and replayed by the whole warp, through the index;
+                    // the tile's list does not learn what that run cleared, so it is rebuilt by the next staging pass
+                    if (__shfl_sync(0xffffffffu, inSub ? 1u : 0u, r)) { warp_row(v, s, rowBase + r, cv, lane, ctrW); if (lane == 0) v.tileState[tile] = 0u; }
                     r++;
                     continue;
                 }
@@ -684,8 +850,15 @@ __global__ void __launch_bounds__(NC_WARPS_PER_BLOCK * 32, MINB) k_neuron_pass(V
                 const uint32_t o = mine ? offL - base : 0u;
                 lanes_replay(v, s, mine, rowBase + lane, tb, sA + o, sD + o, sJ + o, mine ? stc : 0u, mine && stc != 0u, ctrL);
                 __syncwarp();
+                // the entries this replay cleared (arrive negated in the pool) are marked in the persistent list: the next staging pass drops them
+                for (uint32_t i = lane; i < used; i += 32) {
+                    const float a = sA[i];
+                    if (a < 0.0f) { v.stAD[reg + base + i].x = a; anyDead = true; }
+                }
+                __syncwarp();
                 r += nb;
             }
+            if (__any_sync(0xffffffffu, anyDead) && lane == 0) atomicOr(&v.tileState[tile], 4u);
         }
         while (r < nr) {  // (tiles that did not fit their staging region are staged here, through the busy-slot index, row by row)
             // ---- batch: stage rows r, r+1, ... while their occupied slots fit the pool; the i-th staged row goes to lane i ----
@@ -898,27 +1071,31 @@ __global__ void k_mark_events(View v, const nc_event* ev, uint32_t nEv, const ui
 // One block; both lists are short.  bgCtl[0] = number of background events of the run; outCount <- merged length.
 __global__ void __launch_bounds__(1024) k_merge_events(View v, const nc_event* host, uint32_t nHost, const nc_event* bg, const uint32_t* bgCtl, float t0, float t1,
                                                       int strict, nc_event* out, uint32_t outCap, uint32_t* outCount) {
+    const uint32_t SM = 2048;  // background events kept in shared memory (neuron; ~0u when outside the window); longer lists read global memory
+    __shared__ uint32_t sN[SM];
     __shared__ uint32_t sIn;
     const uint32_t nBg = bgCtl[0];
     if (threadIdx.x == 0) sIn = 0u;
-    __syncthreads();
     auto inWin = [&](const nc_event& e) { return (strict ? e.time > t0 : e.time >= t0) && e.time <= t1; };
+    for (uint32_t k = threadIdx.x; k < min(nBg, SM); k += blockDim.x) { const nc_event e = bg[k]; sN[k] = inWin(e) ? e.neuron : 0xffffffffu; }
+    __syncthreads();
+    auto key = [&](uint32_t k) -> uint32_t { if (k < SM) return sN[k]; const nc_event e = bg[k]; return inWin(e) ? e.neuron : 0xffffffffu; };
     // background event j -> position = (in-window background events before it) + (host events with neuron <= its neuron)
     for (uint32_t j = threadIdx.x; j < nBg; j += blockDim.x) {
-        const nc_event e = bg[j];
-        if (!inWin(e)) continue;
+        const uint32_t nj = key(j);
+        if (nj == 0xffffffffu) continue;
         uint32_t before = 0;
-        for (uint32_t k = 0; k < j; k++) before += inWin(bg[k]) ? 1u : 0u;
+        for (uint32_t k = 0; k < j; k++) before += key(k) != 0xffffffffu ? 1u : 0u;
         uint32_t lo = 0, hi = nHost;
-        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (host[mid].neuron <= e.neuron) lo = mid + 1; else hi = mid; }
-        if (before + lo < outCap) out[before + lo] = e;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (host[mid].neuron <= nj) lo = mid + 1; else hi = mid; }
+        if (before + lo < outCap) out[before + lo] = bg[j];
         atomicAdd(&sIn, 1u);
     }
-    // host event i -> position = i + (in-window background events with a smaller neuron)
+    // host event i -> position = i + (in-window background events with a smaller neuron; the list is sorted by neuron)
     for (uint32_t i = threadIdx.x; i < nHost; i += blockDim.x) {
         const nc_event e = host[i];
         uint32_t below = 0;
-        for (uint32_t k = 0; k < nBg; k++) below += (bg[k].neuron < e.neuron && inWin(bg[k])) ? 1u : 0u;
+        for (uint32_t k = 0; k < nBg; k++) { const uint32_t nk = key(k); below += (nk != 0xffffffffu && nk < e.neuron) ? 1u : 0u; }
         if (i + below < outCap) out[i + below] = e;
     }
     __syncthreads();
@@ -1174,7 +1351,7 @@ struct nc_engine {
     bool taping = false; std::vector<TapeStep> tape; nc_event* dTape = nullptr; uint64_t tapeCap = 0, tapeUsed = 0; uint32_t tapeMaxSteps = 0;
     // snapshot
     struct Snap { float2* ad; SynRec* rec; float *lastStart, *lastRan, *lastFire, *lfStart, *actStart; float2* potAct; uint32_t *firings, *busy, *arrived, *wordNext; bool valid; } snap = {};
-    uint64_t busyWords = 0;
+    uint64_t busyWords = 0, nTiles = 0;
     int smCount = 148;
 };
 
@@ -1266,7 +1443,7 @@ static void free_all(nc_engine* e) {
     View& v = e->v;
     cudaFree((void*)v.rowptr); cudaFree(v.rec); cudaFree(v.ad);
     cudaFree(v.lastStart); cudaFree(v.potAct); cudaFree(v.lastRan); cudaFree(v.lastFire); cudaFree(v.lfStart);
-    cudaFree(v.actStart); cudaFree(v.firings); cudaFree(v.localHdr); cudaFree(v.head); cudaFree(v.next); cudaFree(v.mask); cudaFree(v.evMask); cudaFree(v.busy); cudaFree(v.arrived); cudaFree(v.wordNext); cudaFree(v.stCnt); cudaFree(v.stAD); cudaFree(v.stJ); cudaFree(v.flagList); cudaFree(v.flagCtl); cudaFree(e->dCscPtr); cudaFree(e->dCscEnt);
+    cudaFree(v.actStart); cudaFree(v.firings); cudaFree(v.localHdr); cudaFree(v.head); cudaFree(v.next); cudaFree(v.mask); cudaFree(v.evMask); cudaFree(v.busy); cudaFree(v.arrived); cudaFree(v.wordNext); cudaFree(v.stCnt); cudaFree(v.stAD); cudaFree(v.stJ); cudaFree(v.tileState); cudaFree(v.flagList); cudaFree(v.flagCtl); cudaFree(e->dCscPtr); cudaFree(e->dCscEnt);
     cudaFree(v.spillA); cudaFree(v.spillD); cudaFree(v.spillJ);
     cudaFree(e->dGather);
     cudaFree(e->dEv); cudaFree(e->dTape);
@@ -1438,8 +1615,12 @@ static int upload_common(nc_engine* e, uint64_t nGlobal, uint64_t row0, uint64_t
         v.stCap = (uint32_t)cap;
         const uint64_t nTiles = (N1 + 31) / 32;
         CK(cudaMalloc(&v.stCnt, nTiles * 32 * 4));
-        CK(cudaMalloc(&v.stAD, nTiles * cap * 8));
-        CK(cudaMalloc(&v.stJ, nTiles * cap * 4));
+        CK(cudaMalloc(&v.stAD, nTiles * 2 * cap * 8));  // two regions per tile (ping-pong)
+        CK(cudaMalloc(&v.stJ, nTiles * 2 * cap * 4));
+        CK(cudaMalloc(&v.tileState, nTiles * 4));
+        CK(cudaMemsetAsync(v.tileState, 0, nTiles * 4, e->stream));  // no tile has a list yet: the first staging pass builds them
+        e->nTiles = nTiles;
+        { const char* f = getenv("NC_STAGE_MODE"); v.stageRebuild = (f && f[0] == 'r') ? 1u : 0u; }
         e->gridStage = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((nTiles + NC_STG_WARPS - 1) / NC_STG_WARPS, (uint64_t)e->smCount * 8));
     }
     // scratch sized for whichever variant needs more: spill beyond the smaller pool, one pool of slot indices per resident warp
@@ -2103,6 +2284,7 @@ extern "C" int nc_write_synapses(nc_engine* e, const float* weight, const float*
     if (lastStart) CK(cudaMemcpy(e->v.lastStart, lastStart, S * 4, cudaMemcpyHostToDevice));
     if (arrive) {  // the event index follows `arrive`: every busy slot is looked at once by the next staging pass, which sorts out the arrived ones
         k_rebuild_busy<<<(unsigned)std::min<uint64_t>((e->busyWords + 255) / 256, 1u << 20), 256, 0, e->stream>>>(e->v, e->busyWords); e->launches++;
+        CK(cudaMemsetAsync(e->v.tileState, 0, e->nTiles * 4, e->stream));
         CK(cudaStreamSynchronize(e->stream));
     }
     return NC_OK;
@@ -2280,7 +2462,10 @@ static int snap_all(nc_engine* e, bool toSnap) {
     CK(snap_copy(s.actStart, v.actStart, v.nRows, e->stream, toSnap)); CK(snap_copy(s.potAct, v.potAct, v.nRows, e->stream, toSnap));
     CK(snap_copy(s.firings, v.firings, v.nRows, e->stream, toSnap));
     if (toSnap) { CK(cudaMemcpyAsync(e->snapRand, e->dRandState, 31 * 4, cudaMemcpyDeviceToDevice, e->stream)); e->snapRandOn = e->randOn; }
-    else { CK(cudaMemcpyAsync(e->dRandState, e->snapRand, 31 * 4, cudaMemcpyDeviceToDevice, e->stream)); e->randOn = e->snapRandOn; e->hRandFresh = false; }
+    else {
+        CK(cudaMemcpyAsync(e->dRandState, e->snapRand, 31 * 4, cudaMemcpyDeviceToDevice, e->stream)); e->randOn = e->snapRandOn; e->hRandFresh = false;
+        CK(cudaMemsetAsync(v.tileState, 0, e->nTiles * 4, e->stream));  // the staged lists belong to the state that was replaced: rebuilt by the next window
+    }
     CK(snap_copy(s.busy, v.busy, e->busyWords, e->stream, toSnap));
     CK(snap_copy(s.arrived, v.arrived, e->busyWords, e->stream, toSnap));
     CK(snap_copy(s.wordNext, v.wordNext, e->busyWords, e->stream, toSnap));

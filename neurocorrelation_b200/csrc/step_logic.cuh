@@ -106,10 +106,15 @@ struct View {
     uint32_t flagCap;
     // staged rows (k_stage -> k_neuron_pass): per tile of 32 rows a region of stCap entries holding the tile's occupied slots
     // (arrive <= t1) in row order — (arrive, depol) and the slot index relative to the tile's first slot — and per row its count
+    // The lists PERSIST across windows: a slot's (arrive, depol) never changes while it is in the list, so the staging kernel
+    // only merges the (few) slots that arrived in this window and drops the ones the last neuron pass cleared (it negates their
+    // arrive in the list).  Two regions per tile (ping-pong); tileState says which one is current.
     uint32_t* stCnt;       // per row; 0xffffffff on every row of a tile whose occupied slots did not fit its region
-    float2* stAD;
+    float2* stAD;          // [tile][2][stCap]
     uint32_t* stJ;
     uint32_t stCap;
+    uint32_t stageRebuild; // 1: every window rebuilds every list from the index (NC_STAGE_MODE=rebuild; measurements)
+    uint32_t* tileState;   // per tile: bit 0 = the list is valid, bit 1 = which region holds it, bit 2 = the last neuron pass cleared entries
     uint32_t cprLoads, cprRows;  // 128-entry chunks that cover the longest out-list / the longest row (work split of the synapse kernels)
     const uint64_t* cscPtr;  // per GLOBAL presynaptic neuron: its out-synapses that land in this shard are cscEnt[cscPtr[p] .. cscPtr[p+1])
     const SlotRow* cscEnt;

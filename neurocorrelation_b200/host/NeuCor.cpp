@@ -562,23 +562,20 @@ void NeuCor::nearList(coord3 c, float radius, std::vector<uint32_t>& out) {
         return;
     }
     if (gridN_ != N) {  // (re)build: neurons are only ever appended
+        // Only neurons with finite coordinates go into the grid.  An imported network may carry no positions (NaN): the distance
+        // to such a neuron is NaN (or inf), never < a finite radius, so it is near nothing — as in the reference — and costs nothing.
         gridCells_.clear();
         gridLo_[0] = gridLo_[1] = gridLo_[2] = INFINITY;
-        bool ok = true;
-        for (auto& p : positions) {
-            ok = ok && std::isfinite(p.x) && std::isfinite(p.y) && std::isfinite(p.z);
-            gridLo_[0] = std::min(gridLo_[0], p.x); gridLo_[1] = std::min(gridLo_[1], p.y); gridLo_[2] = std::min(gridLo_[2], p.z);
-        }
-        gridOk_ = ok;
-        if (ok)
-            for (std::size_t i = 0; i < N; i++) gridCells_[cellKey(positions[i].x, positions[i].y, positions[i].z)].push_back((uint32_t)i);
+        auto fin = [](const coord3& p) { return std::isfinite(p.x) && std::isfinite(p.y) && std::isfinite(p.z); };
+        for (auto& p : positions)
+            if (fin(p)) { gridLo_[0] = std::min(gridLo_[0], p.x); gridLo_[1] = std::min(gridLo_[1], p.y); gridLo_[2] = std::min(gridLo_[2], p.z); }
+        gridOk_ = std::isfinite(gridLo_[0]);  // false: no neuron has a position
+        if (gridOk_)
+            for (std::size_t i = 0; i < N; i++)
+                if (fin(positions[i])) gridCells_[cellKey(positions[i].x, positions[i].y, positions[i].z)].push_back((uint32_t)i);
         gridN_ = N;
     }
-    if (!gridOk_) {  // imported networks may carry no positions (NaN): nothing is near anything, as in the reference
-        for (std::size_t n = 0; n < N; n++)
-            if (positions[n].getDist(c) < radius) out.push_back((uint32_t)n);
-        return;
-    }
+    if (!gridOk_) return;
     const double r = (double)radius + 1e-3;  // cells that can hold a neuron within the radius (with slack for float rounding)
     const long x0 = (long)std::floor((double)c.x - r - gridLo_[0]), x1 = (long)std::floor((double)c.x + r - gridLo_[0]);
     const long y0 = (long)std::floor((double)c.y - r - gridLo_[1]), y1 = (long)std::floor((double)c.y + r - gridLo_[1]);

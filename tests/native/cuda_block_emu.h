@@ -1,0 +1,272 @@
+// TEST INFRASTRUCTURE — never compiled into or loaded by the product.
+//
+// A small CPU emulator of the CUDA execution model for ONE kernel launch at a time, so that kernel source from
+// neurocorrelation_b200/csrc/*.cuh can be compiled with g++ and exercised in the CPU test-suite (the container that runs
+// `pytest -m "not gpu"` has no GPU).  It checks LOGIC — indexing, the use of barriers and warp collectives, capacities —
+// not performance and not the memory model.
+//
+//   * every CUDA thread of a block is a fibre (ucontext) on one OS thread; blocks of a grid run one after the other;
+//   * __syncthreads() parks a fibre until every live thread of the block has arrived;
+//   * warp collectives (__syncwarp, __ballot_sync, __any_sync, __all_sync, __shfl_*_sync, __reduce_*_sync) park a lane until
+//     every live lane named in the mask has arrived at a collective of the SAME kind (anything else aborts: on the GPU
+//     it would be undefined behaviour);
+//   * __shared__ becomes `static` (one block at a time), atomics are plain read-modify-writes (one OS thread);
+//   * a fibre that leaves the kernel counts as arrived at every later barrier, as on the hardware;
+//   * no progress by any fibre = deadlock (e.g. a barrier inside divergent code): aborts with a message.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <ucontext.h>
+
+#include <algorithm>
+#include <functional>
+#include <vector>
+
+namespace emu {
+
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+
+enum Wait { RUN = 0, AT_BLOCK = 1, AT_WARP = 2, DONE = 3 };
+enum Kind { K_SYNCWARP = 1, K_BALLOT, K_ANY, K_ALL, K_SHFL, K_SHFL_UP, K_SHFL_DOWN, K_SHFL_XOR, K_RED_MAX, K_RED_MIN, K_RED_ADD };
+
+struct Fibre {
+    ucontext_t ctx;
+    char* stack = nullptr;
+    Wait wait = RUN;
+    dim3 tid;
+    unsigned linear = 0;
+    // the warp collective this lane is parked at
+    int kind = 0;
+    uint32_t mask = 0;
+    uint64_t payload = 0;
+    int aux = 0;
+    uint64_t result = 0;
+};
+
+struct State {
+    std::vector<Fibre> f;            // the threads of the block being run
+    std::vector<char*> stacks;       // fibre stacks, kept across blocks and launches
+    ucontext_t sched;
+    Fibre* cur = nullptr;
+    dim3 bIdx, bDim, gDim;
+    const std::function<void()>* body = nullptr;
+    size_t stackBytes = 256 * 1024;
+    unsigned long long collectives = 0, barriers = 0;
+};
+inline State& S() { static State s; return s; }
+
+[[noreturn]] inline void die(const char* what) {
+    fprintf(stderr, "cuda_block_emu: %s (block %u,%u thread %u)\n", what, S().bIdx.x, S().bIdx.y, S().cur ? S().cur->linear : 0u);
+    abort();
+}
+
+inline void yield_to_scheduler() { swapcontext(&S().cur->ctx, &S().sched); }
+
+inline void fibre_entry() {
+    (*S().body)();
+    S().cur->wait = DONE;
+    yield_to_scheduler();
+    die("resumed a finished fibre");
+}
+
+// ---- completion of barriers --------------------------------------------------------------------------------------------
+inline void try_release_block() {
+    State& s = S();
+    bool any = false;
+    for (auto& x : s.f) {
+        if (x.wait == RUN || x.wait == AT_WARP) return;  // somebody is still on the way
+        any = any || x.wait == AT_BLOCK;
+    }
+    if (!any) return;
+    for (auto& x : s.f)
+        if (x.wait == AT_BLOCK) x.wait = RUN;
+    s.barriers++;
+}
+
+inline void try_release_warp(unsigned warp) {
+    State& s = S();
+    const unsigned lo = warp * 32u, hi = std::min<unsigned>(lo + 32u, (unsigned)s.f.size());
+    // the collective is defined by the first parked lane; every live lane of its mask must be parked at the same one
+    Fibre* lead = nullptr;
+    for (unsigned i = lo; i < hi; i++)
+        if (s.f[i].wait == AT_WARP) { lead = &s.f[i]; break; }
+    if (!lead) return;
+    const uint32_t mask = lead->mask;
+    for (unsigned i = lo; i < hi; i++) {
+        Fibre& x = s.f[i];
+        const bool named = (mask >> (i - lo)) & 1u;
+        if (x.wait == AT_WARP) {
+            if (x.kind != lead->kind || x.mask != mask) die("lanes of one warp are parked at different collectives / masks");
+            if (!named) die("a lane takes part in a collective whose mask does not name it");
+        } else if (named && x.wait != DONE) {
+            return;  // a named lane has not arrived yet (RUN, or parked at a block barrier = deadlock, caught by the scheduler)
+        }
+    }
+    auto live = [&](unsigned l) { return lo + l < hi && ((mask >> l) & 1u) && s.f[lo + l].wait == AT_WARP; };
+    uint32_t ballot = 0;
+    bool any = false, all = true;
+    uint64_t rmax = 0, rmin = ~0ull, radd = 0;
+    for (unsigned l = 0; l < 32; l++)
+        if (live(l)) {
+            const uint64_t p = s.f[lo + l].payload;
+            if (p) { ballot |= 1u << l; any = true; } else all = false;
+            rmax = std::max(rmax, p); rmin = std::min(rmin, p); radd += p;
+        }
+    for (unsigned l = 0; l < 32; l++) {
+        if (!live(l)) continue;
+        Fibre& x = s.f[lo + l];
+        int src = (int)l;
+        switch (x.kind) {
+            case K_SYNCWARP: x.result = 0; break;
+            case K_BALLOT: x.result = ballot; break;
+            case K_ANY: x.result = any; break;
+            case K_ALL: x.result = all; break;
+            case K_RED_MAX: x.result = rmax; break;
+            case K_RED_MIN: x.result = rmin; break;
+            case K_RED_ADD: x.result = radd; break;
+            case K_SHFL: src = x.aux & 31; break;
+            case K_SHFL_UP: src = (int)l - x.aux; if (src < 0) src = (int)l; break;
+            case K_SHFL_DOWN: src = (int)l + x.aux; if (src > 31) src = (int)l; break;
+            case K_SHFL_XOR: src = (int)l ^ x.aux; break;
+            default: die("unknown collective");
+        }
+        if (x.kind >= K_SHFL && x.kind <= K_SHFL_XOR) {
+            // reading from a lane that does not take part is undefined on the GPU; the emulator returns the lane's own value
+            x.result = live((unsigned)src) ? s.f[lo + (unsigned)src].payload : x.payload;
+        }
+    }
+    for (unsigned l = 0; l < 32; l++)
+        if (live(l)) s.f[lo + l].wait = RUN;
+    s.collectives++;
+}
+
+inline uint64_t warp_collective(int kind, uint32_t mask, uint64_t payload, int aux) {
+    Fibre* me = S().cur;
+    me->kind = kind; me->mask = mask; me->payload = payload; me->aux = aux;
+    me->wait = AT_WARP;
+    yield_to_scheduler();
+    return me->result;
+}
+
+inline void block_barrier() {
+    S().cur->wait = AT_BLOCK;
+    yield_to_scheduler();
+}
+
+// ---- launch -------------------------------------------------------------------------------------------------------------
+inline void run_block(const std::function<void()>& body) {
+    State& s = S();
+    const unsigned T = s.bDim.x * s.bDim.y * s.bDim.z;
+    s.f.assign(T, Fibre());
+    while (s.stacks.size() < T) s.stacks.push_back((char*)malloc(s.stackBytes));
+    s.body = &body;
+    for (unsigned i = 0; i < T; i++) {
+        Fibre& x = s.f[i];
+        x.stack = s.stacks[i];
+        x.wait = RUN; x.linear = i;
+        x.tid = dim3(i % s.bDim.x, (i / s.bDim.x) % s.bDim.y, i / (s.bDim.x * s.bDim.y));
+        getcontext(&x.ctx);
+        x.ctx.uc_stack.ss_sp = x.stack;
+        x.ctx.uc_stack.ss_size = s.stackBytes;
+        x.ctx.uc_link = nullptr;
+        makecontext(&x.ctx, (void (*)())fibre_entry, 0);
+    }
+    for (;;) {
+        bool progressed = false, allDone = true;
+        for (unsigned i = 0; i < T; i++) {
+            Fibre& x = s.f[i];
+            if (x.wait != DONE) allDone = false;
+            if (x.wait != RUN) continue;
+            s.cur = &x;
+            swapcontext(&s.sched, &x.ctx);
+            s.cur = nullptr;
+            progressed = true;
+            if (x.wait == AT_WARP || x.wait == DONE) try_release_warp(i / 32u);
+            if (x.wait == AT_BLOCK || x.wait == DONE) try_release_block();
+        }
+        if (allDone) break;
+        if (!progressed) {
+            // a lane leaving may complete a warp's collective, a warp completing may complete the block barrier: one more look
+            for (unsigned w = 0; w * 32u < T; w++) try_release_warp(w);
+            try_release_block();
+            bool runnable = false;
+            for (auto& x : s.f) runnable = runnable || x.wait == RUN;
+            if (!runnable) die("deadlock: every live thread is parked (a barrier or collective in divergent code, or a spin-wait)");
+        }
+    }
+}
+
+template <typename F>
+inline void launch(dim3 grid, dim3 block, F&& kernel_call) {
+    State& s = S();
+    s.gDim = grid; s.bDim = block;
+    const std::function<void()> body = kernel_call;
+    for (unsigned z = 0; z < grid.z; z++)
+        for (unsigned y = 0; y < grid.y; y++)
+            for (unsigned x = 0; x < grid.x; x++) {
+                s.bIdx = dim3(x, y, z);
+                run_block(body);
+            }
+}
+
+}  // namespace emu
+
+// ---- the CUDA vocabulary the kernels use ------------------------------------------------------------------------------------
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __restrict__
+#define threadIdx (emu::S().cur->tid)
+#define blockIdx (emu::S().bIdx)
+#define blockDim (emu::S().bDim)
+#define gridDim (emu::S().gDim)
+using emu::dim3;
+
+inline void __syncthreads() { emu::block_barrier(); }
+inline void __syncwarp(uint32_t mask = 0xffffffffu) { emu::warp_collective(emu::K_SYNCWARP, mask, 0, 0); }
+inline uint32_t __ballot_sync(uint32_t mask, int pred) { return (uint32_t)emu::warp_collective(emu::K_BALLOT, mask, pred ? 1 : 0, 0); }
+inline int __any_sync(uint32_t mask, int pred) { return (int)emu::warp_collective(emu::K_ANY, mask, pred ? 1 : 0, 0); }
+inline int __all_sync(uint32_t mask, int pred) { return (int)emu::warp_collective(emu::K_ALL, mask, pred ? 1 : 0, 0); }
+inline uint32_t __reduce_max_sync(uint32_t mask, uint32_t v) { return (uint32_t)emu::warp_collective(emu::K_RED_MAX, mask, v, 0); }
+inline uint32_t __reduce_min_sync(uint32_t mask, uint32_t v) { return (uint32_t)emu::warp_collective(emu::K_RED_MIN, mask, v, 0); }
+inline uint32_t __reduce_add_sync(uint32_t mask, uint32_t v) { return (uint32_t)emu::warp_collective(emu::K_RED_ADD, mask, v, 0); }
+
+namespace emu {
+template <typename T> inline uint64_t to_bits(T v) { uint64_t b = 0; static_assert(sizeof(T) <= 8, "shuffle payload"); memcpy(&b, &v, sizeof(T)); return b; }
+template <typename T> inline T from_bits(uint64_t b) { T v; memcpy(&v, &b, sizeof(T)); return v; }
+}  // namespace emu
+template <typename T> inline T __shfl_sync(uint32_t mask, T v, int src) { return emu::from_bits<T>(emu::warp_collective(emu::K_SHFL, mask, emu::to_bits(v), src)); }
+template <typename T> inline T __shfl_up_sync(uint32_t mask, T v, unsigned d) { return emu::from_bits<T>(emu::warp_collective(emu::K_SHFL_UP, mask, emu::to_bits(v), (int)d)); }
+template <typename T> inline T __shfl_down_sync(uint32_t mask, T v, unsigned d) { return emu::from_bits<T>(emu::warp_collective(emu::K_SHFL_DOWN, mask, emu::to_bits(v), (int)d)); }
+template <typename T> inline T __shfl_xor_sync(uint32_t mask, T v, int x) { return emu::from_bits<T>(emu::warp_collective(emu::K_SHFL_XOR, mask, emu::to_bits(v), x)); }
+
+template <typename T> inline T __ldg(const T* p) { return *p; }
+template <typename T> inline T __ldcs(const T* p) { return *p; }
+template <typename T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
+template <typename T> inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
+template <typename T> inline T atomicMin(T* p, T v) { T o = *p; *p = std::min(o, v); return o; }
+template <typename T> inline T atomicMax(T* p, T v) { T o = *p; *p = std::max(o, v); return o; }
+template <typename T> inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; }
+inline int __popc(uint32_t x) { return __builtin_popcount(x); }
+inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
+inline int __ffs(int x) { return __builtin_ffs(x); }
+inline int __ffsll(long long x) { return __builtin_ffsll(x); }
+inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
+using std::max;
+using std::min;
+// round-to-nearest single operations (the host is built with -ffp-contract=off, so plain operators are the same thing)
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fdiv_rn(float a, float b) { return a / b; }
+inline float __int2float_rn(int x) { return (float)x; }
+inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }

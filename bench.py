@@ -521,6 +521,8 @@ def main():
                           "fire_exchange": km["ms_exchange"], "step_total": ms_step},
             "timed": {"replays_of_K_steps": len(times), "ms_total_each": times, "statistic": "median"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": tr,
+                         "traffic_source": ("profiles/traffic.json (ncu --set full, dram bytes read + written per launch; see its _comment for the build)" if tr is not None
+                                            else "null: no ncu --set full capture of this workload with this build is committed (profiles/traffic.json, profiles/README.md)"),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_survey,
                          "definition": "algorithmic bytes = SURVEY.md section 8(d) (dense formulation: 4 B of `arrive` resp. `pre` per synapse and step + event terms) / CUDA-event time of the launches; "
                                        "the engine reaches the same synapse-updates through a busy-slot index and an out-synapse index and does NOT stream idle synapses, so `traffic` (ncu dram bytes) is far "

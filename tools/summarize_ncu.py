@@ -30,10 +30,11 @@ def launches(path, only_ours=True):
             val *= 1e3
         agg[name][0] += 1
         agg[name][1] += val
-    tot_ours = sum(t for n, (c, t) in agg.items() if n.startswith("k_"))
+    ours = lambda n: n.split("::")[-1].startswith("k_")  # (the engine's kernels, incl. those in namespaces ncr / ncx)
+    tot_ours = sum(t for n, (c, t) in agg.items() if ours(n))
     out = ["kernel,launches,total_us,mean_us,share_of_our_kernels"]
     for n, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
-        if only_ours and not n.startswith("k_"):
+        if only_ours and not ours(n):
             continue
         out.append("%s,%d,%.1f,%.2f,%.4f" % (n, c, t, t / c, t / tot_ours if tot_ours else 0))
     return "\n".join(out)

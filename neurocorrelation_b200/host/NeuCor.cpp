@@ -315,6 +315,7 @@ NeuCor::NeuCor(int n_neurons) {  // NeuCor.cpp:17-42
     postsynapticTraceDecay = 0.65;
     presynapticFactor = 0.13;
     postsynapticFactor = 0.30;
+    neurons.owner_ = this;
 
     totalGenNeurons = n_neurons;
     for (int n = 0; n < n_neurons; n++) {
@@ -364,6 +365,62 @@ void NeuCor::createNeuron(coord3 position) {  // NeuCor.cpp:154-186 (SPAWN_SPHER
     potAct.push_back(-70.0f);  // Neuron ctor: setPotential(baselevel), setActivity(0)  NeuCor.cpp:389,394
     potAct.push_back(0.0f);
     out_.emplace_back();
+    neurons.d_.emplace_back();
+    neurons.d_.back().parentNet = this;
+    neurons.d_.back().ownID = positions.size() - 1;
+}
+
+// ---- object view (NeuCor.h:117-125) ----------------------------------------------------------------------------
+static void viewAddSynapse(std::deque<Neuron>& d, std::size_t from, std::size_t to, float weight, float length, bool inhibitory, uint64_t slot,
+                           void (*set)(Synapse&, std::size_t, std::size_t, float, float, bool, uint64_t)) {
+    d[from].outSynapses.emplace_back();
+    set(d[from].outSynapses.back(), from, to, weight, length, inhibitory, slot);
+    d[to].inSynapses.emplace(from, to);
+}
+void NeuCor::viewSet(Synapse& s, std::size_t from, std::size_t to, float weight, float length, bool inhibitory, uint64_t slot) {
+    s.pN = from; s.tN = to; s.weight = weight; s.length = length; s.inhibitory = inhibitory; s.slot_ = slot;
+}
+void NeuCor::buildImportedView() {  // an imported network has no creation order: every neuron's out-synapses by ascending target
+    neurons.d_.clear();
+    const std::size_t N = positions.size();
+    if (dev_.set || pre_.size() > objectViewLimit) return;
+    neurons.d_.resize(N);
+    for (std::size_t i = 0; i < N; i++) { neurons.d_[i].parentNet = this; neurons.d_[i].ownID = i; }
+    for (std::size_t q = 0; q < N; q++)
+        for (uint64_t k = rowptr_[q]; k < rowptr_[q + 1]; k++)
+            viewAddSynapse(neurons.d_, pre_[k], q, weight_[k], length_[k], flag_[k] != 0, k, &NeuCor::viewSet);
+    viewDirty_ = true;
+}
+Neuron* NeuCor::getNeuron(std::size_t ID) { return &neurons.at(ID); }
+const Neuron* NeuCor::getNeuron(std::size_t ID) const { return &const_cast<NeuCor*>(this)->neurons.at(ID); }
+Synapse* NeuCor::getSynapse(std::size_t fromID, std::size_t toID) {  // NeuCor.cpp:244-250
+    Neuron* n = getNeuron(fromID);
+    for (auto& s : n->outSynapses)
+        if (s.tN == toID) return &s;
+    return nullptr;
+}
+const Synapse* NeuCor::getSynapse(std::size_t fromID, std::size_t toID) const { return const_cast<NeuCor*>(this)->getSynapse(fromID, toID); }
+Synapse* NeuCor::getSynapse(std::pair<std::size_t, std::size_t> ID) { return getSynapse(ID.first, ID.second); }
+const Synapse* NeuCor::getSynapse(std::pair<std::size_t, std::size_t> ID) const { return getSynapse(ID.first, ID.second); }
+
+// Device -> object view.  Nothing happens unless something ran since the last refresh.  Sharded engines keep no view.
+void NeuCor::refreshObjects() {
+    if (!viewDirty_ || !engine_ || world_ > 1 || neurons.d_.empty()) return;
+    viewDirty_ = false;
+    syncState();
+    const std::size_t N = positions.size(), S = pre_.size();
+    d2hBytes_ += N * 12 + S * 24;
+    for (std::size_t i = 0; i < N; i++) neurons.d_[i].lastFire = lastFireMirror_[i];
+    if (!S) return;
+    std::vector<float> w(S), arrive(S), lastArr(S), lastStart(S), prePot(S), postPot(S);
+    check(nc_read_synapses(engine_, w.data(), arrive.data(), nullptr, lastArr.data(), lastStart.data()), "nc_read_synapses");
+    check(nc_read_synapse_pots(engine_, currentTime, prePot.data(), postPot.data()), "nc_read_synapse_pots");
+    for (auto& n : neurons.d_)
+        for (auto& sy : n.outSynapses) {
+            const uint64_t k = sy.slot_;
+            sy.weight = w[k]; sy.AP_fireTime = arrive[k]; sy.lastSpikeArrival = lastArr[k]; sy.lastSpikeStart = lastStart[k];
+            sy.prePot_ = prePot[k]; sy.postPot_ = postPot[k];
+        }
 }
 
 void NeuCor::createSynapse(std::size_t toID, std::size_t fromID, float weight) {  // NeuCor.cpp:187-195
@@ -382,6 +439,7 @@ void NeuCor::createSynapse(std::size_t toID, std::size_t fromID, float weight) {
     s.flag = weight < 0.0;
     s.length = n2.getDist(n1);
     outs.push_back(s);
+    viewAddSynapse(neurons.d_, fromID, toID, s.weight, s.length, s.flag != 0, 0, &NeuCor::viewSet);
 }
 
 void NeuCor::makeConnections() {  // NeuCor.cpp:89-93 → Neuron::makeConnections NeuCor.cpp:418-444
@@ -430,6 +488,7 @@ void NeuCor::makeConnections() {  // NeuCor.cpp:89-93 → Neuron::makeConnection
                 s.flag = s.weight < 0.0;
                 s.length = nPos.getDist(positions[i]);
                 outs.push_back(s);
+                viewAddSynapse(neurons.d_, n, i, s.weight, s.length, s.flag != 0, 0, &NeuCor::viewSet);
             }
         }
     }
@@ -454,6 +513,8 @@ void NeuCor::importNetwork(std::size_t n, const uint64_t* rowptr, const uint32_t
     length_.assign(length, length + S);
     flag_.assign(inhibitory, inhibitory + S);
     imported_ = true;
+    neurons.owner_ = this;
+    buildImportedView();
 }
 
 void NeuCor::importNetworkDevice(std::size_t n, uint64_t synapses, const uint64_t* d_rowptr, const uint32_t* d_pre, const float* d_weight,
@@ -465,6 +526,7 @@ void NeuCor::importNetworkDevice(std::size_t n, uint64_t synapses, const uint64_
     out_.clear();
     dev_.rowptr = d_rowptr; dev_.pre = d_pre; dev_.weight = d_weight; dev_.length = d_length; dev_.inh = d_inhibitory; dev_.S = synapses; dev_.set = true;
     imported_ = true;
+    neurons.d_.clear();  // (no object view of a device-resident network)
 }
 
 void NeuCor::setShard(int rank, int world) {
@@ -494,12 +556,17 @@ void NeuCor::finalize() {
         uint64_t S = rowptr_[N];
         pre_.resize(S); weight_.resize(S); length_.resize(S); flag_.resize(S);
         std::vector<uint64_t> fill(rowptr_.begin(), rowptr_.end() - 1);
-        for (std::size_t p = 0; p < N; p++)  // ascending p => each row ends up ascending in presynaptic ID
+        for (std::size_t p = 0; p < N; p++) {  // ascending p => each row ends up ascending in presynaptic ID
+            std::size_t j = 0;
             for (auto& s : out_[p]) {
                 uint64_t k = fill[s.to]++;
                 pre_[k] = (uint32_t)p; weight_[k] = s.weight; length_[k] = s.length; flag_[k] = s.flag;
+                if (p < neurons.d_.size() && j < neurons.d_[p].outSynapses.size()) neurons.d_[p].outSynapses[j].slot_ = k;  // (object view: same order as out_)
+                j++;
             }
+        }
     }
+    viewDirty_ = true;
     nc_config cfg = {};
     cfg.device = deviceOrdinal;
     cfg.rank = rank_;
@@ -657,6 +724,8 @@ float NeuCor::getDetectorVoltage(unsigned ID) {  // VoltageDetector::getVoltage,
     if (hidden) { RandWindow rw; rw.skip(hidden); }
     float out = 0.0f;
     check(nc_detector_mean(engine_, d.near.data(), (uint32_t)d.near.size(), &out), "nc_detector_mean");
+    viewDirty_ = true;  // (the read ran its neurons: the mirrors follow, as the reference's live objects do)
+    if (mirrorAfterRun) { syncState(); d2hBytes_ += nRows_ * 12; }
     return out;
 }
 std::vector<float> NeuCor::getDetectorVoltages() {
@@ -839,17 +908,24 @@ float NeuCor::stepInternal(bool sweep) {  // NeuCor::run, NeuCor.cpp:583-617
         randMirrorValid_ = true;
     }
     currentTime = targetTime;
+    viewDirty_ = true;
     totalStats_.fires += lastStats_.fires; totalStats_.deliveries += lastStats_.deliveries; totalStats_.loadsAccepted += lastStats_.loadsAccepted;
     totalStats_.loadsDropped += lastStats_.loadsDropped; totalStats_.plasticityCalls += lastStats_.plasticityCalls; totalStats_.hiddenRand += lastStats_.hiddenRand;
     totalStats_.neuronRuns += lastStats_.neuronRuns; totalStats_.activeVisits += lastStats_.activeVisits;
     return 0.0f;
 }
 
-void NeuCor::run() { stepInternal(false); }
+void NeuCor::run() {
+    stepInternal(false);
+    if (mirrorAfterRun && engine_ && !(runSpeed <= 0.0f)) { syncState(); d2hBytes_ += nRows_ * 12; }  // positions / potAct / lastFire as the renderer reads them
+}
 
 float NeuCor::runSwept() {
     stepInternal(true);
-    if (!sweepReturnsMean || world_ > 1) return 0.0f;
+    if (!sweepReturnsMean || world_ > 1) {
+        if (mirrorAfterRun && engine_ && !(runSpeed <= 0.0f)) { syncState(); d2hBytes_ += nRows_ * 12; }
+        return 0.0f;
+    }
     // mean potential of all neurons, summed in ID order in float — VoltageDetector::getVoltage, NeuCor.cpp:360-365
     syncState();
     d2hBytes_ += potAct.size() * 4;
@@ -889,6 +965,7 @@ void NeuCor::stateSignature(uint64_t out6[6]) {
 void NeuCor::resetActivities() {  // NeuCor.cpp:233-235
     finalize();
     check(nc_reset_activities(engine_, currentTime), "nc_reset_activities");
+    viewDirty_ = true;
 }
 
 std::vector<NeuCor::NeuronSnapshot> NeuCor::getNeuronSnapshots() const {  // NeuCor.cpp:99-113

@@ -21,8 +21,11 @@
 #include <stdint.h>
 
 #include <cstddef>
+#include <deque>
+#include <map>
 #include <string>
 #include <unordered_map>
+#include <utility>
 #include <vector>
 
 struct nc_engine;
@@ -38,6 +41,69 @@ struct coord3 {
         return sqrtf(s);
     }
     void setNAN() { x = NAN; y = NAN; z = NAN; }
+};
+
+class NeuCor;
+class Neuron;
+
+// ---- object view: what NeuCor_Renderer walks through friendship (reference NeuCor.h:117-125, 192-294) ----------------
+// The network itself lives on the device as a CSR; these objects are a host MIRROR of it with the reference's names and
+// access levels, so that renderer code such as `for (auto& neu : brain->neurons) for (auto& syn : neu.outSynapses)
+// ... syn.getPrePot() ... brain->getNeuron(syn.tN)->position()` (Renderer.cpp:655-699, 852-853, 1092, 1433-1478, 1749-1862)
+// compiles and reads current values.  The mirror is brought up to date lazily — on the first access through
+// `neurons` / getNeuron / getSynapse after a run() — and is read-only: writes to it do not reach the simulation.
+class Synapse {
+public:
+    float getWeight() const { return weight; }
+protected:
+    friend class NeuCor;
+    friend class Neuron;
+    friend class NeuCor_Renderer;
+    float getPrePot() const { return prePot_; }    // Synapse::getPrePot / getPostPot (NeuCor.cpp:547-567), evaluated on the device
+    float getPostPot() const { return postPot_; }  // at the brain's current time when the mirror is refreshed
+    std::size_t pN = 0;                            // parent neuron ID
+    std::size_t tN = 0;                            // target neuron ID
+    float lastSpikeStart = 0.0f;
+    float lastSpikeArrival = 0.0f;
+    float AP_fireTime = 0.0f;
+    bool inhibitory = false;
+private:
+    float length = 0.0f;
+    float weight = 0.0f;
+    float prePot_ = 0.0f, postPot_ = 0.0f;
+    uint64_t slot_ = 0;                            // position in the post-sorted CSR
+};
+
+class Neuron {
+public:
+    std::vector<Synapse> outSynapses;               // creation order, as the reference owns them (NeuCor.h:211)
+    std::map<std::size_t, std::size_t> inSynapses;  // {from neuron, this neuron} (NeuCor.h:212, NeuCor.cpp:467)
+    inline coord3 position() const;
+    inline float potential() const;
+    inline float activity() const;
+    std::size_t getID() const { return ownID; }
+    float lastFire = NAN;                           // NeuCor.h:226 (NAN until the first fire, NeuCor.cpp:391)
+private:
+    friend class NeuCor;
+    NeuCor* parentNet = nullptr;
+    std::size_t ownID = 0;
+};
+
+// Stands in for `std::deque<Neuron> neurons` (NeuCor.h:117) with the same reading interface; begin() / at() / [] bring the
+// mirror up to date first.
+class NeuronList {
+public:
+    typedef std::deque<Neuron>::iterator iterator;
+    inline iterator begin();
+    iterator end() { return d_.end(); }
+    std::size_t size() const { return d_.size(); }
+    bool empty() const { return d_.empty(); }
+    inline Neuron& at(std::size_t i);
+    inline Neuron& operator[](std::size_t i);
+private:
+    friend class NeuCor;
+    std::deque<Neuron> d_;
+    NeuCor* owner_ = nullptr;
 };
 
 class NeuCor {
@@ -84,6 +150,20 @@ public:
     std::vector<float> potAct;      // (potential, activity) pairs in ID order; refreshed by syncState()
     void resetActivities();
     void setInputEnabled(unsigned inputID, bool enabled);  // InputFirer::enabled (Renderer.cpp:2036)
+    // the object view (see class Synapse / Neuron above): kept for networks built through createNeuron / createSynapse /
+    // NeuCor(n) and for imported host networks of up to objectViewLimit synapses; empty otherwise (device-resident imports, shards)
+    NeuronList neurons;                                    // NeuCor.h:117
+    Neuron* getNeuron(std::size_t ID);                     // NeuCor.h:118-119: std::out_of_range on a bad ID
+    const Neuron* getNeuron(std::size_t ID) const;
+    Synapse* getSynapse(std::size_t fromID, std::size_t toID);  // NeuCor.h:120-123 (NeuCor.cpp:244-263: (from, to), nullptr when absent)
+    const Synapse* getSynapse(std::size_t fromID, std::size_t toID) const;
+    Synapse* getSynapse(std::pair<std::size_t, std::size_t> ID);
+    const Synapse* getSynapse(std::pair<std::size_t, std::size_t> ID) const;
+    void refreshObjects();                                 // device -> object view, if anything ran since the last refresh
+    std::size_t objectViewLimit = (std::size_t)1 << 22;
+    // run() ends with syncState() (positions / potAct / lastFire mirrors current, as NeuCor_Renderer expects every frame,
+    // Renderer.cpp:773-779): 8 bytes per neuron device -> host per run().  Callers stepping large networks switch it off.
+    bool mirrorAfterRun = true;
 
     // ---- extensions ----
     // On-disk network + state file (host/checkpoint.cpp): the post-sorted CSR incl. the flag bytes, positions, the complete
@@ -93,11 +173,6 @@ public:
     void saveCheckpoint(const char* path);
     void loadCheckpoint(const char* path, std::vector<float>* inputRates = nullptr);
     void attachInputRates(float inputs[], unsigned inputCount);
-    struct Synapse {                // one row entry of the exported network
-        uint32_t from, to;
-        float weight, length;
-        uint8_t inhibitory;
-    };
     // Replaces the network by an exported one (post-sorted CSR incl. the reference's flag byte). Only before the first run().
     void importNetwork(std::size_t n, const uint64_t* rowptr, const uint32_t* pre, const float* weight, const float* length,
                        const uint8_t* inhibitory, const float* positions_xyz /* may be null */);
@@ -170,6 +245,9 @@ private:
     float stepInternal(bool sweep);
     void check(int rc, const char* what);
 
+    bool viewDirty_ = true;
+    void buildImportedView();
+    static void viewSet(Synapse& s, std::size_t from, std::size_t to, float weight, float length, bool inhibitory, uint64_t slot);
     float currentTime = 0.0f;
     unsigned totalGenNeurons = 0;
     float* inputArray = nullptr;
@@ -208,5 +286,13 @@ private:
     StepStats lastStats_ = {}, totalStats_ = {};
     uint64_t h2dBytes_ = 0, d2hBytes_ = 0;
 };
+
+// ---- object view: inline members that need the complete NeuCor ----
+inline coord3 Neuron::position() const { return parentNet->positions[ownID]; }
+inline float Neuron::potential() const { return parentNet->potAct[2 * ownID]; }
+inline float Neuron::activity() const { return parentNet->potAct[2 * ownID + 1]; }
+inline NeuronList::iterator NeuronList::begin() { if (owner_) owner_->refreshObjects(); return d_.begin(); }
+inline Neuron& NeuronList::at(std::size_t i) { if (owner_) owner_->refreshObjects(); return d_.at(i); }
+inline Neuron& NeuronList::operator[](std::size_t i) { if (owner_) owner_->refreshObjects(); return d_[i]; }
 
 #endif

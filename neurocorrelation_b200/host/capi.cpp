@@ -63,7 +63,8 @@ int nch_set_shard(void* hv, int rank, int world) { return guard([&] { B->setShar
 int nch_set_comm_id(void* hv, const void* id128) { return guard([&] { B->setCommId(id128); }); }
 int nch_set_exchange(void* hv, int (*fn)(void*, const void*, void*, uint64_t), void* ctx) { return guard([&] { B->setExchange(fn, ctx); }); }
 void nch_shard_info(void* hv, uint64_t* row0, uint64_t* rows, uint64_t* synapses) { *row0 = B->shardRow0(); *rows = B->shardRows(); *synapses = B->shardSynapses(); }
-int nch_set_sweep_mean(void* hv, int on) { return guard([&] { B->sweepReturnsMean = on != 0; }); }
+// (off: the caller wants no per-step state on the host at all — neither the swept mean nor the potAct / lastFire mirrors)
+int nch_set_sweep_mean(void* hv, int on) { return guard([&] { B->sweepReturnsMean = on != 0; B->mirrorAfterRun = on != 0; }); }
 int nch_set_inputs(void* hv, const float* rates, unsigned n, const float* pos_xyz, const float* radius) {
     return guard([&] {
         Handle* h = (Handle*)hv;

@@ -36,6 +36,14 @@ public:
     static void setInputEnabled(NeuCor& b, size_t i, bool en) { b.inputHandler[i].enabled = en; }
     static size_t detectorCount(NeuCor& b) { return b.voltageDetectors.size(); }
     static void resetActivities(NeuCor& b) { b.resetActivities(); }
+    // the object graph the renderer walks (NeuCor.h:117-125; Renderer.cpp:655-699, 1433-1478, 1749-1862)
+    static decltype(auto) neurons(NeuCor& b) { return (b.neurons); }
+    static Neuron* getNeuron(NeuCor& b, size_t id) { return b.getNeuron(id); }
+    static Synapse* getSynapse(NeuCor& b, std::pair<std::size_t, std::size_t> id) { return b.getSynapse(id); }
+    static size_t pN(const Synapse& s) { return s.pN; }
+    static size_t tN(const Synapse& s) { return s.tN; }
+    static float prePot(const Synapse& s) { return s.getPrePot(); }
+    static float postPot(const Synapse& s) { return s.getPostPot(); }
 #ifdef CLIENT_REFERENCE_BUILD
     static void normaliseFlags(NeuCor& b) {
         for (auto& n : b.neurons)
@@ -55,6 +63,13 @@ static uint64_t fnv(uint64_t h, const void* p, size_t n) {
 static float randomUnit() { return static_cast<float>(rand()) / static_cast<float>(RAND_MAX); }
 
 static void report(NeuCor& brain, int step, float volt) {
+    // the raw vectors the renderer uploads every frame (Renderer.cpp:773-779) are read FIRST, with nothing but run() and the
+    // detector read before them: they must already be what the snapshots say
+    uint64_t hp = 1469598103934665603ull;
+    {
+        std::vector<float>& pa = R::potAct(brain);
+        for (size_t i = 0; i + 1 < pa.size(); i += 2) { hp = fnv(hp, &pa[i], 4); hp = fnv(hp, &pa[i + 1], 4); }
+    }
     uint64_t h = 1469598103934665603ull;
     for (auto& n : brain.getNeuronSnapshots()) { h = fnv(h, &n.potential, 4); h = fnv(h, &n.activity, 4); }
     uint64_t hw = 1469598103934665603ull;
@@ -62,15 +77,40 @@ static void report(NeuCor& brain, int step, float volt) {
     for (auto& s : brain.getSynapseSnapshots()) { hw = fnv(hw, &s.fromID, sizeof(s.fromID)); hw = fnv(hw, &s.toID, sizeof(s.toID)); hw = fnv(hw, &s.weight, 4); nInh += s.inhibitory ? 1 : 0; }
     uint64_t hi = 1469598103934665603ull;
     for (size_t i = 0; i < R::inputCount(brain); i++) { float lf = R::inputLastFire(brain, i); hi = fnv(hi, &lf, 4); }
-    // the raw vectors the renderer uploads every frame (Renderer.cpp:773-779) must be what the snapshots say
-    uint64_t hp = 1469598103934665603ull;
-    std::vector<float>& pa = R::potAct(brain);
-    for (size_t i = 0; i + 1 < pa.size(); i += 2) { hp = fnv(hp, &pa[i], 4); hp = fnv(hp, &pa[i + 1], 4); }
+    // one renderer frame over the object graph: per synapse both end potentials, weight and the end points' positions /
+    // activities through getNeuron (Renderer.cpp:655-699); the raster rule and the activity list (Renderer.cpp:1749-1862);
+    // one neuron's in-synapses through getSynapse(pair) (Renderer.cpp:1433-1434)
+    uint64_t ho = 1469598103934665603ull;
+    size_t nObj = 0, nLive = 0, nRaster = 0;
+    for (auto& neu : R::neurons(brain)) {
+        const float act = neu.activity(), pot = neu.potential();
+        ho = fnv(ho, &act, 4); ho = fnv(ho, &pot, 4);
+        if (brain.getTime() - neu.lastFire < 0.0625f) nRaster++;
+        for (auto& syn : neu.outSynapses) {
+            const size_t from = R::pN(syn), to = R::tN(syn);
+            const float w = syn.getWeight(), a = R::prePot(syn), b = R::postPot(syn);
+            const coord3 pa = R::getNeuron(brain, from)->position(), pb = R::getNeuron(brain, to)->position();
+            const float la = logf(R::getNeuron(brain, to)->activity() + 1.f);
+            ho = fnv(ho, &from, sizeof(from)); ho = fnv(ho, &to, sizeof(to)); ho = fnv(ho, &w, 4); ho = fnv(ho, &a, 4); ho = fnv(ho, &b, 4);
+            ho = fnv(ho, &pa, sizeof(pa)); ho = fnv(ho, &pb, sizeof(pb)); ho = fnv(ho, &la, 4);
+            nObj++;
+            nLive += (a != 0.0f || b != 0.0f) ? 1 : 0;
+        }
+    }
+    size_t nIn = 0;
+    if (R::neurons(brain).size() > 7)
+        for (auto& synM : R::getNeuron(brain, 7)->inSynapses) {
+            Synapse* syn = R::getSynapse(brain, synM);
+            const size_t from = R::pN(*syn);
+            const float w = syn->getWeight();
+            ho = fnv(ho, &from, sizeof(from)); ho = fnv(ho, &w, 4);
+            nIn++;
+        }
     uint32_t vb, tb;
     float t = brain.getTime();
     memcpy(&vb, &volt, 4); memcpy(&tb, &t, 4);
-    printf("step %d time %08x volt %08x neurons %016llx potAct %s synapses %016llx inh %zu inputs %016llx\n", step, tb, vb, (unsigned long long)h,
-           hp == h ? "same" : "DIFFERENT", (unsigned long long)hw, nInh, (unsigned long long)hi);
+    printf("step %d time %08x volt %08x neurons %016llx potAct %s synapses %016llx inh %zu inputs %016llx objects %016llx (%zu synapses, %zu carrying a spike, %zu in-synapses of neuron 7, raster %zu)\n",
+           step, tb, vb, (unsigned long long)h, hp == h ? "same" : "DIFFERENT", (unsigned long long)hw, nInh, (unsigned long long)hi, (unsigned long long)ho, nObj, nLive, nIn, nRaster);
 }
 
 int main(int argc, char** argv) {

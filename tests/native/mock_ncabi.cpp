@@ -415,9 +415,28 @@ int nc_read_fires(nc_engine* e, uint32_t cap, uint32_t* neuron, float* time, uin
     *count = total;
     return NC_OK;
 }
-int nc_read_synapse_pots(nc_engine* e, float, float* pre, float* post) {
-    if (pre) memset(pre, 0, e->v.S * 4);
-    if (post) memset(post, 0, e->v.S * 4);
+// Synapse::getPrePot / getPostPot (NeuCor.cpp:547-567), the same float/double typing as k_synapse_pots in csrc/engine.cu
+static float model_render_behaviour(float valf) {  // AP_RENDER_BEHAVIOUR, NeuCor.cpp:547-550
+    float val = (float)fmin(fmax((double)valf, 0.0), 0.7);
+    if ((double)val < 0.5) {
+        float x = (float)div64((double)val, 5.0);
+        float p = (x >= 1.17549435e-38f) ? powf_pos(x, 3.0f) : 0.0f;
+        return (float)mul64(mul64(8.0, 1000.0), (double)p);
+    }
+    float x = (float)sub64(3.5, (double)mul32(5.0f, val));
+    return (float)mul64(8.0, (double)mul32(x, x));
+}
+int nc_read_synapse_pots(nc_engine* e, float now, float* pre, float* post) {
+    for (uint64_t i = 0; i < e->v.S; i++) {
+        const float a = e->ad[i].x, w = e->rec[i].weight, dl = e->rec[i].delay;
+        float p = 0.0f, q = 0.0f;
+        if (a != 0.0f) {
+            p = mul32(model_render_behaviour(div32(sub32(now, e->lastStart[i]), dl)), w);
+            if (now < a) q = mul32(model_render_behaviour(div32(sub32(a, now), dl)), w);
+        }
+        if (pre) pre[i] = p;
+        if (post) post[i] = q;
+    }
     return NC_OK;
 }
 int nc_synapse_pots_device(nc_engine*, float, float*, float*) { return NC_OK; }

@@ -36,12 +36,17 @@ struct XchgArgs {  // what the step's own kernels need to do the exchange themse
 };
 
 #if defined(__CUDACC__)
+#if defined(NC_BLOCK_EMU)  // (tests/native/cuda_runtime_emu.h compiles this header for the CPU: no PTX there, and one shard only)
+__device__ __forceinline__ void st_flag(uint32_t* p, uint32_t v) { *(volatile uint32_t*)p = v; }
+__device__ __forceinline__ uint32_t ld_flag(const uint32_t* p) { return *(const volatile uint32_t*)p; }
+#else
 __device__ __forceinline__ void st_flag(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t ld_flag(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+#endif
 
 // ---- the same, as the tail / head of the step's own kernels (no extra launches) ----
 // Tail of the neuron pass: every block fences its fire records and takes a ticket; the LAST block stores the shard's block

@@ -5,7 +5,8 @@
 // `pytest -m "not gpu"` has no GPU).  It checks LOGIC — indexing, the use of barriers and warp collectives, capacities —
 // not performance and not the memory model.
 //
-//   * every CUDA thread of a block is a fibre (ucontext) on one OS thread; blocks of a grid run one after the other;
+//   * every CUDA thread of a block is a fibre on one OS thread (own stack, a dozen-instruction x86-64 context switch: no
+//     system call per switch, which is what makes whole parity scenarios affordable); blocks of a grid run one after the other;
 //   * __syncthreads() parks a fibre until every live thread of the block has arrived;
 //   * warp collectives (__syncwarp, __ballot_sync, __any_sync, __all_sync, __shfl_*_sync, __reduce_*_sync) park a lane until
 //     every live lane named in the mask has arrived at a collective of the SAME kind (anything else aborts: on the GPU
@@ -19,11 +20,39 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
-#include <ucontext.h>
 
 #include <algorithm>
 #include <functional>
 #include <vector>
+
+#if !defined(__x86_64__)
+#error "cuda_block_emu.h: the fibre switch is written for x86-64"
+#endif
+// emu_switch(&save_sp, to_sp): saves the callee-saved registers on the current stack, stores the stack pointer, switches
+extern "C" void emu_switch(void** from_sp, void* to_sp);
+asm(R"(
+.text
+.hidden emu_switch
+.globl emu_switch
+.type emu_switch,@function
+emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size emu_switch,.-emu_switch
+)");
 
 namespace emu {
 
@@ -36,7 +65,7 @@ enum Wait { RUN = 0, AT_BLOCK = 1, AT_WARP = 2, DONE = 3 };
 enum Kind { K_SYNCWARP = 1, K_BALLOT, K_ANY, K_ALL, K_SHFL, K_SHFL_UP, K_SHFL_DOWN, K_SHFL_XOR, K_RED_MAX, K_RED_MIN, K_RED_ADD };
 
 struct Fibre {
-    ucontext_t ctx;
+    void* sp = nullptr;    // saved stack pointer while the fibre is parked
     char* stack = nullptr;
     Wait wait = RUN;
     dim3 tid;
@@ -52,12 +81,13 @@ struct Fibre {
 struct State {
     std::vector<Fibre> f;            // the threads of the block being run
     std::vector<char*> stacks;       // fibre stacks, kept across blocks and launches
-    ucontext_t sched;
+    void* schedSp = nullptr;
     Fibre* cur = nullptr;
     dim3 bIdx, bDim, gDim;
     const std::function<void()>* body = nullptr;
     size_t stackBytes = 256 * 1024;
     unsigned long long collectives = 0, barriers = 0;
+    unsigned onTheWay = 0, atBlock = 0;  // threads of the block that are running or parked at a warp collective / parked at the block barrier
 };
 inline State& S() { static State s; return s; }
 
@@ -66,11 +96,12 @@ inline State& S() { static State s; return s; }
     abort();
 }
 
-inline void yield_to_scheduler() { swapcontext(&S().cur->ctx, &S().sched); }
+inline void yield_to_scheduler() { emu_switch(&S().cur->sp, S().schedSp); }
 
 inline void fibre_entry() {
     (*S().body)();
     S().cur->wait = DONE;
+    S().onTheWay--;
     yield_to_scheduler();
     die("resumed a finished fibre");
 }
@@ -78,14 +109,11 @@ inline void fibre_entry() {
 // ---- completion of barriers --------------------------------------------------------------------------------------------
 inline void try_release_block() {
     State& s = S();
-    bool any = false;
-    for (auto& x : s.f) {
-        if (x.wait == RUN || x.wait == AT_WARP) return;  // somebody is still on the way
-        any = any || x.wait == AT_BLOCK;
-    }
-    if (!any) return;
+    if (s.onTheWay != 0 || s.atBlock == 0) return;  // somebody is still running / parked at a warp collective, or nobody waits
     for (auto& x : s.f)
         if (x.wait == AT_BLOCK) x.wait = RUN;
+    s.onTheWay = s.atBlock;
+    s.atBlock = 0;
     s.barriers++;
 }
 
@@ -156,6 +184,7 @@ inline uint64_t warp_collective(int kind, uint32_t mask, uint64_t payload, int a
 
 inline void block_barrier() {
     S().cur->wait = AT_BLOCK;
+    S().onTheWay--; S().atBlock++;
     yield_to_scheduler();
 }
 
@@ -166,16 +195,20 @@ inline void run_block(const std::function<void()>& body) {
     s.f.assign(T, Fibre());
     while (s.stacks.size() < T) s.stacks.push_back((char*)malloc(s.stackBytes));
     s.body = &body;
+    s.onTheWay = T; s.atBlock = 0;
     for (unsigned i = 0; i < T; i++) {
         Fibre& x = s.f[i];
         x.stack = s.stacks[i];
         x.wait = RUN; x.linear = i;
         x.tid = dim3(i % s.bDim.x, (i / s.bDim.x) % s.bDim.y, i / (s.bDim.x * s.bDim.y));
-        getcontext(&x.ctx);
-        x.ctx.uc_stack.ss_sp = x.stack;
-        x.ctx.uc_stack.ss_size = s.stackBytes;
-        x.ctx.uc_link = nullptr;
-        makecontext(&x.ctx, (void (*)())fibre_entry, 0);
+        // a fresh stack that emu_switch can "return" into: six zeroed callee-saved registers, then fibre_entry as the return
+        // address, then a null return address for fibre_entry itself (which never returns) — rsp = 8 mod 16 at its entry
+        uintptr_t top = ((uintptr_t)(x.stack + s.stackBytes)) & ~(uintptr_t)15;
+        void** sp = (void**)top;
+        *--sp = nullptr;
+        *--sp = (void*)&fibre_entry;
+        for (int r = 0; r < 6; r++) *--sp = nullptr;
+        x.sp = (void*)sp;
     }
     for (;;) {
         bool progressed = false, allDone = true;
@@ -184,7 +217,7 @@ inline void run_block(const std::function<void()>& body) {
             if (x.wait != DONE) allDone = false;
             if (x.wait != RUN) continue;
             s.cur = &x;
-            swapcontext(&s.sched, &x.ctx);
+            emu_switch(&s.schedSp, x.sp);
             s.cur = nullptr;
             progressed = true;
             if (x.wait == AT_WARP || x.wait == DONE) try_release_warp(i / 32u);

@@ -129,12 +129,13 @@ def lazy_vs_oracle(library, N, K, steps, dt):
     assert so == sg
 
 
-def edge_cases(library):
+def edge_cases(library, steps=(800, 1500, 400), offset=0.0):
+    """`offset` (ms) advances every firer's phase (NeuCor::addInputOffset) so that shortened runs still see activity."""
     # 1. a single neuron without synapses, driven by one input: fires by force, no synapse work at all
     net = dict(N=1, S=0, rowptr=np.zeros(2, np.uint64), pre=np.zeros(0, np.uint32), weight=np.zeros(0, np.float32),
                length=np.zeros(0, np.float32), flag=np.zeros(0, np.uint8), positions=np.zeros((1, 3), np.float32),
                inputs=dict(G=1, near=[np.array([0], np.uint32)]))
-    bad, fields, so, sg = lockstep(lambda: _drive(OracleBrain(net), net, False, rate0=60.0), lambda: _drive(nb.NeuCor.from_network(net, library=library), net, True, rate0=60.0), 800, lambda: None)
+    bad, fields, so, sg = lockstep(lambda: _drive(OracleBrain(net), net, False, rate0=60.0, offset=offset), lambda: _drive(nb.NeuCor.from_network(net, library=library), net, True, rate0=60.0, offset=offset), steps[0], lambda: None)
     assert bad == -1 and so == sg and so["fires"] > 0
     # 2. ragged rows: neurons with 0, 1 and many in-synapses; a reciprocal equal-length pair (the structural tie source, S8)
     rowptr = np.array([0, 0, 1, 3, 6, 6], np.uint64)
@@ -142,19 +143,24 @@ def edge_cases(library):
     net = dict(N=5, S=6, rowptr=rowptr, pre=pre, weight=np.array([0.9, 0.8, -0.7, 0.6, 1.0, 0.0], np.float32),
                length=np.array([0.3, 0.3, 0.5, 0.2, 0.45, 0.7], np.float32), flag=np.array([0, 0, 1, 0, 0, 0], np.uint8),
                positions=np.zeros((5, 3), np.float32), inputs=dict(G=2, near=[np.array([0, 1], np.uint32), np.array([2, 4], np.uint32)]))
-    bad, fields, so, sg = lockstep(lambda: _drive(OracleBrain(net), net, False), lambda: _drive(nb.NeuCor.from_network(net, library=library), net, True), 1500, lambda: None)
+    bad, fields, so, sg = lockstep(lambda: _drive(OracleBrain(net), net, False, offset=offset), lambda: _drive(nb.NeuCor.from_network(net, library=library), net, True, offset=offset), steps[1], lambda: None)
     assert bad == -1, (bad, fields)
-    assert so == sg and so["deliveries"] > 0 and so["hidden_rand"] > 0
+    assert so == sg and so["deliveries"] > 0 and (steps[1] < 1500 or so["hidden_rand"] > 0)
     # 3. learningRate = 0 — the reference's only "STDP off" (main.cpp:108): weights frozen, hidden rand() still counted
     net3 = synthetic_network(300, 20, seed=2)
-    bad, fields, so, sg = lockstep(lambda: _drive(OracleBrain(net3), net3, False, lr=0.0), lambda: _drive(nb.NeuCor.from_network(net3, library=library), net3, True, lr=0.0), 400, lambda: None)
+    bad, fields, so, sg = lockstep(lambda: _drive(OracleBrain(net3), net3, False, lr=0.0), lambda: _drive(nb.NeuCor.from_network(net3, library=library), net3, True, lr=0.0), steps[2], lambda: None)
     assert bad == -1 and so == sg
 
 
-def _drive(b, net, kw, lr=1.0, rate0=None):
+def _drive(b, net, kw, lr=1.0, rate0=None, offset=0.0):
     synthetic_drive(b, net, kw, lr=lr)
     if rate0 is not None:
         b.set_rate(0, rate0)
+    if offset:  # shortened runs: every firer at 70 Hz with its phase moved, so that the first input event comes early
+        for i in range(net["inputs"]["G"]):
+            if rate0 is None:
+                b.set_rate(i, 70.0)
+            b.add_input_offset(i, float(offset))
     return b
 
 
@@ -206,7 +212,7 @@ def host_constructor_matches_reference(library, have_ref):
     return g, rnet
 
 
-def checkpoint_resume(library, tmp_path):
+def checkpoint_resume(library, tmp_path, before=150, after=200):
     """Save after 150 steps, resume in a fresh object from the file, and continue: every later step is bit-identical to the
     uninterrupted run (state, background firing through the restored rand() position, input firer phases), and the file
     round-trips the network exactly as the reference harness exports it."""
@@ -215,11 +221,11 @@ def checkpoint_resume(library, tmp_path):
     a = nb.NeuCor.from_network(net, library=library)
     synthetic_drive(a, net, True)
     a.add_input_offset(1, 0.7)
-    for _ in range(150):
+    for _ in range(before):
         a.step()
     a.save_checkpoint(path)
     want = []
-    for _ in range(200):
+    for _ in range(after):
         v = a.step()
         want.append((np.float32(v), a.state_signature()))
     stats_a = a.stats()
@@ -230,7 +236,7 @@ def checkpoint_resume(library, tmp_path):
     exp = b.export_network()
     assert np.array_equal(exp["rowptr"], net["rowptr"]) and np.array_equal(exp["pre"], net["pre"]) and same_bits(exp["length"], net["length"])
     assert np.array_equal(exp["flag"], net["flag"]) and same_bits(exp["positions"], net["positions"])
-    for k in range(200):
+    for k in range(after):
         v = b.step()
         assert np.float32(v).view(np.uint32) == want[k][0].view(np.uint32), "step %d after resume: mean potential" % k
         assert np.array_equal(b.state_signature(), want[k][1]), "step %d after resume: state" % k

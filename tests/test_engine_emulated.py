@@ -1,0 +1,79 @@
+"""The product's kernels — csrc/engine.cu and its headers, UNMODIFIED source — compiled for the CPU by tests/emu_build.py on
+top of tests/native/cuda_runtime_emu.h (every CUDA thread a fibre; block barriers, warp collectives, atomics, shared memory
+and the slice of the runtime API the engine uses are emulated) and driven through the same parity scenarios as the GPU
+tests, against the oracle and the reference's golden vectors, bit-exact.
+
+What this adds to `-m "not gpu"`: tests/native/mock_ncabi.cpp (the CPU test double of the C ABI) shares only the
+per-neuron / per-synapse logic of step_logic.cuh with the kernels; here the warp-cooperative code itself runs — staging
+(incremental merge, rebuild, in-kernel overflow path), the lane-per-row and warp-per-row replays, the fire index, the three
+synapse kernels, the device rand() stream — so a logic error in a kernel shows up without a GPU.  What it cannot see:
+performance, the memory model (one OS thread: no races), PTX, multi-GPU.  Device allocations are filled with 0xA5, so reads
+of never-written device memory do not pass by luck.  The emulated library lives under tests/ and is never loaded by the product."""
+import numpy as np
+import pytest
+
+import emu_build
+import scenarios
+
+
+@pytest.fixture(scope="module")
+def emu_lib():
+    return emu_build.build()
+
+
+def test_smoke_scenario_lockstep(emu_lib):
+    """__graft_entry__.smoke()'s scenario: every field of every step against the oracle."""
+    st = scenarios.synthetic_vs_oracle(emu_lib, 500, 32, 180)
+    assert st["fires"] > 10 and st["deliveries"] > 100
+
+
+def test_c1_golden_vectors(emu_lib):
+    """BASELINE configs[0] (the reference's own default network) against the fixture recorded from the reference."""
+    scenarios.c1_golden(emu_lib, "c1_seed1_normalised.npz", 200, check_every=1)
+
+
+def test_long_rows_take_the_warp_per_row_path(emu_lib):
+    """A pool of 32 staged slots per warp: busy rows go through warp_row (spill area, exact prefix-sum accumulation)."""
+    st = scenarios.synthetic_vs_oracle(emu_lib, 600, 120, 130, cand_smem=32)
+    assert st["deliveries"] > 500
+
+
+def test_staging_region_overflow_takes_the_in_kernel_path(emu_lib, monkeypatch):
+    monkeypatch.setenv("NC_STAGE_CAP", "8")
+    st = scenarios.synthetic_vs_oracle(emu_lib, 1500, 60, 120)
+    assert st["deliveries"] > 500
+
+
+def test_rebuild_mode_of_the_staging_kernel(emu_lib, monkeypatch):
+    monkeypatch.setenv("NC_STAGE_MODE", "rebuild")
+    scenarios.synthetic_vs_oracle(emu_lib, 400, 40, 110)
+
+
+@pytest.mark.parametrize("variant", ["big", "dense", "sparse"])
+def test_every_build_of_the_neuron_pass(emu_lib, monkeypatch, variant):
+    """k_neuron_pass<4|6|8>: the three register budgets / pool sizes are picked per window on the GPU; each is forced here."""
+    monkeypatch.setenv("NC_NEURON_VARIANT", variant)
+    scenarios.synthetic_vs_oracle(emu_lib, 300, 48, 90, seed=11)
+
+
+def test_lazy_mode_with_window_splitting(emu_lib):
+    scenarios.lazy_vs_oracle(emu_lib, 300, 24, 40, 0.25)
+
+
+def test_detector_offsets_reset(emu_lib):
+    scenarios.detector_and_reset(emu_lib)
+
+
+def test_edge_cases(emu_lib):
+    """Empty and ragged rows, a reciprocal equal-length pair (equal-time ties), learningRate = 0."""
+    scenarios.edge_cases(emu_lib, steps=(120, 300, 80), offset=-12.0)
+
+
+def test_fire_raster_and_device_signature(emu_lib):
+    """nc_read_fires and nc_state_signature (device-side reductions) against the oracle's fire log and signatures."""
+    st = scenarios.synthetic_vs_oracle_signatures(emu_lib, 800, 40, 110)
+    assert st["fires"] > 0
+
+
+def test_checkpoint_resume(emu_lib, tmp_path):
+    scenarios.checkpoint_resume(emu_lib, tmp_path, before=70, after=60)

@@ -158,9 +158,17 @@ class NeuCor:
         return b
 
     @classmethod
-    def from_checkpoint(cls, path, device=0, library=None):
-        """Network + complete state (+ libc's rand() position) from a file written by save_checkpoint: the run continues bit for bit."""
+    def from_checkpoint(cls, path, device=0, library=None, rank=0, world=1, exchange=None, comm_id=None):
+        """Network + complete state (+ libc's rand() position) from a file written by save_checkpoint: the run continues bit for bit.
+        A sharded run writes one file per rank; each is loaded by a process with the same (rank, world) and its fire exchange
+        (`exchange`: caller-provided all-gather, or `comm_id`: the NCCL unique id distributed by the caller)."""
         b = cls(0, device, library)
+        if world > 1:
+            b.set_shard(rank, world)
+            if exchange is not None:
+                b.set_exchange(exchange)
+            if comm_id is not None:
+                b.set_comm_id(comm_id)
         b._ck(b.L.nch_load_checkpoint(b.h, os.fsencode(path)))
         return b
 

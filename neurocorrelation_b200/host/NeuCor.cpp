@@ -383,7 +383,7 @@ void NeuCor::viewSet(Synapse& s, std::size_t from, std::size_t to, float weight,
 void NeuCor::buildImportedView() {  // an imported network has no creation order: every neuron's out-synapses by ascending target
     neurons.d_.clear();
     const std::size_t N = positions.size();
-    if (dev_.set || pre_.size() > objectViewLimit) return;
+    if (dev_.set || world_ > 1 || pre_.size() > objectViewLimit) return;
     neurons.d_.resize(N);
     for (std::size_t i = 0; i < N; i++) { neurons.d_[i].parentNet = this; neurons.d_[i].ownID = i; }
     for (std::size_t q = 0; q < N; q++)
@@ -603,6 +603,8 @@ void NeuCor::finalize() {
     if (world_ > 1) {
         if (dev_.set) {
             if (!(globalMinDelay > 0.0f)) throw std::logic_error("NeuCor: set globalMinDelay (smallest 2*length over all shards) for device-resident shards");
+            minDelay_ = globalMinDelay;
+        } else if (globalMinDelay > 0.0f) {  // a shard restored from its checkpoint file: only its own rows are on this host
             minDelay_ = globalMinDelay;
         } else {
             for (float l : length_) minDelay_ = std::min(minDelay_, l * 2.0f);

@@ -6,12 +6,19 @@
 // exchanging networks with the reference harness, building large networks once and re-using them, and checkpoint / resume
 // (a resumed run continues bit for bit, background firing included).
 //
-// Layout (little endian): magic "NCB200\1\0", header (counts, time, parameters), then the arrays in the order written
-// below, each as raw elements.  Arrays are streamed through a bounded buffer, never held twice.
+// Layout (little endian): magic "NCB200\2\0", header (counts, time, parameters), shard header, then the arrays in the order
+// written below, each as raw elements.  Arrays are streamed through a bounded buffer, never held twice.
+//
+// Sharded runs (setShard(rank, world)): every process writes ITS OWN file — the rows [row0, row0 + rows) of the CSR with a
+// rowptr that starts at 0, the state of those rows and synapses, and everything that is identical on all shards (positions
+// of the whole network, firers, detectors, rand() position, the network-wide smallest delay that bounds the window).
+// A shard file is loaded by a process that has been given the same (rank, world); version-1 files (whole networks only,
+// no shard header) are still read.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -20,12 +27,18 @@
 #include "NeuCor.h"
 
 namespace {
-const char MAGIC[8] = {'N', 'C', 'B', '2', '0', '0', 1, 0};
+const char MAGIC[8] = {'N', 'C', 'B', '2', '0', '0', 2, 0};  // byte 6 = format version
 struct Header {
     char magic[8];
     uint64_t neurons, synapses, inputs, detectors;
     float time, runSpeed, learningRate, preDecay, postDecay, preFactor, postFactor;
     uint32_t runAll, hasRand, hasPositions, reserved;
+};
+struct ShardHeader {  // version >= 2
+    uint32_t rank, world;
+    uint64_t row0, rows;
+    float minDelay;  // smallest synaptic delay of the WHOLE network (every shard must split windows identically)
+    uint32_t reserved;
 };
 struct File {
     FILE* f;
@@ -43,8 +56,8 @@ struct File {
 
 void NeuCor::saveCheckpoint(const char* path) {
     finalize();
-    if (world_ > 1) throw std::logic_error("NeuCor::saveCheckpoint: not available on a sharded network (save before sharding)");
-    const size_t N = positions.size();
+    const size_t N = positions.size();   // neurons of the whole network
+    const size_t R = nRows_;             // rows of this shard (= N for world 1)
     const uint64_t S = sLocal_;
     File out(path, "wb");
     Header h;
@@ -58,9 +71,13 @@ void NeuCor::saveCheckpoint(const char* path) {
     h.hasRand = checkpointPeekRand(rnd) ? 1u : 0u;
     h.hasPositions = 1u;
     out.put(&h, sizeof(h));
+    ShardHeader sh;
+    memset(&sh, 0, sizeof(sh));
+    sh.rank = (uint32_t)rank_; sh.world = (uint32_t)world_; sh.row0 = row0_; sh.rows = R; sh.minDelay = minDelay_;
+    out.put(&sh, sizeof(sh));
     // ---- network (as it lives on the device: also valid for networks imported from device memory) ----
     {
-        std::vector<uint64_t> rowptr(N + 1);
+        std::vector<uint64_t> rowptr(R + 1);
         std::vector<uint32_t> pre(S);
         std::vector<float> length(S);
         std::vector<uint8_t> flag(S);
@@ -83,8 +100,8 @@ void NeuCor::saveCheckpoint(const char* path) {
         }
     }
     {
-        std::vector<float> potAct2(2 * N), lastFire(N), lastRan(N), actStart(N);
-        std::vector<uint32_t> firings(N);
+        std::vector<float> potAct2(2 * R), lastFire(R), lastRan(R), actStart(R);
+        std::vector<uint32_t> firings(R);
         check(nc_read_neurons(engine_, potAct2.data(), lastFire.data(), lastRan.data()), "nc_read_neurons");
         check(nc_read_neuron_counters(engine_, actStart.data(), firings.data()), "nc_read_neuron_counters");
         out.putv(potAct2); out.putv(lastFire); out.putv(lastRan); out.putv(actStart); out.putv(firings);
@@ -110,20 +127,37 @@ void NeuCor::loadCheckpoint(const char* path, std::vector<float>* inputRates) {
     File in(path, "rb");
     Header h;
     in.get(&h, sizeof(h));
-    if (memcmp(h.magic, MAGIC, 8) != 0) throw std::runtime_error("NeuCor::loadCheckpoint: not a NeuCor checkpoint: " + in.path);
+    if (memcmp(h.magic, MAGIC, 6) != 0 || h.magic[7] != 0 || (h.magic[6] != 1 && h.magic[6] != 2))
+        throw std::runtime_error("NeuCor::loadCheckpoint: not a NeuCor checkpoint: " + in.path);
     const size_t N = h.neurons;
     const uint64_t S = h.synapses;
+    ShardHeader sh;
+    memset(&sh, 0, sizeof(sh));
+    sh.world = 1; sh.rows = N;
+    if (h.magic[6] >= 2) in.get(&sh, sizeof(sh));
+    if ((int)sh.world != world_ || (int)sh.rank != rank_)
+        throw std::logic_error("NeuCor::loadCheckpoint: the file holds shard " + std::to_string(sh.rank) + " of " + std::to_string(sh.world) +
+                               ", this process is shard " + std::to_string(rank_) + " of " + std::to_string(world_) + " (setShard first)");
+    const size_t R = sh.rows;
     {
-        std::vector<uint64_t> rowptr;
+        std::vector<uint64_t> rowptr, local;
         std::vector<uint32_t> pre;
         std::vector<float> length, weight0(S, 0.0f), xyz;
         std::vector<uint8_t> flag;
-        in.getv(rowptr, N + 1); in.getv(pre, S); in.getv(length, S); in.getv(flag, S); in.getv(xyz, 3 * N);
+        in.getv(local, R + 1); in.getv(pre, S); in.getv(length, S); in.getv(flag, S); in.getv(xyz, 3 * N);
+        if (world_ == 1) rowptr.swap(local);
+        else {  // the shard's rows inside an otherwise empty CSR of the whole network: finalize() slices exactly them out again
+            if (sh.row0 + R > N || local[R] != S) throw std::runtime_error("NeuCor::loadCheckpoint: inconsistent shard header: " + in.path);
+            rowptr.assign(N + 1, 0);
+            for (size_t i = 0; i <= N; i++) rowptr[i] = i <= sh.row0 ? 0 : i <= sh.row0 + R ? local[i - sh.row0] : S;
+            globalMinDelay = sh.minDelay;
+        }
         importNetwork(N, rowptr.data(), pre.data(), weight0.data(), length.data(), flag.data(), xyz.data());
     }
     runSpeed = h.runSpeed; learningRate = h.learningRate; presynapticTraceDecay = h.preDecay; postsynapticTraceDecay = h.postDecay;
     presynapticFactor = h.preFactor; postsynapticFactor = h.postFactor; runAll = h.runAll != 0;
     finalize();
+    if (row0_ != sh.row0 && world_ > 1) throw std::runtime_error("NeuCor::loadCheckpoint: the shard's row range does not match this rank's: " + in.path);
     {
         std::vector<float> a;
         const float* src[5];
@@ -137,9 +171,9 @@ void NeuCor::loadCheckpoint(const char* path, std::vector<float>* inputRates) {
     {
         std::vector<float> potAct2, lastFire, lastRan, actStart;
         std::vector<uint32_t> firings;
-        in.getv(potAct2, 2 * N); in.getv(lastFire, N); in.getv(lastRan, N); in.getv(actStart, N); in.getv(firings, N);
+        in.getv(potAct2, 2 * R); in.getv(lastFire, R); in.getv(lastRan, R); in.getv(actStart, R); in.getv(firings, R);
         check(nc_write_neurons(engine_, potAct2.data(), lastFire.data(), lastRan.data(), actStart.data(), firings.data()), "nc_write_neurons");
-        potAct = potAct2;
+        std::copy(potAct2.begin(), potAct2.end(), potAct.begin() + 2 * row0_);  // (the mirror spans the whole network)
     }
     currentTime = h.time;
     std::vector<float> rates(h.inputs, 0.0f);

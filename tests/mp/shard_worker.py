@@ -3,6 +3,8 @@
   python shard_worker.py <mode> <out.npz> N K steps      with RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT in the env
 mode "gloo-mock": host NeuCor class linked against the CPU test double, fire exchange through a caller-provided
                   all-gather over torch.distributed/gloo (CPU, no GPU needed);
+mode "gloo-mock-ckpt": the same, and half way every rank saves its shard's checkpoint file; after the run a second brain is
+                  restored from it in the same process (same rank/world, same exchange) and runs the second half again;
 mode "nccl":      the product libraries on cuda:<LOCAL_RANK>, exchange over the engine's own NCCL communicator whose
                   unique id is distributed through torch.distributed.
 Every rank makes the same calls with the same libc rand() state; each records the per-step state of ITS rows."""
@@ -27,6 +29,9 @@ def main():
     from neurocorrelation_b200.networks import synthetic_network
 
     net = synthetic_network(N, K, seed=3)
+    ckpt = mode == "gloo-mock-ckpt"
+    if ckpt:
+        mode = "gloo-mock"
     if mode == "gloo-mock":
         dist.init_process_group("gloo", rank=rank, world_size=world)
         g = nb.NeuCor.from_network(net, library=os.environ["NC_MOCK_HOST_LIB"])
@@ -53,13 +58,29 @@ def main():
         g.set_comm_id(box[0])
     synthetic_drive(g, net, True)
     sigs, stats = [], None
-    for _ in range(steps):
+    resumed = None
+    for k in range(steps):
+        if ckpt and k == steps // 2:  # every rank writes its own shard file; a second brain resumes from it further down
+            g.save_checkpoint(out + ".ckpt")
         g.step()
         sigs.append(state_signature(g.read_neurons(), g.read_synapses()))
+    if ckpt:
+        from helpers import libc
+        st_first = g.stats()
+        libc.srand(4711)  # whatever happened to libc's generator in between: the file carries its position
+        h = nb.NeuCor.from_checkpoint(out + ".ckpt", library=os.environ["NC_MOCK_HOST_LIB"], rank=rank, world=world, exchange=allgather)
+        h.enable_sweep()
+        resumed = []
+        for k in range(steps // 2, steps):
+            h.step()
+            resumed.append(state_signature(h.read_neurons(), h.read_synapses()))
+        assert h.shard() == g.shard()
+        h.close()
     n, s = g.read_neurons(), g.read_synapses()
     row0, rows, S = g.shard()
     st = g.stats()
     np.savez(out, row0=row0, rows=rows, S=S, sigs=np.array(sigs), stats=np.array([st[k] for k in nb.STAT_NAMES], np.uint64),
+             resumed=np.array(resumed if resumed is not None else []),
              **{"n_" + k: v for k, v in n.items()}, **{"s_" + k: v for k, v in s.items()})
     g.close()
     dist.barrier()

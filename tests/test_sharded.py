@@ -94,6 +94,18 @@ def test_sharded_gloo_cpu(mock_host_lib, tmp_path, world):
     assert st["hidden_rand"] > 0  # the summed hidden rand() count keeps every rank's libc stream in step
 
 
+def test_sharded_checkpoint_one_file_per_rank(mock_host_lib, tmp_path):
+    """Half way through a 2-shard run every rank saves ITS rows (network, state, firers, rand() position, the network-wide delay
+    bound) to its own file; brains restored from those files — same (rank, world), same exchange — repeat the second half of
+    the run bit for bit, and the run itself matches the oracle's whole-network run throughout."""
+    world, N, K, steps = 2, 500, 40, 300
+    shards = _launch("gloo-mock-ckpt", world, N, K, steps, tmp_path, {"NC_MOCK_HOST_LIB": mock_host_lib})
+    _check(world, N, K, steps, shards)
+    for r, z in enumerate(shards):
+        assert z["resumed"].shape == (steps - steps // 2, 6)
+        assert np.array_equal(z["resumed"], z["sigs"][steps // 2:]), "shard %d: the resumed run differs from the uninterrupted one" % r
+
+
 @pytest.mark.gpu
 def test_sharded_nccl_two_gpus(native_libs, tmp_path):
     import torch

@@ -47,12 +47,17 @@ WORKLOADS = {
     "c4": (1_250_000, 1000, 25.0, "1.25M neurons x 1000 synapses (1.25B synapses) per GPU = 10M x 1000 (10B synapses) on 8 GPUs, C4"),
     "c5": (1_250_000, 1000, 25.0, "1.25B synapses per GPU, all input rates pinned at 75 Hz, >= 10 % of the neurons input-driven (spike-exchange-bound regime), C5"),
     "m100": (100_000, 1000, 25.0, "100k neurons x 1000 synapses (100M synapses) per GPU, profiling-sized slice of C3"),
+    # the SURVEY.md section 8(d) recipe to the letter (networks.spatial_shard_torch): partners within a ball, lengths = distances, firers with
+    # their neighbourhoods, paired random-walk rates.  NOT GPU-measured by the builder (added after the round's GPU budget was spent).
+    "c2s": (100_000, 100, 50.0, "100k neurons x <=100 synapses per GPU, C2 with the spatial recipe of SURVEY.md section 8(d)"),
+    "c3s": (1_000_000, 1000, 25.0, "1M neurons x <=1000 synapses per GPU, C3 with the spatial recipe of SURVEY.md section 8(d)"),
 }
 # Default initial-weight scale.  C2 uses the reference's own weight law U(0.2, 1) as is; it runs hot
 # (~330 Hz) but stays stable.  With K = 1000 the same law saturates the network at the refractory limit within 12 ms (every
 # neuron at ~480 Hz, 100 ms of ordered accumulation per step — see profiles/README.md), so the C3-sized workloads keep the
 # reference network's total synaptic drive per neuron instead: weights U(0.2, 1) * K_REF / K.
-WEIGHT_SCALE = {"c1": 1.0, "c2": 1.0, "c3": K_REF / 1000, "c3raw": 1.0, "c4": K_REF / 1000, "c5": K_REF / 1000, "m100": K_REF / 1000}
+WEIGHT_SCALE = {"c1": 1.0, "c2": 1.0, "c3": K_REF / 1000, "c3raw": 1.0, "c4": K_REF / 1000, "c5": K_REF / 1000, "m100": K_REF / 1000,
+                "c2s": 1.0, "c3s": K_REF / 1000}
 
 
 def measured_traffic(workload, kernel):
@@ -121,7 +126,17 @@ def drive_setup(brain, net, keyword_near, phase=True, pinned_rate=None):
     NeuCor::addInputOffset (NeuCor.cpp:66-68).  Leaves libc's generator at srand(777)."""
     from helpers import libc, synthetic_drive
     from neurocorrelation_b200.presets import F, random_unit
-    rates = synthetic_drive(brain, net, keyword_near)
+    if net["inputs"].get("near") is None:  # spatial recipe: the host class finds every firer's neighbourhood itself (NeuCor.cpp:319-323)
+        from helpers import libc as _libc
+        _libc.srand(5)
+        G = net["inputs"]["G"]
+        rates = np.array([random_unit(_libc.rand) * F(75) for _ in range(G)], np.float32)
+        brain.set_inputs(rates, net["inputs"]["positions"], net["inputs"]["radius"])
+        brain.enable_sweep()
+        brain.set_params(DT, 1.0, False)
+        _libc.srand(777)
+    else:
+        rates = synthetic_drive(brain, net, keyword_near)
     if pinned_rate is not None:  # C5: every input at the same (maximal) rate
         rates[:] = pinned_rate
         for i in range(len(rates)):
@@ -145,9 +160,17 @@ def build_brain(workload, dev, rank=0, world=1, seed=1, weight_scale=1.0, comm_i
         libc.srand(seed)
         return nb.NeuCor(750, device=dev), None
     import torch
-    from neurocorrelation_b200.networks import stratified_shard_torch
-    net = stratified_shard_torch(N * world, K, N * rank, N, "cuda:%d" % dev, seed=seed, weight_scale=weight_scale,
-                                 near_size=(30 if workload == "c5" else 17))
+    from neurocorrelation_b200.networks import spatial_shard_torch, stratified_shard_torch
+    net = None
+    if workload in ("c2s", "c3s"):
+        try:
+            net = spatial_shard_torch(N * world, K, N * rank, N, "cuda:%d" % dev, seed=seed, weight_scale=weight_scale, time_budget_s=240.0)
+        except Exception as e:  # (out of memory, time budget, ...): the stand-in is always available; the line says which network it timed
+            sys.stderr.write("bench: spatial builder failed (%s: %s), using the stratified stand-in\n" % (type(e).__name__, e))
+            torch.cuda.empty_cache()
+    if net is None:
+        net = stratified_shard_torch(N * world, K, N * rank, N, "cuda:%d" % dev, seed=seed, weight_scale=weight_scale,
+                                     near_size=(30 if workload == "c5" else 17))
     torch.cuda.synchronize()
     md = net["min_delay"]
     if world > 1:
@@ -161,6 +184,8 @@ def build_brain(workload, dev, rank=0, world=1, seed=1, weight_scale=1.0, comm_i
     else:
         g = nb.NeuCor.from_device_shard(net["N"], net["S"], *ptrs, rank=rank, world=world, global_min_delay=md, device=dev)
         g.set_comm_id(comm_id)
+    if net.get("positions") is not None:
+        g.set_positions(net["positions"])
     g._keepalive = net
     return g, net
 
@@ -346,8 +371,12 @@ def main():
     warmup = max(args.warmup, 3)
     state_mb = Nper * (K or 28) * 36 / 1e6
     config = {"workload": wl_desc, "dt_ms": DT, "mode": "sweep (run() + full detector read), STDP on (learningRate 1; the learningRate 0 arm is in `stdp_off`), background firing on",
-              "network": ("stratified random stand-in (in-degree exactly K, lengths ~ r^2 in a ball, weights U(0.2,1)*%g, 20%% inhibitory), %d input firers with random phase%s"
-                          % (args.weight_scale, max(1, Nper * world // 250), ", all rates pinned at 75 Hz, 30 neurons per firer" if args.workload == "c5" else "")) if K else "NeuCor(750)",
+              "network": (("stratified random stand-in (in-degree exactly K, lengths ~ r^2 in a ball, weights U(0.2,1)*%g, 20%% inhibitory), %d input firers with random phase%s"
+                           % (args.weight_scale, max(1, Nper * world // 250), ", all rates pinned at 75 Hz, 30 neurons per firer" if args.workload == "c5" else ""))
+                          if args.workload not in ("c2s", "c3s") else
+                          ("SURVEY 8(d) spatial recipe (positions in a cube at density 8, K partners within the ball that holds 2K, lengths = float32 distances, weights U(0.2,1)*%g, "
+                           "20%% inhibitory), %d input firers of radius 0.8 with random phase, paired rates on the reference's random walk; falls back to the stand-in if the builder fails (stderr says so)"
+                           % (args.weight_scale, max(1, Nper * world // 250)))) if K else "NeuCor(750)",
               "spinup_ms": spinup_ms,
               "l2": ("inputs larger than L2" if state_mb > 126 else "inputs SMALLER than L2") + ": per-GPU state %.0f MB against a 126 MB L2; no flush between steps" % state_mb}
 
@@ -418,12 +447,21 @@ def main():
         step = drv.step
     else:
         drive_setup(g, net, True, pinned_rate=75.0 if args.workload == "c5" else None)
-        step = g.step
+        if net.get("positions") is not None:  # spatial recipe: paired rates on a random walk, one frame per step (main.cpp:100-105)
+            def step():
+                g.random_walk_rates(75.0, True, use_libc=False)  # (a private generator: the taped replay must see the same rand() stream as the live run)
+                return g.step()
+        else:
+            step = g.step
     if os.environ.get("NC_CAND_SMEM"):  # tuning knob: slots in the neuron pass's per-warp shared-memory pool
         g.set_candidate_smem(int(os.environ["NC_CAND_SMEM"]))
     g.set_sweep_mean(False)  # the per-step device->host result is the counter block (hidden rand() count, fires, ...); see e2e.with_potact_readback
     g.finalize()
     Nglob, S_glob = g.counts()[0], (net["S"] * world if net else g.counts()[1])
+    if net and world > 1 and net.get("positions") is not None:  # spatial shards are ragged: sum the shards' synapse counts
+        t = torch.tensor([net["S"]], dtype=torch.int64, device="cuda:%d" % dev)
+        dist.all_reduce(t)
+        S_glob = int(t.item())
     if net:
         g._keepalive = None
         for k in ("pre", "weight", "length", "flag", "rowptr"):

@@ -61,6 +61,8 @@ def load_host_library(path=None):
     L.nch_import_network.argtypes = [vp, C.c_uint64, u64p, u32p, f32p, f32p, u8p, vp]
     L.nch_import_network_device.argtypes = [vp, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp]
     L.nch_import_shard_device.argtypes = [vp, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp, C.c_float]
+    L.nch_set_positions.argtypes = [vp, f32p, C.c_uint64]
+    L.nch_random_walk_rates.argtypes = [vp, C.c_float, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
     L.nch_set_shard.argtypes = [vp, C.c_int, C.c_int]
     L.nch_set_comm_id.argtypes = [vp, C.c_char_p]
     L.nch_set_exchange.argtypes = [vp, ALLGATHER_FN, vp]
@@ -246,6 +248,18 @@ class NeuCor:
         if last_fire is not None:
             for i, t in enumerate(last_fire):
                 self._ck(self.L.nch_set_input_lastfire(self.h, i, float(t)))
+
+    def set_positions(self, xyz):
+        """Positions (N x 3 float32) of a network imported without them; call before set_inputs / add_detector."""
+        xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        self._ck(self.L.nch_set_positions(self.h, xyz.reshape(-1), len(xyz)))
+
+    def random_walk_rates(self, max_rate=75.0, paired=True, use_libc=True):
+        """One frame of main.cpp's input random walk (main.cpp:100-105) over this brain's rate array, in C.  use_libc: draw from
+        libc's rand() as the reference's driver does (returns the number of draws); else from a private generator."""
+        n = C.c_uint64()
+        self._ck(self.L.nch_random_walk_rates(self.h, float(max_rate), int(paired), int(use_libc), C.byref(n)))
+        return n.value
 
     def set_rate(self, i, v):
         self._ck(self.L.nch_set_rate(self.h, i, float(v)))

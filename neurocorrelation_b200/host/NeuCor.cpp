@@ -529,6 +529,12 @@ void NeuCor::importNetworkDevice(std::size_t n, uint64_t synapses, const uint64_
     neurons.d_.clear();  // (no object view of a device-resident network)
 }
 
+void NeuCor::setPositions(const float* xyz, std::size_t n) {
+    if (n != positions.size()) throw std::out_of_range("NeuCor::setPositions: one position per neuron");
+    for (std::size_t i = 0; i < n; i++) positions[i] = coord3{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+    gridN_ = 0;  // the near-list grid is rebuilt from the new positions
+}
+
 void NeuCor::setShard(int rank, int world) {
     if (engine_) throw std::logic_error("NeuCor::setShard: the network is already on the device");
     if (world < 1 || rank < 0 || rank >= world) throw std::out_of_range("NeuCor::setShard: bad rank/world");

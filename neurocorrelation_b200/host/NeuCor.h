@@ -193,6 +193,7 @@ public:
     // The shard's rows of a network of `n` neurons, already resident on the device (local rowptr starting at 0).
     void importShardDevice(std::size_t n, uint64_t localSynapses, const uint64_t* d_rowptr, const uint32_t* d_pre, const float* d_weight,
                            const float* d_length, const uint8_t* d_inhibitory);
+    void setPositions(const float* xyz, std::size_t n);  // positions of a network imported without them (n = neuron count); before setInputRateArray / setDetectors
     void setInputNear(unsigned inputID, const uint32_t* ids, std::size_t n);  // overrides an input's `near` list
     void setInputLastFire(unsigned inputID, float t);
     float runSwept();               // run() + "run every neuron at the new time, ascending ID"; returns the mean potential

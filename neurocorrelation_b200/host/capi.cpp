@@ -16,6 +16,7 @@ thread_local std::string g_err;
 struct Handle {
     NeuCor* brain;
     std::vector<float> rates;  // the caller-owned array NeuCor keeps a pointer to (NeuCor.cpp:47)
+    uint64_t walk = 0x9E3779B97F4A7C15ull;  // private generator of nch_random_walk_rates (xorshift64)
 };
 template <typename F>
 int guard(F f) {
@@ -57,6 +58,29 @@ int nch_import_shard_device(void* hv, uint64_t n, uint64_t S, const void* rowptr
     return guard([&] {
         B->importShardDevice(n, S, (const uint64_t*)rowptr, (const uint32_t*)pre, (const float*)weight, (const float*)length, (const uint8_t*)flag);
         B->globalMinDelay = globalMinDelay;
+    });
+}
+// positions of a network that was imported without them (device-resident imports): what the firers' / detectors' `near` lists are built from
+int nch_set_positions(void* hv, const float* xyz, uint64_t n) { return guard([&] { B->setPositions(xyz, n); }); }
+// One frame of main.cpp's input random walk (main.cpp:100-105) over the handle's rate array: rate += (u - 0.5) * 2 with u uniform
+// in [0, 1], clamped to [0, max]; with `paired`, every odd input shares the rate of the even one before it (inputs[1] = inputs[0]:
+// the "correlated" groups).  use_libc != 0: u = randomUnit() from libc's rand(), exactly as the reference's driver draws it (the
+// brain then sees that the application moved the stream, as with main.cpp); 0: a private generator, libc's stream untouched.
+int nch_random_walk_rates(void* hv, float max_rate, int paired, int use_libc, uint64_t* n_rand) {
+    return guard([&] {
+        Handle* h = (Handle*)hv;
+        std::vector<float>& r = h->rates;
+        uint64_t draws = 0;
+        for (float& input : r) {
+            float u;
+            if (use_libc) { u = static_cast<float>(rand()) / static_cast<float>(RAND_MAX); draws++; }
+            else { h->walk ^= h->walk << 13; h->walk ^= h->walk >> 7; h->walk ^= h->walk << 17; u = (float)(h->walk >> 40) / 16777216.0f; }
+            input += (u - 0.5f) * 2.0f;
+            input = input < 0.0f ? 0.0f : input > max_rate ? max_rate : input;
+        }
+        if (paired)
+            for (size_t i = 1; i < r.size(); i += 2) r[i] = r[i - 1];
+        if (n_rand) *n_rand = draws;
     });
 }
 int nch_set_shard(void* hv, int rank, int world) { return guard([&] { B->setShard(rank, world); }); }

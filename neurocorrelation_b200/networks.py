@@ -192,3 +192,113 @@ def stratified_shard_torch(N, K, row0, n_rows, device, seed=1, chunk_rows=32768,
     return dict(N=N, S=S, row0=row0, n_rows=n_rows, rowptr=rowptr, pre=pre, weight=weight, length=length, flag=flag,
                 min_delay=float(length.min().item()) * 2.0 if S else float("inf"),
                 inputs=dict(G=G, positions=None, radius=np.full(G, 0.8, np.float32), near=near))
+
+
+def spatial_shard_torch(N, K, row0, n_rows, device, seed=1, weight_scale=1.0, time_budget_s=None, pad_rows=65536):
+    """Rows [row0, row0+n_rows) of the SURVEY.md section 8(d) recipe at C2-C4 scale, built in device memory with torch
+    (plumbing only; runs unchanged on CPU tensors, which is how tests/test_networks.py checks it):
+      * positions of ALL N neurons uniform in a cube of side (N/8)^(1/3) — identical on every rank (same seed);
+      * every neuron of this shard draws min(K, candidates) distinct presynaptic partners uniformly from the neurons within
+        radius_for(K) of it, lengths < MIN_LENGTH rejected, no self-synapse; lengths are coord3::getDist in float32
+        (NeuCor.h:16-18), rows ascend in presynaptic ID; neurons near the cube's faces that see fewer than K candidates take
+        all of them (ragged rows);
+      * weights U(0.2, 1) * weight_scale, 20 % negated, flag = sign.
+    A unit-cell grid of side >= R bounds the candidates to the 27 surrounding cells; within a cell block the K partners are
+    the K smallest of one uniform key per candidate pair (topk).  Returns the same dict as stratified_shard_torch plus
+    `positions` (host float32 [N, 3]) — input firers get their `near` lists from the host class's grid (radius 0.8).
+    Raises TimeoutError when time_budget_s is exceeded (callers fall back to the stratified stand-in)."""
+    import time
+    import torch
+    t_start = time.perf_counter()
+    N, K, row0, n_rows = int(N), int(K), int(row0), int(n_rows)
+    dev = torch.device(device)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed * 1000003)
+    L = (N / DENSITY) ** (1.0 / 3.0)
+    R = radius_for(K)
+    pos = torch.rand((N, 3), generator=gen, device=dev, dtype=torch.float32) * L
+    gen.manual_seed(seed * 1000003 + 17 + row0)  # what follows is per shard
+    nc = max(1, int(np.floor(L / R)))
+    cs = L / nc
+    cell3 = torch.clamp((pos / cs).to(torch.int64), max=nc - 1)
+    cid = (cell3[:, 0] * nc + cell3[:, 1]) * nc + cell3[:, 2]
+    order = torch.argsort(cid, stable=True)
+    counts = torch.bincount(cid, minlength=nc ** 3)
+    starts = torch.zeros(nc ** 3 + 1, dtype=torch.int64, device=dev)
+    starts[1:] = torch.cumsum(counts, 0)
+    starts_h = starts.cpu().numpy()
+    mine_mask = torch.zeros(N, dtype=torch.bool, device=dev)
+    mine_mask[row0:row0 + n_rows] = True
+    # padded per-row results, compacted at the end (rows are ragged near the faces)
+    pre_pad = torch.empty((n_rows, K), dtype=torch.int32, device=dev)
+    len_pad = torch.empty((n_rows, K), dtype=torch.float32, device=dev)
+    cnt = torch.zeros(n_rows, dtype=torch.int64, device=dev)
+    Rf, minlen = np.float32(R), np.float32(MIN_LENGTH)
+    for cx in range(nc):
+        for cy in range(nc):
+            if time_budget_s is not None and time.perf_counter() - t_start > time_budget_s:
+                raise TimeoutError("spatial_shard_torch: %.0f s budget exceeded" % time_budget_s)
+            for cz in range(nc):
+                c = (cx * nc + cy) * nc + cz
+                members = order[starts_h[c]:starts_h[c + 1]]
+                mine = members[mine_mask[members]]
+                if mine.numel() == 0:
+                    continue
+                parts = []
+                for dx in (-1, 0, 1):
+                    for dy in (-1, 0, 1):
+                        for dz in (-1, 0, 1):
+                            x, y, z = cx + dx, cy + dy, cz + dz
+                            if 0 <= x < nc and 0 <= y < nc and 0 <= z < nc:
+                                q = (x * nc + y) * nc + z
+                                parts.append(order[starts_h[q]:starts_h[q + 1]])
+                cand = torch.sort(torch.cat(parts)).values
+                pm, pc = pos[mine], pos[cand]
+                d0 = pm[:, None, 0] - pc[None, :, 0]
+                d2 = d0 * d0
+                d1 = pm[:, None, 1] - pc[None, :, 1]
+                d2 = d2 + d1 * d1
+                d1 = pm[:, None, 2] - pc[None, :, 2]
+                d2 = d2 + d1 * d1
+                d = torch.sqrt(d2.double()).float()  # = correctly rounded sqrtf (torch's own float32 sqrt is 1 ulp off on some CPUs)
+                ok = (d < Rf) & (d >= minlen) & (mine[:, None] != cand[None, :])
+                keys = torch.rand(d.shape, generator=gen, device=dev, dtype=torch.float32)
+                keys = torch.where(ok, keys, torch.full_like(keys, 2.0))
+                kk = min(K, cand.numel())
+                vals, idx = torch.topk(keys, kk, dim=1, largest=False)
+                valid = vals < 1.5
+                idx = torch.where(valid, idx, torch.full_like(idx, cand.numel()))
+                idx = torch.sort(idx, dim=1).values  # ascending candidate position = ascending presynaptic ID; rejected ones last
+                n_ok = valid.sum(1)
+                safe = torch.clamp(idx, max=cand.numel() - 1)
+                rows = mine - row0
+                pre_pad[rows, :kk] = cand[safe].to(torch.int32)
+                len_pad[rows, :kk] = torch.gather(d, 1, safe)
+                cnt[rows] = n_ok
+                del d, d0, d1, d2, ok, keys, vals, idx, safe, valid
+    rowptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=dev)
+    rowptr[1:] = torch.cumsum(cnt, 0)
+    S = int(rowptr[-1].item())
+    pre = torch.empty(S, dtype=torch.int32, device=dev)
+    length = torch.empty(S, dtype=torch.float32, device=dev)
+    cols = torch.arange(K, device=dev)
+    for a in range(0, n_rows, pad_rows):  # compact the padded rows chunk by chunk
+        b = min(n_rows, a + pad_rows)
+        m = cols[None, :] < cnt[a:b, None]
+        lo, hi = int(rowptr[a].item()), int(rowptr[b].item())
+        pre[lo:hi] = pre_pad[a:b][m]
+        length[lo:hi] = len_pad[a:b][m]
+    del pre_pad, len_pad
+    weight = torch.empty(S, dtype=torch.float32, device=dev)
+    for a in range(0, S, 1 << 26):
+        b = min(S, a + (1 << 26))
+        w = (torch.rand(b - a, device=dev, generator=gen) * 0.8 + 0.2) * float(weight_scale)
+        neg = torch.rand(b - a, device=dev, generator=gen) < 0.2
+        weight[a:b] = torch.where(neg, -w, w)
+    flag = (weight < 0).to(torch.uint8)
+    rng = np.random.default_rng(seed)
+    G = max(1, N // 250)
+    gpos = (rng.random((G, 3)) * L).astype(np.float32)
+    return dict(N=N, S=S, row0=row0, n_rows=n_rows, rowptr=rowptr, pre=pre, weight=weight, length=length, flag=flag,
+                min_delay=float(length.min().item()) * 2.0 if S else float("inf"), positions=pos.cpu().numpy(),
+                inputs=dict(G=G, positions=gpos, radius=np.full(G, 0.8, np.float32), near=None))

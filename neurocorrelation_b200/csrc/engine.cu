@@ -1,24 +1,26 @@
 // libneucor_b200.so — the device engine behind include/neucor_b200.h.
 //
-// One window (t0, t1] of the reference's event loop (NeuCor::run, /root/reference/src/NeuCor.cpp:583-617)
-// is executed as two data-parallel passes over a post-synaptic-sorted CSR:
+// One window (t0, t1] of the reference's event loop (NeuCor::run, /root/reference/src/NeuCor.cpp:583-617) is executed as two
+// data-parallel passes over a post-synaptic-sorted CSR, neither of which visits idle synapses (DESIGN.md sections 3-4):
 //
-//   neuron pass  (k_neuron_pass)  — warps claim tiles of 32 target neurons.  STAGING (warp-cooperative, coalesced): the
-//       row's `arrive` is streamed in 128-slot groups, the occupied slots (0 < arrive <= t1) of as many rows as fit the
-//       warp's pool are ballot-compacted in row order, the slots that may deliver / be cleared are flagged for the synapse
-//       pass.  REPLAY (lane-per-row): every lane replays one neuron's in-window events (deliveries, +2 ms requeues,
-//       host-scheduled input/background events, the end-of-window sweep) in the canonical order with Neuron::run / fire
-//       semantics (NeuCor.cpp:619-714): ordered accumulation over active slots in ascending presynaptic ID, passive decay,
-//       threshold / refractory check, AP waveform, activity.  Emits fire records (atomic append) and marks cleared slots in
-//       place.  Never touches weights.  Rows whose occupied slots exceed the pool take a warp-per-row path with a spill area.
-//   exchange     — fire records of all shards are made visible to every shard (in-stream NCCL all-gather of
-//       the shards' record blocks; a no-op for world = 1), then k_index_build turns them into a per-neuron
-//       lookup (bitmask + linked records).
-//   synapse pass (k_synapse_pass) — warps claim chunks of rows and stream `pre`: "did my presynaptic neuron fire" is a
-//       probe of the fire bitmask in shared memory (the pull gather); eventful slots — fired parent, fired row, flagged
-//       delivery/clear — are queued per warp and resolved 32 at a time: load (Synapse::fire, NeuCor.cpp:727-738), clear
-//       (NeuCor.cpp:697), post-fire plasticity and delivery plasticity (Synapse::run / synapticPlasticity,
-//       NeuCor.cpp:718-764) in the canonical event order.
+//   k_stage        keeps, per tile of 32 rows, the list of occupied slots (arrived, not yet cleared) current: per-word arrival
+//                  bounds name the few index words worth looking at, the window's arrivals are merged into the persistent
+//                  list, entries the last neuron pass cleared are dropped (rebuild from the busy / arrived bitmaps when needed).
+//   k_neuron_pass  warps claim tiles; a tile's list goes into the warp's shared-memory pool in batches and every lane REPLAYS
+//                  one neuron's in-window events (deliveries, +2 ms requeues, host / background events, the end-of-window
+//                  sweep) in the canonical order with Neuron::run / fire semantics (NeuCor.cpp:619-714): ordered accumulation
+//                  over its active slots in ascending presynaptic ID, passive decay, threshold / refractory check, AP waveform,
+//                  activity.  Emits fire records, marks cleared slots, hands delivered / cleared slots to the synapse pass
+//                  (flag list).  Never touches weights.  Over-long rows take a warp-per-row path with an exact prefix-sum
+//                  form of the ordered accumulation.  On a sharded engine its last block pushes the shard's fire records
+//                  into every peer's memory (peer_exchange.cuh).
+//   k_index_build  fire records of all shards -> bitmask + per-neuron record lists.
+//   k_syn_loads / k_syn_rows / k_syn_flagged   the synapse pass: only eventful slots, each owned by exactly one kernel — the
+//                  out-synapses of fired neurons (Synapse::fire, NeuCor.cpp:727-738), the in-synapses of fired neurons
+//                  (post-fire plasticity), the flagged slots (delivery: Synapse::run / synapticPlasticity, NeuCor.cpp:718-764;
+//                  clear, NeuCor.cpp:697) — resolved in the canonical event order by resolve_slot() (step_logic.cuh).
+//   k_bg_generate / k_bg_walk / k_merge_events / k_finish_step   libc's rand() stream on the device: background firing
+//                  (NeuCor.cpp:604-607), its merge with the host's input-firer events, the hidden rand() calls (rand_stream.cuh).
 //
 // Arithmetic mirrors the reference's float/double typing operator by operator with explicit-rounding
 // intrinsics (no FMA contraction; built with -fmad=false) and glibc-exact powf/exp (glibc_math.cuh).

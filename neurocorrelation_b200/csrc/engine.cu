@@ -2162,6 +2162,7 @@ extern "C" int nc_step(nc_engine* e, float t0, float t1, int sweep, const nc_eve
     return nc_step_collect(e, hidden, st);
 }
 
+static int scratch(nc_engine* e, size_t bytes, void** out);
 extern "C" int nc_run_neurons(nc_engine* e, float now, const uint32_t* ids, uint32_t nIds, uint64_t* hidden, nc_step_stats* st) {
     if (e->cfg.world != 1) return fail(e, NC_ERR_STATE, "nc_run_neurons: single-shard engines only");
     if (!e->uploaded) return fail(e, NC_ERR_STATE, "nc_run_neurons: no network uploaded");
@@ -2173,7 +2174,10 @@ extern "C" int nc_run_neurons(nc_engine* e, float now, const uint32_t* ids, uint
             if (ids[i] < e->v.row0 || ids[i] >= e->v.row0 + e->v.nRows) return fail(e, NC_ERR_INVALID, "nc_run_neurons: neuron outside this shard");
             if (i && ids[i] <= ids[i - 1]) return fail(e, NC_ERR_INVALID, "nc_run_neurons: ids must be strictly ascending");
         }
-        CK(cudaMalloc(&dIds, (size_t)nIds * 4));
+        void* d = nullptr;  // (the engine's persistent read-back scratch: no allocation per call, nothing to leak on an error path)
+        int rcs = scratch(e, (size_t)nIds * 4, &d);
+        if (rcs) return rcs;
+        dIds = (uint32_t*)d;
         CK(cudaMemcpyAsync(dIds, ids, (size_t)nIds * 4, cudaMemcpyHostToDevice, e->stream));
     }
     StepArgs a;
@@ -2183,7 +2187,6 @@ extern "C" int nc_run_neurons(nc_engine* e, float now, const uint32_t* ids, uint
     if (!rc) rc = launch_pass2(e, a, std::max<uint32_t>(e->lastCounts[0], 256u), 0);
     if (!rc) rc = finish_counters(e, hidden, st);
     if (!rc) { e->lastCounts[0] = (uint32_t)std::min<unsigned long long>(e->hOut[8], e->v.fireCap); e->lastStride = e->v.fireCap + 1u; }
-    cudaFree(dIds);
     return rc;
 }
 
@@ -2202,18 +2205,18 @@ extern "C" int nc_read_synapses(nc_engine* e, float* weight, float* arrive, floa
     CK(cudaStreamSynchronize(e->stream));
     uint64_t b = e->v.S * 4;
     if ((arrive || depol || weight || lastArr) && e->v.S) {  // these live in interleaved records on the device: de-interleave through a temporary
-        float* tmp = nullptr;
-        CK(cudaMalloc(&tmp, b));
+        void* d = nullptr;
+        int rcs = scratch(e, b, &d);
+        if (rcs) return rcs;
+        float* tmp = (float*)d;
         float* dsts[4] = {arrive, depol, weight, lastArr};
         for (int which = 0; which < 4; which++) {
             float* dst = dsts[which];
             if (!dst) continue;
             k_extract_ad<<<(unsigned)std::min<uint64_t>((e->v.S + 255) / 256, 1u << 20), 256, 0, e->stream>>>(e->v, which, tmp); e->launches++;
-            cudaError_t ce = cudaMemcpyAsync(dst, tmp, b, cudaMemcpyDeviceToHost, e->stream);
-            if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
-            if (ce != cudaSuccess) { cudaFree(tmp); e->err = std::string("nc_read_synapses: ") + cudaGetErrorString(ce); return NC_ERR_CUDA; }
+            CK(cudaMemcpyAsync(dst, tmp, b, cudaMemcpyDeviceToHost, e->stream));
+            CK(cudaStreamSynchronize(e->stream));
         }
-        cudaFree(tmp);
     }
     if (lastStart) CK(cudaMemcpy(lastStart, e->v.lastStart, b, cudaMemcpyDeviceToHost));
     return NC_OK;

@@ -1281,7 +1281,8 @@ __global__ void k_synapse_pots(View v, float now, float* prePot, float* postPot)
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 
-struct TapeStep { float t0, t1; int sweep; uint64_t evOff; uint32_t nEv; uint32_t units; uint32_t fires; bool bgDraw, bgActive, bgStrict; ncr::BgArgs bg; };
+struct TapeStep { float t0, t1; int sweep; uint64_t evOff; uint32_t nEv; uint32_t units; uint32_t fires; bool bgDraw, bgActive, bgStrict; ncr::BgArgs bg;
+                  int32_t randIdx; };  // randIdx >= 0: the application moved libc's stream before this window (entry of the taped rand() states)
 
 // NCCL is bound at run time (dlopen) so that single-GPU users need no NCCL at all; only the five entry points below are used.
 struct NcclApi {
@@ -1351,6 +1352,9 @@ struct nc_engine {
     float breakdown[4] = {0, 0, 0, 0};      // last per-kernel replay: k_stage, k_neuron_pass, fire exchange, synapse kernels [ms, summed]
     // tape
     bool taping = false; std::vector<TapeStep> tape; nc_event* dTape = nullptr; uint64_t tapeCap = 0, tapeUsed = 0; uint32_t tapeMaxSteps = 0;
+    // rand() states the host handed over while taping (nc_rand_set_state: the application drew from libc between two run() calls):
+    // a replay puts them back at the same windows, so that it sees the stream the live run saw
+    std::vector<uint32_t> tapeRand; uint32_t* dTapeRand = nullptr; bool tapeRandPending = false; uint32_t tapeRandPend[32] = {0};
     // snapshot
     struct Snap { float2* ad; SynRec* rec; float *lastStart, *lastRan, *lastFire, *lfStart, *actStart; float2* potAct; uint32_t *firings, *busy, *arrived, *wordNext; bool valid; } snap = {};
     uint64_t busyWords = 0, nTiles = 0;
@@ -1448,7 +1452,7 @@ static void free_all(nc_engine* e) {
     cudaFree(v.actStart); cudaFree(v.firings); cudaFree(v.localHdr); cudaFree(v.head); cudaFree(v.next); cudaFree(v.mask); cudaFree(v.evMask); cudaFree(v.busy); cudaFree(v.arrived); cudaFree(v.wordNext); cudaFree(v.stCnt); cudaFree(v.stAD); cudaFree(v.stJ); cudaFree(v.tileState); cudaFree(v.flagList); cudaFree(v.flagCtl); cudaFree(e->dCscPtr); cudaFree(e->dCscEnt);
     cudaFree(v.spillA); cudaFree(v.spillD); cudaFree(v.spillJ);
     cudaFree(e->dGather);
-    cudaFree(e->dEv); cudaFree(e->dTape);
+    cudaFree(e->dEv); cudaFree(e->dTape); cudaFree(e->dTapeRand);
     auto& s = e->snap;
     cudaFree(s.ad); cudaFree(s.rec); cudaFree(s.lastStart); cudaFree(s.lastRan);
     cudaFree(s.lastFire); cudaFree(s.lfStart); cudaFree(s.actStart); cudaFree(s.potAct); cudaFree(s.firings); cudaFree(s.busy); cudaFree(s.arrived); cudaFree(s.wordNext);
@@ -2087,7 +2091,9 @@ static int step_second_half(nc_engine* e) {
         else { int rc = exchange_fires(e, a, &expect); if (rc) return rc; }
     }
     if (e->taping) {
-        TapeStep ts = {a.t0, a.t1, a.sweep, e->tapeUsed, a.nEv, a.gStride, expect, e->bgPendingTape, e->pendingBgActive, e->pendingBgStrict, e->bgPendingArgs};
+        int32_t randIdx = -1;
+        if (e->tapeRandPending) { randIdx = (int32_t)(e->tapeRand.size() / 32); e->tapeRand.insert(e->tapeRand.end(), e->tapeRandPend, e->tapeRandPend + 32); e->tapeRandPending = false; }
+        TapeStep ts = {a.t0, a.t1, a.sweep, e->tapeUsed, a.nEv, a.gStride, expect, e->bgPendingTape, e->pendingBgActive, e->pendingBgStrict, e->bgPendingArgs, randIdx};
         e->tape.push_back(ts);
         e->tapeUsed += a.nEv;
         e->bgPendingTape = false;
@@ -2446,9 +2452,18 @@ extern "C" int nc_tape_begin(nc_engine* e, uint32_t maxSteps, uint64_t maxEvents
     e->tapeCap = std::max<uint64_t>(maxEvents, 1);
     CK(cudaMalloc(&e->dTape, e->tapeCap * sizeof(nc_event)));
     e->tape.clear(); e->tapeUsed = 0; e->tapeMaxSteps = maxSteps; e->taping = true;
+    e->tapeRand.clear(); e->tapeRandPending = false; cudaFree(e->dTapeRand); e->dTapeRand = nullptr;
     return NC_OK;
 }
-extern "C" int nc_tape_end(nc_engine* e) { e->taping = false; return NC_OK; }
+extern "C" int nc_tape_end(nc_engine* e) {
+    e->taping = false;
+    if (!e->tapeRand.empty()) {
+        cudaSetDevice(e->cfg.device);
+        CK(cudaMalloc(&e->dTapeRand, e->tapeRand.size() * 4));
+        CK(cudaMemcpy(e->dTapeRand, e->tapeRand.data(), e->tapeRand.size() * 4, cudaMemcpyHostToDevice));
+    }
+    return NC_OK;
+}
 
 template <typename T>
 static cudaError_t snap_copy(T*& dst, const T* src, uint64_t n, cudaStream_t st, bool toSnap) {
@@ -2513,6 +2528,7 @@ extern "C" int nc_tape_replay(nc_engine* e, uint32_t first, uint32_t count, floa
         fill_args(e, a, ts.t0, ts.t1, ts.sweep, e->dTape + ts.evOff, ts.nEv);
         a.gStride = ts.units;
         if (e->cfg.world > 1) begin_exchange(e, a);
+        if (ts.randIdx >= 0) CK(cudaMemcpyAsync(e->dRandState, e->dTapeRand + (size_t)ts.randIdx * 32, 31 * 4, cudaMemcpyDeviceToDevice, e->stream));
         if (ts.bgDraw) { int rc = launch_background(e, ts.bg); if (rc) return rc; }
         if (ts.bgActive) { int rc = merge_background(e, a, ts.bgStrict); if (rc) return rc; }
         if (!a.nEvDev) mark_events(e, a, 1);
@@ -2564,6 +2580,7 @@ extern "C" int nc_rand_set_state(nc_engine* e, const uint32_t* x31) {
     if (!x31) return fail(e, NC_ERR_INVALID, "nc_rand_set_state: null state");
     cudaSetDevice(e->cfg.device);
     memcpy(e->hRand, x31, 31 * 4);
+    if (e->taping) { memcpy(e->tapeRandPend, x31, 31 * 4); e->tapeRandPending = true; }
     CK(cudaMemcpyAsync(e->dRandState, e->hRand, 31 * 4, cudaMemcpyHostToDevice, e->stream));
     CK(cudaStreamSynchronize(e->stream));  // (hRand is reused by the read-back of the next window)
     e->randOn = true; e->hRandFresh = true;

@@ -77,3 +77,37 @@ def test_fire_raster_and_device_signature(emu_lib):
 
 def test_checkpoint_resume(emu_lib, tmp_path):
     scenarios.checkpoint_resume(emu_lib, tmp_path, before=70, after=60)
+
+
+@pytest.mark.parametrize("app_draws", [0, 3])
+def test_tape_replay_is_the_live_computation(emu_lib, app_draws):
+    """bench.py times a device-resident REPLAY of taped live steps: it must be the same computation — same counters, same final
+    state — also when the application draws from libc's rand() between two run() calls (main.cpp:100-105: the host then hands
+    the moved stream over, and the tape has to put it back at the same window)."""
+    import neurocorrelation_b200 as nb
+    from helpers import libc, synthetic_drive
+    from neurocorrelation_b200 import engine
+    from neurocorrelation_b200.networks import synthetic_network
+    net = synthetic_network(400, 30, seed=4)
+    g = nb.NeuCor.from_network(net, library=emu_lib)
+    synthetic_drive(g, net, True)
+    for _ in range(50):
+        g.step()
+    E = engine.Engine(borrowed=g.engine_handle(), library=emu_lib)
+    E.snapshot()
+    E.tape_begin(40, 1 << 16)
+    s0 = g.stats()
+    for _ in range(30):
+        for _ in range(app_draws):
+            libc.rand()
+        g.step()
+    E.tape_end()
+    s1 = g.stats()
+    live_sig = g.state_signature()
+    E.restore()
+    assert not np.array_equal(g.state_signature(), live_sig)
+    rep = E.tape_replay(0, 30, per_kernel=False)
+    assert np.array_equal(g.state_signature(), live_sig)
+    for k in ("fires", "deliveries", "loads_accepted", "loads_dropped", "plasticity_calls", "neuron_runs", "active_visits"):
+        assert rep["stats"][k] == s1[k] - s0[k], k
+    g.close()

@@ -94,6 +94,18 @@ def test_sharded_gloo_cpu(mock_host_lib, tmp_path, world):
     assert st["hidden_rand"] > 0  # the summed hidden rand() count keeps every rank's libc stream in step
 
 
+def test_sharded_emulated_engine_gloo(tmp_path):
+    """The same two-shard run with the ENGINE'S OWN KERNELS on the CPU (tests/emu_build.py: csrc/engine.cu compiled unmodified on
+    the block emulator) instead of the test double: the out-synapse index over global IDs restricted to a shard's rows, the
+    fire index over the gathered blocks of all shards (k_index_build with one grid row per shard), the synapse kernels'
+    ownership rules — against the oracle's run of the whole network.  The exchange is the caller-provided all-gather over gloo
+    (the peer-memory path needs CUDA IPC and cannot be emulated)."""
+    import emu_build
+    world, N, K, steps = 2, 500, 40, 320
+    shards = _launch("gloo-mock", world, N, K, steps, tmp_path, {"NC_MOCK_HOST_LIB": emu_build.build()})
+    _check(world, N, K, steps, shards)
+
+
 def test_sharded_checkpoint_one_file_per_rank(mock_host_lib, tmp_path):
     """Half way through a 2-shard run every rank saves ITS rows (network, state, firers, rand() position, the network-wide delay
     bound) to its own file; brains restored from those files — same (rank, world), same exchange — repeat the second half of

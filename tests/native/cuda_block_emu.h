@@ -81,6 +81,7 @@ struct Fibre {
 struct State {
     std::vector<Fibre> f;            // the threads of the block being run
     std::vector<char*> stacks;       // fibre stacks, kept across blocks and launches
+    std::vector<unsigned> perm;      // resume order of the current block's threads
     void* schedSp = nullptr;
     Fibre* cur = nullptr;
     dim3 bIdx, bDim, gDim;
@@ -210,9 +211,20 @@ inline void run_block(const std::function<void()>& body) {
         for (int r = 0; r < 6; r++) *--sp = nullptr;
         x.sp = (void*)sp;
     }
+    // NC_EMU_ORDER: the order in which runnable threads are resumed — 0 ascending (default), 1 descending, 2 a fresh pseudo-random
+    // permutation per pass.  Results must not depend on it: a difference means threads communicate through memory without
+    // a barrier between them (on the GPU: a race, or reliance on lock-step execution of a warp).
+    const int order = getenv("NC_EMU_ORDER") ? atoi(getenv("NC_EMU_ORDER")) : 0;  // (read per block: tests switch it within one process)
+    static uint64_t rng = 0x2545F4914F6CDD1Dull;
+    std::vector<unsigned>& perm = s.perm;
+    perm.resize(T);
+    for (unsigned i = 0; i < T; i++) perm[i] = order == 1 ? T - 1 - i : i;
     for (;;) {
         bool progressed = false, allDone = true;
-        for (unsigned i = 0; i < T; i++) {
+        if (order == 2)
+            for (unsigned i = T; i > 1; i--) { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; std::swap(perm[i - 1], perm[rng % i]); }
+        for (unsigned pi = 0; pi < T; pi++) {
+            const unsigned i = perm[pi];
             Fibre& x = s.f[i];
             if (x.wait != DONE) allDone = false;
             if (x.wait != RUN) continue;
@@ -240,12 +252,14 @@ inline void launch(dim3 grid, dim3 block, F&& kernel_call) {
     State& s = S();
     s.gDim = grid; s.bDim = block;
     const std::function<void()> body = kernel_call;
-    for (unsigned z = 0; z < grid.z; z++)
-        for (unsigned y = 0; y < grid.y; y++)
-            for (unsigned x = 0; x < grid.x; x++) {
-                s.bIdx = dim3(x, y, z);
-                run_block(body);
-            }
+    const int order = getenv("NC_EMU_ORDER") ? atoi(getenv("NC_EMU_ORDER")) : 0;
+    const unsigned long long nBlocks = (unsigned long long)grid.x * grid.y * grid.z;
+    for (unsigned long long k = 0; k < nBlocks; k++) {
+        unsigned long long b = order == 1 ? nBlocks - 1 - k : order == 2 ? (k * 0x9E3779B1ull + 7) % nBlocks : k;  // (order 2: a stride walk; a permutation when nBlocks is odd or a power of two, else some blocks repeat — so fall back)
+        if (order == 2 && (nBlocks & (nBlocks - 1)) != 0 && (nBlocks % 2 == 0)) b = nBlocks - 1 - k;
+        s.bIdx = dim3((unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y), (unsigned)(b / ((unsigned long long)grid.x * grid.y)));
+        run_block(body);
+    }
 }
 
 }  // namespace emu

@@ -27,6 +27,17 @@ def test_smoke_scenario_lockstep(emu_lib):
     assert st["fires"] > 10 and st["deliveries"] > 100
 
 
+@pytest.mark.parametrize("order", ["1", "2"])
+def test_results_do_not_depend_on_the_scheduling_order(emu_lib, monkeypatch, order):
+    """NC_EMU_ORDER: runnable threads resumed in descending ID / in a fresh pseudo-random permutation per pass, blocks in another
+    order.  Threads that communicate through memory without a barrier between them (a race on the GPU, or reliance on a warp
+    running in lock-step) would produce different results; the scenario must stay bit-exact.  (The whole file passes under
+    NC_EMU_ORDER=1 and =2 as well; this is the slice that runs every time.)"""
+    monkeypatch.setenv("NC_EMU_ORDER", order)
+    st = scenarios.synthetic_vs_oracle(emu_lib, 500, 32, 140)
+    assert st["deliveries"] > 100
+
+
 def test_c1_golden_vectors(emu_lib):
     """BASELINE configs[0] (the reference's own default network) against the fixture recorded from the reference."""
     scenarios.c1_golden(emu_lib, "c1_seed1_normalised.npz", 200, check_every=1)

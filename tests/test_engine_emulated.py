@@ -122,3 +122,54 @@ def test_tape_replay_is_the_live_computation(emu_lib, app_draws):
     for k in ("fires", "deliveries", "loads_accepted", "loads_dropped", "plasticity_calls", "neuron_runs", "active_visits"):
         assert rep["stats"][k] == s1[k] - s0[k], k
     g.close()
+
+
+def test_renderer_statistics_kernels(emu_lib):
+    """The Statistics panel's reductions (Renderer.cpp:1733-1876: k_render_histogram, k_render_raster) and the per-frame synapse
+    potentials written into a caller's "device" buffer (k_synapse_pots), against numpy on the state read back — the emulated
+    twin of tests/test_gpu_parity.py::test_renderer_statistics_on_device, plus the potentials recorded from the reference."""
+    import os
+    import neurocorrelation_b200 as nb
+    from helpers import GOLDEN, load_golden, run_c1_golden, same_bits
+    from neurocorrelation_b200 import engine
+    zp = np.load(os.path.join(GOLDEN, "c1_seed1_pots.npz"))
+    z, net, near = load_golden("c1_seed1_normalised.npz")
+    g = nb.NeuCor.from_network(net, library=emu_lib)
+    E = None
+    checked = []
+
+    def on_step(k):
+        if k in zp["steps"]:
+            pre, post = E.read_synapse_pots(g.time())
+            assert same_bits(pre, zp["pre_%d" % k]) and same_bits(post, zp["post_%d" % k]), "potentials differ from the reference's at step %d" % k
+            checked.append(k)
+
+    g.finalize()
+    E = engine.Engine(borrowed=g.engine_handle(), library=emu_lib)
+    E.N, E.S, E.row0, E.n_rows = net["N"], net["S"], 0, net["N"]
+    steps = int(min(s for s in zp["steps"] if s >= 100)) + 1
+    bad, fields = run_c1_golden(g, z, near, steps, keyword_near=True, check_every=50, on_step=on_step)
+    assert bad == -1 and len(checked) >= 1
+    n, s = g.read_neurons(), g.read_synapses()
+    F = np.float32
+
+    def hist(x, spans, lo, hi):
+        f = np.floor((F(spans) * (x.astype(F) - F(lo))).astype(F) / F(hi - lo)).astype(F)
+        ok = (f >= 0) & (f < spans)
+        return np.bincount(f[ok].astype(np.int64), minlength=spans).astype(np.uint32), int(np.sum(~(f >= 0))), int(np.sum(f >= spans))
+
+    for which, x, spans, lo, hi in (("activity", n["act"], 25, 0.0, 6.0), ("activity", n["act"], 7, 0.5, 3.0),
+                                    ("weight", s["weight"], 20, -1.0, 1.0), ("weight", s["weight"], 9, -0.3, 0.45)):
+        bins, below, above = E.render_histogram(which, spans, lo, hi)
+        wb, wl, wh = hist(x, spans, lo, hi)
+        assert np.array_equal(bins, wb) and (below, above) == (wl, wh), which
+    now, dt = F(g.time()), F(0.0625)
+    ids, count = E.render_raster(float(now), float(dt))
+    with np.errstate(invalid="ignore"):
+        want = np.nonzero((now - n["lastFire"]).astype(F) < dt)[0]
+    assert count == len(want) and np.array_equal(np.sort(ids), want.astype(np.uint32))
+    pre_h, post_h = E.read_synapse_pots(float(now))
+    d = np.zeros(2 * net["S"], np.float32)
+    E._ck(E.L.nc_synapse_pots_device(E.h, float(now), d.ctypes.data, d.ctypes.data + 4 * net["S"]))
+    assert same_bits(d[:net["S"]], pre_h) and same_bits(d[net["S"]:], post_h)
+    g.close()

@@ -173,3 +173,27 @@ def test_renderer_statistics_kernels(emu_lib):
     E._ck(E.L.nc_synapse_pots_device(E.h, float(now), d.ctypes.data, d.ctypes.data + 4 * net["S"]))
     assert same_bits(d[:net["S"]], pre_h) and same_bits(d[net["S"]:], post_h)
     g.close()
+
+
+def test_saturated_regime(emu_lib):
+    """All-excitatory weights drive the network to the refractory limit (the regime of the recipe's literal weight law at K = 1000,
+    bench workload c3raw): most load attempts hit a busy slot and are dropped, every row carries dozens of active slots."""
+    import neurocorrelation_b200 as nb
+    from helpers import lockstep, synthetic_drive
+    from neurocorrelation_b200.networks import synthetic_network
+    from oracle.orcbind import OracleBrain
+    net = synthetic_network(400, 150, seed=4)
+    net["weight"] = np.abs(net["weight"]).astype(np.float32)
+    net["flag"] = np.zeros_like(net["flag"])
+
+    def drive(b, kw):
+        synthetic_drive(b, net, kw)
+        for i in range(net["inputs"]["G"]):
+            b.set_rate(i, 70.0)
+            b.add_input_offset(i, -12.0)
+        return b
+
+    steps = 170
+    bad, fields, so, sg = lockstep(lambda: drive(OracleBrain(net), False), lambda: drive(nb.NeuCor.from_network(net, library=emu_lib), True), steps, lambda: None)
+    assert bad == -1, (bad, fields)
+    assert so == sg and so["loads_dropped"] > so["loads_accepted"] // 2 and so["fires"] / 400 / (steps * 0.0625e-3) > 150  # mean rate in Hz

@@ -511,8 +511,12 @@ __device__ void warp_row(const View& v, const StepArgs& s, uint64_t row, CandVie
     bool hasEv;
     const uint32_t cnt = stage_row<true>(v, s, rs, re, cv, nullptr, nullptr, 0u, 0u, lane, hasEv);
     __syncwarp();
-    uint32_t evLo, evHi;
-    host_event_range(v, s, row, q, evLo, evHi);
+    // the row's host events: looked up by ONE lane and broadcast — host_event_range takes the row's mark down after reading it, so
+    // 32 lanes calling it for the same row only agree as long as they run in lock-step (found by the CPU emulator, where they do not)
+    uint32_t evLo = 0, evHi = 0;
+    if (lane == 0) host_event_range(v, s, row, q, evLo, evHi);
+    evLo = __shfl_sync(0xffffffffu, evLo, 0);
+    evHi = __shfl_sync(0xffffffffu, evHi, 0);
     NeuronState n;
     float lfS0;
     {

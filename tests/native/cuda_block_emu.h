@@ -88,12 +88,13 @@ struct State {
     const std::function<void()>* body = nullptr;
     size_t stackBytes = 256 * 1024;
     unsigned long long collectives = 0, barriers = 0;
+    const char* kernel = "?";           // text of the launch being run (diagnostics)
     unsigned onTheWay = 0, atBlock = 0;  // threads of the block that are running or parked at a warp collective / parked at the block barrier
 };
 inline State& S() { static State s; return s; }
 
 [[noreturn]] inline void die(const char* what) {
-    fprintf(stderr, "cuda_block_emu: %s (block %u,%u thread %u)\n", what, S().bIdx.x, S().bIdx.y, S().cur ? S().cur->linear : 0u);
+    fprintf(stderr, "cuda_block_emu: %s (kernel %s, block %u,%u thread %u)\n", what, S().kernel, S().bIdx.x, S().bIdx.y, S().cur ? S().cur->linear : 0u);
     abort();
 }
 
@@ -131,7 +132,11 @@ inline void try_release_warp(unsigned warp) {
         Fibre& x = s.f[i];
         const bool named = (mask >> (i - lo)) & 1u;
         if (x.wait == AT_WARP) {
-            if (x.kind != lead->kind || x.mask != mask) die("lanes of one warp are parked at different collectives / masks");
+            if (x.kind != lead->kind || x.mask != mask) {
+                for (unsigned k = lo; k < hi; k++)
+                    fprintf(stderr, "  lane %2u: state %d kind %d mask %08x payload %llx aux %d\n", k - lo, (int)s.f[k].wait, s.f[k].kind, s.f[k].mask, (unsigned long long)s.f[k].payload, s.f[k].aux);
+                die("lanes of one warp are parked at different collectives / masks");
+            }
             if (!named) die("a lane takes part in a collective whose mask does not name it");
         } else if (named && x.wait != DONE) {
             return;  // a named lane has not arrived yet (RUN, or parked at a block barrier = deadlock, caught by the scheduler)

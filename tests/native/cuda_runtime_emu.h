@@ -177,6 +177,7 @@ inline Prof& prof() { static Prof p; return p; }
         emu::dyn().assign((size_t)(smem) + 64, 0xA5);                                                \
         emu::launches()++;                                                                           \
         const dim3 g_ = dim3(grid), b_ = dim3(block);                                                \
+        emu::S().kernel = #call;                                                                     \
         const auto t_ = std::chrono::steady_clock::now();                                            \
         emu::launch(g_, b_, [&] { call; });                                                          \
         if (emu::prof().on) {                                                                        \

@@ -60,8 +60,31 @@ for case in range(cases):
             g.set_candidate_smem(cand)
         return drive(g, True)
 
+    # mid-run actions of the GUI, applied to both sides at the same steps: toggle an input (Renderer.cpp:2036), reset the activities (:1619)
+    toggle_at, reset_at = int(rng.integers(5, steps)), int(rng.integers(5, steps))
+
+    class Acting:  # steps the brain and performs the actions before the chosen steps
+        def __init__(self, b, is_oracle):
+            self.b, self.k, self.is_oracle = b, 0, is_oracle
+
+        def step(self):
+            if self.k == toggle_at:
+                self.b.set_input_enabled(0, False)
+            if self.k == toggle_at + 7:
+                self.b.set_input_enabled(0, True)
+            if self.k == reset_at:
+                if self.is_oracle:
+                    self.b.L.orc_reset_activities(self.b.h)
+                else:
+                    self.b.reset_activities()
+            self.k += 1
+            return self.b.step()
+
+        def __getattr__(self, name):
+            return getattr(self.b, name)
+
     t0 = time.time()
-    bad, fields, so, sg = lockstep(lambda: drive(OracleBrain(net), False), make_g, steps, lambda: None)
+    bad, fields, so, sg = lockstep(lambda: Acting(drive(OracleBrain(net), False), True), lambda: Acting(make_g(), False), steps, lambda: None)
     ok = bad == -1 and so == sg
     print("case %d: N=%d K=%d S=%d dt=%g lr=%g %s cand=%d hot=%d steps=%d seed=%d -> %s fires=%d deliveries=%d dropped=%d hidden=%d (%.0f s)"
           % (case, N, K, net["S"], dt, lr, mode, cand, hot, steps, nseed, "ok" if ok else "DIVERGES at step %d in %s" % (bad, fields),

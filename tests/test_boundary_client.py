@@ -65,7 +65,8 @@ def test_client_compiles_against_both_headers_and_runs_in_lockstep():
 def test_client_against_the_emulated_engine():
     """The same client linked against the engine's own kernels on the CPU emulator (tests/emu_build.py): the renderer-frame walk
     over the object graph — every synapse's end potentials from k_synapse_pots, weights, potentials, activities, the raster
-    rule — prints the reference's lines.  First preset only (the emulator is slow)."""
+    rule — detector reads, input toggles and resetActivities print the same lines as the build on the CPU test double, which
+    the test above holds to the reference's own output.  A shortened first preset (the emulator is slow)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import emu_build
     lib = emu_build.build()
@@ -73,9 +74,10 @@ def test_client_against_the_emulated_engine():
     exe = os.path.join(BUILD, "client_emu")
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-pthread", "-I" + HOST, "-I" + ROOT, os.path.join(NATIVE, "client_presets.cpp"),
                            lib, "-Wl,-rpath," + os.path.dirname(lib), "-o", exe])
-    r = subprocess.run([exe, *RUNS[0]], capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stderr[-2000:]
-    want = open(GOLDEN).read()
-    assert r.stdout.count("\n") >= 9 and "DIFFERENT" not in r.stdout
-    assert want.startswith(r.stdout), "the drop-in on the emulated engine and the reference print different lines"
-
+    run = ("standard", "1", "150")
+    got = subprocess.run([exe, *run], capture_output=True, text=True, timeout=900)
+    assert got.returncode == 0, got.stderr[-2000:]
+    want = subprocess.run([_build_dropin_client(mock=True), *run], capture_output=True, text=True, timeout=900)
+    assert want.returncode == 0, want.stderr[-2000:]
+    assert got.stdout.count("\n") >= 4 and "DIFFERENT" not in got.stdout and "carrying a spike" in got.stdout
+    assert got.stdout == want.stdout, "the drop-in prints different lines on the emulated engine and on the test double"

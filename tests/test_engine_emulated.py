@@ -23,7 +23,7 @@ def emu_lib():
 
 def test_smoke_scenario_lockstep(emu_lib):
     """__graft_entry__.smoke()'s scenario: every field of every step against the oracle."""
-    st = scenarios.synthetic_vs_oracle(emu_lib, 500, 32, 180)
+    st = scenarios.synthetic_vs_oracle(emu_lib, 500, 32, 150)
     assert st["fires"] > 10 and st["deliveries"] > 100
 
 
@@ -40,7 +40,7 @@ def test_results_do_not_depend_on_the_scheduling_order(emu_lib, monkeypatch, ord
 
 def test_c1_golden_vectors(emu_lib):
     """BASELINE configs[0] (the reference's own default network) against the fixture recorded from the reference."""
-    scenarios.c1_golden(emu_lib, "c1_seed1_normalised.npz", 200, check_every=1)
+    scenarios.c1_golden(emu_lib, "c1_seed1_normalised.npz", 150, check_every=1)
 
 
 def test_long_rows_take_the_warp_per_row_path(emu_lib):
@@ -51,7 +51,7 @@ def test_long_rows_take_the_warp_per_row_path(emu_lib):
 
 def test_staging_region_overflow_takes_the_in_kernel_path(emu_lib, monkeypatch):
     monkeypatch.setenv("NC_STAGE_CAP", "8")
-    st = scenarios.synthetic_vs_oracle(emu_lib, 1500, 60, 120)
+    st = scenarios.synthetic_vs_oracle(emu_lib, 1000, 60, 110)
     assert st["deliveries"] > 500
 
 
@@ -77,7 +77,7 @@ def test_detector_offsets_reset(emu_lib):
 
 def test_edge_cases(emu_lib):
     """Empty and ragged rows, a reciprocal equal-length pair (equal-time ties), learningRate = 0."""
-    scenarios.edge_cases(emu_lib, steps=(120, 300, 80), offset=-12.0)
+    scenarios.edge_cases(emu_lib, steps=(100, 220, 60), offset=-12.0)
 
 
 def test_fire_raster_and_device_signature(emu_lib):
@@ -87,7 +87,7 @@ def test_fire_raster_and_device_signature(emu_lib):
 
 
 def test_checkpoint_resume(emu_lib, tmp_path):
-    scenarios.checkpoint_resume(emu_lib, tmp_path, before=70, after=60)
+    scenarios.checkpoint_resume(emu_lib, tmp_path, before=50, after=45)
 
 
 @pytest.mark.parametrize("app_draws", [0, 3])
@@ -193,7 +193,7 @@ def test_saturated_regime(emu_lib):
             b.add_input_offset(i, -12.0)
         return b
 
-    steps = 170
+    steps = 130
     bad, fields, so, sg = lockstep(lambda: drive(OracleBrain(net), False), lambda: drive(nb.NeuCor.from_network(net, library=emu_lib), True), steps, lambda: None)
     assert bad == -1, (bad, fields)
     assert so == sg and so["loads_dropped"] > so["loads_accepted"] // 2 and so["fires"] / 400 / (steps * 0.0625e-3) > 150  # mean rate in Hz

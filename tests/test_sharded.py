@@ -101,7 +101,7 @@ def test_sharded_emulated_engine_gloo(tmp_path):
     ownership rules — against the oracle's run of the whole network.  The exchange is the caller-provided all-gather over gloo
     (the peer-memory path needs CUDA IPC and cannot be emulated)."""
     import emu_build
-    world, N, K, steps = 2, 500, 40, 320
+    world, N, K, steps = 2, 500, 40, 290
     shards = _launch("gloo-mock", world, N, K, steps, tmp_path, {"NC_MOCK_HOST_LIB": emu_build.build()})
     _check(world, N, K, steps, shards)
 

@@ -1224,11 +1224,21 @@ __global__ void k_reset_activities(View v, float now) {  // Neuron::resetActivit
     float2 pa = v.potAct[i]; pa.y = 0.0f; v.potAct[i] = pa;
 }
 // VoltageDetector::getVoltage's sequential float sum (NeuCor.cpp:360-365) — one thread, exact order.
+// One warp.  The sum itself is the reference's: sequential, in list order, one float rounding per addition (NeuCor.cpp:360-365) —
+// every lane carries the same running sum; what is parallel is the memory side: 32 potentials are gathered per round trip
+// (the next 32 already in flight) and handed round by shuffles, instead of one dependent load pair per neuron on one thread.
 __global__ void k_detector_mean(View v, const uint32_t* near, uint32_t n, float* out) {
-    if (blockIdx.x || threadIdx.x) return;
+    const uint32_t lane = threadIdx.x & 31u;
     float avg = 0.0f;
-    for (uint32_t i = 0; i < n; i++) avg = add32(avg, v.potAct[near[i] - v.row0].x);
-    *out = div32(avg, (float)n);
+    float nxt = lane < n ? v.potAct[near[lane] - v.row0].x : 0.0f;
+    for (uint32_t base = 0; base < n; base += 32u) {
+        const float cur = nxt;
+        const uint32_t ahead = base + 32u + lane;
+        nxt = ahead < n ? v.potAct[near[ahead] - v.row0].x : 0.0f;
+        const uint32_t cnt = min(32u, n - base);  // (the same in every lane: the shuffles below stay converged)
+        for (uint32_t j = 0; j < cnt; j++) avg = add32(avg, __shfl_sync(0xffffffffu, cur, (int)j));
+    }
+    if (lane == 0) *out = div32(avg, (float)n);
 }
 // ---- NeuCor_Renderer's "Statistics" panel on the device (/root/reference/src/NeuCor_Renderer.cpp:1733-1876) -----------------------
 // span index = floor(spans * (x - range_min) / range) with the reference's float typing (int * float, float / float, floor);

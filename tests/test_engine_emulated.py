@@ -197,3 +197,30 @@ def test_saturated_regime(emu_lib):
     bad, fields, so, sg = lockstep(lambda: drive(OracleBrain(net), False), lambda: drive(nb.NeuCor.from_network(net, library=emu_lib), True), steps, lambda: None)
     assert bad == -1, (bad, fields)
     assert so == sg and so["loads_dropped"] > so["loads_accepted"] // 2 and so["fires"] / 400 / (steps * 0.0625e-3) > 150  # mean rate in Hz
+
+
+def test_detector_mean_is_the_sequential_float_sum(emu_lib):
+    """k_detector_mean gathers 32 potentials per round trip but adds them one after the other, in list order, one float rounding per
+    addition — VoltageDetector::getVoltage's `avgV += potential` (NeuCor.cpp:360-365): bit-equal to the loop in numpy float32 for
+    list lengths around the warp size, with potentials of mixed sign and magnitude."""
+    import ctypes as C
+    from neurocorrelation_b200 import engine
+    N = 1100
+    net = dict(N=N, S=0, rowptr=np.zeros(N + 1, np.uint64), pre=np.zeros(1, np.uint32), weight=np.zeros(1, np.float32),
+               length=np.zeros(1, np.float32), flag=np.zeros(1, np.uint8))
+    E = engine.Engine(library=emu_lib)
+    E.upload(net)
+    rng = np.random.default_rng(3)
+    pot = np.where(rng.random(N) < 0.8, rng.normal(-70.0, 6.0, N), rng.normal(20.0, 30.0, N)).astype(np.float32)
+    potAct = np.zeros(2 * N, np.float32)
+    potAct[0::2] = pot
+    E._ck(E.L.nc_write_neurons(E.h, potAct.ctypes.data_as(C.c_void_p), None, None, None, None))
+    for n in (1, 2, 31, 32, 33, 64, 65, 750, N):
+        near = np.sort(rng.choice(N, size=n, replace=False)).astype(np.uint32)
+        s = np.float32(0.0)
+        for x in pot[near]:
+            s = np.float32(s + x)
+        want = np.float32(s / np.float32(n))
+        got = np.float32(E.detector_mean(near))
+        assert got.view(np.uint32) == want.view(np.uint32), (n, got, want)
+    E.close()

@@ -11,7 +11,7 @@
 //   * warp collectives (__syncwarp, __ballot_sync, __any_sync, __all_sync, __shfl_*_sync, __reduce_*_sync) park a lane until
 //     every live lane named in the mask has arrived at a collective of the SAME kind (anything else aborts: on the GPU
 //     it would be undefined behaviour);
-//   * __shared__ becomes `static` (one block at a time), atomics are plain read-modify-writes (one OS thread);
+//   * __shared__ becomes `static thread_local` (an OS thread runs one block at a time), atomics are real atomic operations;
 //   * a fibre that leaves the kernel counts as arrived at every later barrier, as on the hardware;
 //   * no progress by any fibre = deadlock (e.g. a barrier inside divergent code): aborts with a message.
 #pragma once
@@ -22,7 +22,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <functional>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #if !defined(__x86_64__)
@@ -91,7 +95,10 @@ struct State {
     const char* kernel = "?";           // text of the launch being run (diagnostics)
     unsigned onTheWay = 0, atBlock = 0;  // threads of the block that are running or parked at a warp collective / parked at the block barrier
 };
-inline State& S() { static State s; return s; }
+inline State& S() { static thread_local State s; return s; }  // (one per OS thread: NC_EMU_THREADS runs blocks on several)
+// dynamic shared memory of the block this OS thread is running, and the size the current launch asked for
+inline std::vector<unsigned char>& dyn() { static thread_local std::vector<unsigned char> b; return b; }
+inline size_t& dyn_bytes() { static size_t n = 0; return n; }
 
 [[noreturn]] inline void die(const char* what) {
     fprintf(stderr, "cuda_block_emu: %s (kernel %s, block %u,%u thread %u)\n", what, S().kernel, S().bIdx.x, S().bIdx.y, S().cur ? S().cur->linear : 0u);
@@ -220,7 +227,7 @@ inline void run_block(const std::function<void()>& body) {
     // permutation per pass.  Results must not depend on it: a difference means threads communicate through memory without
     // a barrier between them (on the GPU: a race, or reliance on lock-step execution of a warp).
     const int order = getenv("NC_EMU_ORDER") ? atoi(getenv("NC_EMU_ORDER")) : 0;  // (read per block: tests switch it within one process)
-    static uint64_t rng = 0x2545F4914F6CDD1Dull;
+    static thread_local uint64_t rng = 0x2545F4914F6CDD1Dull;
     std::vector<unsigned>& perm = s.perm;
     perm.resize(T);
     for (unsigned i = 0; i < T; i++) perm[i] = order == 1 ? T - 1 - i : i;
@@ -252,19 +259,82 @@ inline void run_block(const std::function<void()>& body) {
     }
 }
 
+struct Pool {  // worker threads that live as long as the process (their fibre stacks are reused from launch to launch)
+    std::mutex m;
+    std::condition_variable wake, done;
+    std::vector<std::thread> workers;
+    unsigned long long generation = 0;
+    int running = 0;
+    const std::function<void()>* body = nullptr;
+    dim3 grid, block;
+    const char* kernel = "?";
+    unsigned long long nBlocks = 0;
+    int order = 0;
+    std::atomic<unsigned long long> next{0};
+};
+inline dim3 block_of(unsigned long long k, unsigned long long nBlocks, int order, dim3 grid) {
+    unsigned long long b = order == 1 ? nBlocks - 1 - k : order == 2 ? (k * 0x9E3779B1ull + 7) % nBlocks : k;  // (order 2: a stride walk over the blocks)
+    return dim3((unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y), (unsigned)(b / ((unsigned long long)grid.x * grid.y)));
+}
+inline void run_block(const std::function<void()>& body);
+inline Pool& pool(int threads) {
+    static Pool* p = new Pool();  // (never destroyed: the workers are detached daemons of the test process)
+    while ((int)p->workers.size() < threads) {
+        p->workers.emplace_back([] {
+            Pool& q = *p;
+            unsigned long long seen = 0;
+            for (;;) {
+                {
+                    std::unique_lock<std::mutex> lk(q.m);
+                    q.wake.wait(lk, [&] { return q.generation != seen; });
+                    seen = q.generation;
+                }
+                State& w = S();
+                w.gDim = q.grid; w.bDim = q.block; w.kernel = q.kernel;
+                dyn().assign(dyn_bytes() + 64, 0xA5);
+                for (;;) {
+                    const unsigned long long k = q.next.fetch_add(1);
+                    if (k >= q.nBlocks) break;
+                    w.bIdx = block_of(k, q.nBlocks, q.order, q.grid);
+                    run_block(*q.body);
+                }
+                {
+                    std::unique_lock<std::mutex> lk(q.m);
+                    if (--q.running == 0) q.done.notify_all();
+                }
+            }
+        });
+        p->workers.back().detach();
+    }
+    return *p;
+}
+
+// NC_EMU_THREADS=n (default 1): the blocks of a launch are run by n OS threads at once (each with its own fibres, shared
+// memory and block index), atomics are real atomic operations.  Results must not depend on it: blocks may only meet through
+// atomics.  (x86's memory model is stronger than the GPU's, so this finds logic that depends on block order, not missing fences.)
 template <typename F>
 inline void launch(dim3 grid, dim3 block, F&& kernel_call) {
     State& s = S();
     s.gDim = grid; s.bDim = block;
     const std::function<void()> body = kernel_call;
     const int order = getenv("NC_EMU_ORDER") ? atoi(getenv("NC_EMU_ORDER")) : 0;
+    const int threads = getenv("NC_EMU_THREADS") ? atoi(getenv("NC_EMU_THREADS")) : 1;
     const unsigned long long nBlocks = (unsigned long long)grid.x * grid.y * grid.z;
-    for (unsigned long long k = 0; k < nBlocks; k++) {
-        unsigned long long b = order == 1 ? nBlocks - 1 - k : order == 2 ? (k * 0x9E3779B1ull + 7) % nBlocks : k;  // (order 2: a stride walk; a permutation when nBlocks is odd or a power of two, else some blocks repeat — so fall back)
-        if (order == 2 && (nBlocks & (nBlocks - 1)) != 0 && (nBlocks % 2 == 0)) b = nBlocks - 1 - k;
-        s.bIdx = dim3((unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y), (unsigned)(b / ((unsigned long long)grid.x * grid.y)));
-        run_block(body);
+    if (threads <= 1 || nBlocks < 2) {
+        for (unsigned long long k = 0; k < nBlocks; k++) { s.bIdx = block_of(k, nBlocks, order, grid); run_block(body); }
+        return;
     }
+    Pool& p = pool(threads);
+    {
+        std::unique_lock<std::mutex> lk(p.m);
+        p.body = &body; p.grid = grid; p.block = block; p.kernel = s.kernel; p.nBlocks = nBlocks; p.order = order;
+        p.next.store(0);
+        p.running = (int)p.workers.size();
+        p.generation++;
+    }
+    p.wake.notify_all();
+    std::unique_lock<std::mutex> lk(p.m);
+    p.done.wait(lk, [&] { return p.running == 0; });
 }
 
 }  // namespace emu
@@ -275,7 +345,7 @@ inline void launch(dim3 grid, dim3 block, F&& kernel_call) {
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
-#define __shared__ static
+#define __shared__ static thread_local
 #define __restrict__
 #define threadIdx (emu::S().cur->tid)
 #define blockIdx (emu::S().bIdx)
@@ -303,11 +373,22 @@ template <typename T> inline T __shfl_xor_sync(uint32_t mask, T v, int x) { retu
 
 template <typename T> inline T __ldg(const T* p) { return *p; }
 template <typename T> inline T __ldcs(const T* p) { return *p; }
-template <typename T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
-template <typename T> inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
-template <typename T> inline T atomicMin(T* p, T v) { T o = *p; *p = std::min(o, v); return o; }
-template <typename T> inline T atomicMax(T* p, T v) { T o = *p; *p = std::max(o, v); return o; }
-template <typename T> inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; }
+// atomics: real ones (blocks may run on several OS threads)
+template <typename T> inline T atomicAdd(T* p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+template <typename T> inline T atomicOr(T* p, T v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+template <typename T> inline T atomicAnd(T* p, T v) { return __atomic_fetch_and(p, v, __ATOMIC_SEQ_CST); }
+template <typename T> inline T atomicExch(T* p, T v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+template <typename T> inline T atomicCAS(T* p, T cmp, T v) { __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }
+template <typename T> inline T atomicMin(T* p, T v) {
+    T o = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (v < o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return o;
+}
+template <typename T> inline T atomicMax(T* p, T v) {
+    T o = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (v > o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return o;
+}
 inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 inline int __ffs(int x) { return __builtin_ffs(x); }

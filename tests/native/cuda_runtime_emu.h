@@ -33,7 +33,7 @@ inline void __threadfence() {}
 inline void __threadfence_block() {}
 inline void __threadfence_system() {}
 inline void __nanosleep(unsigned) {}
-inline long long clock64() { static long long c = 0; return c += 64; }
+inline long long clock64() { static thread_local long long c = 0; return c += 64; }
 inline float __fsub_rn(float a, float b) { return a - b; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dsub_rn(double a, double b) { return a - b; }
@@ -65,25 +65,23 @@ inline float min(float a, float b) { return fminf(a, b); }
 inline float max(float a, float b) { return fmaxf(a, b); }
 inline double min(double a, double b) { return fmin(a, b); }
 inline double max(double a, double b) { return fmax(a, b); }
-// atomics on the signed / mixed types the engine uses
-inline int atomicExch(int* p, int v) { int o = *p; *p = v; return o; }
-inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
-inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
-inline unsigned atomicOr(unsigned* p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
-inline unsigned atomicAnd(unsigned* p, unsigned v) { unsigned o = *p; *p = o & v; return o; }
-inline unsigned atomicMin(unsigned* p, unsigned v) { unsigned o = *p; *p = o < v ? o : v; return o; }
-inline unsigned atomicMax(unsigned* p, unsigned v) { unsigned o = *p; *p = o > v ? o : v; return o; }
-inline unsigned atomicCAS(unsigned* p, unsigned cmp, unsigned v) { unsigned o = *p; if (o == cmp) *p = v; return o; }
+// atomics on the signed / mixed argument types the engine uses (the templates in cuda_block_emu.h need both arguments of one type)
+inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicAnd(unsigned* p, unsigned v) { return __atomic_fetch_and(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicMin(unsigned* p, unsigned v) { return atomicMin<unsigned>(p, v); }
+inline unsigned atomicMax(unsigned* p, unsigned v) { return atomicMax<unsigned>(p, v); }
+inline unsigned atomicCAS(unsigned* p, unsigned cmp, unsigned v) { return atomicCAS<unsigned>(p, cmp, v); }
 
 // ---- dynamic shared memory ----------------------------------------------------------------------------------------------------
 namespace emu {
-inline std::vector<unsigned char>& dyn() { static std::vector<unsigned char> b; return b; }
 inline unsigned char* dyn_smem() { return dyn().data(); }
 struct Limits { int sms = 1; int blocksPerSm = 2; };  // one "SM" with two resident blocks: persistent grids still have several blocks (NC_EMU_SMS overrides)
-inline Limits& limits() {
-    static Limits l;
-    static bool init = false;
-    if (!init) { init = true; if (const char* s = getenv("NC_EMU_SMS")) l.sms = std::max(1, atoi(s)); }
+inline Limits limits() {  // (read per call: tests switch NC_EMU_SMS between engines)
+    Limits l;
+    if (const char* s = getenv("NC_EMU_SMS")) l.sms = std::max(1, atoi(s));
     return l;
 }
 inline unsigned long long& launches() { static unsigned long long n = 0; return n; }
@@ -174,6 +172,7 @@ inline Prof& prof() { static Prof p; return p; }
 }  // namespace emu
 #define EMU_LAUNCH(grid, block, smem, call)                                                          \
     do {                                                                                             \
+        emu::dyn_bytes() = (size_t)(smem);                                                           \
         emu::dyn().assign((size_t)(smem) + 64, 0xA5);                                                \
         emu::launches()++;                                                                           \
         const dim3 g_ = dim3(grid), b_ = dim3(block);                                                \

@@ -38,6 +38,16 @@ def test_results_do_not_depend_on_the_scheduling_order(emu_lib, monkeypatch, ord
     assert st["deliveries"] > 100
 
 
+def test_results_do_not_depend_on_blocks_running_concurrently(emu_lib, monkeypatch):
+    """NC_EMU_THREADS: the blocks of every launch run on four OS threads at once (four emulated SMs, so the persistent grids have
+    more blocks), atomics are real atomic operations.  Blocks may only meet through atomics — tile claims, append cursors, index
+    bits, arrival bounds, counters — so the scenario must stay bit-exact.  (The whole file passes this way too.)"""
+    monkeypatch.setenv("NC_EMU_THREADS", "4")
+    monkeypatch.setenv("NC_EMU_SMS", "4")
+    st = scenarios.synthetic_vs_oracle(emu_lib, 700, 48, 130)
+    assert st["deliveries"] > 100
+
+
 def test_c1_golden_vectors(emu_lib):
     """BASELINE configs[0] (the reference's own default network) against the fixture recorded from the reference."""
     scenarios.c1_golden(emu_lib, "c1_seed1_normalised.npz", 150, check_every=1)

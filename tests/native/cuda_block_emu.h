@@ -58,6 +58,14 @@ emu_switch:
 .size emu_switch,.-emu_switch
 )");
 
+#if defined(__SANITIZE_THREAD__)  // built by tools/emu_tsan.sh: ThreadSanitizer must be told about the fibres
+extern "C" void* __tsan_get_current_fiber(void);
+extern "C" void* __tsan_create_fiber(unsigned flags);
+extern "C" void __tsan_destroy_fiber(void* fiber);
+extern "C" void __tsan_switch_to_fiber(void* fiber, unsigned flags);
+#define EMU_TSAN 1
+#endif
+
 namespace emu {
 
 struct dim3 {
@@ -70,6 +78,7 @@ enum Kind { K_SYNCWARP = 1, K_BALLOT, K_ANY, K_ALL, K_SHFL, K_SHFL_UP, K_SHFL_DO
 
 struct Fibre {
     void* sp = nullptr;    // saved stack pointer while the fibre is parked
+    void* tsan = nullptr;  // ThreadSanitizer's handle of this fibre (EMU_TSAN builds)
     char* stack = nullptr;
     Wait wait = RUN;
     dim3 tid;
@@ -87,6 +96,7 @@ struct State {
     std::vector<char*> stacks;       // fibre stacks, kept across blocks and launches
     std::vector<unsigned> perm;      // resume order of the current block's threads
     void* schedSp = nullptr;
+    void* schedTsan = nullptr;
     Fibre* cur = nullptr;
     dim3 bIdx, bDim, gDim;
     const std::function<void()>* body = nullptr;
@@ -105,7 +115,12 @@ inline size_t& dyn_bytes() { static size_t n = 0; return n; }
     abort();
 }
 
-inline void yield_to_scheduler() { emu_switch(&S().cur->sp, S().schedSp); }
+inline void yield_to_scheduler() {
+#if defined(EMU_TSAN)
+    __tsan_switch_to_fiber(S().schedTsan, 0);
+#endif
+    emu_switch(&S().cur->sp, S().schedSp);
+}
 
 inline void fibre_entry() {
     (*S().body)();
@@ -241,7 +256,15 @@ inline void run_block(const std::function<void()>& body) {
             if (x.wait != DONE) allDone = false;
             if (x.wait != RUN) continue;
             s.cur = &x;
+#if defined(EMU_TSAN)
+            if (!s.schedTsan) s.schedTsan = __tsan_get_current_fiber();
+            if (!x.tsan) x.tsan = __tsan_create_fiber(0);
+            __tsan_switch_to_fiber(x.tsan, 0);
+#endif
             emu_switch(&s.schedSp, x.sp);
+#if defined(EMU_TSAN)
+            if (x.wait == DONE) { __tsan_destroy_fiber(x.tsan); x.tsan = nullptr; }
+#endif
             s.cur = nullptr;
             progressed = true;
             if (x.wait == AT_WARP || x.wait == DONE) try_release_warp(i / 32u);

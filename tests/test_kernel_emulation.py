@@ -147,3 +147,19 @@ def test_rand_advance_moves_the_stream_by_the_hidden_calls(emu, hidden):
         c[5] = 300_007
         emu.emu_rand_advance(st3.ctypes.data, c.ctypes.data, 1)
         assert stream_from(st3, 8) == stream_from(state, 300_007 + 8)[300_007:]
+
+
+def test_thread_sanitizer_sees_races_between_emulated_blocks(tmp_path):
+    """tools/emu_tsan.sh runs the engine's kernels under ThreadSanitizer with the blocks of a launch on several OS threads.  That it
+    stays silent there only means something if it speaks up for a real race in the same setup: a kernel whose blocks all
+    increment one word without an atomic is reported, the same kernel with atomicAdd is not."""
+    exe = str(tmp_path / "tsan_probe")
+    r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-pthread", "-I" + NATIVE, os.path.join(NATIVE, "tsan_probe.cpp"), "-o", exe],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("no ThreadSanitizer runtime for g++ here: " + r.stderr[-200:])
+    env = dict(os.environ, NC_EMU_THREADS="4")
+    ok = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=120)
+    assert "x = 64" in ok.stdout and "ThreadSanitizer" not in ok.stderr
+    racy = subprocess.run([exe, "racy"], capture_output=True, text=True, env=env, timeout=120)
+    assert "ThreadSanitizer: data race" in racy.stderr

@@ -30,6 +30,11 @@ for case in range(cases):
     mode = str(rng.choice(["sweep", "sweep", "lazy", "runall"]))
     cand = int(rng.choice([0, 0, 32, 64]))
     hot = bool(rng.random() < 0.4)       # all-excitatory, high rates: dense activity
+    if os.environ.get("NC_FUZZ_BIAS") == "warp":  # small pools, dense activity: the warp-per-row and overflow paths
+        cand = 32
+        hot = bool(rng.random() < 0.8)
+        N = max(N, 64)
+        K = max(K, min(N - 1, 90))
     steps = int(rng.choice([40, 80, 120]))
     nseed = int(rng.integers(1, 1000))
     if case < first_case:

@@ -160,7 +160,7 @@ public:
     Synapse* getSynapse(std::pair<std::size_t, std::size_t> ID);
     const Synapse* getSynapse(std::pair<std::size_t, std::size_t> ID) const;
     void refreshObjects();                                 // device -> object view, if anything ran since the last refresh
-    std::size_t objectViewLimit = (std::size_t)1 << 22;
+    std::size_t objectViewLimit = (std::size_t)1 << 20;
     // run() ends with syncState() (positions / potAct / lastFire mirrors current, as NeuCor_Renderer expects every frame,
     // Renderer.cpp:773-779): 8 bytes per neuron device -> host per run().  Callers stepping large networks switch it off.
     bool mirrorAfterRun = true;

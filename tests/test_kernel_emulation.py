@@ -80,9 +80,9 @@ def draw(L, seed, N, period, t0, dt, row0=0, n_rows=None, cand_cap=0):
 
 
 # (1_000_003, 150): ~6 700 hits — more candidates than k_bg_walk keeps in shared memory, so the walk reads global memory
-# (5, 274 100 / 276 550, 97): ~3 050 and ~3 090 candidates — just below and just above the 3 072 that k_bg_walk keeps in shared memory
+# (5, 284 500 / 285 000, 97): 3 068 and 3 076 candidates — just below and just above the 3 072 that k_bg_walk keeps in shared memory
 @pytest.mark.parametrize("seed,N,period", [(1, 5000, 97), (777, 200_000, 9600), (5, 40, 2), (9, 300_000, 9600), (123456789, 1_000_003, 150), (3, 31, 1),
-                                           (5, 274_100, 97), (5, 276_550, 97)])
+                                           (5, 284_500, 97), (5, 285_000, 97)])
 def test_background_draw_kernels_against_libc(emu, seed, N, period):
     t0, dt = F(12.5), F(0.0625)
     want, tail = reference_loop(seed, N, period, t0, dt)
